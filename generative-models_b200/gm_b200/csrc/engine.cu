@@ -1,0 +1,666 @@
+// libgm_b200.so — host side of the C ABI (include/gm_b200.h): context, GEMM plans
+// (TMA tensor maps + launch config), the GAN train-step engine.  No torch types.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "gm_b200.h"
+#include "gemm_umma.cuh"
+#include "kernels.cuh"
+
+using namespace gm;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct gm_ctx {
+  int device = 0;
+  int num_sms = 0;
+  PFN_encodeTiled encode = nullptr;
+  std::string err;
+  long long launches = 0;
+  float* scratch = nullptr;   // split-K partials for the generic gm_gemm_bf16
+  size_t scratch_bytes = 0;
+};
+
+static int fail(gm_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU_OK(ctx, expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(ctx, GM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int rup(int a, int b) { return cdiv(a, b) * b; }
+
+// ------------------------------------------------------------------ tensor maps
+// 2-D bf16 row-major matrix: `inner` contiguous elements per row (logical extent, may
+// be smaller than ld), `outer` rows, 128-byte swizzle, OOB elements read as zero.
+static int make_tmap(gm_ctx* c, CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_inner, uint32_t box_outer) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16 != 0)
+    return fail(c, GM_ERR_ARG, "tensor map: pointer/ld must be 16-byte aligned (ptr=%p ld=%llu)", ptr, (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, GM_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", int(r));
+  return GM_OK;
+}
+
+// ------------------------------------------------------------------ GEMM plans
+enum PlanKind { PK_NT_208 = 0, PK_NT_64, PK_TN_448, PK_TN_64 };
+
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmParams p;
+  int kind;
+  int grid;
+};
+
+template <int BN1, int BN2, bool AMN, bool BMN>
+static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
+  using Cfg = GemmCfg<BN1, BN2>;
+  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<pl.grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
+  return cudaGetLastError();
+}
+
+static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
+  cudaError_t e;
+  switch (pl.kind) {
+    case PK_NT_208: e = launch_inst<208, 0, false, false>(pl, s); break;
+    case PK_NT_64: e = launch_inst<64, 0, false, false>(pl, s); break;
+    case PK_TN_448: e = launch_inst<256, 192, true, true>(pl, s); break;
+    default: e = launch_inst<64, 0, true, true>(pl, s); break;
+  }
+  c->launches++;
+  if (e != cudaSuccess) return fail(c, GM_ERR_CUDA, "GEMM launch failed: %s", cudaGetErrorString(e));
+  return GM_OK;
+}
+
+// mode 0 (NT): A [M, lda] K-contiguous, B [N, ldb] K-contiguous.
+// mode 1 (TN): A [K, lda] M-contiguous, B [K, ldb] N-contiguous.
+// `ncover` = number of output columns the tiling must cover (>= N; out_cols for bf16).
+static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, const void* A, int lda, const void* B,
+                     int ldb, int ncover, int max_splits) {
+  memset(pl, 0, sizeof *pl);
+  if (M <= 0 || N <= 0 || K <= 0) return fail(c, GM_ERR_ARG, "gemm: bad extents %d %d %d", M, N, K);
+  int bn, boxn;
+  if (mode == 0) {
+    if (ncover <= 64) { pl->kind = PK_NT_64; bn = 64; boxn = 64; }
+    else { pl->kind = PK_NT_208; bn = 208; boxn = 208; }
+    int rc = make_tmap(c, &pl->tmA, A, K, M, lda, BK, BM);
+    if (rc) return rc;
+    rc = make_tmap(c, &pl->tmB, B, K, N, ldb, BK, boxn);
+    if (rc) return rc;
+  } else {
+    if (K % BK) return fail(c, GM_ERR_ARG, "gemm TN: K (%d) must be a multiple of %d", K, BK);
+    if (ncover <= 64) { pl->kind = PK_TN_64; bn = 64; }
+    else { pl->kind = PK_TN_448; bn = 448; }
+    int rc = make_tmap(c, &pl->tmA, A, M, K, lda, 64, BK);
+    if (rc) return rc;
+    rc = make_tmap(c, &pl->tmB, B, N, K, ldb, 64, BK);
+    if (rc) return rc;
+  }
+  GemmParams& p = pl->p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = cdiv(M, BM);
+  p.n_tiles = cdiv(ncover, bn);
+  p.kblocks = cdiv(K, BK);
+  const int tiles = p.m_tiles * p.n_tiles;
+  int splits = 1;
+  if (max_splits > 1) {
+    splits = c->num_sms / tiles;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > p.kblocks) splits = p.kblocks;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = cdiv(p.kblocks, splits);
+  p.splits = cdiv(p.kblocks, p.kb_per_split);
+  const int total = tiles * p.splits;
+  pl->grid = total < c->num_sms ? total : c->num_sms;
+  return GM_OK;
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nsplit, long long stride, long long n,
+                                       float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = 0.f;
+  for (int s = 0; s < nsplit; ++s) t += part[i + s * stride];
+  out[i] = t;
+}
+
+// ------------------------------------------------------------------ ctx
+extern "C" int gm_version(void) { return 100; }
+
+extern "C" int gm_ctx_create(int device, gm_ctx** out) {
+  if (!out) return GM_ERR_ARG;
+  *out = nullptr;
+  gm_ctx* c = new gm_ctx();
+  c->device = device;
+  *out = c;  // returned even on failure so the caller can read gm_last_error
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+    return fail(c, GM_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+  CU_OK(c, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU_OK(c, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(c, GM_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a (B200) only", prop.major, prop.minor);
+  c->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CU_OK(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return fail(c, GM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return GM_OK;
+}
+extern "C" int gm_ctx_destroy(gm_ctx* c) {
+  if (!c) return GM_OK;
+  if (c->scratch) cudaFree(c->scratch);
+  delete c;
+  return GM_OK;
+}
+extern "C" const char* gm_last_error(const gm_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+extern "C" int gm_ctx_num_sms(const gm_ctx* c) { return c ? c->num_sms : 0; }
+extern "C" long long gm_launch_count(gm_ctx* c, int reset) {
+  if (!c) return 0;
+  const long long n = c->launches;
+  if (reset) c->launches = 0;
+  return n;
+}
+
+// ------------------------------------------------------------------ generic GEMM / Adam
+extern "C" int gm_gemm_bf16(gm_ctx* c, const gm_gemm_desc* d, gm_stream stream) {
+  if (!c || !d) return GM_ERR_ARG;
+  if (!c->encode) return fail(c, GM_ERR_STATE, "context has no device");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GemmPlan pl;
+  const bool f32 = d->out_kind == 1;
+  const int ncover = f32 ? d->N : (d->out_cols > d->N ? d->out_cols : d->N);
+  if (!f32 && (d->N % 16)) return fail(c, GM_ERR_ARG, "bf16 output needs N %% 16 == 0 (N=%d)", d->N);
+  int rc = plan_gemm(c, &pl, d->mode, d->M, d->N, d->K, d->A_dev, d->lda, d->B_dev, d->ldb, ncover, f32 ? 64 : 1);
+  if (rc) return rc;
+  GemmParams& p = pl.p;
+  if (!f32) {
+    p.epi = EPI_BF16;
+    p.out = static_cast<__nv_bfloat16*>(d->C_dev);
+    p.ldo = d->ldc;
+    p.out_cols = ncover;
+    p.pad_one = d->pad_one;
+    p.bias = d->bias_dev;
+    p.act = d->act;
+    p.aux = static_cast<const __nv_bfloat16*>(d->aux_dev);
+    p.ld_aux = d->ld_aux;
+    p.aux_mode = d->aux_dev ? d->aux_mode : AUX_NONE;
+    p.dot_w = d->dot_w_dev;
+    p.dot_out = d->dot_out_dev;
+    p.dot_ld = d->dot_ld;
+    return launch_plan(c, pl, s);
+  }
+  p.epi = EPI_F32;
+  p.transpose = d->transpose;
+  p.ldp = d->ldc;
+  const long long per = (long long)(d->transpose ? d->N : d->M) * d->ldc;
+  if (p.splits == 1) {
+    p.part = static_cast<float*>(d->C_dev);
+    p.part_stride = 0;
+    return launch_plan(c, pl, s);
+  }
+  const size_t need = size_t(per) * p.splits * sizeof(float);
+  if (need > c->scratch_bytes) {
+    if (c->scratch) cudaFree(c->scratch);
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
+    CU_OK(c, cudaMalloc(&c->scratch, need));
+    c->scratch_bytes = need;
+  }
+  p.part = c->scratch;
+  p.part_stride = per;
+  rc = launch_plan(c, pl, s);
+  if (rc) return rc;
+  reduce_partials_kernel<<<unsigned((per + 255) / 256), 256, 0, s>>>(c->scratch, p.splits, per, per,
+                                                                     static_cast<float*>(d->C_dev));
+  c->launches++;
+  CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}
+
+static void fill_adam(AdamParams& a, const gm_adam_hp* hp, int step) {
+  a.lr = hp->lr; a.b1 = hp->beta1; a.b2 = hp->beta2; a.eps = hp->eps; a.wd = hp->weight_decay; a.clamp = hp->clamp;
+  a.bc1 = float(1.0 - pow(double(hp->beta1), double(step)));
+  a.bc2_sqrt = float(sqrt(1.0 - pow(double(hp->beta2), double(step))));
+  a.update = 1;
+}
+
+extern "C" int gm_adam_step(gm_ctx* c, float* p, const float* g, float* m, float* v, int n, const gm_adam_hp* hp,
+                            int step, gm_stream stream) {
+  if (!c || !p || !g || !m || !v || !hp || n <= 0 || step <= 0) return fail(c, GM_ERR_ARG, "gm_adam_step: bad argument");
+  AdamParams a;
+  memset(&a, 0, sizeof a);
+  a.p = p; a.g = g; a.m = m; a.v = v; a.total = n; a.nseg = 0;
+  fill_adam(a, hp, step);
+  adam_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  c->launches++;
+  CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}
+
+// ------------------------------------------------------------------ GAN engine
+struct NetLayout {
+  int in, hid, out;
+  int off_w1, off_b1, off_w2, off_b2, total;
+  void init(int in_, int hid_, int out_) {
+    in = in_; hid = hid_; out = out_;
+    off_w1 = 0; off_b1 = hid * in; off_w2 = off_b1 + hid; off_b2 = off_w2 + out * hid; total = off_b2 + out;
+  }
+};
+
+struct StepPlans {
+  GemmPlan g1, g2, d1_d, d1_g, dw1d, dx, dw2g, dhg, dw1g;
+};
+
+struct gm_gan {
+  gm_ctx* ctx;
+  gm_gan_desc d;
+  int X, H, Z, XP, HP, ZP, Bmax;
+  NetLayout G, D;
+  float* par[2] = {nullptr, nullptr};
+  float* grd[2] = {nullptr, nullptr};
+  float* am[2] = {nullptr, nullptr};
+  float* av[2] = {nullptr, nullptr};
+  // bf16 activations
+  __nv_bfloat16 *Zb = nullptr, *Hg = nullptr, *Xall = nullptr, *Aall = nullptr, *DHall = nullptr, *DA2 = nullptr, *DHg = nullptr;
+  // bf16 operand copies of the weight matrices
+  __nv_bfloat16 *W1g_s = nullptr, *W2g_s = nullptr, *W2g_t = nullptr, *W1d_s = nullptr, *W1d_t = nullptr;
+  float *slots = nullptr, *ds = nullptr, *scores = nullptr, *lossbuf = nullptr, *fisher = nullptr, *dw2p = nullptr;
+  float *PD = nullptr, *PG2 = nullptr, *PG1 = nullptr;
+  int dh_blocks = 0, dh_rows_per_iter = 0, dh_threads = 0;
+  int max_splits = 0;
+  int last_rows = 0;
+  int region_rows = 0;   // rows per region of Xall/Aall/DHall (3 regions)
+  std::map<int, StepPlans> plans;
+  std::vector<void*> allocs;
+};
+
+template <typename T>
+static int dev_alloc(gm_gan* g, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+  if (e != cudaSuccess) return fail(g->ctx, GM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  e = cudaMemset(q, 0, count * sizeof(T));
+  if (e != cudaSuccess) return fail(g->ctx, GM_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+  g->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return GM_OK;
+}
+
+extern "C" int gm_gan_destroy(gm_gan* g) {
+  if (!g) return GM_OK;
+  for (void* p : g->allocs) cudaFree(p);
+  delete g;
+  return GM_OK;
+}
+
+extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
+  if (!c || !d || !out) return GM_ERR_ARG;
+  *out = nullptr;
+  if (!c->encode) return fail(c, GM_ERR_STATE, "context has no device");
+  if (d->image_size % 16 || d->hidden_dim % 16 || d->image_size <= 0 || d->hidden_dim <= 0 || d->z_dim <= 0)
+    return fail(c, GM_ERR_ARG, "image_size and hidden_dim must be positive multiples of 16 (got %d, %d, z=%d)",
+                d->image_size, d->hidden_dim, d->z_dim);
+  if (d->max_batch <= 0 || d->max_batch % 64)
+    return fail(c, GM_ERR_ARG, "max_batch must be a positive multiple of 64 (got %d)", d->max_batch);
+  if (d->variant == GM_WGP || d->variant == GM_DRA || d->variant == GM_INFO)
+    return fail(c, GM_ERR_UNSUPPORTED, "variant %d is not built yet", d->variant);
+  gm_gan* g = new gm_gan();
+  g->ctx = c;
+  g->d = *d;
+  g->X = d->image_size; g->H = d->hidden_dim; g->Z = d->z_dim; g->Bmax = d->max_batch;
+  g->XP = rup(g->X + 1, 16);
+  g->HP = rup(g->H + 1, 16);
+  g->ZP = rup(g->Z + 1, 64);
+  g->G.init(g->Z, g->H, g->X);
+  g->D.init(g->X, g->H, 1);
+  g->region_rows = g->Bmax;
+  const size_t B = g->Bmax;
+  int rc = GM_OK;
+#define TRY(x) do { rc = (x); if (rc) { gm_gan_destroy(g); return rc; } } while (0)
+  TRY(dev_alloc(g, &g->Zb, B * g->ZP));
+  TRY(dev_alloc(g, &g->Hg, B * g->HP));
+  TRY(dev_alloc(g, &g->Xall, 3 * B * g->XP));
+  TRY(dev_alloc(g, &g->Aall, 3 * B * g->HP));
+  TRY(dev_alloc(g, &g->DHall, 3 * B * g->HP));
+  TRY(dev_alloc(g, &g->DA2, B * g->XP));
+  TRY(dev_alloc(g, &g->DHg, B * g->HP));
+  TRY(dev_alloc(g, &g->W1g_s, size_t(g->H) * g->ZP));
+  TRY(dev_alloc(g, &g->W2g_s, size_t(g->X) * g->H));
+  TRY(dev_alloc(g, &g->W2g_t, size_t(g->H) * g->X));
+  TRY(dev_alloc(g, &g->W1d_s, size_t(g->H) * g->X));
+  TRY(dev_alloc(g, &g->W1d_t, size_t(g->X) * g->H));
+  const int nslots = 2 * cdiv(g->H, 208);
+  TRY(dev_alloc(g, &g->slots, size_t(nslots) * 3 * B));
+  TRY(dev_alloc(g, &g->ds, 3 * B));
+  TRY(dev_alloc(g, &g->scores, 3 * B));
+  TRY(dev_alloc(g, &g->lossbuf, 16));
+  TRY(dev_alloc(g, &g->fisher, 4));
+  // dh kernel geometry
+  const int groups = g->HP / 8;
+  g->dh_rows_per_iter = 256 / groups > 0 ? 256 / groups : 1;
+  g->dh_threads = groups * g->dh_rows_per_iter;
+  g->dh_blocks = c->num_sms * 4;
+  TRY(dev_alloc(g, &g->dw2p, size_t(g->dh_blocks) * g->HP));
+  // split-K partials
+  g->max_splits = c->num_sms;
+  const int sp_d = c->num_sms / cdiv(g->X + 1, BM) > 0 ? c->num_sms / cdiv(g->X + 1, BM) : 1;
+  const int sp_g2 = c->num_sms / cdiv(g->X, BM) > 0 ? c->num_sms / cdiv(g->X, BM) : 1;
+  const int sp_g1 = c->num_sms / cdiv(g->H, BM) > 0 ? c->num_sms / cdiv(g->H, BM) : 1;
+  TRY(dev_alloc(g, &g->PD, size_t(sp_d) * g->H * (cdiv(g->X + 1, BM) * BM)));
+  TRY(dev_alloc(g, &g->PG2, size_t(sp_g2) * g->X * rup(g->H + 1, 64)));
+  TRY(dev_alloc(g, &g->PG1, size_t(sp_g1) * g->H * 64 * cdiv(g->Z + 1, 64)));
+#undef TRY
+  if (g->H + 1 > 448 || g->Z + 1 > 64) {
+    gm_gan_destroy(g);
+    return fail(c, GM_ERR_UNSUPPORTED, "hidden_dim <= 447 and z_dim <= 63 in this build (got %d, %d)", d->hidden_dim, d->z_dim);
+  }
+  *out = g;
+  return GM_OK;
+}
+
+extern "C" int gm_gan_param_count(const gm_gan* g, int net) {
+  if (!g) return GM_ERR_ARG;
+  return net == GM_NET_G ? g->G.total : g->D.total;
+}
+
+extern "C" int gm_gan_bind(gm_gan* g, int net, float* p, float* gr, float* m, float* v) {
+  if (!g || net < 0 || net > 1 || !p || !gr) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_bind: bad argument") : GM_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(p) & 15)
+    return fail(g->ctx, GM_ERR_ARG, "parameter buffer must be 16-byte aligned");
+  g->par[net] = p; g->grd[net] = gr; g->am[net] = m; g->av[net] = v;
+  g->plans.clear();
+  return GM_OK;
+}
+
+static void adam_segs(gm_gan* g, int net, AdamParams& a) {
+  if (net == GM_NET_G) {
+    a.total = g->G.total;
+    a.nseg = 2;
+    a.seg[0] = {g->G.off_w1, g->H * g->Z, g->Z, g->W1g_s, g->ZP, nullptr, 0};
+    a.seg[1] = {g->G.off_w2, g->X * g->H, g->H, g->W2g_s, g->H, g->W2g_t, g->X};
+  } else {
+    a.total = g->D.total;
+    a.nseg = 1;
+    a.seg[0] = {g->D.off_w1, g->H * g->X, g->X, g->W1d_s, g->X, g->W1d_t, g->H};
+  }
+}
+
+extern "C" int gm_gan_sync_shadows(gm_gan* g, int net, gm_stream stream) {
+  if (!g || net < 0 || net > 1) return GM_ERR_ARG;
+  if (!g->par[net]) return fail(g->ctx, GM_ERR_STATE, "net %d not bound", net);
+  AdamParams a;
+  memset(&a, 0, sizeof a);
+  a.p = g->par[net];
+  a.update = 0;
+  adam_segs(g, net, a);
+  adam_kernel<<<cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, gm_stream stream) {
+  if (!g || net < 0 || net > 1 || !hp || step <= 0) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_apply: bad argument") : GM_ERR_ARG;
+  if (!g->par[net] || !g->am[net] || !g->av[net]) return fail(g->ctx, GM_ERR_STATE, "net %d not fully bound", net);
+  AdamParams a;
+  memset(&a, 0, sizeof a);
+  a.p = g->par[net]; a.g = g->grd[net]; a.m = g->am[net]; a.v = g->av[net];
+  fill_adam(a, hp, step);
+  adam_segs(g, net, a);
+  adam_kernel<<<cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+static void set_bf16_epi(GemmParams& p, __nv_bfloat16* out, int ldo, int out_cols, int pad_one, const float* bias, int act) {
+  p.epi = EPI_BF16; p.out = out; p.ldo = ldo; p.out_cols = out_cols; p.pad_one = pad_one; p.bias = bias; p.act = act;
+  p.aux = nullptr; p.aux_mode = AUX_NONE; p.dot_w = nullptr; p.dot_out = nullptr;
+}
+
+static int build_plans(gm_gan* g, int B, StepPlans** out) {
+  auto it = g->plans.find(B);
+  if (it != g->plans.end()) { *out = &it->second; return GM_OK; }
+  gm_ctx* c = g->ctx;
+  StepPlans sp;
+  const int X = g->X, H = g->H, Z = g->Z, XP = g->XP, HP = g->HP, ZP = g->ZP;
+  const float* pG = g->par[GM_NET_G];
+  const float* pD = g->par[GM_NET_D];
+  __nv_bfloat16* Xfake = g->Xall + size_t(B) * XP;
+  __nv_bfloat16* Afake = g->Aall + size_t(B) * HP;
+  __nv_bfloat16* DHfake = g->DHall + size_t(B) * HP;
+  const int slot_ld = 3 * g->Bmax;
+  int rc;
+  // G layer 1: Hg = relu(Zb W1g^T + b1g), ones column at H
+  if ((rc = plan_gemm(c, &sp.g1, 0, B, H, rup(Z, 16), g->Zb, ZP, g->W1g_s, ZP, HP, 1))) return rc;
+  set_bf16_epi(sp.g1.p, g->Hg, HP, HP, 1, pG + g->G.off_b1, ACT_RELU);
+  // G layer 2: fake = sigmoid(Hg W2g^T + b2g) -> fake rows of Xall, ones column at X
+  if ((rc = plan_gemm(c, &sp.g2, 0, B, X, H, g->Hg, HP, g->W2g_s, H, XP, 1))) return rc;
+  set_bf16_epi(sp.g2.p, Xfake, XP, XP, 1, pG + g->G.off_b2, ACT_SIGMOID);
+  // D layer 1 (+ fused 400->1 row-dot) on [real; fake] (D step) and on fake only (G step)
+  if ((rc = plan_gemm(c, &sp.d1_d, 0, 2 * B, H, X, g->Xall, XP, g->W1d_s, X, H, 1))) return rc;
+  set_bf16_epi(sp.d1_d.p, g->Aall, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
+  sp.d1_d.p.dot_w = pD + g->D.off_w2; sp.d1_d.p.dot_out = g->slots; sp.d1_d.p.dot_ld = slot_ld;
+  if ((rc = plan_gemm(c, &sp.d1_g, 0, B, H, X, Xfake, XP, g->W1d_s, X, H, 1))) return rc;
+  set_bf16_epi(sp.d1_g.p, Afake, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
+  sp.d1_g.p.dot_w = pD + g->D.off_w2; sp.d1_g.p.dot_out = g->slots + B; sp.d1_g.p.dot_ld = slot_ld;
+  // dW1d^T (+ db1 row from the ones column): [X+1, H] = Xall^T DHall over 2B rows
+  if ((rc = plan_gemm(c, &sp.dw1d, 1, X + 1, H, 2 * B, g->Xall, XP, g->DHall, HP, H, g->max_splits))) return rc;
+  {
+    GemmParams& p = sp.dw1d.p;
+    p.epi = EPI_F32; p.part = g->PD; p.ldp = p.m_tiles * BM; p.part_stride = (long long)H * p.ldp; p.transpose = 1;
+  }
+  // dX of D w.r.t. fake, times sigmoid'(fake): DA2 = (DHfake W1d) * fake(1-fake)
+  if ((rc = plan_gemm(c, &sp.dx, 0, B, X, H, DHfake, HP, g->W1d_t, H, X, 1))) return rc;
+  set_bf16_epi(sp.dx.p, g->DA2, XP, X, 0, nullptr, ACT_NONE);
+  sp.dx.p.aux = Xfake; sp.dx.p.ld_aux = XP; sp.dx.p.aux_mode = AUX_SIGMOID_GRAD;
+  // [dW2g | db2g] = DA2^T [Hg | 1]
+  if ((rc = plan_gemm(c, &sp.dw2g, 1, X, H + 1, B, g->DA2, XP, g->Hg, HP, H + 1, g->max_splits))) return rc;
+  {
+    GemmParams& p = sp.dw2g.p;
+    p.epi = EPI_F32; p.part = g->PG2; p.ldp = rup(H + 1, 64); p.part_stride = (long long)X * p.ldp; p.transpose = 0;
+  }
+  // DHg = (DA2 W2g) * 1[Hg > 0]
+  if ((rc = plan_gemm(c, &sp.dhg, 0, B, H, X, g->DA2, XP, g->W2g_t, X, H, 1))) return rc;
+  set_bf16_epi(sp.dhg.p, g->DHg, HP, H, 0, nullptr, ACT_NONE);
+  sp.dhg.p.aux = g->Hg; sp.dhg.p.ld_aux = HP; sp.dhg.p.aux_mode = AUX_RELU_MASK;
+  // [dW1g | db1g] = DHg^T [Zb | 1]
+  if ((rc = plan_gemm(c, &sp.dw1g, 1, H, Z + 1, B, g->DHg, HP, g->Zb, ZP, Z + 1, g->max_splits))) return rc;
+  {
+    GemmParams& p = sp.dw1g.p;
+    p.epi = EPI_F32; p.part = g->PG1; p.ldp = 64; p.part_stride = (long long)H * 64; p.transpose = 0;
+  }
+  g->plans[B] = sp;
+  *out = &g->plans[B];
+  return GM_OK;
+}
+
+static int check_step_args(gm_gan* g, int batch) {
+  if (!g) return GM_ERR_ARG;
+  if (batch <= 0 || batch % 64 || batch > g->Bmax)
+    return fail(g->ctx, GM_ERR_ARG, "batch must be a multiple of 64 in (0, %d] (got %d)", g->Bmax, batch);
+  if (!g->par[0] || !g->par[1] || !g->grd[0] || !g->grd[1]) return fail(g->ctx, GM_ERR_STATE, "bind both nets first");
+  return GM_OK;
+}
+
+static int run_generator(gm_gan* g, StepPlans* sp, int B, const float* noise, uint64_t seed, uint64_t stream_id, cudaStream_t s) {
+  stage_noise_kernel<<<cdiv(B, 128), 128, 0, s>>>(noise, g->Zb, B, g->Z, g->ZP, seed, stream_id);
+  g->ctx->launches++;
+  int rc;
+  if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
+  if ((rc = launch_plan(g->ctx, sp->g2, s))) return rc;
+  return GM_OK;
+}
+
+static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t s) {
+  LossParams lp;
+  lp.slots = g->slots + (g_step ? B : 0);
+  lp.nslots = 2 * cdiv(g->H, 208);
+  lp.slot_ld = 3 * g->Bmax;
+  lp.b2 = g->par[GM_NET_D] + g->D.off_b2;
+  lp.B = B; lp.g_step = g_step; lp.variant = g->d.variant; lp.out_act = g->d.d_out_act; lp.inv_b = inv_b;
+  lp.ds = g->ds + (g_step ? B : 0);
+  lp.d_out = g->scores + (g_step ? B : 0);
+  lp.loss = g->lossbuf;
+  lp.fisher = g->fisher;
+  loss_kernel<1024><<<1, 1024, 0, s>>>(lp);
+  g->ctx->launches++;
+}
+
+extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const int* gather_idx, int batch,
+                             const float* noise, const float* aux, float inv_global_batch, uint64_t seed,
+                             uint64_t step, float* loss_dev, gm_stream stream) {
+  int rc = check_step_args(g, batch);
+  if (rc) return rc;
+  if (!images) return fail(g->ctx, GM_ERR_ARG, "images is null");
+  (void)aux;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StepPlans* sp;
+  if ((rc = build_plans(g, batch, &sp))) return rc;
+  const int B = batch;
+  gm_ctx* c = g->ctx;
+  // real rows -> Xall[0:B] (bf16, ones column)
+  stage_images_kernel<<<c->num_sms * 8, 256, 0, s>>>(images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP);
+  c->launches++;
+  if ((rc = run_generator(g, sp, B, noise, seed, 2 * step, s))) return rc;
+  if ((rc = launch_plan(c, sp->d1_d, s))) return rc;
+  launch_loss(g, B, 0, inv_global_batch, s);
+  dh_kernel<<<g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * g->HP * sizeof(float), s>>>(
+      g->Aall, g->ds, g->par[GM_NET_D] + g->D.off_w2, g->DHall, g->dw2p, 2 * B, g->H, g->HP, g->dh_rows_per_iter);
+  c->launches++;
+  if ((rc = launch_plan(c, sp->dw1d, s))) return rc;
+  GradSegs gs;
+  memset(&gs, 0, sizeof gs);
+  const GemmParams& pw = sp->dw1d.p;
+  gs.nseg = 4;
+  gs.total = g->D.total;
+  gs.s[0] = {g->D.off_w1, g->H * g->X, 0, g->X, pw.ldp, 0, pw.splits, pw.part_stride, g->PD};
+  gs.s[1] = {g->D.off_b1, g->H, 2, 0, pw.ldp, g->X, pw.splits, pw.part_stride, g->PD};
+  gs.s[2] = {g->D.off_w2, g->H, 3, 0, 0, 0, g->dh_blocks, (long long)g->HP, g->dw2p};
+  gs.s[3] = {g->D.off_b2, 1, 3, 0, 0, 0, 1, 0, g->lossbuf + 1};
+  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_D]);
+  c->launches++;
+  if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  g->last_rows = 2 * B;
+  CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}
+
+extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv_global_batch, uint64_t seed,
+                             uint64_t step, float* loss_dev, gm_stream stream) {
+  int rc = check_step_args(g, batch);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StepPlans* sp;
+  if ((rc = build_plans(g, batch, &sp))) return rc;
+  const int B = batch;
+  gm_ctx* c = g->ctx;
+  if ((rc = run_generator(g, sp, B, noise, seed, 2 * step + 1, s))) return rc;
+  if ((rc = launch_plan(c, sp->d1_g, s))) return rc;
+  launch_loss(g, B, 1, inv_global_batch, s);
+  dh_kernel<<<g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * g->HP * sizeof(float), s>>>(
+      g->Aall + size_t(B) * g->HP, g->ds + B, g->par[GM_NET_D] + g->D.off_w2, g->DHall + size_t(B) * g->HP, nullptr, B,
+      g->H, g->HP, g->dh_rows_per_iter);
+  c->launches++;
+  if ((rc = launch_plan(c, sp->dx, s))) return rc;
+  if ((rc = launch_plan(c, sp->dw2g, s))) return rc;
+  if ((rc = launch_plan(c, sp->dhg, s))) return rc;
+  if ((rc = launch_plan(c, sp->dw1g, s))) return rc;
+  GradSegs gs;
+  memset(&gs, 0, sizeof gs);
+  const GemmParams& p2 = sp->dw2g.p;
+  const GemmParams& p1 = sp->dw1g.p;
+  gs.nseg = 4;
+  gs.total = g->G.total;
+  gs.s[0] = {g->G.off_w1, g->H * g->Z, 0, g->Z, p1.ldp, 0, p1.splits, p1.part_stride, g->PG1};
+  gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
+  gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
+  gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
+  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_G]);
+  c->launches++;
+  if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  g->last_rows = B;
+  CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}
+
+extern "C" int gm_gan_scores(gm_gan* g, float* dst, int n, gm_stream stream) {
+  if (!g || !dst || n <= 0) return GM_ERR_ARG;
+  if (n > 3 * g->Bmax) return fail(g->ctx, GM_ERR_ARG, "n too large");
+  CU_OK(g->ctx, cudaMemcpyAsync(dst, g->scores, size_t(n) * sizeof(float), cudaMemcpyDeviceToDevice,
+                                static_cast<cudaStream_t>(stream)));
+  return GM_OK;
+}
+
+__global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int ld, float* __restrict__ dst, int rows, int cols) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = int(i / cols), cidx = int(i % cols);
+  dst[i] = __bfloat162float(src[(long long)r * ld + cidx]);
+}
+
+extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* images, gm_stream stream) {
+  if (!g || !images || n <= 0) return GM_ERR_ARG;
+  if (!g->par[0]) return fail(g->ctx, GM_ERR_STATE, "bind G first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = rup(n, 64);
+  if (B > g->Bmax) return fail(g->ctx, GM_ERR_ARG, "n (%d) exceeds max_batch", n);
+  if (!g->par[1]) return fail(g->ctx, GM_ERR_STATE, "bind D too (plans cover the whole step)");
+  StepPlans* sp;
+  int rc;
+  if ((rc = build_plans(g, B, &sp))) return rc;
+  // stage n noise rows (rows n..B-1 keep whatever they held; their outputs are not read)
+  stage_noise_kernel<<<cdiv(n, 128), 128, 0, s>>>(noise, g->Zb, n, g->Z, g->ZP, 0, 0);
+  g->ctx->launches++;
+  if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
+  if ((rc = launch_plan(g->ctx, sp->g2, s))) return rc;
+  const long long tot = (long long)n * g->X;
+  bf16_rows_to_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, s>>>(g->Xall + size_t(B) * g->XP, g->XP, images, n, g->X);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+extern "C" int gm_gan_fisher_state(gm_gan* g, float* lambda_rho_host, int set, gm_stream stream) {
+  if (!g || !lambda_rho_host) return GM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (set) CU_OK(g->ctx, cudaMemcpyAsync(g->fisher, lambda_rho_host, 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  else {
+    CU_OK(g->ctx, cudaMemcpyAsync(lambda_rho_host, g->fisher, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_OK(g->ctx, cudaStreamSynchronize(s));
+  }
+  return GM_OK;
+}

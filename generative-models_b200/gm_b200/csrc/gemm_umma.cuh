@@ -1,0 +1,322 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a (hand-written).
+//
+//   C[M,N] = sum_k A(m,k) * B(n,k)        bf16 operands, fp32 accumulation in TMEM
+//
+// Operand memory forms (row-major bf16 matrices in HBM, leading dim multiple of 8):
+//   K-major  : matrix [MN rows, K cols]  (activations [batch, feat] as A; nn.Linear
+//              weights [out, in] as B)            -> forward and dX GEMMs
+//   MN-major : matrix [K rows, MN cols]  (contraction over the batch rows)
+//                                                   -> dW GEMMs (A^T * B)
+// Tiles: 128 x (BN1+BN2) x 64, 128-byte TMA/UMMA swizzle; BN2 > 0 issues two MMAs
+// per k-step (N <= 256 each) into one wide accumulator.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> fused math -> HBM).  Pipelines:
+// smem ring full/empty mbarriers (TMA <-> MMA), accumulator full/empty mbarriers
+// (MMA <-> epilogue, double-buffered when 2*BN <= 512 TMEM columns), static
+// round-robin tile scheduler (grid = #SMs).
+#pragma once
+#include "ptx.cuh"
+
+namespace gm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kSmemBudget = 220 * 1024;
+
+enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2 };
+
+struct GemmParams {
+  int M, N, K;          // logical extents; K counts contraction elements
+  int m_tiles, n_tiles;
+  int splits, kblocks, kb_per_split;
+  int epi;
+  // ---- EPI_BF16: out[m, n] = bf16( f(acc + bias[n]) * g(aux[m,n]) ), row-major, ld = ldo
+  __nv_bfloat16* out;
+  int ldo;
+  int out_cols;         // columns [N, out_cols) are padding: zero, except col N = 1 if pad_one
+  int pad_one;
+  const float* bias;    // nullable
+  int act;
+  const __nv_bfloat16* aux;  // nullable, same [m, n] indexing, ld = ld_aux
+  int ld_aux;
+  int aux_mode;
+  const float* dot_w;   // nullable: row-dot of the *stored* values with dot_w[n]
+  float* dot_out;       // partial slots [(n_tile*2 + half) * dot_ld + m]
+  int dot_ld;
+  // ---- EPI_F32: part[split*part_stride + (transpose ? n*ldp + m : m*ldp + n)] = acc
+  float* part;
+  long long part_stride;
+  int ldp;
+  int transpose;
+};
+
+template <int BN1, int BN2>
+struct GemmCfg {
+  static constexpr int BN = BN1 + BN2;
+  static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  // K-major B is loaded with boxes of BOXN rows (<= 256, divides BN1 and BN2)
+  static constexpr int gcd(int a, int b) { return b == 0 ? a : gcd(b, a % b); }
+  static constexpr int BOXN = (BN2 == 0) ? BN1 : gcd(BN1, BN2);
+  static_assert(BN1 % 16 == 0 && BN2 % 16 == 0 && BN1 <= 256 && BN2 <= 256, "UMMA N constraint");
+  static_assert(BN <= 512, "TMEM has 512 columns");
+  static_assert(STAGES >= 2, "need a pipeline");
+};
+
+template <int BN1, int BN2, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN1, BN2>;
+  constexpr int BN = Cfg::BN;
+  constexpr int NACC = Cfg::NACC;
+  constexpr int STAGES = Cfg::STAGES;
+  static_assert(!B_MN || (BN1 % 64 == 0 && BN2 % 64 == 0), "MN-major B needs 64-wide atoms");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + NACC + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * NACC);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < NACC; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int total = tiles * p.splits;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int split = item / tiles;
+        const int rem = item - split * tiles;
+        const int m0 = (rem / p.n_tiles) * BM;
+        const int n0 = (rem % p.n_tiles) * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if constexpr (!A_MN) {
+            tma_load_2d(a_dst, &tmA, full_bar(stage), k0, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a)
+              tma_load_2d(a_dst + a * (BK * 128), &tmA, full_bar(stage), m0 + a * 64, k0);
+          }
+          if constexpr (!B_MN) {
+#pragma unroll
+            for (int b = 0; b < BN / Cfg::BOXN; ++b)
+              tma_load_2d(b_dst + b * (Cfg::BOXN * 128), &tmB, full_bar(stage), k0, n0 + b * Cfg::BOXN);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_2d(b_dst + b * (BK * 128), &tmB, full_bar(stage), n0 + b * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(BM, BN1, A_MN, B_MN);
+      constexpr uint32_t idesc2 = make_idesc_bf16(BM, BN2 > 0 ? BN2 : 16, A_MN, B_MN);
+      // descriptor strides: K-major: SBO = 8 rows * 128 B; MN-major: LBO = atom
+      // stride (BK*128 B), SBO = 8 k-rows * 128 B.  Per UMMA_K (16) advance:
+      // K-major 32 B, MN-major 16 rows * 128 B.
+      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0, A_KADV = A_MN ? kUmmaK * 128 : kUmmaK * 2;
+      constexpr uint32_t B_LBO = B_MN ? BK * 128 : 0, B_KADV = B_MN ? kUmmaK * 128 : kUmmaK * 2;
+      constexpr uint32_t B2_OFF = B_MN ? (BN1 / 64) * (BK * 128) : BN1 * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_iter = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
+        const int split = item / tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+        const int as = acc_iter % NACC;
+        const uint32_t aphase = (acc_iter / NACC) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_src = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_src = a_src + Cfg::A_BYTES;
+          const int krem = p.K - kb * BK;
+          const int nk = krem >= BK ? BK / kUmmaK : (krem + kUmmaK - 1) / kUmmaK;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t da = make_smem_desc(a_src + k * A_KADV, A_LBO, 1024);
+            const uint64_t db = make_smem_desc(b_src + k * B_KADV, B_LBO, 1024);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            umma_bf16(d_tmem, da, db, idesc1, acc);
+            if constexpr (BN2 > 0) {
+              const uint64_t db2 = make_smem_desc(b_src + B2_OFF + k * B_KADV, B_LBO, 1024);
+              umma_bf16(d_tmem + BN1, da, db2, idesc2, acc);
+            }
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));       // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int e = warp - 2;
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+    const int half = e >> 2;        // which half of the 16-column chunks
+    int acc_iter = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
+      const int split = item / tiles;
+      const int rem = item - split * tiles;
+      const int n_tile = rem % p.n_tiles;
+      const int m0 = (rem / p.n_tiles) * BM;
+      const int n0 = n_tile * BN;
+      const int as = acc_iter % NACC;
+      const uint32_t aphase = (acc_iter / NACC) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
+      float dot = 0.f;
+      for (int c = half; c < BN / 16; c += 2) {
+        const int col0 = n0 + c * 16;
+        if (p.epi == EPI_BF16) {
+          if (col0 >= p.out_cols) break;
+          float v[16];
+          if (col0 < p.N) {
+            tmem_ld16(t_row + c * 16, v);
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 b = __ldg(b4 + q);
+                v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+              }
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fast_sigmoid(v[j]);
+            }
+            if (p.aux_mode != AUX_NONE && row_ok) {
+              const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.ld_aux + col0);
+              const uint4 x0 = __ldg(a4), x1 = __ldg(a4 + 1);
+              const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float a_lo = bf16_lo(w[q]), a_hi = bf16_hi(w[q]);
+                if (p.aux_mode == AUX_SIGMOID_GRAD) {
+                  v[2 * q] *= a_lo * (1.f - a_lo);
+                  v[2 * q + 1] *= a_hi * (1.f - a_hi);
+                } else {
+                  v[2 * q] = a_lo > 0.f ? v[2 * q] : 0.f;
+                  v[2 * q + 1] = a_hi > 0.f ? v[2 * q + 1] : 0.f;
+                }
+              }
+            }
+            if (p.dot_w != nullptr) {
+              const float4* w4 = reinterpret_cast<const float4*>(p.dot_w + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w = __ldg(w4 + q);
+                dot = fmaf(v[4 * q + 0], w.x, dot); dot = fmaf(v[4 * q + 1], w.y, dot);
+                dot = fmaf(v[4 * q + 2], w.z, dot); dot = fmaf(v[4 * q + 3], w.w, dot);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            if (col0 == p.N && p.pad_one) v[0] = 1.f;
+          }
+          if (row_ok && p.out != nullptr) {
+            uint4* o = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldo + col0);
+            o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          }
+        } else {  // EPI_F32 split-K partial
+          if (col0 >= p.N) break;
+          float v[16];
+          tmem_ld16(t_row + c * 16, v);
+          float* base = p.part + size_t(split) * p.part_stride;
+          if (row_ok) {
+            if (p.transpose) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.N) base[size_t(col0 + j) * p.ldp + row] = v[j];
+            } else if (col0 + 16 <= p.N) {
+              float4* o = reinterpret_cast<float4*>(base + size_t(row) * p.ldp + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j < p.N) base[size_t(row) * p.ldp + col0 + j] = v[j];
+            }
+          }
+        }
+      }
+      if (p.epi == EPI_BF16 && p.dot_out != nullptr && row_ok)
+        p.dot_out[size_t(n_tile * 2 + half) * p.dot_ld + row] = dot;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace gm

@@ -1,0 +1,348 @@
+// Non-GEMM kernels of the train step: input staging, per-variant loss + upstream
+// gradient, hidden-layer backward, gradient finalisation, fused Adam (+ bf16
+// operand shadows).  All HBM-bound or tiny; 128-bit accesses where it matters.
+#pragma once
+#include <curand_kernel.h>
+
+#include "ptx.cuh"
+
+namespace gm {
+
+// ---------------------------------------------------------------- variants
+// Order is the ABI (include/gm_b200.h: gm_variant).
+enum : int {
+  V_NS = 0, V_MM, V_W, V_WGP, V_LS, V_DRA, V_RA, V_FISHER,
+  V_F_TV, V_F_FKL, V_F_RKL, V_F_PEARSON, V_F_HELLINGER, V_F_JS, V_INFO
+};
+enum : int { OUT_SIGMOID = 0, OUT_RELU = 1, OUT_NONE = 2 };
+constexpr float kEps = 1e-8f;  // the reference's log stabiliser (src/ns_gan.py:191)
+
+// ---------------------------------------------------------------- staging
+// images (fp32 | u8 | 1-bit packed, {0,1}) -> bf16 rows [n, ld] with a ones column at
+// `x` (bias-gradient trick: dW GEMMs then produce db as one extra row) and zero pad.
+// Optional row gather (idx != nullptr): row r reads source row idx[r].
+enum : int { IMG_F32 = 0, IMG_U8 = 1, IMG_BITS = 2, IMG_BF16PAD = 3 };
+__global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const int* __restrict__ idx,
+                                    __nv_bfloat16* __restrict__ dst, int rows, int x, int ld) {
+  const int groups = ld / 8;
+  const long long total = (long long)rows * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = int(i / groups), g = int(i % groups);
+    const long long sr = idx ? idx[r] : r;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float f = 0.f;
+      if (c < x) {
+        if (fmt == IMG_F32) f = reinterpret_cast<const float*>(src)[sr * x + c];
+        else if (fmt == IMG_U8) f = reinterpret_cast<const uint8_t*>(src)[sr * x + c] ? 1.f : 0.f;
+        else if (fmt == IMG_BITS) {
+          const long long bit = sr * x + c;  // np.packbits order: MSB first
+          f = (reinterpret_cast<const uint8_t*>(src)[bit >> 3] >> (7 - (bit & 7))) & 1 ? 1.f : 0.f;
+        } else f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[sr * ld + c]);
+      } else if (c == x) f = 1.f;
+      v[j] = f;
+    }
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// noise fp32 [rows, z] (or Philox N(0,1) when src == nullptr) -> bf16 [rows, ld], ones col at z.
+__global__ void stage_noise_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
+                                   int z, int ld, unsigned long long seed, unsigned long long stream_id) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  curandStatePhilox4_32_10_t st;
+  if (src == nullptr) curand_init(seed, (unsigned long long)r, stream_id * (unsigned long long)((ld + 3) / 4), &st);
+  for (int c0 = 0; c0 < ld; c0 += 8) {
+    float v[8];
+    if (src == nullptr) {
+      const float4 a = curand_normal4(&st), b = curand_normal4(&st);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      if (c < z) { if (src) v[j] = src[(long long)r * z + c]; }
+      else v[j] = (c == z) ? 1.f : 0.f;
+    }
+    reinterpret_cast<uint4*>(dst + (long long)r * ld)[c0 / 8] =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// ---------------------------------------------------------------- block reduction (deterministic)
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < NT / 32; ++i) t += sh[i];
+  return t;
+}
+
+// ---------------------------------------------------------------- loss + upstream gradient
+// One CTA.  Reads the row-dot partial slots the D-layer GEMM epilogue wrote, forms the
+// logit s = sum(slots) + b2, D's output d (sigmoid / relu / id) and, per variant
+// (SURVEY.md A.1), the loss and dL/ds for each row.  D step: rows [0,B) real,
+// [B,2B) fake.  G step: B fake rows.  `inv_b` = 1/(global batch) so data-parallel
+// ranks can SUM gradients.  Loss means are over the local batch.
+struct LossParams {
+  const float* slots; int nslots; int slot_ld;   // slots[k*slot_ld + row]
+  const float* b2;
+  int B;                 // local batch
+  int g_step;            // 0: D step (2B rows), 1: G step (B rows, all fake)
+  int variant, out_act;
+  float inv_b;
+  float* ds;             // out: dL/ds per row
+  float* d_out;          // out (nullable): D output per row
+  float* loss;           // out: [0] loss  [1] sum(ds) (= db2 grad)  [2..] variant scratch
+  float* fisher;         // [0] LAMBDA  [1] RHO  (device state, V_FISHER only)
+};
+
+__device__ __forceinline__ float act_out(float s, int a) {
+  return a == OUT_SIGMOID ? 1.f / (1.f + expf(-s)) : (a == OUT_RELU ? fmaxf(s, 0.f) : s);
+}
+__device__ __forceinline__ float act_grad(float s, float d, int a) {
+  return a == OUT_SIGMOID ? d * (1.f - d) : (a == OUT_RELU ? (s > 0.f ? 1.f : 0.f) : 1.f);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) loss_kernel(const LossParams p) {
+  __shared__ double sh[NT / 32];
+  const int rows = p.g_step ? p.B : 2 * p.B;
+  const float b2 = p.b2[0];
+  auto logit = [&](int r) {
+    float s = 0.f;
+    for (int k = 0; k < p.nslots; ++k) s += p.slots[(long long)k * p.slot_ld + r];
+    return s + b2;
+  };
+  // ---- batch statistics some variants need before any gradient
+  double st0 = 0, st1 = 0, st2 = 0, st3 = 0;
+  float mg = 0.f, gq_mean = 0.f, c_f = 0.f, omega = 0.f;
+  if (!p.g_step && (p.variant == V_RA || p.variant == V_FISHER)) {
+    for (int r = threadIdx.x; r < rows; r += NT) {
+      const float s = logit(r), d = act_out(s, p.out_act);
+      if (r < p.B) { st0 += d; st2 += (double)d * d; } else { st1 += d; st3 += (double)d * d; }
+    }
+    st0 = block_sum<NT>(st0, sh); st1 = block_sum<NT>(st1, sh);
+    st2 = block_sum<NT>(st2, sh); st3 = block_sum<NT>(st3, sh);
+    mg = float(st1 / p.B);
+    if (p.variant == V_RA) {
+      double a = 0;
+      for (int r = threadIdx.x; r < p.B; r += NT) {
+        const float d = act_out(logit(r), p.out_act);
+        const float q = 1.f / (1.f + expf(-(d - mg)));
+        a += q * (1.f - q) / (q + kEps);
+      }
+      gq_mean = float(block_sum<NT>(a, sh) / p.B);
+    } else {
+      const float lam = p.fisher[0], rho = p.fisher[1];
+      omega = 1.f - (0.5f * float(st2 / p.B) + 0.5f * float(st3 / p.B));
+      c_f = lam - rho * omega;
+    }
+  }
+  double lsum = 0, dssum = 0;
+  const float ib = p.inv_b;
+  for (int r = threadIdx.x; r < rows; r += NT) {
+    const float s = logit(r), d = act_out(s, p.out_act);
+    const bool fake = p.g_step || r >= p.B;
+    float l = 0.f, g = 0.f;  // per-row loss term (to be averaged) and dL/dd * B
+    if (p.g_step) {
+      switch (p.variant) {
+        case V_NS: case V_DRA: case V_RA: case V_INFO: l = -logf(d + kEps); g = -1.f / (d + kEps); break;
+        case V_MM: l = logf((1.f - d) + kEps); g = -1.f / ((1.f - d) + kEps); break;
+        case V_W: case V_WGP: case V_FISHER: l = -d; g = -1.f; break;
+        case V_LS: l = 0.5f * (d - 1.f) * (d - 1.f); g = d - 1.f; break;
+        case V_F_TV: { const float t = tanhf(d); l = -0.5f * t; g = -0.5f * (1.f - t * t); } break;
+        case V_F_FKL: { const float e = expf(d - 1.f); l = -e; g = -e; } break;
+        case V_F_RKL: l = 1.f + d; g = 1.f; break;
+        case V_F_PEARSON: l = -(0.25f * d * d + d); g = -(0.5f * d + 1.f); break;
+        case V_F_HELLINGER: { const float e = expf(-d); l = -(e - 1.f); g = e; } break;
+        case V_F_JS: { const float e = expf(d); l = 2.f - e; g = -e; } break;
+      }
+    } else if (!fake) {
+      switch (p.variant) {
+        case V_NS: case V_MM: case V_DRA: case V_INFO: l = -logf(d + kEps); g = -1.f / (d + kEps); break;
+        case V_W: case V_WGP: l = -d; g = -1.f; break;
+        case V_LS: l = 0.5f * (d - 1.f) * (d - 1.f); g = d - 1.f; break;
+        case V_RA: { const float q = 1.f / (1.f + expf(-(d - mg)));
+                     l = -0.5f * logf(q + kEps); g = -0.5f * q * (1.f - q) / (q + kEps); } break;
+        case V_FISHER: l = -d; g = -(1.f - c_f * d); break;   // lambda/rho terms added once below
+        case V_F_TV: { const float t = tanhf(d); l = -0.5f * t; g = -0.5f * (1.f - t * t); } break;
+        case V_F_FKL: l = -d; g = -1.f; break;
+        case V_F_RKL: { const float e = expf(d); l = e; g = e; } break;
+        case V_F_PEARSON: l = -d; g = -1.f; break;
+        case V_F_HELLINGER: { const float e = expf(d); l = -(1.f - e); g = e; } break;
+        case V_F_JS: { const float e = expf(-d); l = -(1.f - e); g = -e; } break;
+      }
+    } else {
+      switch (p.variant) {
+        case V_NS: case V_MM: case V_DRA: case V_INFO: l = -logf((1.f - d) + kEps); g = 1.f / ((1.f - d) + kEps); break;
+        case V_W: case V_WGP: l = d; g = 1.f; break;
+        case V_LS: l = 0.5f * d * d; g = d; break;
+        case V_RA: { const float q = 1.f / (1.f + expf(-(1.f - d)));
+                     l = -0.5f * logf(q + kEps); g = 0.5f * (gq_mean + q * (1.f - q) / (q + kEps)); } break;
+        case V_FISHER: l = d; g = 1.f + c_f * d; break;
+        case V_F_TV: { const float t = tanhf(d); l = 0.5f * t; g = 0.5f * (1.f - t * t); } break;
+        case V_F_FKL: { const float e = expf(d - 1.f); l = e; g = e; } break;
+        case V_F_RKL: l = -1.f - d; g = -1.f; break;
+        case V_F_PEARSON: l = 0.25f * d * d + d; g = 0.5f * d + 1.f; break;
+        case V_F_HELLINGER: { const float e = expf(-d); l = e - 1.f; g = -e; } break;
+        case V_F_JS: { const float e = expf(d); l = -(2.f - e); g = e; } break;
+      }
+    }
+    const float dsr = g * ib * act_grad(s, d, p.out_act);
+    p.ds[r] = dsr;
+    if (p.d_out) p.d_out[r] = d;
+    lsum += l;
+    dssum += dsr;
+  }
+  lsum = block_sum<NT>(lsum, sh);
+  dssum = block_sum<NT>(dssum, sh);
+  if (threadIdx.x == 0) {
+    float L = float(lsum / p.B);
+    if (!p.g_step && p.variant == V_FISHER) {
+      const float lam = p.fisher[0], rho = p.fisher[1];
+      L = L - lam * omega + 0.5f * rho * omega * omega;   // src/fisher_gan.py:221-223
+      p.fisher[0] = lam + rho * (-omega);                 // src/fisher_gan.py:155: lambda += rho * dL/dlambda
+      p.loss[2] = omega;
+    }
+    p.loss[0] = L;
+    p.loss[1] = float(dssum);
+  }
+}
+
+// ---------------------------------------------------------------- hidden-layer backward of D
+// dh[r,n] = ds[r] * w2[n] * 1[a[r,n] > 0] (bf16), and (optionally) per-block partial
+// column sums dw2p[block, n] = sum_r ds[r] * a[r,n].  One uint4 (8 bf16) per thread;
+// blockDim = (ld/8) * rows_per_iter so a thread always owns the same 8 columns.
+__global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ ds,
+                          const float* __restrict__ w2, __nv_bfloat16* __restrict__ dh, float* __restrict__ dw2p,
+                          int rows, int h, int ld, int rows_per_iter) {
+  extern __shared__ float sh_acc[];  // [rows_per_iter][ld]
+  const int groups = ld / 8;
+  const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float w[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    w[j] = c < h ? w2[c] : 0.f;
+    acc[j] = 0.f;
+  }
+  for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < rows; r += (long long)gridDim.x * rows_per_iter) {
+    const uint4 av = __ldg(reinterpret_cast<const uint4*>(a + r * ld) + g);
+    const float d = ds[r];
+    const uint32_t u[4] = {av.x, av.y, av.z, av.w};
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float lo = bf16_lo(u[q]), hi = bf16_hi(u[q]);
+      o[2 * q] = lo > 0.f ? d * w[2 * q] : 0.f;
+      o[2 * q + 1] = hi > 0.f ? d * w[2 * q + 1] : 0.f;
+      acc[2 * q] = fmaf(d, lo, acc[2 * q]);
+      acc[2 * q + 1] = fmaf(d, hi, acc[2 * q + 1]);
+    }
+    reinterpret_cast<uint4*>(dh + r * ld)[g] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                           pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+  if (dw2p == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh_acc[rl * ld + g * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float t = 0.f;
+    for (int i = 0; i < rows_per_iter; ++i) t += sh_acc[i * ld + c];
+    dw2p[(long long)blockIdx.x * ld + c] = t;
+  }
+}
+
+// ---------------------------------------------------------------- gradient finalisation
+// flat_grad[dst_off + i] = sum over `nsplit` partial copies of src[map(i)]:
+//   kind 0 (matrix, rows x cols):  src[r*ld + c]        (partial stored as [rows][ld])
+//   kind 1 (matrix, transposed) :  src[r*ld + c] with i = r*cols + c, same formula —
+//          the GEMM epilogue already wrote the torch layout; kept for clarity
+//   kind 2 (bias from the ones-column trick): src[i*ld + col]
+//   kind 3 (plain vector): src[i]
+struct GradSeg {
+  int dst_off, n, kind, cols, ld, col, nsplit;
+  long long split_stride;
+  const float* src;
+};
+struct GradSegs { GradSeg s[6]; int nseg; int total; };
+
+__global__ void finalize_grads_kernel(const GradSegs segs, float* __restrict__ flat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= segs.total) return;
+#pragma unroll 1
+  for (int k = 0; k < segs.nseg; ++k) {
+    const GradSeg& s = segs.s[k];
+    const int j = i - s.dst_off;
+    if (j < 0 || j >= s.n) continue;
+    long long off;
+    if (s.kind <= 1) off = (long long)(j / s.cols) * s.ld + (j % s.cols);
+    else if (s.kind == 2) off = (long long)j * s.ld + s.col;
+    else off = j;
+    float t = 0.f;
+    for (int q = 0; q < s.nsplit; ++q) t += s.src[off + q * s.split_stride];
+    flat[i] = t;
+    return;
+  }
+}
+
+// ---------------------------------------------------------------- fused Adam + operand shadows
+// torch.optim.Adam semantics (src/ns_gan.py:107-110; coupled weight decay for
+// src/vae.py:139-142; optional clamp = WGAN clipping src/w_gan.py:158).  After the
+// update each weight matrix element is also written as bf16 into the GEMM operand
+// copies: `shadow` [rows, ld_s] (K-major, zero-padded) and `shadow_t` [cols, ld_t].
+struct AdamSeg {
+  int off, n, cols;              // flat range, matrix column count (0 for vectors)
+  __nv_bfloat16* shadow; int ld_s;
+  __nv_bfloat16* shadow_t; int ld_t;
+};
+struct AdamParams {
+  float* p; const float* g; float* m; float* v;
+  int total;
+  float lr, b1, b2, eps, wd, bc1, bc2_sqrt, clamp;   // clamp <= 0: off
+  int update;                                        // 0: only refresh shadows
+  AdamSeg seg[6]; int nseg;
+};
+
+__global__ void adam_kernel(const AdamParams a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  float p = a.p[i];
+  if (a.update) {
+    float g = a.g[i];
+    if (a.wd != 0.f) g = fmaf(a.wd, p, g);
+    const float m = a.b1 * a.m[i] + (1.f - a.b1) * g;
+    const float v = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
+    a.m[i] = m;
+    a.v[i] = v;
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p = p - (a.lr / a.bc1) * (m / denom);
+    if (a.clamp > 0.f) p = fminf(fmaxf(p, -a.clamp), a.clamp);
+    a.p[i] = p;
+  }
+#pragma unroll 1
+  for (int k = 0; k < a.nseg; ++k) {
+    const AdamSeg& s = a.seg[k];
+    const int j = i - s.off;
+    if (j < 0 || j >= s.n) continue;
+    if (s.cols > 0) {
+      const int r = j / s.cols, c = j % s.cols;
+      const __nv_bfloat16 b = __float2bfloat16_rn(p);
+      if (s.shadow) s.shadow[(long long)r * s.ld_s + c] = b;
+      if (s.shadow_t) s.shadow_t[(long long)c * s.ld_t + r] = b;
+    }
+    return;
+  }
+}
+
+}  // namespace gm

@@ -1,0 +1,121 @@
+"""GanEngine — owns the flat fp32 parameter / gradient / Adam-state tensors (torch
+allocations) and drives the C-ABI train-step engine on them."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AdamHP, GanDesc, GmError, VARIANTS, OUT_ACTS, IMG_FMTS, check, lib, _ptr, _stream
+
+G, D = 0, 1
+
+
+class GanEngine:
+    """One MLP GAN (z -> hidden -> image ; image -> hidden -> 1) on one GPU.
+
+    Flat layouts follow nn.Module.parameters() order of the reference modules
+    (src/ns_gan.py:40-41,54-55): [linear.weight, linear.bias, generate|discriminate.weight, .bias].
+    """
+
+    def __init__(self, image_size=784, hidden_dim=400, z_dim=20, max_batch=64, variant="ns",
+                 d_out_act="sigmoid", device=None):
+        if not torch.cuda.is_available():
+            raise GmError("gm_b200 needs a CUDA (B200) device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.h = _lib.ctx(self.device.index)
+        self.image_size, self.hidden_dim, self.z_dim = image_size, hidden_dim, z_dim
+        self.max_batch = max_batch
+        self.variant = variant
+        d = GanDesc(image_size, hidden_dim, z_dim, max_batch, VARIANTS[variant], OUT_ACTS[d_out_act])
+        self.g = C.c_void_p()
+        check(self.h, lib().gm_gan_create(self.h, C.byref(d), C.byref(self.g)))
+        self.n = [lib().gm_gan_param_count(self.g, G), lib().gm_gan_param_count(self.g, D)]
+        kw = dict(device=self.device, dtype=torch.float32)
+        self.params = [torch.zeros(n, **kw) for n in self.n]
+        self.grads = [torch.zeros(n, **kw) for n in self.n]
+        self.exp_avg = [torch.zeros(n, **kw) for n in self.n]
+        self.exp_avg_sq = [torch.zeros(n, **kw) for n in self.n]
+        self.loss_buf = torch.zeros(2, **kw)
+        for net in (G, D):
+            check(self.h, lib().gm_gan_bind(self.g, net, _ptr(self.params[net]), _ptr(self.grads[net]),
+                                            _ptr(self.exp_avg[net]), _ptr(self.exp_avg_sq[net])))
+        H, X, Z = hidden_dim, image_size, z_dim
+        self.shapes = [[(H, Z), (H,), (X, H), (X,)], [(H, X), (H,), (1, H), (1,)]]
+        self.steps = [0, 0]
+
+    def __del__(self):
+        try:
+            if getattr(self, "g", None):
+                lib().gm_gan_destroy(self.g)
+                self.g = None
+        except Exception:
+            pass
+
+    # ---- parameter views -------------------------------------------------
+    def views(self, net, flat=None):
+        flat = self.params[net] if flat is None else flat
+        out, off = [], 0
+        for shp in self.shapes[net]:
+            n = 1
+            for s in shp:
+                n *= s
+            out.append(flat[off:off + n].view(shp))
+            off += n
+        return out
+
+    def load(self, net, tensors):
+        """Copy [W1, b1, W2, b2] into the flat fp32 master and refresh the bf16 copies."""
+        for dst, src in zip(self.views(net), tensors):
+            dst.copy_(torch.as_tensor(src, dtype=torch.float32).reshape(dst.shape))
+        self.sync_shadows(net)
+
+    def sync_shadows(self, net):
+        check(self.h, lib().gm_gan_sync_shadows(self.g, net, _stream()))
+
+    def reset_optimizer(self):
+        for net in (G, D):
+            self.exp_avg[net].zero_()
+            self.exp_avg_sq[net].zero_()
+        self.steps = [0, 0]
+
+    # ---- the hot path ----------------------------------------------------
+    def d_grad(self, images, noise=None, aux=None, fmt="f32", gather_idx=None, batch=None, inv_global_batch=None,
+               seed=0, step=0):
+        """train_D + backward (src/ns_gan.py:172-194,138). Returns the device loss (0-dim view)."""
+        B = batch if batch is not None else (gather_idx.numel() if gather_idx is not None else images.shape[0])
+        inv = 1.0 / B if inv_global_batch is None else inv_global_batch
+        check(self.h, lib().gm_gan_d_grad(self.g, _ptr(images), IMG_FMTS[fmt], _ptr(gather_idx), B, _ptr(noise),
+                                          _ptr(aux), inv, seed, step, _ptr(self.loss_buf), _stream()))
+        return self.loss_buf[0]
+
+    def g_grad(self, batch, noise=None, inv_global_batch=None, seed=0, step=0):
+        """train_G + backward (src/ns_gan.py:196-216,155)."""
+        inv = 1.0 / batch if inv_global_batch is None else inv_global_batch
+        check(self.h, lib().gm_gan_g_grad(self.g, batch, _ptr(noise), inv, seed, step,
+                                          C.c_void_p(self.loss_buf.data_ptr() + 4), _stream()))
+        return self.loss_buf[1]
+
+    def apply(self, net, hp):
+        """optimizer.step() (src/ns_gan.py:139,156)."""
+        self.steps[net] += 1
+        check(self.h, lib().gm_gan_apply(self.g, net, C.byref(hp), self.steps[net], _stream()))
+
+    def scores(self, n):
+        out = torch.empty(n, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_gan_scores(self.g, _ptr(out), n, _stream()))
+        return out
+
+    def generate(self, noise):
+        n = noise.shape[0]
+        out = torch.empty(n, self.image_size, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_gan_generate(self.g, _ptr(noise.contiguous().float()), n, _ptr(out), _stream()))
+        return out
+
+    def fisher_state(self, lam=None, rho=None):
+        buf = (C.c_float * 2)()
+        if lam is not None:
+            buf[0], buf[1] = lam, rho
+            check(self.h, lib().gm_gan_fisher_state(self.g, buf, 1, _stream()))
+            return lam, rho
+        check(self.h, lib().gm_gan_fisher_state(self.g, buf, 0, _stream()))
+        return buf[0], buf[1]

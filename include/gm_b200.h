@@ -1,0 +1,146 @@
+/* gm_b200 — C ABI of the B200-native GAN/VAE train-step hot path.
+ *
+ * The reference (shayneobrien/generative-models) is pure Python/PyTorch and has no
+ * FFI of its own; each entry point below replaces the reference call sites cited
+ * beside it (paths relative to the reference tree).  Conventions:
+ *   - every function returns 0 on success, a negative GM_ERR_* otherwise;
+ *     gm_last_error(ctx) holds a message.  Nothing throws across the ABI.
+ *   - all pointers named *_dev are DEVICE pointers; work is ENQUEUED on the
+ *     caller's cudaStream_t (passed as void*), never synchronised.
+ *   - the caller (torch) owns parameter / gradient / optimizer-state storage; the
+ *     library borrows the pointers given to gm_gan_bind until re-bind/destroy and
+ *     owns only its workspaces and bf16 operand copies.
+ *   - one engine per process per GPU; not re-entrant on one engine from 2 threads.
+ */
+#ifndef GM_B200_H_
+#define GM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_OK 0
+#define GM_ERR_ARG (-1)
+#define GM_ERR_CUDA (-2)
+#define GM_ERR_STATE (-3)
+#define GM_ERR_UNSUPPORTED (-4)
+
+typedef struct gm_ctx gm_ctx;
+typedef struct gm_gan gm_gan;
+typedef struct gm_vae gm_vae;
+typedef void* gm_stream; /* cudaStream_t */
+
+/* loss variants: one per reference file */
+typedef enum {
+  GM_NS = 0,      /* src/ns_gan.py:172-216      */
+  GM_MM,          /* src/mm_gan.py:195-237      */
+  GM_W,           /* src/w_gan.py:190-229       */
+  GM_WGP,         /* src/w_gp_gan.py:177-239    */
+  GM_LS,          /* src/ls_gan.py:173-215      */
+  GM_DRA,         /* src/dra_gan.py:174-245     */
+  GM_RA,          /* src/ra_gan.py:183-229      */
+  GM_FISHER,      /* src/fisher_gan.py:193-248  */
+  GM_F_TV, GM_F_FKL, GM_F_RKL, GM_F_PEARSON, GM_F_HELLINGER, GM_F_JS, /* src/f_gan.py:99-142 */
+  GM_INFO         /* src/info_gan.py:223-304    */
+} gm_variant;
+
+typedef enum { GM_OUT_SIGMOID = 0, GM_OUT_RELU = 1, GM_OUT_NONE = 2 } gm_out_act;
+typedef enum { GM_IMG_F32 = 0, GM_IMG_U8 = 1, GM_IMG_BITS = 2 } gm_img_fmt;
+typedef enum { GM_NET_G = 0, GM_NET_D = 1 } gm_net;
+
+/* torch.optim.Adam hyper-parameters (src/ns_gan.py:107-110, src/vae.py:139-142);
+ * clamp > 0 applies WGAN weight clipping after the update (src/w_gan.py:158). */
+typedef struct {
+  float lr, beta1, beta2, eps, weight_decay, clamp;
+} gm_adam_hp;
+
+int gm_version(void);
+int gm_ctx_create(int device, gm_ctx** out);
+int gm_ctx_destroy(gm_ctx* ctx);
+const char* gm_last_error(const gm_ctx* ctx);
+int gm_ctx_num_sms(const gm_ctx* ctx);
+
+/* ---- dense building blocks (unit tests; level-(ii) interception) ------------
+ * C[M,N] = epilogue( sum_k A(m,k) B(n,k) ), bf16 operands, fp32 accumulate, on
+ * tcgen05 tensor cores.  Replaces ATen addmm/mm under nn.Linear
+ * (src/ns_gan.py:44-45,58-59) and autograd's AddmmBackward (src/ns_gan.py:138,155).
+ *   mode 0 "NT": A_dev [M, lda] (K contiguous), B_dev [N, ldb] (K contiguous)
+ *   mode 1 "TN": A_dev [K, lda] (M contiguous), B_dev [K, ldb] (N contiguous);
+ *                K % 64 == 0 (contraction over batch rows: dW = X^T dY)
+ * out_kind 0: bf16 C_dev [M, ldc] with optional bias[N], act (0 none, 1 relu,
+ *             2 sigmoid), aux (bf16 [M, ld_aux]; aux_mode 1: *= aux(1-aux),
+ *             2: *= (aux > 0)); columns [N, out_cols) are written as padding
+ *             (col N = 1 if pad_one).  dot_w/dot_out: optional fused row-dot,
+ *             dot_out holds 2*ceil(out_cols/208) partial slots of dot_ld floats.
+ * out_kind 1: fp32 C_dev (ldc floats; transposed store if transpose), split-K
+ *             partials summed by the library into C_dev. */
+typedef struct {
+  int mode, M, N, K;
+  const void* A_dev; int lda;
+  const void* B_dev; int ldb;
+  int out_kind;
+  void* C_dev; int ldc;
+  int out_cols, pad_one;
+  const float* bias_dev; int act;
+  const void* aux_dev; int ld_aux, aux_mode;
+  const float* dot_w_dev; float* dot_out_dev; int dot_ld;
+  int transpose;
+} gm_gemm_desc;
+int gm_gemm_bf16(gm_ctx* ctx, const gm_gemm_desc* d, gm_stream stream);
+
+/* One fused Adam update over n contiguous fp32 elements; `step` is the 1-based
+ * step count (bias correction).  Replaces optim.Adam.step (src/ns_gan.py:139,156). */
+int gm_adam_step(gm_ctx* ctx, float* p_dev, const float* g_dev, float* m_dev, float* v_dev, int n,
+                 const gm_adam_hp* hp, int step, gm_stream stream);
+
+/* ---- GAN train-step engine --------------------------------------------------
+ * MLP generator z -> hidden -> image (sigmoid) and discriminator image -> hidden
+ * -> 1 (src/ns_gan.py:35-60).  Flat fp32 parameter layout per net, in
+ * nn.Module.parameters() order: [linear.weight | linear.bias | out.weight | out.bias]. */
+typedef struct {
+  int image_size, hidden_dim, z_dim; /* NSGAN(image_size, hidden_dim, z_dim), src/ns_gan.py:66 */
+  int max_batch;                     /* largest local batch; multiple of 64 */
+  int variant;                       /* gm_variant */
+  int d_out_act;                     /* gm_out_act: sigmoid, or relu for src/w_gp_gan.py:61 */
+} gm_gan_desc;
+
+int gm_gan_create(gm_ctx* ctx, const gm_gan_desc* desc, gm_gan** out);
+int gm_gan_destroy(gm_gan* gan);
+int gm_gan_param_count(const gm_gan* gan, int net);
+int gm_gan_bind(gm_gan* gan, int net, float* params_dev, float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev);
+/* refresh the bf16 operand copies from the bound fp32 parameters (after init /
+ * load_state_dict, src/ns_gan.py:287-290) */
+int gm_gan_sync_shadows(gm_gan* gan, int net, gm_stream stream);
+
+/* train_D + D_loss.backward() (src/ns_gan.py:172-194,138): forward G (fresh noise),
+ * D on real and fake rows, variant loss, backward through D only; writes the flat D
+ * gradient (already scaled by inv_global_batch so data-parallel ranks SUM) and the
+ * loss (loss_dev[0]).  noise_dev [batch, z] fp32 or NULL for on-device Philox
+ * (seed, step); aux_dev: WGAN-GP eps [batch] / DRAGAN (delta [batch] then u
+ * [batch, image_size]) or NULL for on-device Philox; gather_idx_dev: optional row
+ * indices into images_dev (the DataLoader shuffle of src/ns_gan.py:222-226). */
+int gm_gan_d_grad(gm_gan* gan, const void* images_dev, int img_fmt, const int* gather_idx_dev, int batch,
+                  const float* noise_dev, const float* aux_dev, float inv_global_batch, uint64_t seed,
+                  uint64_t step, float* loss_dev, gm_stream stream);
+/* train_G + G_loss.backward() (src/ns_gan.py:196-216,155), G gradients only. */
+int gm_gan_g_grad(gm_gan* gan, int batch, const float* noise_dev, float inv_global_batch, uint64_t seed,
+                  uint64_t step, float* loss_dev, gm_stream stream);
+/* optimizer.step() on one net (src/ns_gan.py:139,156) + operand-copy refresh. */
+int gm_gan_apply(gm_gan* gan, int net, const gm_adam_hp* hp, int step, gm_stream stream);
+/* D outputs of the last *_grad call (D step: batch real then batch fake; G step:
+ * batch fake) -> dst_dev; what the reference names DX_score / DG_score. */
+int gm_gan_scores(gm_gan* gan, float* dst_dev, int n, gm_stream stream);
+/* Generator.forward (src/ns_gan.py:43-46) for sampling: noise [n, z] fp32 -> images
+ * [n, image_size] fp32. */
+int gm_gan_generate(gm_gan* gan, const float* noise_dev, int n, float* images_dev, gm_stream stream);
+/* Fisher GAN scalar state (src/fisher_gan.py:117-118,155): get/set LAMBDA, RHO. */
+int gm_gan_fisher_state(gm_gan* gan, float* lambda_rho_host, int set, gm_stream stream);
+/* number of this library's kernels launched since the last call with reset != 0 */
+long long gm_launch_count(gm_ctx* ctx, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GM_B200_H_ */

@@ -1,0 +1,168 @@
+"""Parity of the CUDA train step (through the C ABI) with (a) the golden fixtures
+made by the unmodified reference and (b) the numpy oracle on the same seeded inputs.
+
+Arithmetic: bf16 GEMM operands (8-bit mantissa), fp32 accumulation/epilogues/Adam.
+Tolerances are stated per quantity below; measured errors are dumped to
+gpurun_out/parity_gan.json so they can be quoted."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from inputs import (GAN_SHAPES, STEPS, B, gm_init_weights, params_dict, load_case, unpack_draws,
+                    images_from_bits)
+from oracle import ref_math as R
+
+pytestmark = pytest.mark.gpu
+
+ROW_VARIANTS = ["ns", "mm", "ls", "w", "ra", "fisher", "f_total_variation", "f_forward_kl", "f_reverse_kl",
+                "f_pearson", "f_hellinger", "f_jensen_shannon"]
+KW = {"ns": dict(G_lr=2e-4, D_lr=2e-4), "mm": dict(G_lr=2e-4, D_lr=2e-4, G_init=2),
+      "ls": dict(G_lr=1e-4, D_lr=1e-4), "w": dict(G_lr=5e-5, D_lr=5e-5, D_steps=2, clip=0.01),
+      "ra": dict(G_lr=2e-4, D_lr=2e-4), "fisher": dict(G_lr=1e-4, D_lr=1e-4, RHO=1e-6)}
+for _m in ROW_VARIANTS:
+    KW.setdefault(_m, dict(G_lr=1e-4, D_lr=1e-4))
+
+# tolerances (bf16 operands): losses and scores relative 3e-3; gradients norm-relative 1e-2
+TOL_LOSS, TOL_SCORE, TOL_GRAD = 3e-3, 3e-3, 1e-2
+_REPORT = {}
+
+
+def _dump():
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_gan.json", "w") as f:
+        json.dump(_REPORT, f, indent=1, sort_keys=True)
+
+
+def _engine(variant, batch=B):
+    import gm_b200
+    eng = gm_b200.GanEngine(784, 400, 20, max_batch=batch, variant=variant)
+    W = gm_init_weights(GAN_SHAPES, 1234)
+    eng.load(0, [W["G.linear"][0], W["G.linear"][1], W["G.generate"][0], W["G.generate"][1]])
+    eng.load(1, [W["D.linear"][0], W["D.linear"][1], W["D.discriminate"][0], W["D.discriminate"][1]])
+    return eng
+
+
+def _nrel(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("case", ROW_VARIANTS)
+def test_step1_against_golden_and_oracle(case):
+    fx = load_case("gan_" + case)
+    eng = _engine(case)
+    x = images_from_bits(fx)
+    draws = unpack_draws(fx, "step1_")
+    z1, z2 = draws[0], draws[-1]
+    P = params_dict(gm_init_weights(GAN_SHAPES, 1234), np.float64)
+    st = dict(LAMBDA=0.0, RHO=1e-6) if case == "fisher" else None
+    if case == "fisher":
+        eng.fisher_state(0.0, 1e-6)
+    Lo, go, info = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), None, st)
+    xd = torch.from_numpy(x).cuda()
+    Ld = eng.d_grad(xd, noise=torch.from_numpy(z1).cuda()).item()
+    sc = eng.scores(2 * B).cpu().numpy()
+    gD = [v.cpu().numpy() for v in eng.views(1, eng.grads[1])]
+    rep = {}
+    rep["D_loss_vs_golden"] = abs(Ld - float(fx["step1_D_loss"])) / max(abs(float(fx["step1_D_loss"])), 1e-3)
+    rep["D_loss_vs_oracle"] = abs(Ld - Lo) / max(abs(Lo), 1e-3)
+    rep["DX_score"] = _nrel(sc[:B], fx["step1_score_0"])
+    rep["DG_score"] = _nrel(sc[B:], fx["step1_score_1"])
+    names = ["D.linear.weight", "D.linear.bias", "D.discriminate.weight", "D.discriminate.bias"]
+    for nme, g in zip(names, gD):
+        rep["grad_" + nme] = _nrel(g, go[nme])
+    Lgo, ggo, _ = R.gan_g_step(P, case, z2.astype(np.float64))
+    Lg = eng.g_grad(B, noise=torch.from_numpy(z2).cuda()).item()
+    gG = [v.cpu().numpy() for v in eng.views(0, eng.grads[0])]
+    rep["G_loss_vs_golden"] = abs(Lg - float(fx["step1_G_loss"])) / max(abs(float(fx["step1_G_loss"])), 1e-3)
+    for nme, g in zip(["G.linear.weight", "G.linear.bias", "G.generate.weight", "G.generate.bias"], gG):
+        rep["grad_" + nme] = _nrel(g, ggo[nme])
+    _REPORT["step1_" + case] = rep
+    _dump()
+    assert rep["D_loss_vs_golden"] < TOL_LOSS and rep["G_loss_vs_golden"] < TOL_LOSS, rep
+    assert rep["DX_score"] < TOL_SCORE and rep["DG_score"] < TOL_SCORE, rep
+    for k, v in rep.items():
+        if k.startswith("grad_"):
+            # WGAN/fGAN bias gradients are differences of nearly equal sums: allow absolute slack
+            assert v < TOL_GRAD or "bias" in k and v < 5e-2, (k, v, rep)
+
+
+@pytest.mark.parametrize("case", ROW_VARIANTS)
+def test_three_step_trajectory_against_golden(case):
+    import gm_b200
+    fx = load_case("gan_" + case)
+    kw = KW[case]
+    eng = _engine(case)
+    x = torch.from_numpy(images_from_bits(fx)).cuda()
+    draws = [torch.from_numpy(d).cuda() for d in unpack_draws(fx)]
+    it = iter(draws)
+    hpG = gm_b200.AdamHP.make(kw["G_lr"])
+    hpD = gm_b200.AdamHP.make(kw["D_lr"], clamp=kw.get("clip", 0.0) or 0.0)
+    if case == "fisher":
+        eng.fisher_state(0.0, kw["RHO"])
+    for _ in range(kw.get("G_init", 0)):
+        eng.g_grad(B, noise=next(it))
+        eng.apply(0, hpG)
+    Dl, Gl = [], []
+    for _ in range(STEPS):
+        acc = []
+        for _ in range(kw.get("D_steps", 1)):
+            acc.append(eng.d_grad(x, noise=next(it)).item())
+            eng.apply(1, hpD)
+        Dl.append(np.mean(acc))
+        Gl.append(eng.g_grad(B, noise=next(it)).item())
+        eng.apply(0, hpG)
+    rep = {"D": [abs(a - b) / max(abs(b), 1e-2) for a, b in zip(Dl, fx["D_loss"])],
+           "G": [abs(a - b) / max(abs(b), 1e-2) for a, b in zip(Gl, fx["G_loss"])]}
+    _REPORT["traj_" + case] = rep
+    _dump()
+    assert max(rep["D"]) < 2 * TOL_LOSS and max(rep["G"]) < 2 * TOL_LOSS, (rep, Dl, Gl)
+    if case == "fisher":
+        lam, _ = eng.fisher_state()
+        assert abs(lam - float(fx["final_LAMBDA"][0])) <= 1e-2 * abs(float(fx["final_LAMBDA"][0])) + 1e-12
+
+
+def test_property_batch_4096_gradients_match_fp32_torch():
+    """Size-independent check at a larger batch: flat D/G gradients vs a plain PyTorch
+    fp32 autograd evaluation of the same NSGAN losses on the GPU."""
+    Bb = 4096
+    eng = _engine("ns", Bb)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = (torch.rand(Bb, 784, device="cuda", generator=g) < 0.1307).float()
+    z = torch.randn(Bb, 20, device="cuda", generator=g)
+    Wg1, bg1, Wg2, bg2 = [t.clone().requires_grad_() for t in eng.views(0)]
+    Wd1, bd1, Wd2, bd2 = [t.clone().requires_grad_() for t in eng.views(1)]
+
+    def Gf(zz):
+        return torch.sigmoid(torch.relu(zz @ Wg1.t() + bg1) @ Wg2.t() + bg2)
+
+    def Df(xx):
+        return torch.sigmoid(torch.relu(xx @ Wd1.t() + bd1) @ Wd2.t() + bd2)
+    with torch.backends.cuda.sdp_kernel() if False else torch.enable_grad():
+        torch.backends.cuda.matmul.allow_tf32 = False
+        Ld_ref = -torch.mean(torch.log(Df(x) + 1e-8) + torch.log(1 - Df(Gf(z)) + 1e-8))
+        gd = torch.autograd.grad(Ld_ref, [Wd1, bd1, Wd2, bd2])
+        Lg_ref = -torch.mean(torch.log(Df(Gf(z)) + 1e-8))
+        gg = torch.autograd.grad(Lg_ref, [Wg1, bg1, Wg2, bg2])
+    Ld = eng.d_grad(x, noise=z).item()
+    flatD = eng.grads[1].clone()
+    Lg = eng.g_grad(Bb, noise=z).item()
+    flatG = eng.grads[0].clone()
+    rep = {"D_loss": abs(Ld - Ld_ref.item()) / abs(Ld_ref.item()), "G_loss": abs(Lg - Lg_ref.item()) / abs(Lg_ref.item()),
+           "gD": _nrel(flatD.cpu().numpy(), torch.cat([t.reshape(-1) for t in gd]).cpu().numpy()),
+           "gG": _nrel(flatG.cpu().numpy(), torch.cat([t.reshape(-1) for t in gg]).cpu().numpy())}
+    _REPORT["b4096_ns"] = rep
+    _dump()
+    assert rep["D_loss"] < TOL_LOSS and rep["G_loss"] < TOL_LOSS and rep["gD"] < TOL_GRAD and rep["gG"] < TOL_GRAD, rep
+
+
+def test_generate_matches_reference_forward():
+    eng = _engine("ns")
+    z = torch.randn(36, 20, device="cuda")
+    out = eng.generate(z)
+    Wg1, bg1, Wg2, bg2 = eng.views(0)
+    ref = torch.sigmoid(torch.relu(z @ Wg1.t() + bg1) @ Wg2.t() + bg2)
+    assert _nrel(out.cpu().numpy(), ref.cpu().numpy()) < 5e-3
