@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — train-step images/sec of the NSGAN MLP hot path on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+  python bench.py --impl reference [--gpus N] ...               # the reference's CPU path
+  torchrun --nproc-per-node N bench.py --gpus N ...             # N > 1 (driver does this)
+
+One "step" = one reference train step (src/ns_gan.py:126-156): fetch a batch of real
+images, D update (forward G and D, NS loss, backward, Adam), G update (forward,
+loss, backward, Adam).  Workload: BASELINE.json configs[1] — NSGAN 784-400-1 /
+20-400-784, bf16 tensor-core operands, B = 65536 images per GPU per step (weak
+scaling), synthetic Bernoulli(0.1307) 28x28 binary images, nn.Linear-default
+random-init weights.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "generative-models_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+X, H, Z = 784, 400, 20
+FLOP_PER_IMG = 6326400.0        # algorithmic FLOPs of one NSGAN train step per image
+METRIC = "train_step_images_per_sec"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx, pw = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw) if pw else None)
+        return out
+
+
+def init_weights_like_reference(eng):
+    """nn.Linear default init under torch.manual_seed(1234) on CPU."""
+    import torch
+    import torch.nn as nn
+    torch.manual_seed(1234)
+    g1, g2 = nn.Linear(Z, H), nn.Linear(H, X)
+    d1, d2 = nn.Linear(X, H), nn.Linear(H, 1)
+    eng.load(0, [g1.weight.data, g1.bias.data, g2.weight.data, g2.bias.data])
+    eng.load(1, [d1.weight.data, d1.bias.data, d2.weight.data, d2.bias.data])
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gm_b200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    eng = gm_b200.GanEngine(X, H, Z, max_batch=B, variant="ns")
+    init_weights_like_reference(eng)
+    hpG, hpD = gm_b200.AdamHP.make(2e-4), gm_b200.AdamHP.make(2e-4)
+    inv = 1.0 / (B * world)
+    # device-resident synthetic dataset, 1 bit per pixel (binarised MNIST carries exactly
+    # that: src/utils.py:31); pool of 4*B images = 412 MB as bf16 rows, > 126 MB L2
+    N = 4 * B
+    gen = torch.Generator(device=dev).manual_seed(3435 + rank)
+    nbytes = N * X // 8
+    bits = torch.randint(0, 256, (nbytes,), device=dev, dtype=torch.uint8, generator=gen)
+    # Bernoulli(0.1307)-like density: AND three random bytes (p = 1/8)
+    bits &= torch.randint(0, 256, (nbytes,), device=dev, dtype=torch.uint8, generator=gen)
+    bits &= torch.randint(0, 256, (nbytes,), device=dev, dtype=torch.uint8, generator=gen)
+    step_no = [0]
+
+    def train_step(images, fmt, idx):
+        s = step_no[0]
+        step_no[0] += 1
+        eng.d_grad(images, fmt=fmt, gather_idx=idx, batch=B, inv_global_batch=inv, seed=1000 + rank, step=s)
+        if world > 1:
+            dist.all_reduce(eng.grads[1])
+        eng.apply(1, hpD)
+        eng.g_grad(B, inv_global_batch=inv, seed=1000 + rank, step=s)
+        if world > 1:
+            dist.all_reduce(eng.grads[0])
+        eng.apply(0, hpG)
+
+    def resident_step():
+        idx = torch.randint(0, N, (B,), device=dev, dtype=torch.int32)   # the DataLoader shuffle, on device
+        train_step(bits, "bits", idx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    gm_b200.launch_count(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(lambda i: resident_step(), args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = gm_b200.launch_count(reset=True)
+    value = B * world * args.steps / (ms * 1e-3)
+    loss_d, loss_g = float(eng.loss_buf[0].item()), float(eng.loss_buf[1].item())
+
+    # ---- e2e: same step through the host-facing call, HOST (pinned) batches; the H2D
+    # copy of each step's batch and the D2H read of its losses are inside the timed region
+    e2e_steps = args.steps
+    nb = 4
+    host = [torch.empty(B * X // 8, dtype=torch.uint8).pin_memory() for _ in range(nb)]
+    for hb in host:
+        hb.copy_(bits[: B * X // 8].cpu())
+    stage = [torch.empty(B * X // 8, dtype=torch.uint8, device=dev) for _ in range(2)]
+    host_loss = torch.zeros(e2e_steps + 8, 2).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[i % 2])
+            stage[i % 2].copy_(host[i % nb], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_step(i):
+        if i == 0:
+            prefetch(0)
+        prefetch(i + 1)                       # overlaps with this step's compute
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        train_step(stage[i % 2], "bits", None)
+        freed[i % 2].record()
+        host_loss[i].copy_(eng.loss_buf, non_blocking=True)
+    for f in freed:
+        f.record()
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    for f in freed:
+        f.record()
+    ms_e2e = timed(e2e_step, e2e_steps)
+    e2e_value = B * world * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel: CUDA events around every GEMM launch
+    pk, pk_src = peaks()
+    gm_b200.prof_enable(True)
+    for _ in range(3):
+        resident_step()
+    prof = gm_b200.prof_collect()
+    gm_b200.prof_enable(False)
+    dom = max(prof, key=lambda r: r[1])
+    peak_tf = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+    dom_tf = dom[2] / (dom[1] * 1e-3) / 1e12 if dom[1] > 0 else 0.0
+    gemm_ms_per_step = sum(r[1] for r in prof) / 3.0
+    roofline = {"bound": "tensor", "kernel": dom[0], "achieved": round(dom_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(dom_tf / peak_tf, 4), "traffic": None, "peak_source": pk_src + ", sustained cuBLAS bf16",
+                "launches_per_step": dom[3] / 3.0, "avg_launch_ms": round(dom[1] / max(dom[3], 1), 4),
+                "all_gemm_ms_per_step": round(gemm_ms_per_step, 4),
+                "step_frac_of_tensor_roofline": round(value / world * FLOP_PER_IMG / (peak_tf * 1e12), 4),
+                "by_kernel": [{"kernel": r[0], "ms_per_step": round(r[1] / 3.0, 4),
+                               "tflops": round(r[2] / (r[1] * 1e-3) / 1e12, 1) if r[1] > 0 else 0.0,
+                               "launches_per_step": r[3] / 3.0} for r in prof if r[3]]}
+
+    if rank != 0:
+        return
+    out = {"metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "NSGAN MLP (D 784-400-1, G 20-400-784), BASELINE configs[1]: B=%d per GPU, "
+                                  "1 D update + 1 G update per step, Adam lr 2e-4" % B,
+                      "global_batch": B * world, "parallelism": "dp%d" % world,
+                      "inputs": "device-resident 1-bit synthetic images, pool 4*B (412 MB as bf16 rows) > L2; "
+                                "per-step working set ~1.5 GB, no L2 flush needed",
+                      "noise": "on-device Philox"},
+           "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / e2e_steps, 4),
+                   "h2d_bytes_per_step": B * X // 8, "d2h_bytes_per_step": 8,
+                   "input_format": "1 bit/pixel packed rows in pinned host memory, double-buffered H2D"},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+           "losses_last_step": {"D": loss_d, "G": loss_g}}
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(out))
+
+
+def cpu_baseline():
+    """The reference's CPU path (oracle/torch_port.py: same nn.Linear/autograd/Adam calls
+    as src/ns_gan.py) on this box's host cores, bounded samples."""
+    from oracle import torch_port as TP
+    cores = os.cpu_count() or 1
+    # BASELINE config 1: B=64, N=50000, 1 epoch = 782 steps, reference DataLoader fetch included
+    ips64, dt64, th = TP.time_cpu_steps(64, steps=782, warmup=10, threads=cores, with_loader=True,
+                                        pool=None if False else _pool(50000))
+    ips64c, _, _ = TP.time_cpu_steps(64, steps=300, warmup=10, threads=cores, with_loader=False, pool=_pool(50000))
+    big = 16384
+    ipsb, dtb, _ = TP.time_cpu_steps(big, steps=4, warmup=1, threads=cores, with_loader=False)
+    return {"value": round(ips64, 1), "unit": "images/s", "cores": th, "kind": "port",
+            "sample": "BASELINE configs[0]: B=64, 782 steps (1 epoch of N=50000) incl. the reference's per-step "
+                      "shuffling DataLoader fetch, %.1f s" % dt64,
+            "compute_only_b64": round(ips64c, 1),
+            "large_batch": {"batch": big, "value": round(ipsb, 1), "seconds": round(dtb, 2), "steps": 4}}
+
+
+def _pool(n):
+    import torch
+    g = torch.Generator().manual_seed(3435)
+    return (torch.rand(n, X, generator=g) < 0.1307).float()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the same step on the host
+    cores (rank 0 only), same metric/config, each step a bounded batch."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from oracle import torch_port as TP
+    cores = os.cpu_count() or 1
+    # calibrate so the whole run stays within a few minutes
+    ips, dt, th = TP.time_cpu_steps(4096, steps=2, warmup=1, threads=cores)
+    budget = 150.0
+    n_steps = args.steps + args.warmup
+    batch = args.batch
+    while batch > 4096 and (batch / ips) * n_steps > budget:
+        batch //= 2
+    ips, dt, th = TP.time_cpu_steps(batch, steps=args.steps, warmup=args.warmup, threads=cores)
+    out = {"impl": "reference", "metric": METRIC, "value": round(ips, 1), "unit": "images/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "NSGAN MLP (D 784-400-1, G 20-400-784), BASELINE configs[1] on host CPU: "
+                                  "reference train step (autograd + 2x Adam), bounded batch %d per step" % batch,
+                      "global_batch": batch, "parallelism": "cpu"},
+           "cpu_baseline": {"value": round(ips, 1), "unit": "images/s", "cores": th, "kind": "port",
+                            "sample": "%d steps of batch %d (of the 65536-image step), %.1f s" % (args.steps, batch, dt)},
+           "e2e": {"value": round(ips, 1), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=65536, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,8 @@ def lib():
     L.gm_ctx_num_sms.argtypes = [vp]
     L.gm_launch_count.argtypes = [vp, i]
     L.gm_launch_count.restype = C.c_longlong
+    L.gm_prof_enable.argtypes = [vp, i]
+    L.gm_prof_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.gm_gemm_bf16.argtypes = [vp, C.POINTER(GemmDesc), vp]
     L.gm_adam_step.argtypes = [vp, vp, vp, vp, vp, i, C.POINTER(AdamHP), i, vp]
     L.gm_gan_create.argtypes = [vp, C.POINTER(GanDesc), C.POINTER(vp)]
@@ -116,6 +118,21 @@ def _ptr(t):
 
 def launch_count(reset=False):
     return int(lib().gm_launch_count(ctx(), 1 if reset else 0))
+
+
+GEMM_KINDS = ["gemm_umma<208,0,K-major>", "gemm_umma<64,0,K-major>", "gemm_umma<256,192,MN-major>",
+              "gemm_umma<64,0,MN-major>"]
+
+
+def prof_enable(on=True):
+    check(ctx(), lib().gm_prof_enable(ctx(), 1 if on else 0))
+
+
+def prof_collect():
+    """-> list of (kernel name, total ms, algorithmic flops, launches)."""
+    ms, fl, cn = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_longlong * 4)()
+    check(ctx(), lib().gm_prof_collect(ctx(), ms, fl, cn))
+    return [(GEMM_KINDS[k], ms[k], fl[k], cn[k]) for k in range(4)]
 
 
 def gemm_bf16(A, B, out, mode="nt", N=None, K=None, M=None, bias=None, act=0, aux=None, aux_mode=0, pad_one=False,

@@ -25,6 +25,10 @@ struct gm_ctx {
   long long launches = 0;
   float* scratch = nullptr;   // split-K partials for the generic gm_gemm_bf16
   size_t scratch_bytes = 0;
+  // optional per-launch GEMM timing (bench.py roofline): CUDA events on the launch stream
+  bool prof = false;
+  struct ProfRec { cudaEvent_t e0, e1; int kind; double flops; };
+  std::vector<ProfRec> prof_recs;
 };
 
 static int fail(gm_ctx* c, int code, const char* fmt, ...) {
@@ -72,6 +76,7 @@ struct GemmPlan {
   GemmParams p;
   int kind;
   int grid;
+  double flops;   // algorithmic 2*M*N*K of the logical problem (no padding)
 };
 
 template <int BN1, int BN2, bool AMN, bool BMN>
@@ -90,6 +95,14 @@ static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
 
 static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
   cudaError_t e;
+  gm_ctx::ProfRec rec;
+  if (c->prof) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    rec.kind = pl.kind;
+    rec.flops = pl.flops;
+    cudaEventRecord(rec.e0, s);
+  }
   switch (pl.kind) {
     case PK_NT_208: e = launch_inst<208, 0, false, false>(pl, s); break;
     case PK_NT_64: e = launch_inst<64, 0, false, false>(pl, s); break;
@@ -97,6 +110,10 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
     default: e = launch_inst<64, 0, true, true>(pl, s); break;
   }
   c->launches++;
+  if (c->prof) {
+    cudaEventRecord(rec.e1, s);
+    c->prof_recs.push_back(rec);
+  }
   if (e != cudaSuccess) return fail(c, GM_ERR_CUDA, "GEMM launch failed: %s", cudaGetErrorString(e));
   return GM_OK;
 }
@@ -126,6 +143,7 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
     if (rc) return rc;
   }
   GemmParams& p = pl->p;
+  pl->flops = 2.0 * M * N * K;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = cdiv(M, BM);
   p.n_tiles = cdiv(ncover, bn);
@@ -192,6 +210,29 @@ extern "C" long long gm_launch_count(gm_ctx* c, int reset) {
   const long long n = c->launches;
   if (reset) c->launches = 0;
   return n;
+}
+
+extern "C" int gm_prof_enable(gm_ctx* c, int on) {
+  if (!c) return GM_ERR_ARG;
+  c->prof = on != 0;
+  return GM_OK;
+}
+// Synchronises the device, then sums per plan kind (0: NT 128x208, 1: NT 128x64,
+// 2: TN 128x448 split-K, 3: TN 128x64 split-K) the launch durations (ms), algorithmic
+// FLOPs and launch counts recorded since the last collect.
+extern "C" int gm_prof_collect(gm_ctx* c, double* ms, double* flops, long long* count) {
+  if (!c || !ms || !flops || !count) return GM_ERR_ARG;
+  for (int i = 0; i < 4; ++i) { ms[i] = 0; flops[i] = 0; count[i] = 0; }
+  CU_OK(c, cudaDeviceSynchronize());
+  for (auto& r : c->prof_recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms[r.kind] += t; flops[r.kind] += r.flops; count[r.kind]++;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  c->prof_recs.clear();
+  return GM_OK;
 }
 
 // ------------------------------------------------------------------ generic GEMM / Adam
@@ -467,6 +508,7 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   // G layer 1: Hg = relu(Zb W1g^T + b1g), ones column at H
   if ((rc = plan_gemm(c, &sp.g1, 0, B, H, rup(Z, 16), g->Zb, ZP, g->W1g_s, ZP, HP, 1))) return rc;
   set_bf16_epi(sp.g1.p, g->Hg, HP, HP, 1, pG + g->G.off_b1, ACT_RELU);
+  sp.g1.flops = 2.0 * B * H * Z;
   // G layer 2: fake = sigmoid(Hg W2g^T + b2g) -> fake rows of Xall, ones column at X
   if ((rc = plan_gemm(c, &sp.g2, 0, B, X, H, g->Hg, HP, g->W2g_s, H, XP, 1))) return rc;
   set_bf16_epi(sp.g2.p, Xfake, XP, XP, 1, pG + g->G.off_b2, ACT_SIGMOID);
@@ -482,6 +524,7 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   {
     GemmParams& p = sp.dw1d.p;
     p.epi = EPI_F32; p.part = g->PD; p.ldp = p.m_tiles * BM; p.part_stride = (long long)H * p.ldp; p.transpose = 1;
+    sp.dw1d.flops = 2.0 * X * H * (2.0 * B);
   }
   // dX of D w.r.t. fake, times sigmoid'(fake): DA2 = (DHfake W1d) * fake(1-fake)
   if ((rc = plan_gemm(c, &sp.dx, 0, B, X, H, DHfake, HP, g->W1d_t, H, X, 1))) return rc;
@@ -492,6 +535,7 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   {
     GemmParams& p = sp.dw2g.p;
     p.epi = EPI_F32; p.part = g->PG2; p.ldp = rup(H + 1, 64); p.part_stride = (long long)X * p.ldp; p.transpose = 0;
+    sp.dw2g.flops = 2.0 * X * H * B;
   }
   // DHg = (DA2 W2g) * 1[Hg > 0]
   if ((rc = plan_gemm(c, &sp.dhg, 0, B, H, X, g->DA2, XP, g->W2g_t, X, H, 1))) return rc;
@@ -502,6 +546,7 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   {
     GemmParams& p = sp.dw1g.p;
     p.epi = EPI_F32; p.part = g->PG1; p.ldp = 64; p.part_stride = (long long)H * 64; p.transpose = 0;
+    sp.dw1g.flops = 2.0 * H * Z * B;
   }
   g->plans[B] = sp;
   *out = &g->plans[B];

@@ -139,6 +139,11 @@ int gm_gan_generate(gm_gan* gan, const float* noise_dev, int n, float* images_de
 int gm_gan_fisher_state(gm_gan* gan, float* lambda_rho_host, int set, gm_stream stream);
 /* number of this library's kernels launched since the last call with reset != 0 */
 long long gm_launch_count(gm_ctx* ctx, int reset);
+/* measurement aid (bench.py roofline): record CUDA events around every tensor-core
+ * GEMM launch on its launch stream; gm_prof_collect synchronises and returns, per
+ * kernel instantiation (4 slots), total ms, algorithmic FLOPs and launch count. */
+int gm_prof_enable(gm_ctx* ctx, int on);
+int gm_prof_collect(gm_ctx* ctx, double* ms4, double* flops4, long long* count4);
 
 #ifdef __cplusplus
 }

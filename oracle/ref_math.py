@@ -21,6 +21,26 @@ EPS = 1e-8  # the reference's log-stabiliser, e.g. src/ns_gan.py:191
 
 
 # ---------------------------------------------------------------- primitives
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16, returned in x's dtype (what the CUDA path
+    stores for GEMM operands)."""
+    a = np.asarray(x, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    return r.view(np.float32).astype(np.asarray(x).dtype)
+
+
+def _exact(name, v):
+    return v
+
+
+def bf16_points(name, v):
+    """Quantisation hook modelling the CUDA bf16 path: every tensor that is a
+    tensor-core GEMM operand (weights, z, hidden, fake, dh, da2, dhg) is bf16;
+    biases, the 400->1 row-dot, losses and all accumulation stay fp32."""
+    return bf16_round(v)
+
+
 def sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 
@@ -30,18 +50,20 @@ def linear(x, W, b):
     return x @ W.T + b
 
 
-def g_forward(P, z, pre="G."):
-    """Generator.forward, src/ns_gan.py:43-46: sigmoid(W2 relu(W1 z + b1) + b2)."""
-    a1 = linear(z, P[pre + "linear.weight"], P[pre + "linear.bias"])
-    h = np.maximum(a1, 0)
-    a2 = linear(h, P[pre + "generate.weight"], P[pre + "generate.bias"])
-    return dict(z=z, a1=a1, h=h, a2=a2, out=sigmoid(a2))
+def g_forward(P, z, pre="G.", q=_exact):
+    """Generator.forward, src/ns_gan.py:43-46: sigmoid(W2 relu(W1 z + b1) + b2).
+    q: optional operand-quantisation hook (bf16_points models the CUDA path)."""
+    z = q("z", z)
+    a1 = linear(z, q("W", P[pre + "linear.weight"]), P[pre + "linear.bias"])
+    h = q("h", np.maximum(a1, 0))
+    a2 = linear(h, q("W", P[pre + "generate.weight"]), P[pre + "generate.bias"])
+    return dict(z=z, a1=a1, h=h, a2=a2, out=q("fake", sigmoid(a2)))
 
 
-def d_forward(P, x, out_act="sigmoid", pre="D."):
+def d_forward(P, x, out_act="sigmoid", pre="D.", q=_exact):
     """Discriminator.forward, src/ns_gan.py:57-60 (sigmoid out);
     src/w_gp_gan.py:59-62 (ReLU out)."""
-    a1 = linear(x, P[pre + "linear.weight"], P[pre + "linear.bias"])
+    a1 = linear(x, q("W", P[pre + "linear.weight"]), P[pre + "linear.bias"])
     h = np.maximum(a1, 0)
     s = linear(h, P[pre + "discriminate.weight"], P[pre + "discriminate.bias"])  # [B,1]
     if out_act == "sigmoid":
@@ -50,7 +72,7 @@ def d_forward(P, x, out_act="sigmoid", pre="D."):
         d = np.maximum(s, 0)
     else:
         d = s
-    return dict(x=x, a1=a1, h=h, s=s, d=d)
+    return dict(x=x, a1=a1, h=h, hq=q("a", h), s=s, d=d)
 
 
 def d_out_grad(fw, dd, out_act):
@@ -62,28 +84,28 @@ def d_out_grad(fw, dd, out_act):
     return dd
 
 
-def d_backward(P, fw, ds, need_dx=False, pre="D."):
+def d_backward(P, fw, ds, need_dx=False, pre="D.", q=_exact):
     """Backward of the 2-layer D from dL/ds [B,1] (autograd of src/ns_gan.py:57-60;
     ReLU' = 0 at 0 like torch's threshold_backward)."""
     W1 = P[pre + "linear.weight"]
     w2 = P[pre + "discriminate.weight"]
     g = {}
-    g[pre + "discriminate.weight"] = ds.T @ fw["h"]
+    g[pre + "discriminate.weight"] = ds.T @ fw["hq"]
     g[pre + "discriminate.bias"] = ds.sum(0)
-    dh = (ds @ w2) * (fw["a1"] > 0)
+    dh = q("dh", (ds @ w2) * (fw["hq"] > 0))
     g[pre + "linear.weight"] = dh.T @ fw["x"]
     g[pre + "linear.bias"] = dh.sum(0)
-    dx = dh @ W1 if need_dx else None
+    dx = dh @ q("W", W1) if need_dx else None
     return g, dx
 
 
-def g_backward(P, fw, dout, pre="G."):
+def g_backward(P, fw, dout, pre="G.", q=_exact):
     """Backward of G from dL/d(out) [B,X] (autograd of src/ns_gan.py:43-46)."""
-    da2 = dout * fw["out"] * (1 - fw["out"])
+    da2 = q("da2", dout * fw["out"] * (1 - fw["out"]))
     g = {}
     g[pre + "generate.weight"] = da2.T @ fw["h"]
     g[pre + "generate.bias"] = da2.sum(0)
-    dh = (da2 @ P[pre + "generate.weight"]) * (fw["a1"] > 0)
+    dh = q("dhg", (da2 @ q("W", P[pre + "generate.weight"])) * (fw["h"] > 0))
     g[pre + "linear.weight"] = dh.T @ fw["z"]
     g[pre + "linear.bias"] = dh.sum(0)
     return g
@@ -228,18 +250,18 @@ def gradient_penalty(P, xhat, out_act, lam=10.0, K=1.0, pre="D."):
 
 
 # ---------------------------------------------------------------- train steps
-def gan_d_step(P, variant, images, z, aux=None, st=None, lam=10.0):
+def gan_d_step(P, variant, images, z, aux=None, st=None, lam=10.0, q=_exact):
     """Trainer.train_D + D_loss.backward(), restricted to D's gradients (the G
     gradients the reference also computes are discarded at src/ns_gan.py:148).
     aux: for 'wgp' eps [B,1] (src/w_gp_gan.py:197); for 'dra' (delta [B,1],
     u [B,X]) (src/dra_gan.py:200,205)."""
     act = D_OUT_ACT.get(variant, "sigmoid")
-    gf = g_forward(P, z)
-    fx = d_forward(P, images, act)
-    fg = d_forward(P, gf["out"], act)
+    gf = g_forward(P, z, q=q)
+    fx = d_forward(P, images, act, q=q)
+    fg = d_forward(P, gf["out"], act, q=q)
     L, ddx, ddg = d_loss(variant, fx["d"], fg["d"], st)
-    gx, _ = d_backward(P, fx, d_out_grad(fx, ddx, act))
-    gg, _ = d_backward(P, fg, d_out_grad(fg, ddg, act))
+    gx, _ = d_backward(P, fx, d_out_grad(fx, ddx, act), q=q)
+    gg, _ = d_backward(P, fg, d_out_grad(fg, ddg, act), q=q)
     grads = {k: gx[k] + gg[k] for k in gx}
     info = dict(dx=fx["d"], dg=fg["d"], fake=gf["out"])
     if variant == "wgp":
@@ -260,15 +282,15 @@ def gan_d_step(P, variant, images, z, aux=None, st=None, lam=10.0):
     return L, grads, info
 
 
-def gan_g_step(P, variant, z):
+def gan_g_step(P, variant, z, q=_exact):
     """Trainer.train_G + G_loss.backward(), restricted to G's gradients
     (src/ns_gan.py:196-216,155)."""
     act = D_OUT_ACT.get(variant, "sigmoid")
-    gf = g_forward(P, z)
-    fg = d_forward(P, gf["out"], act)
+    gf = g_forward(P, z, q=q)
+    fg = d_forward(P, gf["out"], act, q=q)
     L, ddg = g_loss(variant, fg["d"])
-    _, dxg = d_backward(P, fg, d_out_grad(fg, ddg, act), need_dx=True)
-    return L, g_backward(P, gf, dxg), dict(dg=fg["d"], fake=gf["out"])
+    _, dxg = d_backward(P, fg, d_out_grad(fg, ddg, act), need_dx=True, q=q)
+    return L, g_backward(P, gf, dxg, q=q), dict(dg=fg["d"], fake=gf["out"])
 
 
 class Adam:

