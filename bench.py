@@ -251,20 +251,30 @@ def run_ours(args):
 
 def cpu_baseline():
     """The reference's CPU path (oracle/torch_port.py: same nn.Linear/autograd/Adam calls
-    as src/ns_gan.py) on this box's host cores, bounded samples."""
+    as src/ns_gan.py) on this box's host cores, bounded samples (~10-30 s total)."""
     from oracle import torch_port as TP
     cores = os.cpu_count() or 1
-    # BASELINE config 1: B=64, N=50000, 1 epoch = 782 steps, reference DataLoader fetch included
-    ips64, dt64, th = TP.time_cpu_steps(64, steps=782, warmup=10, threads=cores, with_loader=True,
-                                        pool=None if False else _pool(50000))
-    ips64c, _, _ = TP.time_cpu_steps(64, steps=300, warmup=10, threads=cores, with_loader=False, pool=_pool(50000))
+    pool = _pool(50000)
+    # small-batch steps do not scale to every core: pick the best thread count quickly
+    best = None
+    for th in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+        ips, _, _ = TP.time_cpu_steps(64, steps=15, warmup=3, threads=th, with_loader=True, pool=pool)
+        if best is None or ips > best[0]:
+            best = (ips, th)
+    th = best[1]
+    # BASELINE config 1: B=64, N=50000, 1 epoch = 782 steps incl. the reference's DataLoader
+    # fetch; bounded to ~10 s (the number of steps actually run is reported)
+    steps = int(max(50, min(782, best[0] * 10.0 / 64)))
+    ips64, dt64, _ = TP.time_cpu_steps(64, steps=steps, warmup=5, threads=th, with_loader=True, pool=pool)
+    ips64c, _, _ = TP.time_cpu_steps(64, steps=max(50, steps // 3), warmup=5, threads=th, with_loader=False, pool=pool)
     big = 16384
-    ipsb, dtb, _ = TP.time_cpu_steps(big, steps=4, warmup=1, threads=cores, with_loader=False)
-    return {"value": round(ips64, 1), "unit": "images/s", "cores": th, "kind": "port",
-            "sample": "BASELINE configs[0]: B=64, 782 steps (1 epoch of N=50000) incl. the reference's per-step "
-                      "shuffling DataLoader fetch, %.1f s" % dt64,
+    ipsb, dtb, _ = TP.time_cpu_steps(big, steps=3, warmup=1, threads=cores, with_loader=False)
+    return {"value": round(ips64, 1), "unit": "images/s", "cores": th, "host_cores": cores, "kind": "port",
+            "sample": "BASELINE configs[0]: B=64, %d of the 782 steps of one N=50000 epoch, incl. the reference's "
+                      "per-step shuffling DataLoader fetch, %.1f s" % (steps, dt64),
             "compute_only_b64": round(ips64c, 1),
-            "large_batch": {"batch": big, "value": round(ipsb, 1), "seconds": round(dtb, 2), "steps": 4}}
+            "large_batch": {"batch": big, "value": round(ipsb, 1), "seconds": round(dtb, 2), "steps": 3,
+                            "threads": cores}}
 
 
 def _pool(n):

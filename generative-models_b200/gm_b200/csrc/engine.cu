@@ -81,7 +81,7 @@ struct GemmPlan {
 
 template <int BN1, int BN2, bool AMN, bool BMN>
 static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
-  using Cfg = GemmCfg<BN1, BN2>;
+  using Cfg = GemmCfg<BN1, BN2, !AMN>;
   auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN>;
   static bool configured = false;
   if (!configured) {
@@ -339,6 +339,9 @@ struct gm_gan {
   // bf16 operand copies of the weight matrices
   __nv_bfloat16 *W1g_s = nullptr, *W2g_s = nullptr, *W2g_t = nullptr, *W1d_s = nullptr, *W1d_t = nullptr;
   float *slots = nullptr, *ds = nullptr, *scores = nullptr, *lossbuf = nullptr, *fisher = nullptr, *dw2p = nullptr;
+  float* dw2sum = nullptr;
+  double* loss_part = nullptr;   // 3 x [loss_blocks][4]
+  int loss_blocks = 0;
   float *PD = nullptr, *PG2 = nullptr, *PG1 = nullptr;
   int dh_blocks = 0, dh_rows_per_iter = 0, dh_threads = 0;
   int max_splits = 0;
@@ -413,8 +416,11 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   const int groups = g->HP / 8;
   g->dh_rows_per_iter = 256 / groups > 0 ? 256 / groups : 1;
   g->dh_threads = groups * g->dh_rows_per_iter;
-  g->dh_blocks = c->num_sms * 4;
+  g->dh_blocks = c->num_sms * 2;
   TRY(dev_alloc(g, &g->dw2p, size_t(g->dh_blocks) * g->HP));
+  TRY(dev_alloc(g, &g->dw2sum, size_t(g->HP)));
+  g->loss_blocks = c->num_sms * 2;
+  TRY(dev_alloc(g, &g->loss_part, size_t(3) * g->loss_blocks * 4));
   // split-K partials
   g->max_splits = c->num_sms;
   const int sp_d = c->num_sms / cdiv(g->X + 1, BM) > 0 ? c->num_sms / cdiv(g->X + 1, BM) : 1;
@@ -581,8 +587,23 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   lp.d_out = g->scores + (g_step ? B : 0);
   lp.loss = g->lossbuf;
   lp.fisher = g->fisher;
-  loss_kernel<1024><<<1, 1024, 0, s>>>(lp);
-  g->ctx->launches++;
+  const int rows = g_step ? B : 2 * B;
+  lp.nblk = cdiv(rows, kLossThreads) < g->loss_blocks ? cdiv(rows, kLossThreads) : g->loss_blocks;
+  lp.partA = g->loss_part;
+  lp.partB = g->loss_part + size_t(g->loss_blocks) * 4;
+  lp.partR = g->loss_part + size_t(g->loss_blocks) * 8;
+  const int v = g->d.variant;
+  if (!g_step && (v == V_RA || v == V_FISHER)) {
+    loss_pass_kernel<0><<<lp.nblk, kLossThreads, 0, s>>>(lp);
+    g->ctx->launches++;
+    if (v == V_RA) {
+      loss_pass_kernel<1><<<lp.nblk, kLossThreads, 0, s>>>(lp);
+      g->ctx->launches++;
+    }
+  }
+  loss_pass_kernel<2><<<lp.nblk, kLossThreads, 0, s>>>(lp);
+  loss_final_kernel<<<1, kLossThreads, 0, s>>>(lp);
+  g->ctx->launches += 2;
 }
 
 extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const int* gather_idx, int batch,
@@ -605,7 +626,8 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   launch_loss(g, B, 0, inv_global_batch, s);
   dh_kernel<<<g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * g->HP * sizeof(float), s>>>(
       g->Aall, g->ds, g->par[GM_NET_D] + g->D.off_w2, g->DHall, g->dw2p, 2 * B, g->H, g->HP, g->dh_rows_per_iter);
-  c->launches++;
+  colsum_kernel<<<cdiv(g->HP * 32, 256), 256, 0, s>>>(g->dw2p, g->dh_blocks, g->HP, g->HP, g->dw2sum);
+  c->launches += 2;
   if ((rc = launch_plan(c, sp->dw1d, s))) return rc;
   GradSegs gs;
   memset(&gs, 0, sizeof gs);
@@ -614,7 +636,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   gs.total = g->D.total;
   gs.s[0] = {g->D.off_w1, g->H * g->X, 0, g->X, pw.ldp, 0, pw.splits, pw.part_stride, g->PD};
   gs.s[1] = {g->D.off_b1, g->H, 2, 0, pw.ldp, g->X, pw.splits, pw.part_stride, g->PD};
-  gs.s[2] = {g->D.off_w2, g->H, 3, 0, 0, 0, g->dh_blocks, (long long)g->HP, g->dw2p};
+  gs.s[2] = {g->D.off_w2, g->H, 3, 0, 0, 0, 1, 0, g->dw2sum};
   gs.s[3] = {g->D.off_b2, 1, 3, 0, 0, 0, 1, 0, g->lossbuf + 1};
   finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_D]);
   c->launches++;

@@ -25,7 +25,7 @@ constexpr int BK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + kEpiWarps * 32;
-constexpr int kSmemBudget = 220 * 1024;
+constexpr int kSmemBudget = 224 * 1024;
 
 enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
@@ -56,16 +56,22 @@ struct GemmParams {
   int transpose;
 };
 
-template <int BN1, int BN2>
+// per-epilogue-warp staging tile: 32 rows x (128 B data + 16 B pad) -> conflict-free
+// row-wise writes (thread = row) and row-contiguous reads (8 lanes = 128 B of one row)
+constexpr int kEpiPitch = 144;
+constexpr int kEpiStageBytes = 32 * kEpiPitch;
+
+template <int BN1, int BN2, bool STAGED_EPI = true>
 struct GemmCfg {
   static constexpr int BN = BN1 + BN2;
   static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
+  static constexpr int EPI_BYTES = STAGED_EPI ? kEpiWarps * kEpiStageBytes : 0;
+  static constexpr int STAGES_RAW = (kSmemBudget - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
   // K-major B is loaded with boxes of BOXN rows (<= 256, divides BN1 and BN2)
   static constexpr int gcd(int a, int b) { return b == 0 ? a : gcd(b, a % b); }
   static constexpr int BOXN = (BN2 == 0) ? BN1 : gcd(BN1, BN2);
@@ -78,10 +84,11 @@ template <int BN1, int BN2, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN1, BN2>;
+  using Cfg = GemmCfg<BN1, BN2, !A_MN>;
   constexpr int BN = Cfg::BN;
   constexpr int NACC = Cfg::NACC;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int EPI_ARRIVALS = (NACC == 2) ? kEpiWarps / 2 : kEpiWarps;
   static_assert(!B_MN || (BN1 % 64 == 0 && BN2 % 64 == 0), "MN-major B needs 64-wide atoms");
 
   extern __shared__ uint8_t smem_raw[];
@@ -107,7 +114,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < NACC; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps);
+      mbar_init(tempty_bar(s), EPI_ARRIVALS);
     }
     fence_mbar_init();
   }
@@ -206,86 +213,155 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // =========================== epilogue ===========================
+    // 8 warps = 2 groups of 4 (one warp per TMEM lane quarter).  With a double-buffered
+    // accumulator the groups alternate tiles (group g owns accumulator stage g), each
+    // warp covering all columns of its 32 rows; with a single wide accumulator both
+    // groups work on the same tile and split its 16-column chunks by parity.
     const int e = warp - 2;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
-    const int half = e >> 2;        // which half of the 16-column chunks
+    const int grp = e >> 2;
+    const uint32_t stage_s = bar_base + 256u + uint32_t(e) * kEpiStageBytes;  // staging tile (NT kernels)
     int acc_iter = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
+      const int as = acc_iter % NACC;
+      if (NACC == 2 && as != grp) continue;
       const int split = item / tiles;
       const int rem = item - split * tiles;
       const int n_tile = rem % p.n_tiles;
       const int m0 = (rem / p.n_tiles) * BM;
       const int n0 = n_tile * BN;
-      const int as = acc_iter % NACC;
       const uint32_t aphase = (acc_iter / NACC) & 1;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
+      const int wrow0 = m0 + quarter * 32;   // first row of this warp
+      const int row = wrow0 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
-      float dot = 0.f;
-      for (int c = half; c < BN / 16; c += 2) {
-        const int col0 = n0 + c * 16;
-        if (p.epi == EPI_BF16) {
-          if (col0 >= p.out_cols) break;
-          float v[16];
-          if (col0 < p.N) {
-            tmem_ld16(t_row + c * 16, v);
-            if (p.bias != nullptr) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+      if (p.epi == EPI_BF16) {
+        if constexpr (!A_MN) {
+          float dot = 0.f;
+          bool released = false;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 b = __ldg(b4 + q);
-                v[4 * q + 0] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+          for (int cb = 0; cb < BN; cb += 64) {
+            constexpr int kFull = 4;
+            const int nch = (BN - cb) >= 64 ? kFull : (BN - cb) / 16;   // compile-time per unrolled cb
+            const int col0 = n0 + cb;
+            if (col0 >= p.out_cols) break;
+            const bool last_block = (cb + 64 >= BN) || (col0 + 64 >= p.out_cols);
+            // ---- aux tile -> smem (coalesced) -> registers (own row)
+            uint4 ax[8];
+            if (p.aux_mode != AUX_NONE) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + (lane >> 3), c16 = lane & 7;
+                uint4 t = make_uint4(0, 0, 0, 0);
+                if (wrow0 + r < p.M && col0 + c16 * 8 < p.out_cols)
+                  t = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(wrow0 + r) * p.ld_aux + col0 + c16 * 8));
+                sts128(stage_s + r * kEpiPitch + c16 * 16, t);
               }
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 8; ++q) ax[q] = lds128(stage_s + lane * kEpiPitch + q * 16);
+              __syncwarp();
             }
-            if (p.act == ACT_RELU) {
+            // ---- accumulator columns -> registers (all chunks in flight, one wait)
+            uint32_t raw[4][16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-            } else if (p.act == ACT_SIGMOID) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fast_sigmoid(v[j]);
+            for (int q = 0; q < kFull; ++q)
+              if (q < nch && col0 + q * 16 < p.N) tmem_ld16_issue(t_row + cb + q * 16, raw[q]);
+            tmem_ld_wait();
+            if (last_block && !released) {   // accumulator stage fully read: hand it back to the MMA warp
+              released = true;
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty_bar(as));
             }
-            if (p.aux_mode != AUX_NONE && row_ok) {
-              const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.ld_aux + col0);
-              const uint4 x0 = __ldg(a4), x1 = __ldg(a4 + 1);
-              const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float a_lo = bf16_lo(w[q]), a_hi = bf16_hi(w[q]);
-                if (p.aux_mode == AUX_SIGMOID_GRAD) {
-                  v[2 * q] *= a_lo * (1.f - a_lo);
-                  v[2 * q + 1] *= a_hi * (1.f - a_hi);
-                } else {
-                  v[2 * q] = a_lo > 0.f ? v[2 * q] : 0.f;
-                  v[2 * q + 1] = a_hi > 0.f ? v[2 * q + 1] : 0.f;
+            for (int q = 0; q < kFull; ++q) {
+              if (q >= nch) continue;
+              const int c0 = col0 + q * 16;
+              float v[16];
+              if (c0 < p.N) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[q][j]);
+                if (p.bias != nullptr) {
+                  const float4* b4 = reinterpret_cast<const float4*>(p.bias + c0);
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 b = __ldg(b4 + k4);
+                    v[4 * k4 + 0] += b.x; v[4 * k4 + 1] += b.y; v[4 * k4 + 2] += b.z; v[4 * k4 + 3] += b.w;
+                  }
                 }
+                if (p.act == ACT_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = fast_sigmoid(v[j]);
+                }
+                if (p.aux_mode != AUX_NONE) {
+                  const uint32_t w[8] = {ax[2 * q].x, ax[2 * q].y, ax[2 * q].z, ax[2 * q].w,
+                                         ax[2 * q + 1].x, ax[2 * q + 1].y, ax[2 * q + 1].z, ax[2 * q + 1].w};
+#pragma unroll
+                  for (int k2 = 0; k2 < 8; ++k2) {
+                    const float a_lo = bf16_lo(w[k2]), a_hi = bf16_hi(w[k2]);
+                    if (p.aux_mode == AUX_SIGMOID_GRAD) {
+                      v[2 * k2] *= a_lo * (1.f - a_lo);
+                      v[2 * k2 + 1] *= a_hi * (1.f - a_hi);
+                    } else {
+                      v[2 * k2] = a_lo > 0.f ? v[2 * k2] : 0.f;
+                      v[2 * k2 + 1] = a_hi > 0.f ? v[2 * k2 + 1] : 0.f;
+                    }
+                  }
+                }
+                if (p.dot_w != nullptr) {
+                  const float4* w4 = reinterpret_cast<const float4*>(p.dot_w + c0);
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 w = __ldg(w4 + k4);
+                    dot = fmaf(v[4 * k4 + 0], w.x, dot); dot = fmaf(v[4 * k4 + 1], w.y, dot);
+                    dot = fmaf(v[4 * k4 + 2], w.z, dot); dot = fmaf(v[4 * k4 + 3], w.w, dot);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                if (c0 == p.N && p.pad_one) v[0] = 1.f;
+              }
+              sts128(stage_s + lane * kEpiPitch + q * 32,
+                     make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+              sts128(stage_s + lane * kEpiPitch + q * 32 + 16,
+                     make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])));
+            }
+            __syncwarp();
+            // ---- coalesced store: 8 lanes cover 128 contiguous bytes of one row, 4 rows per pass
+            if (p.out != nullptr) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + (lane >> 3), c16 = lane & 7;
+                if (c16 < nch * 2 && wrow0 + r < p.M && col0 + c16 * 8 < p.out_cols)
+                  *reinterpret_cast<uint4*>(p.out + size_t(wrow0 + r) * p.ldo + col0 + c16 * 8) =
+                      lds128(stage_s + r * kEpiPitch + c16 * 16);
               }
             }
-            if (p.dot_w != nullptr) {
-              const float4* w4 = reinterpret_cast<const float4*>(p.dot_w + col0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 w = __ldg(w4 + q);
-                dot = fmaf(v[4 * q + 0], w.x, dot); dot = fmaf(v[4 * q + 1], w.y, dot);
-                dot = fmaf(v[4 * q + 2], w.z, dot); dot = fmaf(v[4 * q + 3], w.w, dot);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            if (col0 == p.N && p.pad_one) v[0] = 1.f;
+            __syncwarp();
           }
-          if (row_ok && p.out != nullptr) {
-            uint4* o = reinterpret_cast<uint4*>(p.out + size_t(row) * p.ldo + col0);
-            o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            o[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          if (p.dot_out != nullptr && row_ok) p.dot_out[size_t(n_tile * 2) * p.dot_ld + row] = dot;
+          if (!released) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
           }
-        } else {  // EPI_F32 split-K partial
+        }
+      } else {  // EPI_F32 split-K partial: direct stores (transposed store is lane-contiguous)
+        const int c_first = (NACC == 2) ? 0 : grp;
+        const int c_step = (NACC == 2) ? 1 : 2;
+        float* base = p.part + size_t(split) * p.part_stride;
+        for (int c = c_first; c < BN / 16; c += c_step) {
+          const int col0 = n0 + c * 16;
           if (col0 >= p.N) break;
           float v[16];
           tmem_ld16(t_row + c * 16, v);
-          float* base = p.part + size_t(split) * p.part_stride;
           if (row_ok) {
             if (p.transpose) {
 #pragma unroll
@@ -302,18 +378,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      if (p.epi == EPI_BF16 && p.dot_out != nullptr && row_ok)
-        p.dot_out[size_t(n_tile * 2 + half) * p.dot_ld + row] = dot;
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -31,6 +31,18 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
     const int r = int(i / groups), g = int(i % groups);
     const long long sr = idx ? idx[r] : r;
     float v[8];
+    if (fmt == IMG_BITS && (x & 7) == 0) {
+      // one packed byte (MSB first) expands to this thread's 8 bf16 values
+      const int c0 = g * 8;
+      uint32_t byte = 0;
+      if (c0 < x) byte = __ldg(reinterpret_cast<const uint8_t*>(src) + sr * (x >> 3) + g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (byte >> (7 - j)) & 1u ? 1.f : 0.f;
+      if (c0 == x) v[0] = 1.f;
+      reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
@@ -88,7 +100,7 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 // ---------------------------------------------------------------- loss + upstream gradient
-// One CTA.  Reads the row-dot partial slots the D-layer GEMM epilogue wrote, forms the
+// Reads the row-dot partial slots the D-layer GEMM epilogue wrote, forms the
 // logit s = sum(slots) + b2, D's output d (sigmoid / relu / id) and, per variant
 // (SURVEY.md A.1), the loss and dL/ds for each row.  D step: rows [0,B) real,
 // [B,2B) fake.  G step: B fake rows.  `inv_b` = 1/(global batch) so data-parallel
@@ -104,6 +116,8 @@ struct LossParams {
   float* d_out;          // out (nullable): D output per row
   float* loss;           // out: [0] loss  [1] sum(ds) (= db2 grad)  [2..] variant scratch
   float* fisher;         // [0] LAMBDA  [1] RHO  (device state, V_FISHER only)
+  double* partA; double* partB; double* partR;   // per-block partials [nblk][4]
+  int nblk;
 };
 
 __device__ __forceinline__ float act_out(float s, int a) {
@@ -113,9 +127,24 @@ __device__ __forceinline__ float act_grad(float s, float d, int a) {
   return a == OUT_SIGMOID ? d * (1.f - d) : (a == OUT_RELU ? (s > 0.f ? 1.f : 0.f) : 1.f);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 1) loss_kernel(const LossParams p) {
-  __shared__ double sh[NT / 32];
+// Multi-block passes.  Every pass writes per-block partial sums (doubles, fixed tree ->
+// deterministic); a later pass re-reduces the earlier partials redundantly per block.
+//   PASS 0 (RA, Fisher): sum d, d^2 per branch            -> partA[blk][4]
+//   PASS 1 (RA):         sum q(1-q)/(q+eps) over real rows -> partB[blk][4] (slot 0)
+//   PASS 2 (all):        per-row loss term + dL/ds         -> partR[blk][4] (loss, sum ds)
+// loss_final_kernel (1 block) reduces partR into loss[0..1] and applies the Fisher
+// lambda update (src/fisher_gan.py:155).
+constexpr int kLossThreads = 256;
+
+__device__ __forceinline__ double reduce_partials4(const double* part, int nblk, int slot, double* sh) {
+  double t = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += kLossThreads) t += part[(long long)i * 4 + slot];
+  return block_sum<kLossThreads>(t, sh);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kLossThreads) loss_pass_kernel(const LossParams p) {
+  __shared__ double sh[kLossThreads / 32];
   const int rows = p.g_step ? p.B : 2 * p.B;
   const float b2 = p.b2[0];
   auto logit = [&](int r) {
@@ -123,36 +152,31 @@ __global__ void __launch_bounds__(NT, 1) loss_kernel(const LossParams p) {
     for (int k = 0; k < p.nslots; ++k) s += p.slots[(long long)k * p.slot_ld + r];
     return s + b2;
   };
-  // ---- batch statistics some variants need before any gradient
-  double st0 = 0, st1 = 0, st2 = 0, st3 = 0;
-  float mg = 0.f, gq_mean = 0.f, c_f = 0.f, omega = 0.f;
-  if (!p.g_step && (p.variant == V_RA || p.variant == V_FISHER)) {
-    for (int r = threadIdx.x; r < rows; r += NT) {
-      const float s = logit(r), d = act_out(s, p.out_act);
-      if (r < p.B) { st0 += d; st2 += (double)d * d; } else { st1 += d; st3 += (double)d * d; }
-    }
-    st0 = block_sum<NT>(st0, sh); st1 = block_sum<NT>(st1, sh);
-    st2 = block_sum<NT>(st2, sh); st3 = block_sum<NT>(st3, sh);
-    mg = float(st1 / p.B);
-    if (p.variant == V_RA) {
-      double a = 0;
-      for (int r = threadIdx.x; r < p.B; r += NT) {
-        const float d = act_out(logit(r), p.out_act);
-        const float q = 1.f / (1.f + expf(-(d - mg)));
-        a += q * (1.f - q) / (q + kEps);
-      }
-      gq_mean = float(block_sum<NT>(a, sh) / p.B);
-    } else {
-      const float lam = p.fisher[0], rho = p.fisher[1];
-      omega = 1.f - (0.5f * float(st2 / p.B) + 0.5f * float(st3 / p.B));
-      c_f = lam - rho * omega;
+  float mg = 0.f, gq_mean = 0.f, c_f = 0.f;
+  if (PASS >= 1 && !p.g_step && (p.variant == V_RA || p.variant == V_FISHER)) {
+    const double s1 = reduce_partials4(p.partA, p.nblk, 1, sh);
+    mg = float(s1 / p.B);
+    if (p.variant == V_FISHER) {
+      const double s2 = reduce_partials4(p.partA, p.nblk, 2, sh), s3 = reduce_partials4(p.partA, p.nblk, 3, sh);
+      const float omega = 1.f - (0.5f * float(s2 / p.B) + 0.5f * float(s3 / p.B));
+      c_f = p.fisher[0] - p.fisher[1] * omega;
+    } else if (PASS == 2) {
+      gq_mean = float(reduce_partials4(p.partB, p.nblk, 0, sh) / p.B);
     }
   }
-  double lsum = 0, dssum = 0;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
   const float ib = p.inv_b;
-  for (int r = threadIdx.x; r < rows; r += NT) {
+  for (int r = blockIdx.x * kLossThreads + threadIdx.x; r < rows; r += gridDim.x * kLossThreads) {
     const float s = logit(r), d = act_out(s, p.out_act);
     const bool fake = p.g_step || r >= p.B;
+    if (PASS == 0) {
+      if (!fake) { a0 += d; a2 += (double)d * d; } else { a1 += d; a3 += (double)d * d; }
+      continue;
+    }
+    if (PASS == 1) {
+      if (!fake) { const float q = 1.f / (1.f + expf(-(d - mg))); a0 += q * (1.f - q) / (q + kEps); }
+      continue;
+    }
     float l = 0.f, g = 0.f;  // per-row loss term (to be averaged) and dL/dd * B
     if (p.g_step) {
       switch (p.variant) {
@@ -174,7 +198,7 @@ __global__ void __launch_bounds__(NT, 1) loss_kernel(const LossParams p) {
         case V_LS: l = 0.5f * (d - 1.f) * (d - 1.f); g = d - 1.f; break;
         case V_RA: { const float q = 1.f / (1.f + expf(-(d - mg)));
                      l = -0.5f * logf(q + kEps); g = -0.5f * q * (1.f - q) / (q + kEps); } break;
-        case V_FISHER: l = -d; g = -(1.f - c_f * d); break;   // lambda/rho terms added once below
+        case V_FISHER: l = -d; g = -(1.f - c_f * d); break;   // lambda/rho terms added once in loss_final
         case V_F_TV: { const float t = tanhf(d); l = -0.5f * t; g = -0.5f * (1.f - t * t); } break;
         case V_F_FKL: l = -d; g = -1.f; break;
         case V_F_RKL: { const float e = expf(d); l = e; g = e; } break;
@@ -201,15 +225,29 @@ __global__ void __launch_bounds__(NT, 1) loss_kernel(const LossParams p) {
     const float dsr = g * ib * act_grad(s, d, p.out_act);
     p.ds[r] = dsr;
     if (p.d_out) p.d_out[r] = d;
-    lsum += l;
-    dssum += dsr;
+    a0 += l;
+    a1 += dsr;
   }
-  lsum = block_sum<NT>(lsum, sh);
-  dssum = block_sum<NT>(dssum, sh);
+  a0 = block_sum<kLossThreads>(a0, sh); a1 = block_sum<kLossThreads>(a1, sh);
+  a2 = block_sum<kLossThreads>(a2, sh); a3 = block_sum<kLossThreads>(a3, sh);
+  if (threadIdx.x == 0) {
+    double* out = (PASS == 0 ? p.partA : (PASS == 1 ? p.partB : p.partR)) + (long long)blockIdx.x * 4;
+    out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
+  }
+}
+
+__global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossParams p) {
+  __shared__ double sh[kLossThreads / 32];
+  const double lsum = reduce_partials4(p.partR, p.nblk, 0, sh);
+  const double dssum = reduce_partials4(p.partR, p.nblk, 1, sh);
+  double s2 = 0, s3 = 0;
+  const bool fisher = !p.g_step && p.variant == V_FISHER;
+  if (fisher) { s2 = reduce_partials4(p.partA, p.nblk, 2, sh); s3 = reduce_partials4(p.partA, p.nblk, 3, sh); }
   if (threadIdx.x == 0) {
     float L = float(lsum / p.B);
-    if (!p.g_step && p.variant == V_FISHER) {
+    if (fisher) {
       const float lam = p.fisher[0], rho = p.fisher[1];
+      const float omega = 1.f - (0.5f * float(s2 / p.B) + 0.5f * float(s3 / p.B));
       L = L - lam * omega + 0.5f * rho * omega * omega;   // src/fisher_gan.py:221-223
       p.fisher[0] = lam + rho * (-omega);                 // src/fisher_gan.py:155: lambda += rho * dL/dlambda
       p.loss[2] = omega;
@@ -217,6 +255,17 @@ __global__ void __launch_bounds__(NT, 1) loss_kernel(const LossParams p) {
     p.loss[0] = L;
     p.loss[1] = float(dssum);
   }
+}
+
+// out[c] = sum_p part[p*ld + c]: one warp per column (deterministic shuffle tree)
+__global__ void colsum_kernel(const float* __restrict__ part, int nparts, int ld, int cols, float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int i = lane; i < nparts; i += 32) t += part[(long long)i * ld + c];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) out[c] = t;
 }
 
 // ---------------------------------------------------------------- hidden-layer backward of D
