@@ -68,7 +68,9 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = STAGED_EPI ? kEpiWarps * kEpiStageBytes : 0;
+  // per-warp staging tile + per-warp copies of the tile's bias / row-dot weight slices
+  static constexpr int EPI_VEC_BYTES = BN * 2 * 4;
+  static constexpr int EPI_BYTES = STAGED_EPI ? kEpiWarps * (kEpiStageBytes + EPI_VEC_BYTES) : 0;
   static constexpr int STAGES_RAW = (kSmemBudget - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
@@ -221,6 +223,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
     const int grp = e >> 2;
     const uint32_t stage_s = bar_base + 256u + uint32_t(e) * kEpiStageBytes;  // staging tile (NT kernels)
+    const uint32_t vec_s = bar_base + 256u + kEpiWarps * kEpiStageBytes + uint32_t(e) * Cfg::EPI_VEC_BYTES;
     int acc_iter = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
       const int as = acc_iter % NACC;
@@ -231,10 +234,40 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m0 = (rem / p.n_tiles) * BM;
       const int n0 = n_tile * BN;
       const uint32_t aphase = (acc_iter / NACC) & 1;
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
+      if constexpr (!A_MN) {
+        // bias / row-dot weights of this tile's columns -> smem, while the MMAs still run
+        // (global-load latency must not sit between the TMEM read and the stores)
+        if (p.epi == EPI_BF16 && (p.bias != nullptr || p.dot_w != nullptr)) {
+          for (int i = lane; i < BN / 4; i += 32) {
+            const int c = n0 + i * 4;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f), w = b;
+            if (c < p.N) {
+              if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+              if (p.dot_w != nullptr) w = __ldg(reinterpret_cast<const float4*>(p.dot_w + c));
+            }
+            sts128(vec_s + i * 16, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
+            sts128(vec_s + BN * 4 + i * 16, make_uint4(__float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(w.z), __float_as_uint(w.w)));
+          }
+          __syncwarp();
+        }
+      }
       const int wrow0 = m0 + quarter * 32;   // first row of this warp
       const int row = wrow0 + lane;
+      uint4 pre[8];
+      auto aux_fetch = [&](int c_first) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3), c = c_first + (lane & 7) * 8;
+          pre[it] = make_uint4(0, 0, 0, 0);
+          if (wrow0 + r < p.M && c < p.out_cols)
+            pre[it] = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(wrow0 + r) * p.ld_aux + c));
+        }
+      };
+      if constexpr (!A_MN) {
+        if (p.epi == EPI_BF16 && p.aux_mode != AUX_NONE) aux_fetch(n0);
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
       if (p.epi == EPI_BF16) {
@@ -248,21 +281,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int col0 = n0 + cb;
             if (col0 >= p.out_cols) break;
             const bool last_block = (cb + 64 >= BN) || (col0 + 64 >= p.out_cols);
-            // ---- aux tile -> smem (coalesced) -> registers (own row)
+            // ---- aux tile: prefetched registers (coalesced mapping) -> smem -> own row
             uint4 ax[8];
             if (p.aux_mode != AUX_NONE) {
 #pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + (lane >> 3), c16 = lane & 7;
-                uint4 t = make_uint4(0, 0, 0, 0);
-                if (wrow0 + r < p.M && col0 + c16 * 8 < p.out_cols)
-                  t = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(wrow0 + r) * p.ld_aux + col0 + c16 * 8));
-                sts128(stage_s + r * kEpiPitch + c16 * 16, t);
-              }
+              for (int it = 0; it < 8; ++it)
+                sts128(stage_s + (it * 4 + (lane >> 3)) * kEpiPitch + (lane & 7) * 16, pre[it]);
               __syncwarp();
 #pragma unroll
               for (int q = 0; q < 8; ++q) ax[q] = lds128(stage_s + lane * kEpiPitch + q * 16);
               __syncwarp();
+              if (!last_block) aux_fetch(col0 + 64);   // overlaps with this block's math + stores
             }
             // ---- accumulator columns -> registers (all chunks in flight, one wait)
             uint32_t raw[4][16];
@@ -285,11 +314,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[q][j]);
                 if (p.bias != nullptr) {
-                  const float4* b4 = reinterpret_cast<const float4*>(p.bias + c0);
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 b = __ldg(b4 + k4);
-                    v[4 * k4 + 0] += b.x; v[4 * k4 + 1] += b.y; v[4 * k4 + 2] += b.z; v[4 * k4 + 3] += b.w;
+                    const uint4 b = lds128(vec_s + (cb + q * 16 + k4 * 4) * 4);
+                    v[4 * k4 + 0] += __uint_as_float(b.x); v[4 * k4 + 1] += __uint_as_float(b.y);
+                    v[4 * k4 + 2] += __uint_as_float(b.z); v[4 * k4 + 3] += __uint_as_float(b.w);
                   }
                 }
                 if (p.act == ACT_RELU) {
@@ -315,12 +344,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   }
                 }
                 if (p.dot_w != nullptr) {
-                  const float4* w4 = reinterpret_cast<const float4*>(p.dot_w + c0);
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 w = __ldg(w4 + k4);
-                    dot = fmaf(v[4 * k4 + 0], w.x, dot); dot = fmaf(v[4 * k4 + 1], w.y, dot);
-                    dot = fmaf(v[4 * k4 + 2], w.z, dot); dot = fmaf(v[4 * k4 + 3], w.w, dot);
+                    const uint4 w = lds128(vec_s + BN * 4 + (cb + q * 16 + k4 * 4) * 4);
+                    dot = fmaf(v[4 * k4 + 0], __uint_as_float(w.x), dot); dot = fmaf(v[4 * k4 + 1], __uint_as_float(w.y), dot);
+                    dot = fmaf(v[4 * k4 + 2], __uint_as_float(w.z), dot); dot = fmaf(v[4 * k4 + 3], __uint_as_float(w.w), dot);
                   }
                 }
               } else {
