@@ -79,10 +79,10 @@ struct GemmPlan {
   double flops;   // algorithmic 2*M*N*K of the logical problem (no padding)
 };
 
-template <int BN1, int BN2, bool AMN, bool BMN>
+template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
 static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
   using Cfg = GemmCfg<BN1, BN2, !AMN>;
-  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN>;
+  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -91,6 +91,21 @@ static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
   }
   kern<<<pl.grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
   return cudaGetLastError();
+}
+
+// K-major 128x208 kernel: pick the compile-time-specialised epilogue when the plan's
+// fused-epilogue combination is one of the train step's, else the universal variant.
+static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
+  const GemmParams& p = pl.p;
+  const bool bias = p.bias != nullptr, dot = p.dot_w != nullptr;
+  const int aux = p.aux_mode;
+  if (bias && !dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 0>(pl, s);
+  if (bias && !dot && aux == AUX_NONE && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_NONE, 1, 0>(pl, s);
+  if (bias && dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 1>(pl, s);
+  if (!bias && !dot && aux == AUX_SIGMOID_GRAD && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_SIGMOID_GRAD, 0, 0>(pl, s);
+  if (!bias && !dot && aux == AUX_RELU_MASK && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_RELU_MASK, 0, 0>(pl, s);
+  if (!bias && !dot && aux == AUX_NONE && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONE, 0, 0>(pl, s);
+  return launch_inst<208, 0, false, false>(pl, s);
 }
 
 static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
@@ -104,7 +119,7 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
     cudaEventRecord(rec.e0, s);
   }
   switch (pl.kind) {
-    case PK_NT_208: e = launch_inst<208, 0, false, false>(pl, s); break;
+    case PK_NT_208: e = launch_nt208(pl, s); break;
     case PK_NT_64: e = launch_inst<64, 0, false, false>(pl, s); break;
     case PK_TN_448: e = launch_inst<256, 192, true, true>(pl, s); break;
     default: e = launch_inst<64, 0, true, true>(pl, s); break;

@@ -82,7 +82,10 @@ struct GemmCfg {
   static_assert(STAGES >= 2, "need a pipeline");
 };
 
-template <int BN1, int BN2, bool A_MN, bool B_MN>
+// Epilogue specialisation: ACT_T / AUX_T / BIAS_T / DOT_T >= 0 fix the fused epilogue at
+// compile time (small code: the whole kernel must stay inside the instruction cache);
+// -1 selects the universal variant that reads the choice from GemmParams at run time.
+template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -224,7 +227,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int grp = e >> 2;
     const uint32_t stage_s = bar_base + 256u + uint32_t(e) * kEpiStageBytes;  // staging tile (NT kernels)
     const uint32_t vec_s = bar_base + 256u + kEpiWarps * kEpiStageBytes + uint32_t(e) * Cfg::EPI_VEC_BYTES;
+    const int act = ACT_T >= 0 ? ACT_T : p.act;
+    const int aux_mode = AUX_T >= 0 ? AUX_T : p.aux_mode;
+    const bool has_bias = BIAS_T >= 0 ? (BIAS_T != 0) : (p.bias != nullptr);
+    const bool has_dot = DOT_T >= 0 ? (DOT_T != 0) : (p.dot_w != nullptr);
     int acc_iter = 0;
+#pragma unroll 1
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
       const int as = acc_iter % NACC;
       if (NACC == 2 && as != grp) continue;
@@ -234,86 +242,82 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m0 = (rem / p.n_tiles) * BM;
       const int n0 = n_tile * BN;
       const uint32_t aphase = (acc_iter / NACC) & 1;
+      const int wrow0 = m0 + quarter * 32;   // first row of this warp
+      const int row = wrow0 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
       if constexpr (!A_MN) {
-        // bias / row-dot weights of this tile's columns -> smem, while the MMAs still run
-        // (global-load latency must not sit between the TMEM read and the stores)
-        if (p.epi == EPI_BF16 && (p.bias != nullptr || p.dot_w != nullptr)) {
+        // ================= bf16 epilogue (K-major kernels) =================
+        // coalesced lane mapping for aux reads / output writes: 8 lanes x 16 B = one 128-byte
+        // row segment, 4 rows per pass
+        const int lr = lane >> 3, lc = lane & 7;
+        uint4 pre[8];
+        auto aux_fetch = [&](int c_first) {
+          const int c = c_first + lc * 8;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = wrow0 + it * 4 + lr;
+            pre[it] = make_uint4(0, 0, 0, 0);
+            if (r < p.M && c < p.out_cols) pre[it] = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(r) * p.ld_aux + c));
+          }
+        };
+        // bias / row-dot weights of this tile's columns -> smem and the first aux tile ->
+        // registers while the MMAs still run: no global-load latency after the TMEM read
+        if (has_bias || has_dot) {
           for (int i = lane; i < BN / 4; i += 32) {
             const int c = n0 + i * 4;
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f), w = b;
+            uint4 b = make_uint4(0, 0, 0, 0), w = b;
             if (c < p.N) {
-              if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-              if (p.dot_w != nullptr) w = __ldg(reinterpret_cast<const float4*>(p.dot_w + c));
+              if (has_bias) b = __ldg(reinterpret_cast<const uint4*>(p.bias + c));
+              if (has_dot) w = __ldg(reinterpret_cast<const uint4*>(p.dot_w + c));
             }
-            sts128(vec_s + i * 16, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
-            sts128(vec_s + BN * 4 + i * 16, make_uint4(__float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(w.z), __float_as_uint(w.w)));
+            if (has_bias) sts128(vec_s + i * 16, b);
+            if (has_dot) sts128(vec_s + BN * 4 + i * 16, w);
           }
           __syncwarp();
         }
-      }
-      const int wrow0 = m0 + quarter * 32;   // first row of this warp
-      const int row = wrow0 + lane;
-      uint4 pre[8];
-      auto aux_fetch = [&](int c_first) {
+        if (aux_mode != AUX_NONE) aux_fetch(n0);
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        float dot = 0.f;
+        bool released = false;
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 64) {
+          const int col0 = n0 + cb;
+          if (col0 >= p.out_cols) break;
+          const int nch = (BN - cb) >= 64 ? 4 : (BN - cb) / 16;
+          const bool last_block = (cb + 64 >= BN) || (col0 + 64 >= p.out_cols);
+          uint4 ax[8];
+          if (aux_mode != AUX_NONE) {   // prefetched aux (coalesced mapping) -> smem -> own row
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + (lane >> 3), c = c_first + (lane & 7) * 8;
-          pre[it] = make_uint4(0, 0, 0, 0);
-          if (wrow0 + r < p.M && c < p.out_cols)
-            pre[it] = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(wrow0 + r) * p.ld_aux + c));
-        }
-      };
-      if constexpr (!A_MN) {
-        if (p.epi == EPI_BF16 && p.aux_mode != AUX_NONE) aux_fetch(n0);
-      }
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      const bool row_ok = row < p.M;
-      const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
-      if (p.epi == EPI_BF16) {
-        if constexpr (!A_MN) {
-          float dot = 0.f;
-          bool released = false;
+            for (int it = 0; it < 8; ++it) sts128(stage_s + (it * 4 + lr) * kEpiPitch + lc * 16, pre[it]);
+            __syncwarp();
 #pragma unroll
-          for (int cb = 0; cb < BN; cb += 64) {
-            constexpr int kFull = 4;
-            const int nch = (BN - cb) >= 64 ? kFull : (BN - cb) / 16;   // compile-time per unrolled cb
-            const int col0 = n0 + cb;
-            if (col0 >= p.out_cols) break;
-            const bool last_block = (cb + 64 >= BN) || (col0 + 64 >= p.out_cols);
-            // ---- aux tile: prefetched registers (coalesced mapping) -> smem -> own row
-            uint4 ax[8];
-            if (p.aux_mode != AUX_NONE) {
+            for (int q = 0; q < 8; ++q) ax[q] = lds128(stage_s + lane * kEpiPitch + q * 16);
+            __syncwarp();
+            if (!last_block) aux_fetch(col0 + 64);   // overlaps with this block's math + stores
+          }
+          // accumulator columns -> registers: all chunks in flight, one wait
+          uint32_t raw[4][16];
 #pragma unroll
-              for (int it = 0; it < 8; ++it)
-                sts128(stage_s + (it * 4 + (lane >> 3)) * kEpiPitch + (lane & 7) * 16, pre[it]);
-              __syncwarp();
+          for (int q = 0; q < 4; ++q)
+            if (q < nch && col0 + q * 16 < p.N) tmem_ld16_issue(t_row + cb + q * 16, raw[q]);
+          tmem_ld_wait();
+          if (last_block) {   // accumulator stage fully read: hand it back to the MMA warp
+            released = true;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+          }
 #pragma unroll
-              for (int q = 0; q < 8; ++q) ax[q] = lds128(stage_s + lane * kEpiPitch + q * 16);
-              __syncwarp();
-              if (!last_block) aux_fetch(col0 + 64);   // overlaps with this block's math + stores
-            }
-            // ---- accumulator columns -> registers (all chunks in flight, one wait)
-            uint32_t raw[4][16];
-#pragma unroll
-            for (int q = 0; q < kFull; ++q)
-              if (q < nch && col0 + q * 16 < p.N) tmem_ld16_issue(t_row + cb + q * 16, raw[q]);
-            tmem_ld_wait();
-            if (last_block && !released) {   // accumulator stage fully read: hand it back to the MMA warp
-              released = true;
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(as));
-            }
-#pragma unroll
-            for (int q = 0; q < kFull; ++q) {
-              if (q >= nch) continue;
+          for (int q = 0; q < 4; ++q) {
+            if (q < nch) {
               const int c0 = col0 + q * 16;
               float v[16];
               if (c0 < p.N) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[q][j]);
-                if (p.bias != nullptr) {
+                if (has_bias) {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
                     const uint4 b = lds128(vec_s + (cb + q * 16 + k4 * 4) * 4);
@@ -321,20 +325,20 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     v[4 * k4 + 2] += __uint_as_float(b.z); v[4 * k4 + 3] += __uint_as_float(b.w);
                   }
                 }
-                if (p.act == ACT_RELU) {
+                if (act == ACT_RELU) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-                } else if (p.act == ACT_SIGMOID) {
+                } else if (act == ACT_SIGMOID) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = fast_sigmoid(v[j]);
                 }
-                if (p.aux_mode != AUX_NONE) {
+                if (aux_mode != AUX_NONE) {
                   const uint32_t w[8] = {ax[2 * q].x, ax[2 * q].y, ax[2 * q].z, ax[2 * q].w,
                                          ax[2 * q + 1].x, ax[2 * q + 1].y, ax[2 * q + 1].z, ax[2 * q + 1].w};
 #pragma unroll
                   for (int k2 = 0; k2 < 8; ++k2) {
                     const float a_lo = bf16_lo(w[k2]), a_hi = bf16_hi(w[k2]);
-                    if (p.aux_mode == AUX_SIGMOID_GRAD) {
+                    if (aux_mode == AUX_SIGMOID_GRAD) {
                       v[2 * k2] *= a_lo * (1.f - a_lo);
                       v[2 * k2 + 1] *= a_hi * (1.f - a_hi);
                     } else {
@@ -343,7 +347,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                   }
                 }
-                if (p.dot_w != nullptr) {
+                if (has_dot) {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
                     const uint4 w = lds128(vec_s + BN * 4 + (cb + q * 16 + k4 * 4) * 4);
@@ -361,30 +365,33 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               sts128(stage_s + lane * kEpiPitch + q * 32 + 16,
                      make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])));
             }
-            __syncwarp();
-            // ---- coalesced store: 8 lanes cover 128 contiguous bytes of one row, 4 rows per pass
-            if (p.out != nullptr) {
+          }
+          __syncwarp();
+          // coalesced store: 8 lanes cover 128 contiguous bytes of one row, 4 rows per pass
+          if (p.out != nullptr && lc < nch * 2 && col0 + lc * 8 < p.out_cols) {
+            __nv_bfloat16* o = p.out + size_t(wrow0 + lr) * p.ldo + col0 + lc * 8;
+            const uint32_t sa = stage_s + lr * kEpiPitch + lc * 16;
 #pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + (lane >> 3), c16 = lane & 7;
-                if (c16 < nch * 2 && wrow0 + r < p.M && col0 + c16 * 8 < p.out_cols)
-                  *reinterpret_cast<uint4*>(p.out + size_t(wrow0 + r) * p.ldo + col0 + c16 * 8) =
-                      lds128(stage_s + r * kEpiPitch + c16 * 16);
-              }
-            }
-            __syncwarp();
+            for (int it = 0; it < 8; ++it)
+              if (wrow0 + it * 4 + lr < p.M)
+                *reinterpret_cast<uint4*>(o + size_t(it * 4) * p.ldo) = lds128(sa + it * 4 * kEpiPitch);
           }
-          if (p.dot_out != nullptr && row_ok) p.dot_out[size_t(n_tile * 2) * p.dot_ld + row] = dot;
-          if (!released) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
-          }
+          __syncwarp();
         }
-      } else {  // EPI_F32 split-K partial: direct stores (transposed store is lane-contiguous)
+        if (has_dot && p.dot_out != nullptr && row_ok) p.dot_out[size_t(n_tile * 2) * p.dot_ld + row] = dot;
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+      } else {
+        // ================= fp32 split-K partial epilogue (MN-major kernels) =================
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
         const int c_first = (NACC == 2) ? 0 : grp;
         const int c_step = (NACC == 2) ? 1 : 2;
         float* base = p.part + size_t(split) * p.part_stride;
+#pragma unroll 1
         for (int c = c_first; c < BN / 16; c += c_step) {
           const int col0 = n0 + c * 16;
           if (col0 >= p.N) break;
