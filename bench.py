@@ -104,18 +104,15 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import gm_b200
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from gm_b200 import parallel as par
+    rank, world, local = par.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     eng = gm_b200.GanEngine(X, H, Z, max_batch=B, variant="ns")
     init_weights_like_reference(eng)
     hpG, hpD = gm_b200.AdamHP.make(2e-4), gm_b200.AdamHP.make(2e-4)
-    inv = 1.0 / (B * world)
+    inv = par.inv_global_batch(B, world)
     # device-resident synthetic dataset, 1 bit per pixel (binarised MNIST carries exactly
     # that: src/utils.py:31); pool of 4*B images = 412 MB as bf16 rows, > 126 MB L2
     N = 4 * B
@@ -130,13 +127,11 @@ def run_ours(args):
     def train_step(images, fmt, idx):
         s = step_no[0]
         step_no[0] += 1
-        eng.d_grad(images, fmt=fmt, gather_idx=idx, batch=B, inv_global_batch=inv, seed=1000 + rank, step=s)
-        if world > 1:
-            dist.all_reduce(eng.grads[1])
+        eng.d_grad(images, fmt=fmt, gather_idx=idx, batch=B, inv_global_batch=inv, seed=par.rank_seed(1000, rank), step=s)
+        par.sum_gradients(eng.grads[1])     # NCCL all-reduce of the D gradient only (no-op on 1 GPU)
         eng.apply(1, hpD)
-        eng.g_grad(B, inv_global_batch=inv, seed=1000 + rank, step=s)
-        if world > 1:
-            dist.all_reduce(eng.grads[0])
+        eng.g_grad(B, inv_global_batch=inv, seed=par.rank_seed(1000, rank), step=s)
+        par.sum_gradients(eng.grads[0])     # ... and of the G gradient
         eng.apply(0, hpG)
 
     def resident_step():
@@ -228,8 +223,11 @@ def run_ours(args):
                                "tflops": round(r[2] / (r[1] * 1e-3) / 1e12, 1) if r[1] > 0 else 0.0,
                                "launches_per_step": r[3] / 3.0} for r in prof if r[3]]}
 
-    if rank != 0:
-        return
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     out = {"metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -247,6 +245,8 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def cpu_baseline():

@@ -77,6 +77,7 @@ def lib():
     L.gm_gan_apply.argtypes = [vp, i, C.POINTER(AdamHP), i, vp]
     L.gm_gan_scores.argtypes = [vp, vp, i, vp]
     L.gm_gan_generate.argtypes = [vp, vp, i, vp, vp]
+    L.gm_gan_discriminate.argtypes = [vp, vp, i, i, vp, vp]
     L.gm_gan_fisher_state.argtypes = [vp, C.POINTER(C.c_float), i, vp]
     _lib = L
     return L

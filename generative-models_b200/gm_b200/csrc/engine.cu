@@ -149,7 +149,7 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
     rc = make_tmap(c, &pl->tmB, B, K, N, ldb, BK, boxn);
     if (rc) return rc;
   } else {
-    if (K % BK) return fail(c, GM_ERR_ARG, "gemm TN: K (%d) must be a multiple of %d", K, BK);
+    // K (batch rows) need not be a multiple of 64: rows past the extent are TMA zero-fill
     if (ncover <= 64) { pl->kind = PK_TN_64; bn = 64; }
     else { pl->kind = PK_TN_448; bn = 448; }
     int rc = make_tmap(c, &pl->tmA, A, M, K, lda, 64, BK);
@@ -337,7 +337,7 @@ struct NetLayout {
 };
 
 struct StepPlans {
-  GemmPlan g1, g2, d1_d, d1_g, dw1d, dx, dw2g, dhg, dw1g;
+  GemmPlan g1, g2, d1_d, d1_g, d1_x, dw1d, dx, dw2g, dhg, dw1g;
 };
 
 struct gm_gan {
@@ -392,8 +392,7 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   if (d->image_size % 16 || d->hidden_dim % 16 || d->image_size <= 0 || d->hidden_dim <= 0 || d->z_dim <= 0)
     return fail(c, GM_ERR_ARG, "image_size and hidden_dim must be positive multiples of 16 (got %d, %d, z=%d)",
                 d->image_size, d->hidden_dim, d->z_dim);
-  if (d->max_batch <= 0 || d->max_batch % 64)
-    return fail(c, GM_ERR_ARG, "max_batch must be a positive multiple of 64 (got %d)", d->max_batch);
+  if (d->max_batch <= 0) return fail(c, GM_ERR_ARG, "max_batch must be positive (got %d)", d->max_batch);
   if (d->variant == GM_WGP || d->variant == GM_DRA || d->variant == GM_INFO)
     return fail(c, GM_ERR_UNSUPPORTED, "variant %d is not built yet", d->variant);
   gm_gan* g = new gm_gan();
@@ -540,6 +539,10 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   if ((rc = plan_gemm(c, &sp.d1_g, 0, B, H, X, Xfake, XP, g->W1d_s, X, H, 1))) return rc;
   set_bf16_epi(sp.d1_g.p, Afake, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
   sp.d1_g.p.dot_w = pD + g->D.off_w2; sp.d1_g.p.dot_out = g->slots + B; sp.d1_g.p.dot_ld = slot_ld;
+  // D layer 1 on the real rows only (inference: gm_gan_discriminate)
+  if ((rc = plan_gemm(c, &sp.d1_x, 0, B, H, X, g->Xall, XP, g->W1d_s, X, H, 1))) return rc;
+  set_bf16_epi(sp.d1_x.p, g->Aall, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
+  sp.d1_x.p.dot_w = pD + g->D.off_w2; sp.d1_x.p.dot_out = g->slots; sp.d1_x.p.dot_ld = slot_ld;
   // dW1d^T (+ db1 row from the ones column): [X+1, H] = Xall^T DHall over 2B rows
   if ((rc = plan_gemm(c, &sp.dw1d, 1, X + 1, H, 2 * B, g->Xall, XP, g->DHall, HP, H, g->max_splits))) return rc;
   {
@@ -576,8 +579,8 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
 
 static int check_step_args(gm_gan* g, int batch) {
   if (!g) return GM_ERR_ARG;
-  if (batch <= 0 || batch % 64 || batch > g->Bmax)
-    return fail(g->ctx, GM_ERR_ARG, "batch must be a multiple of 64 in (0, %d] (got %d)", g->Bmax, batch);
+  if (batch <= 0 || batch > g->Bmax)
+    return fail(g->ctx, GM_ERR_ARG, "batch must be in (0, %d] (got %d)", g->Bmax, batch);
   if (!g->par[0] || !g->par[1] || !g->grd[0] || !g->grd[1]) return fail(g->ctx, GM_ERR_STATE, "bind both nets first");
   return GM_OK;
 }
@@ -718,7 +721,7 @@ extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* imag
   if (!g || !images || n <= 0) return GM_ERR_ARG;
   if (!g->par[0]) return fail(g->ctx, GM_ERR_STATE, "bind G first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int B = rup(n, 64);
+  const int B = n;
   if (B > g->Bmax) return fail(g->ctx, GM_ERR_ARG, "n (%d) exceeds max_batch", n);
   if (!g->par[1]) return fail(g->ctx, GM_ERR_STATE, "bind D too (plans cover the whole step)");
   StepPlans* sp;
@@ -731,6 +734,24 @@ extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* imag
   if ((rc = launch_plan(g->ctx, sp->g2, s))) return rc;
   const long long tot = (long long)n * g->X;
   bf16_rows_to_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, s>>>(g->Xall + size_t(B) * g->XP, g->XP, images, n, g->X);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+extern "C" int gm_gan_discriminate(gm_gan* g, const void* images, int img_fmt, int n, float* scores, gm_stream stream) {
+  if (!g || !images || !scores || n <= 0) return GM_ERR_ARG;
+  if (n > g->Bmax) return fail(g->ctx, GM_ERR_ARG, "n (%d) exceeds max_batch", n);
+  if (!g->par[0] || !g->par[1]) return fail(g->ctx, GM_ERR_STATE, "bind both nets first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StepPlans* sp;
+  int rc;
+  if ((rc = build_plans(g, n, &sp))) return rc;
+  stage_images_kernel<<<g->ctx->num_sms * 8, 256, 0, s>>>(images, img_fmt, nullptr, g->Xall, n, g->X, g->XP);
+  g->ctx->launches++;
+  if ((rc = launch_plan(g->ctx, sp->d1_x, s))) return rc;
+  scores_kernel<<<cdiv(n, 256), 256, 0, s>>>(g->slots, 2 * cdiv(g->H, 208), 3 * g->Bmax, g->par[GM_NET_D] + g->D.off_b2,
+                                            g->d.d_out_act, scores, n);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;

@@ -257,6 +257,16 @@ __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossPara
   }
 }
 
+// D's output for inference: d[r] = act(sum(slots[:, r]) + b2)
+__global__ void scores_kernel(const float* __restrict__ slots, int nslots, int slot_ld, const float* __restrict__ b2,
+                              int out_act, float* __restrict__ out, int rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int k = 0; k < nslots; ++k) s += slots[(long long)k * slot_ld + r];
+  out[r] = act_out(s + b2[0], out_act);
+}
+
 // out[c] = sum_p part[p*ld + c]: one warp per column (deterministic shuffle tree)
 __global__ void colsum_kernel(const float* __restrict__ part, int nparts, int ld, int cols, float* __restrict__ out) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

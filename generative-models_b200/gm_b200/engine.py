@@ -72,6 +72,23 @@ class GanEngine:
     def sync_shadows(self, net):
         check(self.h, lib().gm_gan_sync_shadows(self.g, net, _stream()))
 
+    def sync_all(self):
+        """Refresh both nets' bf16 operand copies from the fp32 masters (call after anything
+        outside the engine — torch.optim, load_state_dict, clamp_ — touched the parameters)."""
+        self.sync_shadows(G)
+        self.sync_shadows(D)
+
+    sync_if_stale = sync_all
+
+    def track_versions(self, param_lists):
+        self._tracked = param_lists
+
+    def discriminate(self, images, fmt="f32"):
+        n = images.shape[0]
+        out = torch.empty(n, 1, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_gan_discriminate(self.g, _ptr(images.contiguous()), IMG_FMTS[fmt], n, _ptr(out), _stream()))
+        return out
+
     def reset_optimizer(self):
         for net in (G, D):
             self.exp_avg[net].zero_()

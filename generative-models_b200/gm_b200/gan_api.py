@@ -1,0 +1,298 @@
+"""Host-side mirror of the reference's GAN class surface (src/ns_gan.py:35-290 and its
+per-variant copies), backed by the CUDA train-step engine.
+
+What a reference user sees is unchanged: `Generator`, `Discriminator`, an `XGAN`
+container with `.G .D .z_dim .image_size .hidden_dim .shape`, and an `XTrainer` with
+`train / train_D / train_G / compute_noise / process_batch / generate_images /
+viz_loss / save_model / load_model` and the `Glosses / Dlosses / num_epochs / name`
+attributes.  What changes is where the arithmetic runs: the nn.Linear parameters
+become views into the engine's flat fp32 buffers and every forward / loss / backward /
+Adam is a hand-written sm_100a kernel behind the C ABI.  No autograd on the hot path.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import AdamHP, GmError
+from .engine import GanEngine
+
+G_NET, D_NET = 0, 1
+
+
+def to_cuda(x):
+    """src/utils.py:10-14."""
+    if torch.cuda.is_available():
+        x = x.cuda()
+    return x
+
+
+def to_var(x):
+    """src/utils.py:6-8."""
+    return to_cuda(x).requires_grad_()
+
+
+class _EngineBacked(nn.Module):
+    """nn.Module whose Linear parameters alias an engine's flat fp32 buffer once a
+    Trainer has attached it; forward runs the CUDA kernels (inference, no autograd)."""
+    _engine = None
+    _net = None
+
+    def _attach(self, engine, net):
+        object.__setattr__(self, "_engine", engine)
+        object.__setattr__(self, "_net", net)
+
+
+class Generator(_EngineBacked):
+    """Generator. Input is noise, output is a generated image (src/ns_gan.py:35-46)."""
+
+    def __init__(self, image_size, hidden_dim, z_dim):
+        super().__init__()
+        self.linear = nn.Linear(z_dim, hidden_dim)
+        self.generate = nn.Linear(hidden_dim, image_size)
+
+    def forward(self, x):
+        if self._engine is None:
+            raise GmError("Generator is not attached to a CUDA engine yet: construct the Trainer first "
+                          "(there is no eager/CPU path)")
+        self._engine.sync_if_stale()
+        return self._engine.generate(to_cuda(x))
+
+
+class Discriminator(_EngineBacked):
+    """Discriminator. Input is an image, output is D's score (src/ns_gan.py:49-60)."""
+
+    def __init__(self, image_size, hidden_dim, output_dim):
+        super().__init__()
+        if output_dim != 1:
+            raise GmError("only output_dim=1 discriminators are built (as in every reference model)")
+        self.linear = nn.Linear(image_size, hidden_dim)
+        self.discriminate = nn.Linear(hidden_dim, output_dim)
+
+    def forward(self, x):
+        if self._engine is None:
+            raise GmError("Discriminator is not attached to a CUDA engine yet: construct the Trainer first")
+        self._engine.sync_if_stale()
+        return self._engine.discriminate(to_cuda(x))
+
+
+class GANBase(nn.Module):
+    """Container for G and D (src/ns_gan.py:63-74): keeps the hyper-parameters as
+    attributes the way `self.__dict__.update(locals())` does in the reference."""
+
+    def __init__(self, image_size, hidden_dim, z_dim, output_dim=1):
+        super().__init__()
+        self.__dict__.update(dict(image_size=image_size, hidden_dim=hidden_dim, z_dim=z_dim, output_dim=output_dim))
+        self.G = Generator(image_size, hidden_dim, z_dim)
+        self.D = Discriminator(image_size, hidden_dim, output_dim)
+        self.shape = int(image_size ** 0.5)
+
+
+class _FusedLoss(torch.autograd.Function):
+    """0-dim loss whose backward() hands the gradients the fused kernels already
+    computed to the parameters' .grad (the reference calls loss.backward() then
+    optimizer.step(), src/ns_gan.py:138-139)."""
+
+    @staticmethod
+    def forward(ctx, flat_params, loss_val, flat_grad, param_list):
+        ctx.flat_grad, ctx.param_list = flat_grad, param_list
+        return loss_val.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        off = 0
+        for p in ctx.param_list:
+            n = p.numel()
+            g = ctx.flat_grad[off:off + n].view_as(p) * gout
+            p.grad = g if p.grad is None else p.grad + g
+            off += n
+        return None, None, None, None
+
+
+class GANTrainerBase:
+    """Object to hold data iterators, train a GAN variant (src/ns_gan.py:77-290)."""
+    variant = "ns"
+    d_out_act = "sigmoid"
+
+    def __init__(self, model, train_iter, val_iter, test_iter, viz=False):
+        self.model = model
+        self.name = model.__class__.__name__
+        self.train_iter, self.val_iter, self.test_iter = train_iter, val_iter, test_iter
+        self.Glosses, self.Dlosses = [], []
+        self.viz = viz
+        self.num_epochs = 0
+        self._engine = None
+        self._max_batch = None
+        self._step = 0
+        self._seed = int(torch.initial_seed() & 0x7FFFFFFF)
+        self._needs_sync = True
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _ensure_engine(self, batch):
+        """Create (or grow) the engine; the model's Linear parameters become views of the
+        engine's flat fp32 buffers (this is the reference's to_cuda(model), src/ns_gan.py:81)."""
+        if self._engine is not None and batch <= self._max_batch and self._engine.variant == self._variant_name():
+            return self._engine
+        m = self.model
+        old = self._engine
+        batch = max(batch, self._max_batch or 0)
+        eng = GanEngine(m.image_size, m.hidden_dim, m.z_dim, max_batch=max(batch, 64), variant=self._variant_name(),
+                        d_out_act=self.d_out_act)
+        for net, mod in ((G_NET, m.G), (D_NET, m.D)):
+            params = list(mod.parameters())
+            eng.load(net, [p.data for p in params])
+            for p, v in zip(params, eng.views(net)):
+                p.data = v                      # alias: nn.Parameter storage == engine master weights
+            mod._attach(eng, net)
+        if old is not None:
+            for net in (G_NET, D_NET):
+                eng.exp_avg[net].copy_(old.exp_avg[net])
+                eng.exp_avg_sq[net].copy_(old.exp_avg_sq[net])
+            eng.steps = list(old.steps)
+        self._engine, self._max_batch = eng, max(batch, 64)
+        self._needs_sync = False
+        self._after_engine_created(eng)
+        return eng
+
+    def _after_engine_created(self, eng):
+        pass
+
+    def _variant_name(self):
+        return self.variant
+
+    def _loss_tensor(self, net, loss_val):
+        eng = self._engine
+        params = list((self.model.G if net == G_NET else self.model.D).parameters())
+        return _FusedLoss.apply(eng.params[net].detach().requires_grad_(True), loss_val, eng.grads[net], params)
+
+    # ------------------------------------------------------------------ reference surface
+    def train(self, num_epochs, G_lr=2e-4, D_lr=2e-4, D_steps=1, **extra):
+        """Trainer.train (src/ns_gan.py:94-170): same loop, same logging; each train_D /
+        train_G + backward + Adam step is one fused kernel sequence and losses are read
+        back once per epoch instead of once per step."""
+        hpG, hpD = AdamHP.make(G_lr), AdamHP.make(D_lr, clamp=float(extra.get("clip", 0.0) or 0.0))
+        epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
+        self._pre_train(num_epochs, hpG, hpD, D_steps, extra)
+        for epoch in range(1, num_epochs + 1):
+            self.model.train()
+            dl, gl = [], []
+            for _ in range(epoch_steps):
+                dstep = []
+                for _ in range(D_steps):
+                    images = self.process_batch(self.train_iter)
+                    dstep.append(self._fused_D(images, hpD))
+                dl.append(torch.stack(dstep).mean())
+                gl.append(self._fused_G(images.shape[0], hpG))
+            G_losses = torch.stack(gl).tolist()     # one device->host read per epoch
+            D_losses = torch.stack(dl).tolist()
+            self.Glosses.extend(G_losses)
+            self.Dlosses.extend(D_losses)
+            print("Epoch[%d/%d], G Loss: %.4f, D Loss: %.4f" % (epoch, num_epochs, np.mean(G_losses), np.mean(D_losses)))
+            self.num_epochs += 1
+            if self.viz:
+                self.generate_images(epoch)
+
+    def _pre_train(self, num_epochs, hpG, hpD, D_steps, extra):
+        # fresh optimizers each train() call, like src/ns_gan.py:107-110; parameters may have
+        # been touched from outside since the last call -> refresh the operand copies once
+        if self._engine is not None:
+            self._engine.reset_optimizer()
+        self._needs_sync = True
+
+    def _sync_once(self, eng):
+        if self._needs_sync:
+            eng.sync_all()
+            self._needs_sync = False
+
+    def _fused_D(self, images, hp):
+        eng = self._ensure_engine(images.shape[0])
+        self._sync_once(eng)
+        noise = self.compute_noise(images.shape[0], self.model.z_dim)
+        loss = eng.d_grad(images, noise=noise, seed=self._seed, step=self._step).clone()
+        eng.apply(D_NET, hp)
+        return loss
+
+    def _fused_G(self, batch, hp):
+        eng = self._ensure_engine(batch)
+        self._sync_once(eng)
+        noise = self.compute_noise(batch, self.model.z_dim)
+        loss = eng.g_grad(batch, noise=noise, seed=self._seed, step=self._step).clone()
+        eng.apply(G_NET, hp)
+        self._step += 1
+        return loss
+
+    def train_D(self, images):
+        """Run 1 step of training for the discriminator (src/ns_gan.py:172-194): returns
+        the loss; `.backward()` delivers the D gradients to model.D's parameters."""
+        images = to_cuda(images)
+        eng = self._ensure_engine(images.shape[0])
+        eng.sync_if_stale()
+        noise = self.compute_noise(images.shape[0], self.model.z_dim)
+        loss = eng.d_grad(images.float().contiguous(), noise=noise.float().contiguous(), seed=self._seed, step=self._step)
+        return self._loss_tensor(D_NET, loss)
+
+    def train_G(self, images):
+        """Run 1 step of training for the generator (src/ns_gan.py:196-216)."""
+        batch = images.shape[0]
+        eng = self._ensure_engine(batch)
+        eng.sync_if_stale()
+        noise = self.compute_noise(batch, self.model.z_dim)
+        loss = eng.g_grad(batch, noise=noise.float().contiguous(), seed=self._seed, step=self._step)
+        self._step += 1
+        return self._loss_tensor(G_NET, loss)
+
+    def compute_noise(self, batch_size, z_dim):
+        """Compute random noise for the generator (src/ns_gan.py:218-220): CPU RNG then
+        H2D, so a torch.manual_seed run draws the same numbers as the reference."""
+        return to_cuda(torch.randn(batch_size, z_dim))
+
+    def process_batch(self, iterator):
+        """Generate a processed batch for D (src/ns_gan.py:222-226)."""
+        images, _ = next(iter(iterator))
+        images = to_cuda(images.view(images.shape[0], -1)).float().contiguous()
+        return images
+
+    def generate_images(self, epoch, num_outputs=36, save=True):
+        """Sample a grid from G (src/ns_gan.py:228-262); saving needs torchvision, plotting
+        needs matplotlib — both optional here."""
+        self.model.eval()
+        noise = self.compute_noise(num_outputs, self.model.z_dim)
+        images = self.model.G(noise)
+        images = images.view(images.shape[0], self.model.shape, self.model.shape, -1).squeeze()
+        if save:
+            try:
+                import torchvision
+                outname = "../viz/" + self.name + "/"
+                os.makedirs(outname, exist_ok=True)
+                torchvision.utils.save_image(images.unsqueeze(1).data.cpu(), outname + "reconst_%d.png" % epoch,
+                                             nrow=int(num_outputs ** 0.5))
+            except Exception as e:  # pragma: no cover
+                print("generate_images: not saved (%s)" % e)
+        return images
+
+    def viz_loss(self):
+        """Loss curves (src/ns_gan.py:264-281); needs matplotlib."""
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError:
+            print("viz_loss: matplotlib is not installed")
+            return
+        plt.plot(np.linspace(1, self.num_epochs, len(self.Dlosses)), self.Dlosses, "r")
+        plt.plot(np.linspace(1, self.num_epochs, len(self.Dlosses)), self.Glosses, "g")
+        plt.legend(["Discriminator", "Generator"])
+        plt.title(self.name)
+        plt.show()
+
+    def save_model(self, savepath):
+        """Save model state dictionary (src/ns_gan.py:283-285); same keys as the reference."""
+        torch.save(self.model.state_dict(), savepath)
+
+    def load_model(self, loadpath):
+        """Load state dictionary into model (src/ns_gan.py:287-290)."""
+        state = torch.load(loadpath)
+        self.model.load_state_dict(state)
+        if self._engine is not None:
+            self._engine.sync_shadows(G_NET)
+            self._engine.sync_shadows(D_NET)

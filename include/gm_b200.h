@@ -68,7 +68,7 @@ int gm_ctx_num_sms(const gm_ctx* ctx);
  * (src/ns_gan.py:44-45,58-59) and autograd's AddmmBackward (src/ns_gan.py:138,155).
  *   mode 0 "NT": A_dev [M, lda] (K contiguous), B_dev [N, ldb] (K contiguous)
  *   mode 1 "TN": A_dev [K, lda] (M contiguous), B_dev [K, ldb] (N contiguous);
- *                K % 64 == 0 (contraction over batch rows: dW = X^T dY)
+ *                (contraction over batch rows: dW = X^T dY; any K)
  * out_kind 0: bf16 C_dev [M, ldc] with optional bias[N], act (0 none, 1 relu,
  *             2 sigmoid), aux (bf16 [M, ld_aux]; aux_mode 1: *= aux(1-aux),
  *             2: *= (aux > 0)); columns [N, out_cols) are written as padding
@@ -101,7 +101,7 @@ int gm_adam_step(gm_ctx* ctx, float* p_dev, const float* g_dev, float* m_dev, fl
  * nn.Module.parameters() order: [linear.weight | linear.bias | out.weight | out.bias]. */
 typedef struct {
   int image_size, hidden_dim, z_dim; /* NSGAN(image_size, hidden_dim, z_dim), src/ns_gan.py:66 */
-  int max_batch;                     /* largest local batch; multiple of 64 */
+  int max_batch;                     /* largest local batch */
   int variant;                       /* gm_variant */
   int d_out_act;                     /* gm_out_act: sigmoid, or relu for src/w_gp_gan.py:61 */
 } gm_gan_desc;
@@ -135,6 +135,9 @@ int gm_gan_scores(gm_gan* gan, float* dst_dev, int n, gm_stream stream);
 /* Generator.forward (src/ns_gan.py:43-46) for sampling: noise [n, z] fp32 -> images
  * [n, image_size] fp32. */
 int gm_gan_generate(gm_gan* gan, const float* noise_dev, int n, float* images_dev, gm_stream stream);
+/* Discriminator.forward (src/ns_gan.py:57-60) for inference: images [n, image_size]
+ * (gm_img_fmt) -> scores [n] fp32. */
+int gm_gan_discriminate(gm_gan* gan, const void* images_dev, int img_fmt, int n, float* scores_dev, gm_stream stream);
 /* Fisher GAN scalar state (src/fisher_gan.py:117-118,155): get/set LAMBDA, RHO. */
 int gm_gan_fisher_state(gm_gan* gan, float* lambda_rho_host, int set, gm_stream stream);
 /* number of this library's kernels launched since the last call with reset != 0 */

@@ -1,0 +1,122 @@
+"""The reference-facing class surface (generative-models_b200/*.py) on the GPU: same
+names / signatures / attributes as src/*.py, the reference's own training loop runs
+unchanged against it, and losses match the golden fixtures of the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from inputs import GAN_SHAPES, STEPS, B, gm_init_weights, load_case, unpack_draws, images_from_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(model, W):
+    sd = model.state_dict()
+    for k, (w, b) in W.items():
+        sd[k + ".weight"] = torch.from_numpy(w.copy())
+        sd[k + ".bias"] = torch.from_numpy(b.copy())
+    model.load_state_dict(sd)
+
+
+class _Replay:
+    """compute_noise replacement feeding the reference's recorded draws."""
+
+    def __init__(self, draws):
+        self.it = iter(draws)
+
+    def __call__(self, batch_size, z_dim):
+        return torch.from_numpy(next(self.it)).cuda()
+
+
+@pytest.mark.parametrize("mod,mcls,tcls,case,kw", [
+    ("ns_gan", "NSGAN", "NSGANTrainer", "ns", dict(G_lr=2e-4, D_lr=2e-4, D_steps=1)),
+    ("mm_gan", "MMGAN", "MMGANTrainer", "mm", dict(G_lr=2e-4, D_lr=2e-4, D_steps=1, G_init=2)),
+    ("w_gan", "WGAN", "WGANTrainer", "w", dict(G_lr=5e-5, D_lr=5e-5, D_steps=2, clip=0.01)),
+    ("ls_gan", "LSGAN", "LSGANTrainer", "ls", dict(G_lr=1e-4, D_lr=1e-4, D_steps=1)),
+    ("ra_gan", "RaNSGAN", "RaNSGANTrainer", "ra", dict(G_lr=2e-4, D_lr=2e-4, D_steps=1)),
+    ("fisher_gan", "FisherGAN", "FisherGANTrainer", "fisher", dict(G_lr=1e-4, D_lr=1e-4, D_steps=1, RHO=1e-6)),
+    ("f_gan", "fGAN", "fGANTrainer", "f_pearson", dict(method="pearson", G_lr=1e-4, D_lr=1e-4, D_steps=1)),
+])
+def test_fused_train_matches_reference_losses(mod, mcls, tcls, case, kw):
+    """trainer.train(num_epochs=1, ...) exactly as the reference's __main__ calls it."""
+    m = __import__(mod)
+    fx = load_case("gan_" + case)
+    model = getattr(m, mcls)(784, 400, 20)
+    _load(model, gm_init_weights(GAN_SHAPES, 1234))
+    x = torch.from_numpy(images_from_bits(fx)).view(B, 1, 28, 28)
+    it = [(x, torch.zeros(B, dtype=torch.long))] * (STEPS * kw.get("D_steps", 1))
+    trainer = getattr(m, tcls)(model, it, it, it, viz=False)
+    trainer.compute_noise = _Replay(unpack_draws(fx))
+    trainer.train(num_epochs=1, **kw)
+    assert trainer.num_epochs == 1 and len(trainer.Dlosses) == STEPS and len(trainer.Glosses) == STEPS
+    scale = lambda v: max(abs(v), 0.5)
+    for a, b in zip(trainer.Dlosses, fx["D_loss"]):
+        assert abs(a - b) < 2e-3 * scale(b), (trainer.Dlosses, fx["D_loss"])
+    for a, b in zip(trainer.Glosses, fx["G_loss"]):
+        assert abs(a - b) < 2e-3 * scale(b), (trainer.Glosses, fx["G_loss"])
+    # parameters are live views of the engine's masters and moved away from the init
+    w0 = gm_init_weights(GAN_SHAPES, 1234)["D.linear"][0]
+    assert model.D.linear.weight.is_cuda and not np.allclose(model.D.linear.weight.detach().cpu().numpy(), w0)
+    sd = model.state_dict()
+    assert list(sd.keys()) == ["G.linear.weight", "G.linear.bias", "G.generate.weight", "G.generate.bias",
+                               "D.linear.weight", "D.linear.bias", "D.discriminate.weight", "D.discriminate.bias"]
+
+
+def test_reference_loop_with_torch_optimizers():
+    """Level-(ii) drop-in: the reference's OWN loop body (src/ns_gan.py:129-156) —
+    zero_grad / train_D / backward / torch.optim.Adam.step / item — against our classes."""
+    import ns_gan
+    fx = load_case("gan_ns")
+    model = ns_gan.NSGAN(784, 400, 20)
+    _load(model, gm_init_weights(GAN_SHAPES, 1234))
+    x = torch.from_numpy(images_from_bits(fx)).view(B, 1, 28, 28)
+    it = [(x, torch.zeros(B, dtype=torch.long))] * STEPS
+    trainer = ns_gan.NSGANTrainer(model, it, it, it)
+    trainer.compute_noise = _Replay(unpack_draws(fx))
+    images = trainer.process_batch(trainer.train_iter)
+    D_loss0 = trainer.train_D(images)            # creates the engine; parameters now live on the GPU
+    G_opt = torch.optim.Adam([p for p in model.G.parameters() if p.requires_grad], lr=2e-4)
+    D_opt = torch.optim.Adam([p for p in model.D.parameters() if p.requires_grad], lr=2e-4)
+    Dl, Gl = [], []
+    for step in range(STEPS):
+        images = trainer.process_batch(trainer.train_iter)
+        D_opt.zero_grad()
+        D_loss = D_loss0 if step == 0 else trainer.train_D(images)
+        D_loss.backward()
+        D_opt.step()
+        Dl.append(D_loss.item())
+        G_opt.zero_grad()
+        G_loss = trainer.train_G(images)
+        Gl.append(G_loss.item())
+        G_loss.backward()
+        G_opt.step()
+    np.testing.assert_allclose(Dl, fx["D_loss"], rtol=2e-3)
+    np.testing.assert_allclose(Gl, fx["G_loss"], rtol=2e-3)
+
+
+def test_modules_forward_and_checkpoint_roundtrip(tmp_path):
+    import ns_gan
+    model = ns_gan.NSGAN(784, 400, 20)
+    it = [(torch.zeros(100, 1, 28, 28), torch.zeros(100, dtype=torch.long))]
+    trainer = ns_gan.NSGANTrainer(model, it, it, it)
+    images = trainer.process_batch(it)           # batch 100: not a multiple of the 64/128 tiles
+    trainer.train_D(images)
+    z = torch.randn(36, 20)
+    out = model.G(z)
+    Wg1, bg1, Wg2, bg2 = [p.detach() for p in model.G.parameters()]
+    ref = torch.sigmoid(torch.relu(z.cuda() @ Wg1.t() + bg1) @ Wg2.t() + bg2)
+    assert out.shape == (36, 784) and float((out - ref).norm() / ref.norm()) < 5e-3
+    d = model.D(ref)
+    Wd1, bd1, Wd2, bd2 = [p.detach() for p in model.D.parameters()]
+    dref = torch.sigmoid(torch.relu(ref @ Wd1.t() + bd1) @ Wd2.t() + bd2)
+    assert d.shape == (36, 1) and float((d - dref).abs().max()) < 2e-3
+    imgs = trainer.generate_images(1, save=False)
+    assert imgs.shape == (36, 28, 28)
+    path = str(tmp_path / "ck.pt")
+    trainer.save_model(path)
+    before = out.clone()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.zero_()
+    trainer.load_model(path)
+    assert float((model.G(z) - before).abs().max()) < 1e-6
