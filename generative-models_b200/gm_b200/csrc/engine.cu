@@ -99,11 +99,13 @@ static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
   const GemmParams& p = pl.p;
   const bool bias = p.bias != nullptr, dot = p.dot_w != nullptr;
   const int aux = p.aux_mode;
+  if (p.dot_sq && (bias || dot || aux != AUX_NONE || p.act != ACT_NONE)) return launch_inst<208, 0, false, false>(pl, s);
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 0>(pl, s);
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_NONE, 1, 0>(pl, s);
   if (bias && dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 1>(pl, s);
   if (!bias && !dot && aux == AUX_SIGMOID_GRAD && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_SIGMOID_GRAD, 0, 0>(pl, s);
   if (!bias && !dot && aux == AUX_RELU_MASK && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_RELU_MASK, 0, 0>(pl, s);
+  if (!bias && !dot && aux == AUX_NONE && p.act == ACT_NONE && p.dot_sq) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONE, 0, 2>(pl, s);
   if (!bias && !dot && aux == AUX_NONE && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONE, 0, 0>(pl, s);
   return launch_inst<208, 0, false, false>(pl, s);
 }
@@ -337,7 +339,7 @@ struct NetLayout {
 };
 
 struct StepPlans {
-  GemmPlan g1, g2, d1_d, d1_g, d1_x, dw1d, dx, dw2g, dhg, dw1g;
+  GemmPlan g1, g2, d1_d, d1_g, d1_x, dw1d, dx, dw2g, dhg, dw1g, gp_v, gp_t;
 };
 
 struct gm_gan {
@@ -354,7 +356,10 @@ struct gm_gan {
   // bf16 operand copies of the weight matrices
   __nv_bfloat16 *W1g_s = nullptr, *W2g_s = nullptr, *W2g_t = nullptr, *W1d_s = nullptr, *W1d_t = nullptr;
   float *slots = nullptr, *ds = nullptr, *scores = nullptr, *lossbuf = nullptr, *fisher = nullptr, *dw2p = nullptr;
-  float* dw2sum = nullptr;
+  float* dw2sum = nullptr;       // [3][HP]: loss path, penalty T path, DRAGAN ds_gp path
+  float *dw2p2 = nullptr, *dw2p3 = nullptr, *slots_v = nullptr, *coef = nullptr, *stats = nullptr;
+  double *gp_part = nullptr, *mom_part = nullptr;
+  int nreg = 2;                  // row regions of Xall/Aall/DHall: real, fake (, xhat, R)
   double* loss_part = nullptr;   // 3 x [loss_blocks][4]
   int loss_blocks = 0;
   float *PD = nullptr, *PG2 = nullptr, *PG1 = nullptr;
@@ -393,8 +398,7 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
     return fail(c, GM_ERR_ARG, "image_size and hidden_dim must be positive multiples of 16 (got %d, %d, z=%d)",
                 d->image_size, d->hidden_dim, d->z_dim);
   if (d->max_batch <= 0) return fail(c, GM_ERR_ARG, "max_batch must be positive (got %d)", d->max_batch);
-  if (d->variant == GM_WGP || d->variant == GM_DRA || d->variant == GM_INFO)
-    return fail(c, GM_ERR_UNSUPPORTED, "variant %d is not built yet", d->variant);
+  if (d->variant == GM_INFO) return fail(c, GM_ERR_UNSUPPORTED, "variant %d is not built yet", d->variant);
   gm_gan* g = new gm_gan();
   g->ctx = c;
   g->d = *d;
@@ -405,14 +409,16 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   g->G.init(g->Z, g->H, g->X);
   g->D.init(g->X, g->H, 1);
   g->region_rows = g->Bmax;
+  g->nreg = d->variant == GM_WGP ? 3 : (d->variant == GM_DRA ? 4 : 2);
   const size_t B = g->Bmax;
+  const size_t NR = g->nreg;
   int rc = GM_OK;
 #define TRY(x) do { rc = (x); if (rc) { gm_gan_destroy(g); return rc; } } while (0)
   TRY(dev_alloc(g, &g->Zb, B * g->ZP));
   TRY(dev_alloc(g, &g->Hg, B * g->HP));
-  TRY(dev_alloc(g, &g->Xall, 3 * B * g->XP));
-  TRY(dev_alloc(g, &g->Aall, 3 * B * g->HP));
-  TRY(dev_alloc(g, &g->DHall, 3 * B * g->HP));
+  TRY(dev_alloc(g, &g->Xall, NR * B * g->XP));
+  TRY(dev_alloc(g, &g->Aall, NR * B * g->HP));
+  TRY(dev_alloc(g, &g->DHall, NR * B * g->HP));
   TRY(dev_alloc(g, &g->DA2, B * g->XP));
   TRY(dev_alloc(g, &g->DHg, B * g->HP));
   TRY(dev_alloc(g, &g->W1g_s, size_t(g->H) * g->ZP));
@@ -421,9 +427,9 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   TRY(dev_alloc(g, &g->W1d_s, size_t(g->H) * g->X));
   TRY(dev_alloc(g, &g->W1d_t, size_t(g->X) * g->H));
   const int nslots = 2 * cdiv(g->H, 208);
-  TRY(dev_alloc(g, &g->slots, size_t(nslots) * 3 * B));
-  TRY(dev_alloc(g, &g->ds, 3 * B));
-  TRY(dev_alloc(g, &g->scores, 3 * B));
+  TRY(dev_alloc(g, &g->slots, size_t(nslots) * NR * B));
+  TRY(dev_alloc(g, &g->ds, NR * B));
+  TRY(dev_alloc(g, &g->scores, NR * B));
   TRY(dev_alloc(g, &g->lossbuf, 16));
   TRY(dev_alloc(g, &g->fisher, 4));
   // dh kernel geometry
@@ -432,7 +438,16 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   g->dh_threads = groups * g->dh_rows_per_iter;
   g->dh_blocks = c->num_sms * 2;
   TRY(dev_alloc(g, &g->dw2p, size_t(g->dh_blocks) * g->HP));
-  TRY(dev_alloc(g, &g->dw2sum, size_t(g->HP)));
+  TRY(dev_alloc(g, &g->dw2sum, size_t(3) * g->HP));
+  if (g->nreg > 2) {
+    TRY(dev_alloc(g, &g->dw2p2, size_t(g->dh_blocks) * g->HP));
+    TRY(dev_alloc(g, &g->dw2p3, size_t(g->dh_blocks) * g->HP));
+    TRY(dev_alloc(g, &g->slots_v, size_t(2 * cdiv(g->X, 208)) * B));
+    TRY(dev_alloc(g, &g->coef, B));
+    TRY(dev_alloc(g, &g->stats, 4));
+    TRY(dev_alloc(g, &g->gp_part, size_t(c->num_sms) * 2 * 4));
+    TRY(dev_alloc(g, &g->mom_part, size_t(c->num_sms) * 2 * 2));
+  }
   g->loss_blocks = c->num_sms * 2;
   TRY(dev_alloc(g, &g->loss_part, size_t(3) * g->loss_blocks * 4));
   // split-K partials
@@ -509,7 +524,7 @@ extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, 
 
 static void set_bf16_epi(GemmParams& p, __nv_bfloat16* out, int ldo, int out_cols, int pad_one, const float* bias, int act) {
   p.epi = EPI_BF16; p.out = out; p.ldo = ldo; p.out_cols = out_cols; p.pad_one = pad_one; p.bias = bias; p.act = act;
-  p.aux = nullptr; p.aux_mode = AUX_NONE; p.dot_w = nullptr; p.dot_out = nullptr;
+  p.aux = nullptr; p.aux_mode = AUX_NONE; p.dot_w = nullptr; p.dot_out = nullptr; p.dot_sq = 0;
 }
 
 static int build_plans(gm_gan* g, int B, StepPlans** out) {
@@ -523,7 +538,7 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   __nv_bfloat16* Xfake = g->Xall + size_t(B) * XP;
   __nv_bfloat16* Afake = g->Aall + size_t(B) * HP;
   __nv_bfloat16* DHfake = g->DHall + size_t(B) * HP;
-  const int slot_ld = 3 * g->Bmax;
+  const int slot_ld = g->nreg * g->Bmax;
   int rc;
   // G layer 1: Hg = relu(Zb W1g^T + b1g), ones column at H
   if ((rc = plan_gemm(c, &sp.g1, 0, B, H, rup(Z, 16), g->Zb, ZP, g->W1g_s, ZP, HP, 1))) return rc;
@@ -533,7 +548,8 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   if ((rc = plan_gemm(c, &sp.g2, 0, B, X, H, g->Hg, HP, g->W2g_s, H, XP, 1))) return rc;
   set_bf16_epi(sp.g2.p, Xfake, XP, XP, 1, pG + g->G.off_b2, ACT_SIGMOID);
   // D layer 1 (+ fused 400->1 row-dot) on [real; fake] (D step) and on fake only (G step)
-  if ((rc = plan_gemm(c, &sp.d1_d, 0, 2 * B, H, X, g->Xall, XP, g->W1d_s, X, H, 1))) return rc;
+  const int nfwd = g->nreg > 2 ? 3 : 2;      // GP variants also score the interpolated rows
+  if ((rc = plan_gemm(c, &sp.d1_d, 0, nfwd * B, H, X, g->Xall, XP, g->W1d_s, X, H, 1))) return rc;
   set_bf16_epi(sp.d1_d.p, g->Aall, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
   sp.d1_d.p.dot_w = pD + g->D.off_w2; sp.d1_d.p.dot_out = g->slots; sp.d1_d.p.dot_ld = slot_ld;
   if ((rc = plan_gemm(c, &sp.d1_g, 0, B, H, X, Xfake, XP, g->W1d_s, X, H, 1))) return rc;
@@ -544,11 +560,22 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   set_bf16_epi(sp.d1_x.p, g->Aall, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
   sp.d1_x.p.dot_w = pD + g->D.off_w2; sp.d1_x.p.dot_out = g->slots; sp.d1_x.p.dot_ld = slot_ld;
   // dW1d^T (+ db1 row from the ones column): [X+1, H] = Xall^T DHall over 2B rows
-  if ((rc = plan_gemm(c, &sp.dw1d, 1, X + 1, H, 2 * B, g->Xall, XP, g->DHall, HP, H, g->max_splits))) return rc;
+  if ((rc = plan_gemm(c, &sp.dw1d, 1, X + 1, H, g->nreg * B, g->Xall, XP, g->DHall, HP, H, g->max_splits))) return rc;
   {
     GemmParams& p = sp.dw1d.p;
     p.epi = EPI_F32; p.part = g->PD; p.ldp = p.m_tiles * BM; p.part_stride = (long long)H * p.ldp; p.transpose = 1;
-    sp.dw1d.flops = 2.0 * X * H * (2.0 * B);
+    sp.dw1d.flops = 2.0 * X * H * (double(g->nreg) * B);
+  }
+  if (g->nreg > 2) {
+    // gradient penalty: V = U W1 (+ row sum of squares), T = (R W1^T) * 1[a_hat > 0]
+    const size_t rreg = size_t(g->nreg - 1) * B;
+    __nv_bfloat16* Rrows = g->Xall + rreg * XP;
+    if ((rc = plan_gemm(c, &sp.gp_v, 0, B, X, H, g->DHall + rreg * HP, HP, g->W1d_t, H, X, 1))) return rc;
+    set_bf16_epi(sp.gp_v.p, Rrows, XP, X, 0, nullptr, ACT_NONE);
+    sp.gp_v.p.dot_sq = 1; sp.gp_v.p.dot_out = g->slots_v; sp.gp_v.p.dot_ld = g->Bmax;
+    if ((rc = plan_gemm(c, &sp.gp_t, 0, B, H, X, Rrows, XP, g->W1d_s, X, H, 1))) return rc;
+    set_bf16_epi(sp.gp_t.p, g->DHg, HP, H, 0, nullptr, ACT_NONE);
+    sp.gp_t.p.aux = g->Aall + size_t(2) * B * HP; sp.gp_t.p.ld_aux = HP; sp.gp_t.p.aux_mode = AUX_RELU_MASK;
   }
   // dX of D w.r.t. fake, times sigmoid'(fake): DA2 = (DHfake W1d) * fake(1-fake)
   if ((rc = plan_gemm(c, &sp.dx, 0, B, X, H, DHfake, HP, g->W1d_t, H, X, 1))) return rc;
@@ -598,7 +625,7 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   LossParams lp;
   lp.slots = g->slots + (g_step ? B : 0);
   lp.nslots = 2 * cdiv(g->H, 208);
-  lp.slot_ld = 3 * g->Bmax;
+  lp.slot_ld = g->nreg * g->Bmax;
   lp.b2 = g->par[GM_NET_D] + g->D.off_b2;
   lp.B = B; lp.g_step = g_step; lp.variant = g->d.variant; lp.out_act = g->d.d_out_act; lp.inv_b = inv_b;
   lp.ds = g->ds + (g_step ? B : 0);
@@ -630,7 +657,6 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   int rc = check_step_args(g, batch);
   if (rc) return rc;
   if (!images) return fail(g->ctx, GM_ERR_ARG, "images is null");
-  (void)aux;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   StepPlans* sp;
   if ((rc = build_plans(g, batch, &sp))) return rc;
@@ -640,12 +666,58 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   stage_images_kernel<<<c->num_sms * 8, 256, 0, s>>>(images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP);
   c->launches++;
   if ((rc = run_generator(g, sp, B, noise, seed, 2 * step, s))) return rc;
+  const bool gp = g->nreg > 2;
+  const int H = g->H, HP = g->HP, X = g->X, XP = g->XP;
+  const float* w2 = g->par[GM_NET_D] + g->D.off_w2;
+  const size_t dh_smem = size_t(g->dh_rows_per_iter) * HP * sizeof(float);
+  if (gp) {
+    // interpolated rows (region 2): WGAN-GP between real and fake, DRAGAN around the real data
+    const int mode = g->d.variant == GM_DRA ? 1 : 0;
+    if (mode == 1) {
+      moments_kernel<<<c->num_sms * 2, 256, 0, s>>>(g->Xall, B, X, XP, g->mom_part);
+      moments_final_kernel<<<1, 256, 0, s>>>(g->mom_part, c->num_sms * 2, g->stats);
+      c->launches += 2;
+    }
+    xhat_kernel<<<cdiv(B, 128), 128, 0, s>>>(g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
+                                           mode, aux, g->stats, seed, 2 * step);
+    c->launches++;
+  }
   if ((rc = launch_plan(c, sp->d1_d, s))) return rc;
   launch_loss(g, B, 0, inv_global_batch, s);
-  dh_kernel<<<g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * g->HP * sizeof(float), s>>>(
-      g->Aall, g->ds, g->par[GM_NET_D] + g->D.off_w2, g->DHall, g->dw2p, 2 * B, g->H, g->HP, g->dh_rows_per_iter);
-  colsum_kernel<<<cdiv(g->HP * 32, 256), 256, 0, s>>>(g->dw2p, g->dh_blocks, g->HP, g->HP, g->dw2sum);
+  dh_kernel<<<g->dh_blocks, g->dh_threads, dh_smem, s>>>(g->Aall, g->ds, w2, g->DHall, g->dw2p, 2 * B, H, HP, g->dh_rows_per_iter);
+  colsum_kernel<<<cdiv(HP * 32, 256), 256, 0, s>>>(g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
   c->launches += 2;
+  if (gp) {
+    const size_t rreg = size_t(g->nreg - 1) * B;
+    // U = 1[a_hat > 0] * w2  -> DHall rows of the R region
+    dh_kernel<<<g->dh_blocks, g->dh_threads, dh_smem, s>>>(g->Aall + size_t(2) * B * HP, nullptr, w2, g->DHall + rreg * HP, nullptr,
+                                                          B, H, HP, g->dh_rows_per_iter);
+    c->launches++;
+    if ((rc = launch_plan(c, sp->gp_v, s))) return rc;          // V = U W1 -> R region of Xall, ||V||^2 -> slots_v
+    GpParams gpp;
+    gpp.slots_s = g->slots + 2 * B; gpp.nslots_s = 2 * cdiv(H, 208); gpp.slot_ld = g->nreg * g->Bmax;
+    gpp.slots_v = g->slots_v; gpp.nslots_v = 2 * cdiv(X, 208); gpp.slotv_ld = g->Bmax;
+    gpp.b2 = g->par[GM_NET_D] + g->D.off_b2;
+    gpp.rows = B; gpp.out_act = g->d.d_out_act;
+    gpp.lam = 10.f; gpp.K = 1.f; gpp.inv_b = inv_global_batch;
+    gpp.coef = g->coef; gpp.ds_gp = g->ds + 2 * B;
+    gpp.part = g->gp_part; gpp.nblk = cdiv(B, kLossThreads) < c->num_sms * 2 ? cdiv(B, kLossThreads) : c->num_sms * 2;
+    gpp.loss = g->lossbuf;
+    gp_rows_kernel<<<gpp.nblk, kLossThreads, 0, s>>>(gpp);
+    gp_final_kernel<<<1, kLossThreads, 0, s>>>(gpp);
+    scale_rows_kernel<<<c->num_sms * 4, 256, 0, s>>>(g->Xall + rreg * XP, g->coef, B, XP);   // R = coef * V
+    c->launches += 3;
+    if ((rc = launch_plan(c, sp->gp_t, s))) return rc;          // T = (R W1^T) * mask -> DHg
+    dh_kernel<<<g->dh_blocks, g->dh_threads, dh_smem, s>>>(g->DHg, nullptr, w2, g->DA2, g->dw2p2, B, H, HP, g->dh_rows_per_iter);
+    colsum_kernel<<<cdiv(HP * 32, 256), 256, 0, s>>>(g->dw2p2, g->dh_blocks, HP, HP, g->dw2sum + HP);
+    c->launches += 2;
+    if (g->nreg == 4) {   // DRAGAN: the penalty also back-propagates through s(xhat)
+      dh_kernel<<<g->dh_blocks, g->dh_threads, dh_smem, s>>>(g->Aall + size_t(2) * B * HP, g->ds + 2 * B, w2,
+                                                            g->DHall + size_t(2) * B * HP, g->dw2p3, B, H, HP, g->dh_rows_per_iter);
+      colsum_kernel<<<cdiv(HP * 32, 256), 256, 0, s>>>(g->dw2p3, g->dh_blocks, HP, HP, g->dw2sum + 2 * HP);
+      c->launches += 2;
+    }
+  }
   if ((rc = launch_plan(c, sp->dw1d, s))) return rc;
   GradSegs gs;
   memset(&gs, 0, sizeof gs);
@@ -654,8 +726,8 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   gs.total = g->D.total;
   gs.s[0] = {g->D.off_w1, g->H * g->X, 0, g->X, pw.ldp, 0, pw.splits, pw.part_stride, g->PD};
   gs.s[1] = {g->D.off_b1, g->H, 2, 0, pw.ldp, g->X, pw.splits, pw.part_stride, g->PD};
-  gs.s[2] = {g->D.off_w2, g->H, 3, 0, 0, 0, 1, 0, g->dw2sum};
-  gs.s[3] = {g->D.off_b2, 1, 3, 0, 0, 0, 1, 0, g->lossbuf + 1};
+  gs.s[2] = {g->D.off_w2, g->H, 3, 0, 0, 0, gp ? g->nreg - 1 : 1, (long long)HP, g->dw2sum};
+  gs.s[3] = {g->D.off_b2, 1, 3, 0, 0, 0, gp ? 2 : 1, 2, g->lossbuf + 1};
   finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_D]);
   c->launches++;
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -704,7 +776,7 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
 
 extern "C" int gm_gan_scores(gm_gan* g, float* dst, int n, gm_stream stream) {
   if (!g || !dst || n <= 0) return GM_ERR_ARG;
-  if (n > 3 * g->Bmax) return fail(g->ctx, GM_ERR_ARG, "n too large");
+  if (n > g->nreg * g->Bmax) return fail(g->ctx, GM_ERR_ARG, "n too large");
   CU_OK(g->ctx, cudaMemcpyAsync(dst, g->scores, size_t(n) * sizeof(float), cudaMemcpyDeviceToDevice,
                                 static_cast<cudaStream_t>(stream)));
   return GM_OK;
@@ -750,7 +822,7 @@ extern "C" int gm_gan_discriminate(gm_gan* g, const void* images, int img_fmt, i
   stage_images_kernel<<<g->ctx->num_sms * 8, 256, 0, s>>>(images, img_fmt, nullptr, g->Xall, n, g->X, g->XP);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->d1_x, s))) return rc;
-  scores_kernel<<<cdiv(n, 256), 256, 0, s>>>(g->slots, 2 * cdiv(g->H, 208), 3 * g->Bmax, g->par[GM_NET_D] + g->D.off_b2,
+  scores_kernel<<<cdiv(n, 256), 256, 0, s>>>(g->slots, 2 * cdiv(g->H, 208), g->nreg * g->Bmax, g->par[GM_NET_D] + g->D.off_b2,
                                             g->d.d_out_act, scores, n);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());

@@ -47,6 +47,7 @@ struct GemmParams {
   int ld_aux;
   int aux_mode;
   const float* dot_w;   // nullable: row-dot of the *stored* values with dot_w[n]
+  int dot_sq;           // 1: dot_out = row sum of squares instead (dot_w unused)
   float* dot_out;       // partial slots [(n_tile*2 + half) * dot_ld + m]
   int dot_ld;
   // ---- EPI_F32: part[split*part_stride + (transpose ? n*ldp + m : m*ldp + n)] = acc
@@ -230,7 +231,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int act = ACT_T >= 0 ? ACT_T : p.act;
     const int aux_mode = AUX_T >= 0 ? AUX_T : p.aux_mode;
     const bool has_bias = BIAS_T >= 0 ? (BIAS_T != 0) : (p.bias != nullptr);
-    const bool has_dot = DOT_T >= 0 ? (DOT_T != 0) : (p.dot_w != nullptr);
+    const bool has_dot = DOT_T >= 0 ? (DOT_T == 1) : (p.dot_w != nullptr);
+    const bool has_sq = DOT_T >= 0 ? (DOT_T == 2) : (p.dot_sq != 0);
     int acc_iter = 0;
 #pragma unroll 1
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
@@ -347,6 +349,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                   }
                 }
+                if (has_sq) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) dot = fmaf(v[j], v[j], dot);
+                }
                 if (has_dot) {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
@@ -378,7 +384,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
         }
-        if (has_dot && p.dot_out != nullptr && row_ok) p.dot_out[size_t(n_tile * 2) * p.dot_ld + row] = dot;
+        if ((has_dot || has_sq) && p.dot_out != nullptr && row_ok) p.dot_out[size_t(n_tile * 2) * p.dot_ld + row] = dot;
         if (!released) {
           tc_fence_before();
           __syncwarp();

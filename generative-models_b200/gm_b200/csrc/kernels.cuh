@@ -297,7 +297,7 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
   }
   for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < rows; r += (long long)gridDim.x * rows_per_iter) {
     const uint4 av = __ldg(reinterpret_cast<const uint4*>(a + r * ld) + g);
-    const float d = ds[r];
+    const float d = ds ? ds[r] : 1.f;
     const uint32_t u[4] = {av.x, av.y, av.z, av.w};
     float o[8];
 #pragma unroll
@@ -319,6 +319,145 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
     float t = 0.f;
     for (int i = 0; i < rows_per_iter; ++i) t += sh_acc[i * ld + c];
     dw2p[(long long)blockIdx.x * ld + c] = t;
+  }
+}
+
+// ---------------------------------------------------------------- gradient penalty (WGAN-GP, DRAGAN)
+// xhat rows (bf16, ld, zero pad, NO ones column: the penalty has no bias gradient):
+//   mode 0 (src/w_gp_gan.py:197-201): xhat = eps*x + (1-eps)*fake,  eps ~ U[0,1) per row
+//   mode 1 (src/dra_gan.py:200-205):  xhat = delta*x + (1-delta)*(x + std*u), delta per row, u per element
+// rnd == nullptr: on-device Philox (row stream), else caller tensors: eps[rows] or
+// delta[rows] followed by u[rows*x].  stats: [0] sum x, [1] sum x^2 over the real rows.
+__global__ void xhat_kernel(const __nv_bfloat16* __restrict__ xr, const __nv_bfloat16* __restrict__ xf,
+                            __nv_bfloat16* __restrict__ out, int rows, int x, int ld, int mode,
+                            const float* __restrict__ rnd, const float* __restrict__ stats,
+                            unsigned long long seed, unsigned long long stream_id) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  curandStatePhilox4_32_10_t st;
+  if (rnd == nullptr) curand_init(seed ^ 0x9E3779B97F4A7C15ull, (unsigned long long)r, stream_id * 256ull, &st);
+  const float e = rnd ? rnd[r] : curand_uniform(&st);   // (0,1]; the reference's rand is [0,1)
+  float sd = 0.f;
+  if (mode == 1) {
+    const double n = double(rows) * x, s1 = stats[0], s2 = stats[1];
+    sd = float(sqrt(fmax((s2 - s1 * s1 / n) / (n - 1.0), 0.0)));   // images.std(): unbiased, global
+  }
+  for (int c0 = 0; c0 < ld; c0 += 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(xr + (long long)r * ld + c0);
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if (mode == 0) b = *reinterpret_cast<const uint4*>(xf + (long long)r * ld + c0);
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int c = c0 + 2 * q + hlf;
+        const float xa = hlf ? bf16_hi(ua[q]) : bf16_lo(ua[q]);
+        float o = (c == x && mode == 1) ? 1.f : 0.f;   // DRAGAN xhat rows carry a true backward path -> ones column
+        if (c < x) {
+          if (mode == 0) {
+            const float xb = hlf ? bf16_hi(ub[q]) : bf16_lo(ub[q]);
+            o = e * xa + (1.f - e) * xb;
+          } else {
+            const float u = rnd ? rnd[rows + (long long)r * x + c] : curand_uniform(&st);
+            o = e * xa + (1.f - e) * (xa + sd * u);
+          }
+        }
+        v[2 * q + hlf] = o;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (long long)r * ld + c0) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// sum and sum of squares of the first x columns of `rows` bf16 rows -> per-block partials [nblk][2]
+__global__ void moments_kernel(const __nv_bfloat16* __restrict__ a, int rows, int x, int ld, double* __restrict__ part) {
+  __shared__ double sh[256 / 32];
+  const int groups = ld / 8;
+  double s1 = 0, s2 = 0;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < (long long)rows * groups; i += gridDim.x * 256ll) {
+    const int g = int(i % groups);
+    const uint4 v = reinterpret_cast<const uint4*>(a)[i];
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float lo = bf16_lo(u[q]), hi = bf16_hi(u[q]);
+      if (g * 8 + 2 * q < x) { s1 += lo; s2 += (double)lo * lo; }
+      if (g * 8 + 2 * q + 1 < x) { s1 += hi; s2 += (double)hi * hi; }
+    }
+  }
+  s1 = block_sum<256>(s1, sh);
+  s2 = block_sum<256>(s2, sh);
+  if (threadIdx.x == 0) { part[blockIdx.x * 2] = s1; part[blockIdx.x * 2 + 1] = s2; }
+}
+__global__ void moments_final_kernel(const double* __restrict__ part, int nblk, float* __restrict__ stats) {
+  __shared__ double sh[256 / 32];
+  double s1 = 0, s2 = 0;
+  for (int i = threadIdx.x; i < nblk; i += 256) { s1 += part[2 * i]; s2 += part[2 * i + 1]; }
+  s1 = block_sum<256>(s1, sh);
+  s2 = block_sum<256>(s2, sh);
+  if (threadIdx.x == 0) { stats[0] = float(s1); stats[1] = float(s2); }
+}
+
+// Per xhat row: nv = ||V|| from the sum-of-squares slots of the V GEMM, q = 1[s>0] (ReLU D)
+// or p(1-p) (sigmoid D), n = q*nv, r = 2*lam*inv_b*(n-K); writes coef = r*q/nv (0 at nv=0:
+// torch's norm subgradient), ds_gp = r*nv*dq/ds, and block partials (sum (n-K)^2, sum ds_gp).
+struct GpParams {
+  const float* slots_s; int nslots_s; int slot_ld;   // logit slots of the xhat rows (+ b2)
+  const float* slots_v; int nslots_v; int slotv_ld;  // sum-of-squares slots of V
+  const float* b2;
+  int rows, out_act;
+  float lam, K, inv_b;
+  float* coef; float* ds_gp;
+  double* part; int nblk;
+  float* loss;   // [0] += lam * sum (n-K)^2 / rows ;  [3] = sum ds_gp
+};
+__global__ void __launch_bounds__(kLossThreads) gp_rows_kernel(const GpParams p) {
+  __shared__ double sh[kLossThreads / 32];
+  double a0 = 0, a1 = 0;
+  for (int r = blockIdx.x * kLossThreads + threadIdx.x; r < p.rows; r += gridDim.x * kLossThreads) {
+    float s = p.b2[0], sq = 0.f;
+    for (int k = 0; k < p.nslots_s; ++k) s += p.slots_s[(long long)k * p.slot_ld + r];
+    for (int k = 0; k < p.nslots_v; ++k) sq += p.slots_v[(long long)k * p.slotv_ld + r];
+    const float nv = sqrtf(sq);
+    float q, dq;
+    if (p.out_act == OUT_RELU) { q = s > 0.f ? 1.f : 0.f; dq = 0.f; }
+    else { const float pr = 1.f / (1.f + expf(-s)); q = pr * (1.f - pr); dq = q * (1.f - 2.f * pr); }
+    const float n = q * nv;
+    const float rr = 2.f * p.lam * p.inv_b * (n - p.K);
+    p.coef[r] = nv > 0.f ? rr * q / nv : 0.f;
+    const float dsg = rr * nv * dq;
+    p.ds_gp[r] = dsg;
+    a0 += (double)(n - p.K) * (n - p.K);
+    a1 += dsg;
+  }
+  a0 = block_sum<kLossThreads>(a0, sh);
+  a1 = block_sum<kLossThreads>(a1, sh);
+  if (threadIdx.x == 0) { p.part[blockIdx.x * 4] = a0; p.part[blockIdx.x * 4 + 1] = a1; }
+}
+__global__ void __launch_bounds__(kLossThreads) gp_final_kernel(const GpParams p) {
+  __shared__ double sh[kLossThreads / 32];
+  const double s0 = reduce_partials4(p.part, p.nblk, 0, sh);
+  const double s1 = reduce_partials4(p.part, p.nblk, 1, sh);
+  if (threadIdx.x == 0) {
+    p.loss[0] += float(p.lam * s0 / p.rows);   // after loss_final wrote the base loss
+    p.loss[3] = float(s1);
+  }
+}
+
+// rows[r, :] *= coef[r]  (bf16, in place)
+__global__ void scale_rows_kernel(__nv_bfloat16* __restrict__ a, const float* __restrict__ coef, int rows, int ld) {
+  const int groups = ld / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)rows * groups;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float c = coef[i / groups];
+    uint4 v = reinterpret_cast<uint4*>(a)[i];
+    uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = pack_bf16x2(bf16_lo(u[q]) * c, bf16_hi(u[q]) * c);
+    reinterpret_cast<uint4*>(a)[i] = make_uint4(u[0], u[1], u[2], u[3]);
   }
 }
 

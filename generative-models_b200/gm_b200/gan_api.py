@@ -159,6 +159,10 @@ class GANTrainerBase:
     def _after_engine_created(self, eng):
         pass
 
+    def _draw_aux(self, images):
+        """Extra random tensors train_D draws after the noise (WGAN-GP eps, DRAGAN delta/u)."""
+        return None
+
     def _variant_name(self):
         return self.variant
 
@@ -210,7 +214,7 @@ class GANTrainerBase:
         eng = self._ensure_engine(images.shape[0])
         self._sync_once(eng)
         noise = self.compute_noise(images.shape[0], self.model.z_dim)
-        loss = eng.d_grad(images, noise=noise, seed=self._seed, step=self._step).clone()
+        loss = eng.d_grad(images, noise=noise, aux=self._draw_aux(images), seed=self._seed, step=self._step).clone()
         eng.apply(D_NET, hp)
         return loss
 
@@ -230,7 +234,8 @@ class GANTrainerBase:
         eng = self._ensure_engine(images.shape[0])
         eng.sync_if_stale()
         noise = self.compute_noise(images.shape[0], self.model.z_dim)
-        loss = eng.d_grad(images.float().contiguous(), noise=noise.float().contiguous(), seed=self._seed, step=self._step)
+        loss = eng.d_grad(images.float().contiguous(), noise=noise.float().contiguous(), aux=self._draw_aux(images),
+                          seed=self._seed, step=self._step)
         return self._loss_tensor(D_NET, loss)
 
     def train_G(self, images):

@@ -210,40 +210,44 @@ def g_loss(variant, dg):
 
 
 # ---------------------------------------------------------------- gradient penalty
-def gradient_penalty(P, xhat, out_act, lam=10.0, K=1.0, pre="D."):
+def gradient_penalty(P, xhat, out_act, lam=10.0, K=1.0, pre="D.", q=_exact):
     """lam * mean((||d D(xhat)/d xhat||_2 - K)^2) and its gradient w.r.t. D's
     parameters, in closed form.  Restates
     src/w_gp_gan.py:201-215 (out_act='relu') and src/dra_gan.py:208-220
-    (out_act='sigmoid'); norm subgradient 0 at 0 like torch's norm backward."""
+    (out_act='sigmoid'); norm subgradient 0 at 0 like torch's norm backward.
+    q: operand-quantisation hook (bf16_points models the CUDA path)."""
     W1, b1 = P[pre + "linear.weight"], P[pre + "linear.bias"]
     w2 = P[pre + "discriminate.weight"]
-    fw = d_forward(P, xhat, out_act, pre)
+    xhat = q("xhat", xhat)
+    fw = d_forward(P, xhat, out_act, pre, q=q)
     B = xhat.shape[0]
-    M = (fw["a1"] > 0).astype(xhat.dtype)
+    M = (fw["hq"] > 0).astype(xhat.dtype)
     if out_act == "relu":
-        q = (fw["s"] > 0).astype(xhat.dtype)         # [B,1]
-        dq_ds = np.zeros_like(q)
+        qq = (fw["s"] > 0).astype(xhat.dtype)        # [B,1]
+        dq_ds = np.zeros_like(qq)
     else:
         p = fw["d"]
-        q = p * (1 - p)
-        dq_ds = q * (1 - 2 * p)
-    U = M * w2                                       # [B,H]
-    V = U @ W1                                       # [B,X]
+        qq = p * (1 - p)
+        dq_ds = qq * (1 - 2 * p)
+    U = q("dh", M * w2)                              # [B,H]
+    V = U @ q("W", W1)                               # [B,X]
     nv = np.sqrt(np.sum(V * V, axis=1, keepdims=True))
-    n = q * nv                                       # = ||q V||, q >= 0
+    V = q("V", V)
+    n = qq * nv                                      # = ||q V||, q >= 0
     gp = lam * np.mean((n - K) ** 2)
     r = (2 * lam / B) * (n - K)                      # dGP/dn  [B,1]
     safe = np.where(nv > 0, nv, 1)
-    R = np.where(nv > 0, r * q * V / safe, 0)        # dGP/dV  [B,X]
+    R = q("R", np.where(nv > 0, r * qq / safe, 0) * V)   # dGP/dV  [B,X]
     g = {}
     g[pre + "linear.weight"] = U.T @ R
-    g[pre + "discriminate.weight"] = np.sum(M * (R @ W1.T), axis=0, keepdims=True)
+    T = q("T", (R @ q("W", W1).T) * M)
+    g[pre + "discriminate.weight"] = np.sum(T, axis=0, keepdims=True)
     g[pre + "linear.bias"] = np.zeros_like(b1)
     g[pre + "discriminate.bias"] = np.zeros(1, dtype=xhat.dtype)
     # path through q(s) (sigmoid out only)
     ds = r * nv * dq_ds
     if np.any(ds != 0):
-        g2, _ = d_backward(P, fw, ds, pre=pre)
+        g2, _ = d_backward(P, fw, ds, pre=pre, q=q)
         for k in g:
             g[k] = g[k] + g2[k].reshape(g[k].shape)
     return gp, g, dict(n=n, fw=fw)
@@ -267,7 +271,7 @@ def gan_d_step(P, variant, images, z, aux=None, st=None, lam=10.0, q=_exact):
     if variant == "wgp":
         eps = aux
         xhat = eps * images + (1 - eps) * gf["out"]                   # src/w_gp_gan.py:201
-        gp, ggp, gi = gradient_penalty(P, xhat, "relu", lam=lam)
+        gp, ggp, gi = gradient_penalty(P, xhat, "relu", lam=lam, q=q)
         L = L + gp
         grads = {k: grads[k] + ggp[k].reshape(grads[k].shape) for k in grads}
         info.update(gp=gp, gp_n=gi["n"])
@@ -275,7 +279,7 @@ def gan_d_step(P, variant, images, z, aux=None, st=None, lam=10.0, q=_exact):
         delta, u = aux
         std = np.std(images.astype(np.float64), ddof=1).astype(images.dtype)  # images.std(): unbiased, global
         xhat = delta * images + (1 - delta) * (images + std * u)      # src/dra_gan.py:203-205 (C=1)
-        gp, ggp, gi = gradient_penalty(P, xhat, "sigmoid", lam=lam)
+        gp, ggp, gi = gradient_penalty(P, xhat, "sigmoid", lam=lam, q=q)
         L = L + gp
         grads = {k: grads[k] + ggp[k].reshape(grads[k].shape) for k in grads}
         info.update(gp=gp, gp_n=gi["n"])

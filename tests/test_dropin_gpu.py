@@ -36,6 +36,8 @@ class _Replay:
     ("ra_gan", "RaNSGAN", "RaNSGANTrainer", "ra", dict(G_lr=2e-4, D_lr=2e-4, D_steps=1)),
     ("fisher_gan", "FisherGAN", "FisherGANTrainer", "fisher", dict(G_lr=1e-4, D_lr=1e-4, D_steps=1, RHO=1e-6)),
     ("f_gan", "fGAN", "fGANTrainer", "f_pearson", dict(method="pearson", G_lr=1e-4, D_lr=1e-4, D_steps=1)),
+    ("w_gp_gan", "WGPGAN", "WGPGANTrainer", "wgp", dict(G_lr=1e-4, D_lr=1e-4, D_steps=1)),
+    ("dra_gan", "DRAGAN", "DRAGANTrainer", "dra", dict(G_lr=1e-4, D_lr=1e-4, D_steps=1)),
 ])
 def test_fused_train_matches_reference_losses(mod, mcls, tcls, case, kw):
     """trainer.train(num_epochs=1, ...) exactly as the reference's __main__ calls it."""
@@ -46,7 +48,12 @@ def test_fused_train_matches_reference_losses(mod, mcls, tcls, case, kw):
     x = torch.from_numpy(images_from_bits(fx)).view(B, 1, 28, 28)
     it = [(x, torch.zeros(B, dtype=torch.long))] * (STEPS * kw.get("D_steps", 1))
     trainer = getattr(m, tcls)(model, it, it, it, viz=False)
-    trainer.compute_noise = _Replay(unpack_draws(fx))
+    replay = _Replay(unpack_draws(fx))
+    trainer.compute_noise = replay
+    if case == "wgp":          # the reference draws eps (and DRAGAN delta, u) right after the noise
+        trainer._draw_aux = lambda images: replay(0, 0).reshape(-1).contiguous()
+    if case == "dra":
+        trainer._draw_aux = lambda images: torch.cat([replay(0, 0).reshape(-1), replay(0, 0).reshape(-1)]).contiguous()
     trainer.train(num_epochs=1, **kw)
     assert trainer.num_epochs == 1 and len(trainer.Dlosses) == STEPS and len(trainer.Glosses) == STEPS
     scale = lambda v: max(abs(v), 0.5)

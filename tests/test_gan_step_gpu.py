@@ -19,7 +19,8 @@ pytestmark = pytest.mark.gpu
 
 ROW_VARIANTS = ["ns", "mm", "ls", "w", "ra", "fisher", "f_total_variation", "f_forward_kl", "f_reverse_kl",
                 "f_pearson", "f_hellinger", "f_jensen_shannon"]
-KW = {"ns": dict(G_lr=2e-4, D_lr=2e-4), "mm": dict(G_lr=2e-4, D_lr=2e-4, G_init=2),
+GP_VARIANTS = ["wgp", "dra"]
+KW = {"wgp": dict(G_lr=1e-4, D_lr=1e-4), "dra": dict(G_lr=1e-4, D_lr=1e-4), "ns": dict(G_lr=2e-4, D_lr=2e-4), "mm": dict(G_lr=2e-4, D_lr=2e-4, G_init=2),
       "ls": dict(G_lr=1e-4, D_lr=1e-4), "w": dict(G_lr=5e-5, D_lr=5e-5, D_steps=2, clip=0.01),
       "ra": dict(G_lr=2e-4, D_lr=2e-4), "fisher": dict(G_lr=1e-4, D_lr=1e-4, RHO=1e-6)}
 for _m in ROW_VARIANTS:
@@ -46,11 +47,24 @@ def _dump():
 
 def _engine(variant, batch=B):
     import gm_b200
-    eng = gm_b200.GanEngine(784, 400, 20, max_batch=batch, variant=variant)
+    eng = gm_b200.GanEngine(784, 400, 20, max_batch=batch, variant=variant,
+                            d_out_act="relu" if variant == "wgp" else "sigmoid")
     W = gm_init_weights(GAN_SHAPES, 1234)
     eng.load(0, [W["G.linear"][0], W["G.linear"][1], W["G.generate"][0], W["G.generate"][1]])
     eng.load(1, [W["D.linear"][0], W["D.linear"][1], W["D.discriminate"][0], W["D.discriminate"][1]])
     return eng
+
+
+def _aux_from(draws_iter, case):
+    """(oracle aux, device aux tensor) for the GP variants, consuming the reference's draws."""
+    if case == "wgp":
+        eps = next(draws_iter)
+        return eps.astype(np.float64), torch.from_numpy(eps.reshape(-1).copy()).cuda()
+    if case == "dra":
+        delta, u = next(draws_iter), next(draws_iter)
+        dev = torch.from_numpy(np.concatenate([delta.reshape(-1), u.reshape(-1)])).cuda()
+        return (delta.astype(np.float64), u.astype(np.float64)), dev
+    return None, None
 
 
 def _nrel(a, b):
@@ -58,22 +72,23 @@ def _nrel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-@pytest.mark.parametrize("case", ROW_VARIANTS)
+@pytest.mark.parametrize("case", ROW_VARIANTS + GP_VARIANTS)
 def test_step1_against_golden_and_oracle(case):
     fx = load_case("gan_" + case)
     eng = _engine(case)
     x = images_from_bits(fx)
     draws = unpack_draws(fx, "step1_")
     z1, z2 = draws[0], draws[-1]
+    aux_o, aux_d = _aux_from(iter(draws[1:]), case)
     P = params_dict(gm_init_weights(GAN_SHAPES, 1234), np.float64)
     st = dict(LAMBDA=0.0, RHO=1e-6) if case == "fisher" else None
     if case == "fisher":
         eng.fisher_state(0.0, 1e-6)
-    Lo, go, info = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), None, st)
+    Lo, go, info = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), aux_o, st)
     stq = dict(st) if st else None
-    _, goq, _ = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), None, stq, q=R.bf16_points)
+    _, goq, _ = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), aux_o, stq, q=R.bf16_points)
     xd = torch.from_numpy(x).cuda()
-    Ld = eng.d_grad(xd, noise=torch.from_numpy(z1).cuda()).item()
+    Ld = eng.d_grad(xd, noise=torch.from_numpy(z1).cuda(), aux=aux_d).item()
     sc = eng.scores(2 * B).cpu().numpy()
     gD = [v.cpu().numpy() for v in eng.views(1, eng.grads[1])]
     rep = {}
@@ -104,15 +119,15 @@ def test_step1_against_golden_and_oracle(case):
             assert v < TOL_GRAD_BF16_B64, (k, v, rep)
 
 
-@pytest.mark.parametrize("case", ROW_VARIANTS)
+@pytest.mark.parametrize("case", ROW_VARIANTS + GP_VARIANTS)
 def test_three_step_trajectory_against_golden(case):
     import gm_b200
     fx = load_case("gan_" + case)
     kw = KW[case]
     eng = _engine(case)
     x = torch.from_numpy(images_from_bits(fx)).cuda()
-    draws = [torch.from_numpy(d).cuda() for d in unpack_draws(fx)]
-    it = iter(draws)
+    raw = iter(unpack_draws(fx))
+    it = (torch.from_numpy(d).cuda() for d in raw)
     hpG = gm_b200.AdamHP.make(kw["G_lr"])
     hpD = gm_b200.AdamHP.make(kw["D_lr"], clamp=kw.get("clip", 0.0) or 0.0)
     if case == "fisher":
@@ -124,7 +139,8 @@ def test_three_step_trajectory_against_golden(case):
     for _ in range(STEPS):
         acc = []
         for _ in range(kw.get("D_steps", 1)):
-            acc.append(eng.d_grad(x, noise=next(it)).item())
+            zd = next(it)
+            acc.append(eng.d_grad(x, noise=zd, aux=_aux_from(raw, case)[1]).item())
             eng.apply(1, hpD)
         Dl.append(np.mean(acc))
         Gl.append(eng.g_grad(B, noise=next(it)).item())
