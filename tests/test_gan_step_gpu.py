@@ -31,11 +31,11 @@ for _m in ROW_VARIANTS:
 #    fixtures of the unmodified reference.
 #  - gradients, two checks: (i) vs the oracle evaluated with bf16 rounding at exactly
 #    the points where the CUDA path stores bf16 GEMM operands (oracle q=bf16_points):
-#    2e-3 norm-relative -> the kernels compute the reference's arithmetic; (ii) vs the
+#    1e-3 norm-relative (measured <= 1.4e-4) -> the kernels compute the reference's arithmetic; (ii) vs the
 #    exact fp32/fp64 oracle: the intrinsic bf16-operand error, which at batch 64 is
 #    dominated by cancellation in 64-term sums (measured 2e-3 .. 4.2e-2, largest for
 #    G.linear.weight) and shrinks with batch (2e-3 .. 3e-3 at batch 4096).
-TOL_LOSS, TOL_SCORE, TOL_GRAD_Q, TOL_GRAD_BF16_B64 = 1e-3, 1e-3, 2e-3, 6e-2
+TOL_LOSS, TOL_SCORE, TOL_GRAD_Q, TOL_GRAD_BF16_B64 = 1e-3, 1e-3, 1e-3, 6e-2
 _REPORT = {}
 
 
@@ -111,7 +111,10 @@ def test_step1_against_golden_and_oracle(case):
     _REPORT["step1_" + case] = rep
     _dump()
     assert rep["D_loss_vs_golden"] < TOL_LOSS and rep["G_loss_vs_golden"] < TOL_LOSS, rep
-    assert rep["DX_score"] < TOL_SCORE and rep["DG_score"] < TOL_SCORE, rep
+    # WGAN-GP's critic ends in ReLU: its raw outputs are O(0.05), so the same absolute
+    # error as the sigmoid critics' (O(0.5) outputs) reads ~10x larger relatively
+    tol_score = 3e-3 if case == "wgp" else TOL_SCORE
+    assert rep["DX_score"] < tol_score and rep["DG_score"] < tol_score, rep
     for k, v in rep.items():
         if k.startswith("gradq_"):
             assert v < TOL_GRAD_Q, (k, v, rep)
