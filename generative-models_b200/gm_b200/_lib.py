@@ -37,6 +37,10 @@ class GemmDesc(C.Structure):
                 ("transpose", C.c_int)]
 
 
+class VaeDesc(C.Structure):
+    _fields_ = [("image_size", C.c_int), ("hidden_dim", C.c_int), ("z_dim", C.c_int), ("max_batch", C.c_int)]
+
+
 class GanDesc(C.Structure):
     _fields_ = [("image_size", C.c_int), ("hidden_dim", C.c_int), ("z_dim", C.c_int),
                 ("max_batch", C.c_int), ("variant", C.c_int), ("d_out_act", C.c_int)]
@@ -78,6 +82,15 @@ def lib():
     L.gm_gan_scores.argtypes = [vp, vp, i, vp]
     L.gm_gan_generate.argtypes = [vp, vp, i, vp, vp]
     L.gm_gan_discriminate.argtypes = [vp, vp, i, i, vp, vp]
+    L.gm_vae_create.argtypes = [vp, C.POINTER(VaeDesc), C.POINTER(vp)]
+    L.gm_vae_destroy.argtypes = [vp]
+    L.gm_vae_param_count.argtypes = [vp]
+    L.gm_vae_bind.argtypes = [vp, vp, vp, vp, vp]
+    L.gm_vae_sync_shadows.argtypes = [vp, vp]
+    L.gm_vae_grad.argtypes = [vp, vp, i, vp, i, vp, f, u64, u64, vp, vp]
+    L.gm_vae_apply.argtypes = [vp, C.POINTER(AdamHP), i, vp]
+    L.gm_vae_forward.argtypes = [vp, vp, i, i, vp, u64, u64, vp, vp, vp, vp]
+    L.gm_vae_decode.argtypes = [vp, vp, i, vp, vp]
     L.gm_gan_fisher_state.argtypes = [vp, C.POINTER(C.c_float), i, vp]
     _lib = L
     return L

@@ -839,3 +839,5 @@ extern "C" int gm_gan_fisher_state(gm_gan* g, float* lambda_rho_host, int set, g
   }
   return GM_OK;
 }
+
+#include "engine_vae.inl"

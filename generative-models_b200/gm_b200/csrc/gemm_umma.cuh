@@ -29,7 +29,7 @@ constexpr int kSmemBudget = 224 * 1024;
 
 enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
-enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2 };
+enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2, AUX_VAE_OUT = 3 };
 
 struct GemmParams {
   int M, N, K;          // logical extents; K counts contraction elements
@@ -248,7 +248,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = wrow0 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
-      if constexpr (!A_MN) {
+      constexpr bool kUniversal = ACT_T < 0;
+      if (!A_MN && !(kUniversal && p.epi == EPI_F32)) {
+       if constexpr (!A_MN) {
         // ================= bf16 epilogue (K-major kernels) =================
         // coalesced lane mapping for aux reads / output writes: 8 lanes x 16 B = one 128-byte
         // row segment, 4 rows per pass
@@ -343,6 +345,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (aux_mode == AUX_SIGMOID_GRAD) {
                       v[2 * k2] *= a_lo * (1.f - a_lo);
                       v[2 * k2 + 1] *= a_hi * (1.f - a_hi);
+                    } else if (aux_mode == AUX_VAE_OUT) {
+                      // v = decoder output, aux = target x: accumulate (x-v)^2 and emit
+                      // d/d(pre-sigmoid) of sum (x-v)^2 = -2 (x-v) v (1-v)   (src/vae.py:203)
+                      const float d0 = a_lo - v[2 * k2], d1 = a_hi - v[2 * k2 + 1];
+                      dot = fmaf(d0, d0, dot); dot = fmaf(d1, d1, dot);
+                      v[2 * k2] = -2.f * d0 * v[2 * k2] * (1.f - v[2 * k2]);
+                      v[2 * k2 + 1] = -2.f * d1 * v[2 * k2 + 1] * (1.f - v[2 * k2 + 1]);
                     } else {
                       v[2 * k2] = a_lo > 0.f ? v[2 * k2] : 0.f;
                       v[2 * k2 + 1] = a_hi > 0.f ? v[2 * k2 + 1] : 0.f;
@@ -384,14 +393,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
         }
-        if ((has_dot || has_sq) && p.dot_out != nullptr && row_ok) p.dot_out[size_t(n_tile * 2) * p.dot_ld + row] = dot;
+        if ((has_dot || has_sq || aux_mode == AUX_VAE_OUT) && p.dot_out != nullptr && row_ok)
+          p.dot_out[size_t(n_tile * 2) * p.dot_ld + row] = dot;
         if (!released) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
+       }
       } else {
-        // ================= fp32 split-K partial epilogue (MN-major kernels) =================
+        // ====== fp32 epilogue: split-K partials (MN-major kernels) or biased fp32 output ======
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
         const int c_first = (NACC == 2) ? 0 : grp;
@@ -403,6 +414,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (col0 >= p.N) break;
           float v[16];
           tmem_ld16(t_row + c * 16, v);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
           if (row_ok) {
             if (p.transpose) {
 #pragma unroll

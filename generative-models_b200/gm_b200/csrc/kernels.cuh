@@ -461,6 +461,82 @@ __global__ void scale_rows_kernel(__nv_bfloat16* __restrict__ a, const float* __
   }
 }
 
+// ---------------------------------------------------------------- VAE (src/vae.py:94-106,193-212)
+// mulv fp32 [rows, ldm]: columns [0,z) = mu, [z,2z) = log_var.  z = mu + eps*exp(lv/2)
+// -> bf16 [rows, ldz] with a ones column at z; eps (caller tensor or Philox) is kept in
+// eps_out for the backward; per-block partial of kl = sum 0.5(mu^2 + e^lv - lv - 1).
+__global__ void vae_reparam_kernel(const float* __restrict__ mulv, int ldm, const float* __restrict__ eps_in,
+                                   float* __restrict__ eps_out, __nv_bfloat16* __restrict__ zb, int ldz, int rows,
+                                   int z, unsigned long long seed, unsigned long long stream_id,
+                                   double* __restrict__ part) {
+  __shared__ double sh[256 / 32];
+  double kl = 0.0;
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r < rows) {
+    curandStatePhilox4_32_10_t st;
+    if (eps_in == nullptr) curand_init(seed ^ 0x5851F42D4C957F2Dull, (unsigned long long)r, stream_id * 64ull, &st);
+    for (int c0 = 0; c0 < ldz; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float o = (c == z) ? 1.f : 0.f;
+        if (c < z) {
+          const float mu = mulv[(long long)r * ldm + c], lv = mulv[(long long)r * ldm + z + c];
+          const float e = eps_in ? eps_in[(long long)r * z + c] : curand_normal(&st);
+          eps_out[(long long)r * z + c] = e;
+          o = mu + e * expf(0.5f * lv);
+          kl += 0.5 * ((double)mu * mu + exp((double)lv) - lv - 1.0);
+        }
+        v[j] = o;
+      }
+      *reinterpret_cast<uint4*>(zb + (long long)r * ldz + c0) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+  }
+  kl = block_sum<256>(kl, sh);
+  if (threadIdx.x == 0 && part) part[blockIdx.x] = kl;
+}
+
+// dmu = mu + dz ; dlv = 0.5(e^lv - 1) + dz * eps * e^{lv/2} * 0.5  -> bf16 [rows, ld]: [dmu | dlv | 0]
+__global__ void vae_dlatent_kernel(const float* __restrict__ mulv, int ldm, const float* __restrict__ dz, int lddz,
+                                   const float* __restrict__ eps, __nv_bfloat16* __restrict__ out, int ld, int rows,
+                                   int z, float scale) {
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= (long long)rows * ld) return;
+  const int r = int(i / ld), c = int(i % ld);
+  float o = 0.f;
+  if (c < z) {
+    o = scale * (mulv[(long long)r * ldm + c] + dz[(long long)r * lddz + c]);
+  } else if (c < 2 * z) {
+    const int k = c - z;
+    const float lv = mulv[(long long)r * ldm + z + k];
+    o = scale * (0.5f * (expf(lv) - 1.f) + dz[(long long)r * lddz + k] * eps[(long long)r * z + k] * expf(0.5f * lv) * 0.5f);
+  }
+  out[i] = __float2bfloat16_rn(o);
+}
+
+// recon = sum over rows of the per-row slots (sum (x-out)^2); losses[0] = recon, [1] = kl
+__global__ void vae_rowsum_kernel(const float* __restrict__ slots, int nslots, int slot_ld, int rows,
+                                  double* __restrict__ part) {
+  __shared__ double sh[256 / 32];
+  double t = 0.0;
+  for (int r = blockIdx.x * 256 + threadIdx.x; r < rows; r += gridDim.x * 256)
+    for (int k = 0; k < nslots; ++k) t += slots[(long long)k * slot_ld + r];
+  t = block_sum<256>(t, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+__global__ void vae_losses_final_kernel(const double* __restrict__ part_r, int nr, const double* __restrict__ part_k,
+                                        int nk, float* __restrict__ losses) {
+  __shared__ double sh[256 / 32];
+  double a = 0, b = 0;
+  for (int i = threadIdx.x; i < nr; i += 256) a += part_r[i];
+  for (int i = threadIdx.x; i < nk; i += 256) b += part_k[i];
+  a = block_sum<256>(a, sh);
+  b = block_sum<256>(b, sh);
+  if (threadIdx.x == 0) { losses[0] = float(a); losses[1] = float(b); }
+}
+
 // ---------------------------------------------------------------- gradient finalisation
 // flat_grad[dst_off + i] = sum over `nsplit` partial copies of src[map(i)]:
 //   kind 0 (matrix, rows x cols):  src[r*ld + c]        (partial stored as [rows][ld])
@@ -473,7 +549,7 @@ struct GradSeg {
   long long split_stride;
   const float* src;
 };
-struct GradSegs { GradSeg s[6]; int nseg; int total; };
+struct GradSegs { GradSeg s[8]; int nseg; int total; };
 
 __global__ void finalize_grads_kernel(const GradSegs segs, float* __restrict__ flat) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

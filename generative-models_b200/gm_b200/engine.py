@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AdamHP, GanDesc, GmError, VARIANTS, OUT_ACTS, IMG_FMTS, check, lib, _ptr, _stream
+from ._lib import AdamHP, GanDesc, VaeDesc, GmError, VARIANTS, OUT_ACTS, IMG_FMTS, check, lib, _ptr, _stream
 
 G, D = 0, 1
 
@@ -136,3 +136,96 @@ class GanEngine:
             return lam, rho
         check(self.h, lib().gm_gan_fisher_state(self.g, buf, 0, _stream()))
         return buf[0], buf[1]
+
+
+class VaeEngine:
+    """One MLP VAE (x -> hidden -> (mu, log_var) ; z -> hidden -> x) on one GPU.  The flat
+    layout puts the two latent heads next to each other (one 400 -> 2z GEMM):
+    [enc.linear.W, .b, enc.mu.W, enc.log_var.W, enc.mu.b, enc.log_var.b, dec.linear.W, .b, dec.recon.W, .b]."""
+    NAMES = ["encoder.linear.weight", "encoder.linear.bias", "encoder.mu.weight", "encoder.log_var.weight",
+             "encoder.mu.bias", "encoder.log_var.bias", "decoder.linear.weight", "decoder.linear.bias",
+             "decoder.recon.weight", "decoder.recon.bias"]
+
+    def __init__(self, image_size=784, hidden_dim=400, z_dim=20, max_batch=64, device=None):
+        if not torch.cuda.is_available():
+            raise GmError("gm_b200 needs a CUDA (B200) device; there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.h = _lib.ctx(self.device.index)
+        self.image_size, self.hidden_dim, self.z_dim, self.max_batch = image_size, hidden_dim, z_dim, max_batch
+        d = VaeDesc(image_size, hidden_dim, z_dim, max_batch)
+        self.g = C.c_void_p()
+        check(self.h, lib().gm_vae_create(self.h, C.byref(d), C.byref(self.g)))
+        n = lib().gm_vae_param_count(self.g)
+        kw = dict(device=self.device, dtype=torch.float32)
+        self.params, self.grads = torch.zeros(n, **kw), torch.zeros(n, **kw)
+        self.exp_avg, self.exp_avg_sq = torch.zeros(n, **kw), torch.zeros(n, **kw)
+        self.loss_buf = torch.zeros(2, **kw)
+        check(self.h, lib().gm_vae_bind(self.g, _ptr(self.params), _ptr(self.grads), _ptr(self.exp_avg), _ptr(self.exp_avg_sq)))
+        X, H, Z = image_size, hidden_dim, z_dim
+        self.shapes = [(H, X), (H,), (Z, H), (Z, H), (Z,), (Z,), (H, Z), (H,), (X, H), (X,)]
+        self.steps = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "g", None):
+                lib().gm_vae_destroy(self.g)
+                self.g = None
+        except Exception:
+            pass
+
+    def views(self, flat=None):
+        """{reference parameter name: view into the flat buffer}"""
+        flat = self.params if flat is None else flat
+        out, off = {}, 0
+        for name, shp in zip(self.NAMES, self.shapes):
+            n = 1
+            for s in shp:
+                n *= s
+            out[name] = flat[off:off + n].view(shp)
+            off += n
+        return out
+
+    def load(self, tensors):
+        v = self.views()
+        for name, src in tensors.items():
+            v[name].copy_(torch.as_tensor(src, dtype=torch.float32).reshape(v[name].shape))
+        self.sync_shadows()
+
+    def sync_shadows(self):
+        check(self.h, lib().gm_vae_sync_shadows(self.g, _stream()))
+
+    sync_all = sync_shadows
+
+    def reset_optimizer(self):
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.steps = 0
+
+    def grad(self, images, eps=None, fmt="f32", gather_idx=None, batch=None, seed=0, step=0):
+        """compute_batch + backward (src/vae.py:157-161). Returns the device tensor [recon, kl]."""
+        B = batch if batch is not None else (gather_idx.numel() if gather_idx is not None else images.shape[0])
+        check(self.h, lib().gm_vae_grad(self.g, _ptr(images), IMG_FMTS[fmt], _ptr(gather_idx), B, _ptr(eps), 1.0, seed, step,
+                                        _ptr(self.loss_buf), _stream()))
+        return self.loss_buf
+
+    def apply(self, hp):
+        self.steps += 1
+        check(self.h, lib().gm_vae_apply(self.g, C.byref(hp), self.steps, _stream()))
+
+    def forward(self, images, eps=None, fmt="f32", want_images=True, want_latent=True, want_losses=False, seed=0, step=0):
+        n = images.shape[0]
+        kw = dict(device=self.device, dtype=torch.float32)
+        out = torch.empty(n, self.image_size, **kw) if want_images else None
+        ml = torch.empty(n, 2 * self.z_dim, **kw) if want_latent else None
+        ls = torch.empty(2, **kw) if want_losses else None
+        check(self.h, lib().gm_vae_forward(self.g, _ptr(images.contiguous()), IMG_FMTS[fmt], n, _ptr(eps), seed, step,
+                                           _ptr(out), _ptr(ml), _ptr(ls), _stream()))
+        mu = ml[:, :self.z_dim] if ml is not None else None
+        lv = ml[:, self.z_dim:] if ml is not None else None
+        return out, mu, lv, ls
+
+    def decode(self, z):
+        n = z.shape[0]
+        out = torch.empty(n, self.image_size, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_vae_decode(self.g, _ptr(z.contiguous().float()), n, _ptr(out), _stream()))
+        return out

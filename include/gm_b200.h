@@ -140,6 +140,32 @@ int gm_gan_generate(gm_gan* gan, const float* noise_dev, int n, float* images_de
 int gm_gan_discriminate(gm_gan* gan, const void* images_dev, int img_fmt, int n, float* scores_dev, gm_stream stream);
 /* Fisher GAN scalar state (src/fisher_gan.py:117-118,155): get/set LAMBDA, RHO. */
 int gm_gan_fisher_state(gm_gan* gan, float* lambda_rho_host, int set, gm_stream stream);
+/* ---- VAE train-step engine (src/vae.py) ---------------------------------------
+ * Encoder x -> hidden -> (mu, log_var), z = mu + eps * exp(log_var/2), Decoder z ->
+ * hidden -> x (sigmoid) (src/vae.py:47-106).  Flat fp32 layout:
+ * [enc.linear.W | .b | enc.mu.W | enc.log_var.W | enc.mu.b | enc.log_var.b |
+ *  dec.linear.W | .b | dec.recon.W | .b]. */
+typedef struct { int image_size, hidden_dim, z_dim, max_batch; } gm_vae_desc;
+int gm_vae_create(gm_ctx* ctx, const gm_vae_desc* desc, gm_vae** out);
+int gm_vae_destroy(gm_vae* vae);
+int gm_vae_param_count(const gm_vae* vae);
+int gm_vae_bind(gm_vae* vae, float* params_dev, float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev);
+int gm_vae_sync_shadows(gm_vae* vae, gm_stream stream);
+/* compute_batch + (recon + kl).backward() (src/vae.py:157-161,193-212): recon =
+ * sum (x - out)^2, kl = sum 0.5 (mu^2 + exp(lv) - lv - 1); writes the flat gradient and
+ * losses_dev[0..1] = {recon, kl}.  eps_dev [batch, z] fp32 or NULL for on-device Philox. */
+int gm_vae_grad(gm_vae* vae, const void* images_dev, int img_fmt, const int* gather_idx_dev, int batch,
+                const float* eps_dev, float grad_scale, uint64_t seed, uint64_t step, float* losses_dev,
+                gm_stream stream);
+/* optimizer.step() with coupled weight decay (src/vae.py:139-142,162). */
+int gm_vae_apply(gm_vae* vae, const gm_adam_hp* hp, int step, gm_stream stream);
+/* VAE.forward (+ losses) without gradients: evaluate / reconstruct (src/vae.py:214-252).
+ * Any of out_images_dev [n, image_size], mu_logvar_dev [n, 2 z], losses_dev [2] may be NULL. */
+int gm_vae_forward(gm_vae* vae, const void* images_dev, int img_fmt, int n, const float* eps_dev, uint64_t seed,
+                   uint64_t step, float* out_images_dev, float* mu_logvar_dev, float* losses_dev, gm_stream stream);
+/* Decoder.forward (src/vae.py:74-77) for sampling. */
+int gm_vae_decode(gm_vae* vae, const float* z_dev, int n, float* out_images_dev, gm_stream stream);
+
 /* number of this library's kernels launched since the last call with reset != 0 */
 long long gm_launch_count(gm_ctx* ctx, int reset);
 /* measurement aid (bench.py roofline): record CUDA events around every tensor-core
