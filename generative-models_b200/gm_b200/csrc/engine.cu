@@ -436,7 +436,7 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   const int groups = g->HP / 8;
   g->dh_rows_per_iter = 256 / groups > 0 ? 256 / groups : 1;
   g->dh_threads = groups * g->dh_rows_per_iter;
-  g->dh_blocks = c->num_sms * 2;
+  g->dh_blocks = c->num_sms * 4;
   TRY(dev_alloc(g, &g->dw2p, size_t(g->dh_blocks) * g->HP));
   TRY(dev_alloc(g, &g->dw2sum, size_t(3) * g->HP));
   if (g->nreg > 2) {

@@ -295,21 +295,39 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
     w[j] = c < h ? w2[c] : 0.f;
     acc[j] = 0.f;
   }
-  for (long long r = (long long)blockIdx.x * rows_per_iter + rl; r < rows; r += (long long)gridDim.x * rows_per_iter) {
-    const uint4 av = __ldg(reinterpret_cast<const uint4*>(a + r * ld) + g);
-    const float d = ds ? ds[r] : 1.f;
-    const uint32_t u[4] = {av.x, av.y, av.z, av.w};
-    float o[8];
+  // 4 independent rows in flight per thread (memory-level parallelism: this kernel is HBM-bound)
+  const long long stride = (long long)gridDim.x * rows_per_iter;
+  for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < rows; r0 += 4 * stride) {
+    uint4 av[4];
+    float dv[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float lo = bf16_lo(u[q]), hi = bf16_hi(u[q]);
-      o[2 * q] = lo > 0.f ? d * w[2 * q] : 0.f;
-      o[2 * q + 1] = hi > 0.f ? d * w[2 * q + 1] : 0.f;
-      acc[2 * q] = fmaf(d, lo, acc[2 * q]);
-      acc[2 * q + 1] = fmaf(d, hi, acc[2 * q + 1]);
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * stride;
+      av[u] = make_uint4(0, 0, 0, 0);
+      dv[u] = 0.f;
+      if (r < rows) {
+        av[u] = __ldg(reinterpret_cast<const uint4*>(a + r * ld) + g);
+        dv[u] = ds ? ds[r] : 1.f;
+      }
     }
-    reinterpret_cast<uint4*>(dh + r * ld)[g] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                           pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * stride;
+      if (r >= rows) break;
+      const float d = dv[u];
+      const uint32_t w4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float lo = bf16_lo(w4[q]), hi = bf16_hi(w4[q]);
+        o[2 * q] = lo > 0.f ? d * w[2 * q] : 0.f;
+        o[2 * q + 1] = hi > 0.f ? d * w[2 * q + 1] : 0.f;
+        acc[2 * q] = fmaf(d, lo, acc[2 * q]);
+        acc[2 * q + 1] = fmaf(d, hi, acc[2 * q + 1]);
+      }
+      reinterpret_cast<uint4*>(dh + r * ld)[g] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                             pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
   }
   if (dw2p == nullptr) return;
 #pragma unroll

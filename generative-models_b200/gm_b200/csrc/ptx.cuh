@@ -161,7 +161,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn_m
 }
 
 // ------------------------------------------------------------------ small math / memory helpers
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid(x) = 0.5 tanh(x/2) + 0.5 with ONE special-function op (tanh.approx.f32, abs err
+// ~2^-11): the GEMM epilogue is MUFU-bound with the 2-op exp + rcp form.  The result is
+// stored as bf16 (half-ulp 2^-9 relative), so the approximation stays below the storage
+// rounding.  fp32 outputs (losses, scores) use expf-based sigmoids instead.
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

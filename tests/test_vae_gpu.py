@@ -38,8 +38,8 @@ def test_step1_losses_and_gradients():
     recon_o, kl_o, g_o, _ = R.vae_step(P, x.astype(np.float64), eps.astype(np.float64))
     ls = eng.grad(torch.from_numpy(x).cuda(), eps=torch.from_numpy(eps).cuda()).cpu().numpy()
     gv = {k: v.cpu().numpy() for k, v in eng.views(eng.grads).items()}
-    rep = {"recon_vs_golden": abs(ls[0] - float(fx["step1_recon"])) / float(fx["step1_recon"]),
-           "kl_vs_golden": abs(ls[1] - float(fx["step1_kl"])) / float(fx["step1_kl"])}
+    rep = {"recon_vs_golden": float(abs(ls[0] - float(fx["step1_recon"])) / float(fx["step1_recon"])),
+           "kl_vs_golden": float(abs(ls[1] - float(fx["step1_kl"])) / float(fx["step1_kl"]))}
     for k in g_o:
         rep["grad_" + k] = _nrel(gv[k], g_o[k])
     os.makedirs("gpurun_out", exist_ok=True)
