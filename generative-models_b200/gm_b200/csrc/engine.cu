@@ -89,7 +89,7 @@ static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<pl.grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
+  kern<<<pl.grid, gemm_threads(AMN), Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
   return cudaGetLastError();
 }
 

@@ -23,8 +23,10 @@ namespace gm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kUmmaK = 16;
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+// epilogue warps: 16 for the K-major (bf16-output) kernels — the epilogue is latency-bound
+// per warp, more warps in flight hide it — 8 for the MN-major split-K kernels
+constexpr int kEpiWarpsNT = 16, kEpiWarpsTN = 8;
+constexpr int gemm_threads(bool a_mn) { return 64 + (a_mn ? kEpiWarpsTN : kEpiWarpsNT) * 32; }
 constexpr int kSmemBudget = 224 * 1024;
 
 enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
@@ -57,10 +59,12 @@ struct GemmParams {
   int transpose;
 };
 
-// per-epilogue-warp staging tile: 32 rows x (128 B data + 16 B pad) -> conflict-free
-// row-wise writes (thread = row) and row-contiguous reads (8 lanes = 128 B of one row)
-constexpr int kEpiPitch = 144;
+// per-epilogue-warp staging tile for one 32-column block: 32 rows x (64 B data + 16 B pad):
+// conflict-free row-wise writes (thread = row), row-contiguous reads (4 lanes = 64 B of a row)
+constexpr int kEpiCols = 32;
+constexpr int kEpiPitch = 80;
 constexpr int kEpiStageBytes = 32 * kEpiPitch;
+constexpr int kEpiVecBytes = 4 * kEpiCols * 4 * 2;   // bias + row-dot weights of up to 4 blocks per warp
 
 template <int BN1, int BN2, bool STAGED_EPI = true>
 struct GemmCfg {
@@ -69,9 +73,10 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // per-warp staging tile + per-warp copies of the tile's bias / row-dot weight slices
-  static constexpr int EPI_VEC_BYTES = BN * 2 * 4;
-  static constexpr int EPI_BYTES = STAGED_EPI ? kEpiWarps * (kEpiStageBytes + EPI_VEC_BYTES) : 0;
+  // per-warp staging tile + per-warp copies of its blocks' bias / row-dot weight slices
+  static constexpr int EPI_WARPS = STAGED_EPI ? kEpiWarpsNT : kEpiWarpsTN;
+  static constexpr int EPI_BYTES = STAGED_EPI ? EPI_WARPS * (kEpiStageBytes + kEpiVecBytes) : 0;
+  static_assert(!STAGED_EPI || (BN + kEpiCols - 1) / kEpiCols <= 4 * (EPI_WARPS / 8), "kEpiVecBytes holds 4 blocks per warp");
   static constexpr int STAGES_RAW = (kSmemBudget - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
@@ -87,14 +92,16 @@ struct GemmCfg {
 // compile time (small code: the whole kernel must stay inside the instruction cache);
 // -1 selects the universal variant that reads the choice from GemmParams at run time.
 template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(A_MN), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN1, BN2, !A_MN>;
   constexpr int BN = Cfg::BN;
   constexpr int NACC = Cfg::NACC;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int kEpiWarps = Cfg::EPI_WARPS;
   constexpr int EPI_ARRIVALS = (NACC == 2) ? kEpiWarps / 2 : kEpiWarps;
+  constexpr int kParts = kEpiWarps / 8;   // column partitions per accumulator stage (K-major kernels)
   static_assert(!B_MN || (BN1 % 64 == 0 && BN2 % 64 == 0), "MN-major B needs 64-wide atoms");
 
   extern __shared__ uint8_t smem_raw[];
@@ -225,9 +232,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // groups work on the same tile and split its 16-column chunks by parity.
     const int e = warp - 2;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
-    const int grp = e >> 2;
+    const int grp = e >> 2;         // 0..kEpiWarps/4-1
+    const int my_stage = grp & 1;   // accumulator stage this warp serves when NACC == 2
+    const int part = A_MN ? 0 : (grp >> 1);   // which interleaved set of 32-column blocks (K-major kernels)
     const uint32_t stage_s = bar_base + 256u + uint32_t(e) * kEpiStageBytes;  // staging tile (NT kernels)
-    const uint32_t vec_s = bar_base + 256u + kEpiWarps * kEpiStageBytes + uint32_t(e) * Cfg::EPI_VEC_BYTES;
+    const uint32_t vec_s = bar_base + 256u + kEpiWarps * kEpiStageBytes + uint32_t(e) * kEpiVecBytes;
     const int act = ACT_T >= 0 ? ACT_T : p.act;
     const int aux_mode = AUX_T >= 0 ? AUX_T : p.aux_mode;
     const bool has_bias = BIAS_T >= 0 ? (BIAS_T != 0) : (p.bias != nullptr);
@@ -237,7 +246,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
       const int as = acc_iter % NACC;
-      if (NACC == 2 && as != grp) continue;
+      if (NACC == 2 && as != my_stage) continue;
       const int split = item / tiles;
       const int rem = item - split * tiles;
       const int n_tile = rem % p.n_tiles;
@@ -252,69 +261,71 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!A_MN && !(kUniversal && p.epi == EPI_F32)) {
        if constexpr (!A_MN) {
         // ================= bf16 epilogue (K-major kernels) =================
-        // coalesced lane mapping for aux reads / output writes: 8 lanes x 16 B = one 128-byte
-        // row segment, 4 rows per pass
-        const int lr = lane >> 3, lc = lane & 7;
-        uint4 pre[8];
+        // coalesced lane mapping for aux reads / output writes: 4 lanes x 16 B = one 64-byte
+        // row segment, 8 rows per pass, 4 passes
+        const int lr = lane >> 2, lc = lane & 3;
+        constexpr int kBlocks = (BN + kEpiCols - 1) / kEpiCols;
+        uint4 pre[4];
         auto aux_fetch = [&](int c_first) {
           const int c = c_first + lc * 8;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = wrow0 + it * 4 + lr;
+          for (int it = 0; it < 4; ++it) {
+            const int r = wrow0 + it * 8 + lr;
             pre[it] = make_uint4(0, 0, 0, 0);
             if (r < p.M && c < p.out_cols) pre[it] = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(r) * p.ld_aux + c));
           }
         };
-        // bias / row-dot weights of this tile's columns -> smem and the first aux tile ->
+        // bias / row-dot weights of this warp's column blocks -> smem and the first aux tile ->
         // registers while the MMAs still run: no global-load latency after the TMEM read
         if (has_bias || has_dot) {
-          for (int i = lane; i < BN / 4; i += 32) {
-            const int c = n0 + i * 4;
-            uint4 b = make_uint4(0, 0, 0, 0), w = b;
-            if (c < p.N) {
-              if (has_bias) b = __ldg(reinterpret_cast<const uint4*>(p.bias + c));
-              if (has_dot) w = __ldg(reinterpret_cast<const uint4*>(p.dot_w + c));
-            }
-            if (has_bias) sts128(vec_s + i * 16, b);
-            if (has_dot) sts128(vec_s + BN * 4 + i * 16, w);
+          const int blk = lane >> 3, c4 = (lane & 7) * 4;          // 4 blocks x 8 float4
+          const int c = n0 + (part + blk * kParts) * kEpiCols + c4;
+          uint4 bz = make_uint4(0, 0, 0, 0), wz = bz;
+          if (part + blk * kParts < kBlocks && c < p.N) {
+            if (has_bias) bz = __ldg(reinterpret_cast<const uint4*>(p.bias + c));
+            if (has_dot) wz = __ldg(reinterpret_cast<const uint4*>(p.dot_w + c));
           }
+          if (has_bias) sts128(vec_s + lane * 16, bz);
+          if (has_dot) sts128(vec_s + 512 + lane * 16, wz);
           __syncwarp();
         }
-        if (aux_mode != AUX_NONE) aux_fetch(n0);
+        if (aux_mode != AUX_NONE) aux_fetch(n0 + part * kEpiCols);
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
         float dot = 0.f;
         bool released = false;
 #pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 64) {
+        for (int bi = 0; part + bi * kParts < kBlocks; ++bi) {
+          const int cb = (part + bi * kParts) * kEpiCols;
           const int col0 = n0 + cb;
           if (col0 >= p.out_cols) break;
-          const int nch = (BN - cb) >= 64 ? 4 : (BN - cb) / 16;
-          const bool last_block = (cb + 64 >= BN) || (col0 + 64 >= p.out_cols);
-          uint4 ax[8];
+          const int nch = (BN - cb) >= kEpiCols ? 2 : (BN - cb) / 16;
+          const int cb_next = cb + kParts * kEpiCols;
+          const bool last_block = (cb_next >= BN) || (n0 + cb_next >= p.out_cols);
+          uint4 ax[4];
           if (aux_mode != AUX_NONE) {   // prefetched aux (coalesced mapping) -> smem -> own row
 #pragma unroll
-            for (int it = 0; it < 8; ++it) sts128(stage_s + (it * 4 + lr) * kEpiPitch + lc * 16, pre[it]);
+            for (int it = 0; it < 4; ++it) sts128(stage_s + (it * 8 + lr) * kEpiPitch + lc * 16, pre[it]);
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) ax[q] = lds128(stage_s + lane * kEpiPitch + q * 16);
+            for (int q = 0; q < 4; ++q) ax[q] = lds128(stage_s + lane * kEpiPitch + q * 16);
             __syncwarp();
-            if (!last_block) aux_fetch(col0 + 64);   // overlaps with this block's math + stores
+            if (!last_block) aux_fetch(n0 + cb_next);   // overlaps with this block's math + stores
           }
-          // accumulator columns -> registers: all chunks in flight, one wait
-          uint32_t raw[4][16];
+          // accumulator columns -> registers: both chunks in flight, one wait
+          uint32_t raw[2][16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < 2; ++q)
             if (q < nch && col0 + q * 16 < p.N) tmem_ld16_issue(t_row + cb + q * 16, raw[q]);
           tmem_ld_wait();
-          if (last_block) {   // accumulator stage fully read: hand it back to the MMA warp
+          if (last_block) {   // accumulator stage fully read by this warp: hand it back to the MMA warp
             released = true;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 2; ++q) {
             if (q < nch) {
               const int c0 = col0 + q * 16;
               float v[16];
@@ -324,7 +335,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (has_bias) {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
-                    const uint4 b = lds128(vec_s + (cb + q * 16 + k4 * 4) * 4);
+                    const uint4 b = lds128(vec_s + (bi * kEpiCols + q * 16 + k4 * 4) * 4);
                     v[4 * k4 + 0] += __uint_as_float(b.x); v[4 * k4 + 1] += __uint_as_float(b.y);
                     v[4 * k4 + 2] += __uint_as_float(b.z); v[4 * k4 + 3] += __uint_as_float(b.w);
                   }
@@ -365,7 +376,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (has_dot) {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
-                    const uint4 w = lds128(vec_s + BN * 4 + (cb + q * 16 + k4 * 4) * 4);
+                    const uint4 w = lds128(vec_s + 512 + (bi * kEpiCols + q * 16 + k4 * 4) * 4);
                     dot = fmaf(v[4 * k4 + 0], __uint_as_float(w.x), dot); dot = fmaf(v[4 * k4 + 1], __uint_as_float(w.y), dot);
                     dot = fmaf(v[4 * k4 + 2], __uint_as_float(w.z), dot); dot = fmaf(v[4 * k4 + 3], __uint_as_float(w.w), dot);
                   }
@@ -382,19 +393,19 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           __syncwarp();
-          // coalesced store: 8 lanes cover 128 contiguous bytes of one row, 4 rows per pass
+          // coalesced store: 4 lanes cover 64 contiguous bytes of one row, 8 rows per pass
           if (p.out != nullptr && lc < nch * 2 && col0 + lc * 8 < p.out_cols) {
             __nv_bfloat16* o = p.out + size_t(wrow0 + lr) * p.ldo + col0 + lc * 8;
             const uint32_t sa = stage_s + lr * kEpiPitch + lc * 16;
 #pragma unroll
-            for (int it = 0; it < 8; ++it)
-              if (wrow0 + it * 4 + lr < p.M)
-                *reinterpret_cast<uint4*>(o + size_t(it * 4) * p.ldo) = lds128(sa + it * 4 * kEpiPitch);
+            for (int it = 0; it < 4; ++it)
+              if (wrow0 + it * 8 + lr < p.M)
+                *reinterpret_cast<uint4*>(o + size_t(it * 8) * p.ldo) = lds128(sa + it * 8 * kEpiPitch);
           }
           __syncwarp();
         }
         if ((has_dot || has_sq || aux_mode == AUX_VAE_OUT) && p.dot_out != nullptr && row_ok)
-          p.dot_out[size_t(n_tile * 2) * p.dot_ld + row] = dot;
+          p.dot_out[size_t(n_tile * 2 + (kParts == 2 ? part : 0)) * p.dot_ld + row] = dot;
         if (!released) {
           tc_fence_before();
           __syncwarp();
@@ -405,8 +416,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ====== fp32 epilogue: split-K partials (MN-major kernels) or biased fp32 output ======
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
-        const int c_first = (NACC == 2) ? 0 : grp;
-        const int c_step = (NACC == 2) ? 1 : 2;
+        const int c_first = (NACC == 2) ? (grp >> 1) : grp;
+        const int c_step = (NACC == 2) ? kEpiWarps / 8 : kEpiWarps / 4;
         float* base = p.part + size_t(split) * p.part_stride;
 #pragma unroll 1
         for (int c = c_first; c < BN / 16; c += c_step) {
