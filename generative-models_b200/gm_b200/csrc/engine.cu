@@ -27,6 +27,7 @@ struct gm_ctx {
   size_t scratch_bytes = 0;
   // optional per-launch GEMM timing (bench.py roofline): CUDA events on the launch stream
   bool prof = false;
+  bool use_clusters = true;   // GM_NO_CLUSTERS=1 disables the CTA-pair multicast path (debug)
   struct ProfRec { cudaEvent_t e0, e1; int kind; double flops; };
   std::vector<ProfRec> prof_recs;
 };
@@ -76,21 +77,40 @@ struct GemmPlan {
   GemmParams p;
   int kind;
   int grid;
+  int cs;         // cluster size (1, or 2 = multicast the shared B tile to a CTA pair)
   double flops;   // algorithmic 2*M*N*K of the logical problem (no padding)
 };
 
-template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
-static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
+template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T, int DOT_T, int CS>
+static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
   using Cfg = GemmCfg<BN1, BN2, !AMN>;
-  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T>;
+  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, CS>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<pl.grid, gemm_threads(AMN), Cfg::SMEM_BYTES, s>>>(pl.tmA, pl.tmB, pl.p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(gemm_threads(AMN));
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = CS > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, pl.tmA, pl.tmB, pl.p);
+}
+
+template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
+static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
+  if (pl.cs == 2) return launch_cs<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, 2>(pl, s);
+  return launch_cs<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, 1>(pl, s);
 }
 
 // K-major 128x208 kernel: pick the compile-time-specialised epilogue when the plan's
@@ -99,12 +119,14 @@ static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
   const GemmParams& p = pl.p;
   const bool bias = p.bias != nullptr, dot = p.dot_w != nullptr;
   const int aux = p.aux_mode;
+  if (p.epi != EPI_BF16) return launch_inst<208, 0, false, false>(pl, s);
   if (p.dot_sq && (bias || dot || aux != AUX_NONE || p.act != ACT_NONE)) return launch_inst<208, 0, false, false>(pl, s);
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 0>(pl, s);
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_NONE, 1, 0>(pl, s);
   if (bias && dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 1>(pl, s);
   if (!bias && !dot && aux == AUX_SIGMOID_GRAD && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_SIGMOID_GRAD, 0, 0>(pl, s);
   if (!bias && !dot && aux == AUX_RELU_MASK && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_RELU_MASK, 0, 0>(pl, s);
+  if (bias && !dot && aux == AUX_VAE_OUT && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_VAE_OUT, 1, 0>(pl, s);
   if (!bias && !dot && aux == AUX_NONE && p.act == ACT_NONE && p.dot_sq) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONE, 0, 2>(pl, s);
   if (!bias && !dot && aux == AUX_NONE && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONE, 0, 0>(pl, s);
   return launch_inst<208, 0, false, false>(pl, s);
@@ -143,9 +165,11 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
   memset(pl, 0, sizeof *pl);
   if (M <= 0 || N <= 0 || K <= 0) return fail(c, GM_ERR_ARG, "gemm: bad extents %d %d %d", M, N, K);
   int bn, boxn;
+  const int cs = (cdiv(M, BM) >= 2 && c->num_sms % 2 == 0 && c->use_clusters) ? 2 : 1;
+  pl->cs = cs;
   if (mode == 0) {
-    if (ncover <= 64) { pl->kind = PK_NT_64; bn = 64; boxn = 64; }
-    else { pl->kind = PK_NT_208; bn = 208; boxn = 208; }
+    if (ncover <= 64) { pl->kind = PK_NT_64; bn = 64; boxn = 64 / cs; }
+    else { pl->kind = PK_NT_208; bn = 208; boxn = 208 / cs; }
     int rc = make_tmap(c, &pl->tmA, A, K, M, lda, BK, BM);
     if (rc) return rc;
     rc = make_tmap(c, &pl->tmB, B, K, N, ldb, BK, boxn);
@@ -165,10 +189,12 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
   p.m_tiles = cdiv(M, BM);
   p.n_tiles = cdiv(ncover, bn);
   p.kblocks = cdiv(K, BK);
-  const int tiles = p.m_tiles * p.n_tiles;
+  p.m_supers = cdiv(p.m_tiles, cs);
+  const int tiles = p.m_supers * p.n_tiles;   // work items per split, one per cluster
+  const int slots = c->num_sms / cs;          // clusters resident at once
   int splits = 1;
   if (max_splits > 1) {
-    splits = c->num_sms / tiles;
+    splits = slots / tiles;
     if (splits > max_splits) splits = max_splits;
     if (splits > p.kblocks) splits = p.kblocks;
     if (splits < 1) splits = 1;
@@ -176,7 +202,7 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
   p.kb_per_split = cdiv(p.kblocks, splits);
   p.splits = cdiv(p.kblocks, p.kb_per_split);
   const int total = tiles * p.splits;
-  pl->grid = total < c->num_sms ? total : c->num_sms;
+  pl->grid = (total < slots ? total : slots) * cs;
   return GM_OK;
 }
 
@@ -212,6 +238,8 @@ extern "C" int gm_ctx_create(int device, gm_ctx** out) {
   CU_OK(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
   if (!fn || q != cudaDriverEntryPointSuccess) return fail(c, GM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
   c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  const char* nc = getenv("GM_NO_CLUSTERS");
+  c->use_clusters = !(nc && nc[0] == '1');
   return GM_OK;
 }
 extern "C" int gm_ctx_destroy(gm_ctx* c) {

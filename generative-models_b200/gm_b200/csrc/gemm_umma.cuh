@@ -36,6 +36,7 @@ enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2, AUX_VAE_OUT 
 struct GemmParams {
   int M, N, K;          // logical extents; K counts contraction elements
   int m_tiles, n_tiles;
+  int m_supers;         // ceil(m_tiles / cluster size): clusters walk (split, m_super, n_tile)
   int splits, kblocks, kb_per_split;
   int epi;
   // ---- EPI_BF16: out[m, n] = bf16( f(acc + bias[n]) * g(aux[m,n]) ), row-major, ld = ldo
@@ -91,7 +92,11 @@ struct GemmCfg {
 // Epilogue specialisation: ACT_T / AUX_T / BIAS_T / DOT_T >= 0 fix the fused epilogue at
 // compile time (small code: the whole kernel must stay inside the instruction cache);
 // -1 selects the universal variant that reads the choice from GemmParams at run time.
-template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
+// CS: cluster size (1 or 2).  With CS = 2 the two CTAs of a cluster work on consecutive
+// m-tiles of the same (split, n-tile); each loads HALF of the shared B tile and TMA-multicasts
+// it to both (L2 -> SM operand traffic per CTA: A + B/2 instead of A + B), and every smem
+// slot is released to both producers with a multicast tcgen05.commit.
+template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1, int CS = 1>
 __global__ void __launch_bounds__(gemm_threads(A_MN), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -117,13 +122,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int crank = CS > 1 ? int(cluster_ctarank()) : 0;
+  constexpr uint16_t kMcMask = uint16_t((1u << CS) - 1u);
+  static_assert(CS == 1 || CS == 2, "cluster size 1 or 2");
+  static_assert(CS == 1 || B_MN || ((BN / CS) % 8 == 0 && Cfg::BOXN == BN), "B slice must keep the 8-row swizzle atoms whole");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CS);   // every CTA of the cluster releases the slot (multicast commit)
     }
     for (int s = 0; s < NACC; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -134,21 +143,26 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int tiles = p.m_tiles * p.n_tiles;
+  // work items are walked per CLUSTER: item -> (split, m_super, n_tile); this CTA's m-tile is
+  // m_super*CS + rank (an m-tile past the end just loads zero rows and stores nothing)
+  const int tiles = p.m_supers * p.n_tiles;
   const int total = tiles * p.splits;
+  const int first_item = blockIdx.x / CS;
+  const int item_step = gridDim.x / CS;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      for (int item = first_item; item < total; item += item_step) {
         const int split = item / tiles;
         const int rem = item - split * tiles;
-        const int m0 = (rem / p.n_tiles) * BM;
+        const int m0 = ((rem / p.n_tiles) * CS + crank) * BM;
         const int n0 = (rem % p.n_tiles) * BN;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
@@ -165,14 +179,25 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int a = 0; a < BM / 64; ++a)
               tma_load_2d(a_dst + a * (BK * 128), &tmA, full_bar(stage), m0 + a * 64, k0);
           }
-          if constexpr (!B_MN) {
+          if constexpr (CS == 1) {
+            if constexpr (!B_MN) {
 #pragma unroll
-            for (int b = 0; b < BN / Cfg::BOXN; ++b)
-              tma_load_2d(b_dst + b * (Cfg::BOXN * 128), &tmB, full_bar(stage), k0, n0 + b * Cfg::BOXN);
+              for (int b = 0; b < BN / Cfg::BOXN; ++b)
+                tma_load_2d(b_dst + b * (Cfg::BOXN * 128), &tmB, full_bar(stage), k0, n0 + b * Cfg::BOXN);
+            } else {
+#pragma unroll
+              for (int b = 0; b < BN / 64; ++b)
+                tma_load_2d(b_dst + b * (BK * 128), &tmB, full_bar(stage), n0 + b * 64, k0);
+            }
           } else {
-#pragma unroll
-            for (int b = 0; b < BN / 64; ++b)
-              tma_load_2d(b_dst + b * (BK * 128), &tmB, full_bar(stage), n0 + b * 64, k0);
+            // this CTA's share of the B tile, multicast to the whole cluster
+            if constexpr (!B_MN) {
+              constexpr int SL = BN / CS;   // rows per CTA (tensor-map box = SL rows)
+              tma_load_2d_mc(b_dst + crank * (SL * 128), &tmB, full_bar(stage), k0, n0 + crank * SL, kMcMask);
+            } else {
+              for (int b = crank; b < BN / 64; b += CS)
+                tma_load_2d_mc(b_dst + b * (BK * 128), &tmB, full_bar(stage), n0 + b * 64, k0, kMcMask);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -192,7 +217,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int acc_iter = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
+      for (int item = first_item; item < total; item += item_step, ++acc_iter) {
         const int split = item / tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
@@ -218,7 +243,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               umma_bf16(d_tmem + BN1, da, db2, idesc2, acc);
             }
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if constexpr (CS == 1) umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          else umma_commit_mc(empty_bar(stage), kMcMask);          // ... in every CTA that multicasts into it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(as));       // accumulator complete -> epilogue
@@ -244,13 +270,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_sq = DOT_T >= 0 ? (DOT_T == 2) : (p.dot_sq != 0);
     int acc_iter = 0;
 #pragma unroll 1
-    for (int item = blockIdx.x; item < total; item += gridDim.x, ++acc_iter) {
+    for (int item = first_item; item < total; item += item_step, ++acc_iter) {
       const int as = acc_iter % NACC;
       if (NACC == 2 && as != my_stage) continue;
       const int split = item / tiles;
       const int rem = item - split * tiles;
       const int n_tile = rem % p.n_tiles;
-      const int m0 = (rem / p.n_tiles) * BM;
+      const int m0 = ((rem / p.n_tiles) * CS + crank) * BM;
       const int n0 = n_tile * BN;
       const uint32_t aphase = (acc_iter / NACC) & 1;
       const int wrow0 = m0 + quarter * 32;   // first row of this warp
@@ -455,6 +481,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer may still signal it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
