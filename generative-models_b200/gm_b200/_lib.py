@@ -68,6 +68,7 @@ def lib():
     L.gm_launch_count.argtypes = [vp, i]
     L.gm_launch_count.restype = C.c_longlong
     L.gm_prof_enable.argtypes = [vp, i]
+    L.gm_debug_phase_buffer.argtypes = [vp, vp]
     L.gm_prof_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.gm_gemm_bf16.argtypes = [vp, C.POINTER(GemmDesc), vp]
     L.gm_adam_step.argtypes = [vp, vp, vp, vp, vp, i, C.POINTER(AdamHP), i, vp]

@@ -27,6 +27,7 @@ struct gm_ctx {
   size_t scratch_bytes = 0;
   // optional per-launch GEMM timing (bench.py roofline): CUDA events on the launch stream
   bool prof = false;
+  long long* dbg = nullptr;   // phase-timing buffer handed to the next generic GEMM (tools/time_phases.py)
   bool use_clusters = true;   // GM_NO_CLUSTERS=1 disables the CTA-pair multicast path (debug)
   struct ProfRec { cudaEvent_t e0, e1; int kind; double flops; };
   std::vector<ProfRec> prof_recs;
@@ -257,6 +258,13 @@ extern "C" long long gm_launch_count(gm_ctx* c, int reset) {
   return n;
 }
 
+// debug aid: 128 int64 SM-clock stamps written by CTA 0 of subsequent gm_gemm_bf16 calls
+extern "C" int gm_debug_phase_buffer(gm_ctx* c, long long* dbg_dev) {
+  if (!c) return GM_ERR_ARG;
+  c->dbg = dbg_dev;
+  return GM_OK;
+}
+
 extern "C" int gm_prof_enable(gm_ctx* c, int on) {
   if (!c) return GM_ERR_ARG;
   c->prof = on != 0;
@@ -292,6 +300,7 @@ extern "C" int gm_gemm_bf16(gm_ctx* c, const gm_gemm_desc* d, gm_stream stream) 
   int rc = plan_gemm(c, &pl, d->mode, d->M, d->N, d->K, d->A_dev, d->lda, d->B_dev, d->ldb, ncover, f32 ? 64 : 1);
   if (rc) return rc;
   GemmParams& p = pl.p;
+  p.dbg = c->dbg;
   if (!f32) {
     p.epi = EPI_BF16;
     p.out = static_cast<__nv_bfloat16*>(d->C_dev);

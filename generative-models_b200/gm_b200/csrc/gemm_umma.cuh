@@ -58,6 +58,8 @@ struct GemmParams {
   long long part_stride;
   int ldp;
   int transpose;
+  // optional phase timing (tools/time_phases.py): CTA 0 writes SM-clock stamps, see the kernel
+  long long* dbg;
 };
 
 // per-epilogue-warp staging tile for one 32-column block: 32 rows x (64 B data + 16 B pad):
@@ -156,18 +158,21 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = first_item; item < total; item += item_step) {
-        const int split = item / tiles;
-        const int rem = item - split * tiles;
-        const int m0 = ((rem / p.n_tiles) * CS + crank) * BM;
-        const int n0 = (rem % p.n_tiles) * BN;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+    // The whole warp walks the loop (warp-uniform control flow and addresses keep the TMA
+    // operands in uniform registers); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    const bool leader = elect_one();
+    for (int item = first_item; item < total; item += item_step) {
+      const int split = item / tiles;
+      const int rem = item - split * tiles;
+      const int m0 = ((rem / p.n_tiles) * CS + crank) * BM;
+      const int n0 = (rem % p.n_tiles) * BN;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (leader) {
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -199,55 +204,76 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_2d_mc(b_dst + b * (BK * 128), &tmB, full_bar(stage), n0 + b * 64, k0, kMcMask);
             }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(BM, BN1, A_MN, B_MN);
-      constexpr uint32_t idesc2 = make_idesc_bf16(BM, BN2 > 0 ? BN2 : 16, A_MN, B_MN);
-      // descriptor strides: K-major: SBO = 8 rows * 128 B; MN-major: LBO = atom
-      // stride (BK*128 B), SBO = 8 k-rows * 128 B.  Per UMMA_K (16) advance:
-      // K-major 32 B, MN-major 16 rows * 128 B.
-      constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0, A_KADV = A_MN ? kUmmaK * 128 : kUmmaK * 2;
-      constexpr uint32_t B_LBO = B_MN ? BK * 128 : 0, B_KADV = B_MN ? kUmmaK * 128 : kUmmaK * 2;
-      constexpr uint32_t B2_OFF = B_MN ? (BN1 / 64) * (BK * 128) : BN1 * 128;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc_iter = 0;
-      for (int item = first_item; item < total; item += item_step, ++acc_iter) {
-        const int split = item / tiles;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-        const int as = acc_iter % NACC;
-        const uint32_t aphase = (acc_iter / NACC) & 1;
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
+    // Whole warp in the loop, one elected lane issues tcgen05.mma / commit.  Descriptors are
+    // a constant high word plus a 14-bit address field advanced by adds (no per-MMA rebuild).
+    constexpr uint32_t idesc1 = make_idesc_bf16(BM, BN1, A_MN, B_MN);
+    constexpr uint32_t idesc2 = make_idesc_bf16(BM, BN2 > 0 ? BN2 : 16, A_MN, B_MN);
+    // descriptor strides: K-major: SBO = 8 rows * 128 B; MN-major: LBO = atom stride
+    // (BK*128 B), SBO = 8 k-rows * 128 B.  Per UMMA_K (16) advance: K-major 32 B,
+    // MN-major 16 rows * 128 B.
+    constexpr uint32_t A_LBO = A_MN ? BK * 128 : 0, A_KADV = A_MN ? kUmmaK * 128 : kUmmaK * 2;
+    constexpr uint32_t B_LBO = B_MN ? BK * 128 : 0, B_KADV = B_MN ? kUmmaK * 128 : kUmmaK * 2;
+    constexpr uint32_t B2_OFF = B_MN ? (BN1 / 64) * (BK * 128) : BN1 * 128;
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, 128B swizzle
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc_iter = 0;
+    for (int item = first_item; item < total; item += item_step, ++acc_iter) {
+      const int split = item / tiles;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+      const int as = acc_iter % NACC;
+      const uint32_t aphase = (acc_iter / NACC) & 1;
+      const long long tm0 = clock64();
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tc_fence_after();
+      const long long tm1 = clock64();
+      long long full_wait = 0;
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const long long tw0 = clock64();
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_src = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t b_src = a_src + Cfg::A_BYTES;
-          const int krem = p.K - kb * BK;
-          const int nk = krem >= BK ? BK / kUmmaK : (krem + kUmmaK - 1) / kUmmaK;
+        full_wait += clock64() - tw0;
+        const uint32_t a_src = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t b_src = a_src + Cfg::A_BYTES;
+        const int krem = p.K - kb * BK;
+        const int nk = krem >= BK ? BK / kUmmaK : (krem + kUmmaK - 1) / kUmmaK;
+        if (leader) {
+          uint32_t a_lo = ((a_src >> 4) & 0x3FFFu) | ((A_LBO >> 4) << 16);
+          uint32_t b_lo = ((b_src >> 4) & 0x3FFFu) | ((B_LBO >> 4) << 16);
+          uint32_t acc = kb > kb0 ? 1u : 0u;
           for (int k = 0; k < nk; ++k) {
-            const uint64_t da = make_smem_desc(a_src + k * A_KADV, A_LBO, 1024);
-            const uint64_t db = make_smem_desc(b_src + k * B_KADV, B_LBO, 1024);
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            const uint64_t da = (uint64_t(DESC_HI) << 32) | a_lo;
+            const uint64_t db = (uint64_t(DESC_HI) << 32) | b_lo;
             umma_bf16(d_tmem, da, db, idesc1, acc);
             if constexpr (BN2 > 0) {
-              const uint64_t db2 = make_smem_desc(b_src + B2_OFF + k * B_KADV, B_LBO, 1024);
+              const uint64_t db2 = (uint64_t(DESC_HI) << 32) | (b_lo + (B2_OFF >> 4));
               umma_bf16(d_tmem + BN1, da, db2, idesc2, acc);
             }
+            acc = 1u;
+            a_lo += A_KADV >> 4;
+            b_lo += B_KADV >> 4;
           }
-          if constexpr (CS == 1) umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if constexpr (CS == 1) umma_commit(empty_bar(stage));   // smem slot reusable once these MMAs retire
           else umma_commit_mc(empty_bar(stage), kMcMask);          // ... in every CTA that multicasts into it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));       // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) umma_commit(tfull_bar(as));       // accumulator complete -> epilogue
+      __syncwarp();
+      if (p.dbg != nullptr && blockIdx.x == 0 && acc_iter < 16 && leader) {
+        long long* d = p.dbg + acc_iter * 4;   // [tile][wait accumulator free, issue loop, of which waiting for TMA, start stamp]
+        d[0] = tm1 - tm0; d[1] = clock64() - tm1; d[2] = full_wait; d[3] = tm0;
       }
     }
   } else {
@@ -316,8 +342,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
         }
         if (aux_mode != AUX_NONE) aux_fetch(n0 + part * kEpiCols);
+        const long long te0 = clock64();
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
+        const long long te1 = clock64();
+        long long t_ld = 0;
         float dot = 0.f;
         bool released = false;
 #pragma unroll 1
@@ -340,10 +369,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           // accumulator columns -> registers: both chunks in flight, one wait
           uint32_t raw[2][16];
+          const long long tl0 = clock64();
 #pragma unroll
           for (int q = 0; q < 2; ++q)
             if (q < nch && col0 + q * 16 < p.N) tmem_ld16_issue(t_row + cb + q * 16, raw[q]);
           tmem_ld_wait();
+          t_ld += clock64() - tl0;
           if (last_block) {   // accumulator stage fully read by this warp: hand it back to the MMA warp
             released = true;
             tc_fence_before();
@@ -436,6 +467,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (e & 3) == 0 && part == 0 && acc_iter < 16) {
+          long long* d = p.dbg + 64 + acc_iter * 4;   // [tile][wait accumulator ready, epilogue work, of which TMEM ld+wait, start stamp]
+          d[0] = te1 - te0; d[1] = clock64() - te1; d[2] = t_ld; d[3] = te0;
         }
        }
       } else {

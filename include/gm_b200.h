@@ -172,6 +172,9 @@ long long gm_launch_count(gm_ctx* ctx, int reset);
  * GEMM launch on its launch stream; gm_prof_collect synchronises and returns, per
  * kernel instantiation (4 slots), total ms, algorithmic FLOPs and launch count. */
 int gm_prof_enable(gm_ctx* ctx, int on);
+/* debug aid: CTA 0 of following gm_gemm_bf16 launches writes per-tile phase durations
+ * (SM clocks) into dbg_dev (128 int64); pass NULL to stop. */
+int gm_debug_phase_buffer(gm_ctx* ctx, long long* dbg_dev);
 int gm_prof_collect(gm_ctx* ctx, double* ms4, double* flops4, long long* count4);
 
 #ifdef __cplusplus
