@@ -84,7 +84,7 @@ struct GemmPlan {
 
 template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T, int DOT_T, int CS>
 static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
-  using Cfg = GemmCfg<BN1, BN2, !AMN>;
+  using Cfg = GemmCfg<BN1, BN2, !AMN, (CS == 2) && !AMN>;
   auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, CS>;
   static bool configured = false;
   if (!configured) {
@@ -166,7 +166,9 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
   memset(pl, 0, sizeof *pl);
   if (M <= 0 || N <= 0 || K <= 0) return fail(c, GM_ERR_ARG, "gemm: bad extents %d %d %d", M, N, K);
   int bn, boxn;
-  const int cs = (cdiv(M, BM) >= 2 && c->num_sms % 2 == 0 && c->use_clusters) ? 2 : 1;
+  // CTA pairs (cta_group::2 MMA) for the K-major kernels; the MN-major split-K kernels stay
+  // single-CTA (pairing 7 m-tiles wastes an eighth of the MMAs and measured slower)
+  const int cs = (mode == 0 && cdiv(M, BM) >= 2 && c->num_sms % 2 == 0 && c->use_clusters) ? 2 : 1;
   pl->cs = cs;
   if (mode == 0) {
     if (ncover <= 64) { pl->kind = PK_NT_64; bn = 64; boxn = 64 / cs; }

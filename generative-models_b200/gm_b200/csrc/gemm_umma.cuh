@@ -69,12 +69,12 @@ constexpr int kEpiPitch = 80;
 constexpr int kEpiStageBytes = 32 * kEpiPitch;
 constexpr int kEpiVecBytes = 4 * kEpiCols * 4 * 2;   // bias + row-dot weights of up to 4 blocks per warp
 
-template <int BN1, int BN2, bool STAGED_EPI = true>
+template <int BN1, int BN2, bool STAGED_EPI = true, bool PAIR = false>
 struct GemmCfg {
   static constexpr int BN = BN1 + BN2;
   static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // per-warp staging tile + per-warp copies of its blocks' bias / row-dot weight slices
   static constexpr int EPI_WARPS = STAGED_EPI ? kEpiWarpsNT : kEpiWarpsTN;
@@ -94,15 +94,21 @@ struct GemmCfg {
 // Epilogue specialisation: ACT_T / AUX_T / BIAS_T / DOT_T >= 0 fix the fused epilogue at
 // compile time (small code: the whole kernel must stay inside the instruction cache);
 // -1 selects the universal variant that reads the choice from GemmParams at run time.
-// CS: cluster size (1 or 2).  With CS = 2 the two CTAs of a cluster work on consecutive
-// m-tiles of the same (split, n-tile); each loads HALF of the shared B tile and TMA-multicasts
-// it to both (L2 -> SM operand traffic per CTA: A + B/2 instead of A + B), and every smem
-// slot is released to both producers with a multicast tcgen05.commit.
+// CS: cluster size (1 or 2).  CS = 2 pairs two CTAs on consecutive m-tiles of the same
+// (split, n-tile):
+//  * K-major kernels: ONE tcgen05.mma.cta_group::2 (M = 256) per k-step spans both SMs; each
+//    CTA stages its own 128 A rows and HALF of the B tile, so the bytes an SM has to pull into
+//    shared memory per MMA cycle drop from A+B to A+B/2 (the measured limiter of the 1-CTA
+//    kernel: the MMA thread waits on TMA, profiles/r1c).  The leader CTA issues the MMAs; TMA
+//    completions of both CTAs are signalled on the leader's full barrier, slots / accumulators
+//    are released with multicast commits, peer epilogue warps release the accumulator remotely.
+//  * MN-major kernels: each CTA TMA-multicasts half of the shared B tile to both CTAs.
 template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1, int CS = 1>
 __global__ void __launch_bounds__(gemm_threads(A_MN), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN1, BN2, !A_MN>;
+  constexpr bool PAIR = (CS == 2) && !A_MN;
+  using Cfg = GemmCfg<BN1, BN2, !A_MN, PAIR>;
   constexpr int BN = Cfg::BN;
   constexpr int NACC = Cfg::NACC;
   constexpr int STAGES = Cfg::STAGES;
@@ -128,21 +134,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint16_t kMcMask = uint16_t((1u << CS) - 1u);
   static_assert(CS == 1 || CS == 2, "cluster size 1 or 2");
   static_assert(CS == 1 || B_MN || ((BN / CS) % 8 == 0 && Cfg::BOXN == BN), "B slice must keep the 8-row swizzle atoms whole");
+  static_assert(!PAIR || BN2 == 0, "pair mode: one MMA per k-step");
+  const bool pair_leader = !PAIR || crank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CS);   // every CTA of the cluster releases the slot (multicast commit)
+      mbar_init(full_bar(s), PAIR ? 2 : 1);          // pair: both producers arrive on the leader's barrier
+      mbar_init(empty_bar(s), PAIR ? 1 : CS);        // multicast mode: every CTA releases the slot
     }
     for (int s = 0; s < NACC; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EPI_ARRIVALS);
+      mbar_init(tempty_bar(s), PAIR ? 2 * EPI_ARRIVALS : EPI_ARRIVALS);   // pair: both CTAs' epilogues
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) { if constexpr (PAIR) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any remote signal
@@ -175,8 +183,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (leader) {
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const int k0 = kb * BK;
+          if constexpr (PAIR) {
+            // own A rows + own half of B into own smem; bytes of BOTH CTAs are counted on the
+            // leader's full barrier (leader expects 2 x stage bytes, the peer just arrives)
+            const uint32_t fb = mapa_cluster(full_bar(stage), 0);
+            if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+            else mbar_arrive_cluster(fb);
+            tma_load_2d_pair(a_dst, &tmA, fb, k0, m0);
+            tma_load_2d_pair(b_dst, &tmB, fb, k0, n0 + crank * (BN / 2));
+          } else {
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           if constexpr (!A_MN) {
             tma_load_2d(a_dst, &tmA, full_bar(stage), k0, m0);
           } else {
@@ -204,6 +221,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_2d_mc(b_dst + b * (BK * 128), &tmB, full_bar(stage), n0 + b * 64, k0, kMcMask);
             }
           }
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -213,7 +231,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =========================== MMA issuer ===========================
     // Whole warp in the loop, one elected lane issues tcgen05.mma / commit.  Descriptors are
     // a constant high word plus a 14-bit address field advanced by adds (no per-MMA rebuild).
-    constexpr uint32_t idesc1 = make_idesc_bf16(BM, BN1, A_MN, B_MN);
+    constexpr uint32_t idesc1 = make_idesc_bf16(PAIR ? 2 * BM : BM, BN1, A_MN, B_MN);
     constexpr uint32_t idesc2 = make_idesc_bf16(BM, BN2 > 0 ? BN2 : 16, A_MN, B_MN);
     // descriptor strides: K-major: SBO = 8 rows * 128 B; MN-major: LBO = atom stride
     // (BK*128 B), SBO = 8 k-rows * 128 B.  Per UMMA_K (16) advance: K-major 32 B,
@@ -226,7 +244,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int acc_iter = 0;
-    for (int item = first_item; item < total; item += item_step, ++acc_iter) {
+    for (int item = first_item; pair_leader && item < total; item += item_step, ++acc_iter) {
       const int split = item / tiles;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
@@ -254,7 +272,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < nk; ++k) {
             const uint64_t da = (uint64_t(DESC_HI) << 32) | a_lo;
             const uint64_t db = (uint64_t(DESC_HI) << 32) | b_lo;
-            umma_bf16(d_tmem, da, db, idesc1, acc);
+            if constexpr (PAIR) umma_bf16_pair(d_tmem, da, db, idesc1, acc);
+            else umma_bf16(d_tmem, da, db, idesc1, acc);
             if constexpr (BN2 > 0) {
               const uint64_t db2 = (uint64_t(DESC_HI) << 32) | (b_lo + (B2_OFF >> 4));
               umma_bf16(d_tmem + BN1, da, db2, idesc2, acc);
@@ -263,13 +282,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             a_lo += A_KADV >> 4;
             b_lo += B_KADV >> 4;
           }
-          if constexpr (CS == 1) umma_commit(empty_bar(stage));   // smem slot reusable once these MMAs retire
-          else umma_commit_mc(empty_bar(stage), kMcMask);          // ... in every CTA that multicasts into it
+          if constexpr (PAIR) umma_commit_pair(empty_bar(stage), kMcMask);   // frees the slot in both CTAs
+          else if constexpr (CS == 1) umma_commit(empty_bar(stage));           // smem slot reusable once these MMAs retire
+          else umma_commit_mc(empty_bar(stage), kMcMask);                      // ... in every CTA that multicasts into it
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (leader) umma_commit(tfull_bar(as));       // accumulator complete -> epilogue
+      if (leader) {                                 // accumulator complete -> epilogue (of both CTAs in pair mode)
+        if constexpr (PAIR) umma_commit_pair(tfull_bar(as), kMcMask);
+        else umma_commit(tfull_bar(as));
+      }
       __syncwarp();
       if (p.dbg != nullptr && blockIdx.x == 0 && acc_iter < 16 && leader) {
         long long* d = p.dbg + acc_iter * 4;   // [tile][wait accumulator free, issue loop, of which waiting for TMA, start stamp]
@@ -379,7 +402,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             released = true;
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(mapa_cluster(tempty_bar(as), 0));
+              else mbar_arrive(tempty_bar(as));
+            }
           }
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
@@ -466,7 +492,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!released) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(mapa_cluster(tempty_bar(as), 0));
+            else mbar_arrive(tempty_bar(as));
+          }
         }
         if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (e & 3) == 0 && part == 0 && acc_iter < 16) {
           long long* d = p.dbg + 64 + acc_iter * 4;   // [tile][wait accumulator ready, epilogue work, of which TMEM ld+wait, start stamp]
@@ -509,7 +538,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(mapa_cluster(tempty_bar(as), 0));
+          else mbar_arrive(tempty_bar(as));
+        }
       }
     }
   }
@@ -520,7 +552,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
