@@ -23,11 +23,12 @@ namespace gm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kUmmaK = 16;
-// epilogue warps: 16 for the K-major (bf16-output) kernels — the epilogue is latency-bound
-// per warp, more warps in flight hide it — 8 for the MN-major split-K kernels
-constexpr int kEpiWarpsNT = 16, kEpiWarpsTN = 8;
+// epilogue warps (2 per TMEM lane quarter).  16 warps on the K-major kernels measured no
+// faster than 8 (the epilogue is issue-bound, not latency-bound) and cost a pipeline stage
+// of shared memory, so both kernel families use 8
+constexpr int kEpiWarpsNT = 8, kEpiWarpsTN = 8;
 constexpr int gemm_threads(bool a_mn) { return 64 + (a_mn ? kEpiWarpsTN : kEpiWarpsNT) * 32; }
-constexpr int kSmemBudget = 224 * 1024;
+constexpr int kSmemBudget = 225 * 1024;
 
 enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
@@ -67,7 +68,8 @@ struct GemmParams {
 constexpr int kEpiCols = 32;
 constexpr int kEpiPitch = 80;
 constexpr int kEpiStageBytes = 32 * kEpiPitch;
-constexpr int kEpiVecBytes = 4 * kEpiCols * 4 * 2;   // bias + row-dot weights of up to 4 blocks per warp
+constexpr int kEpiVecBlocks = 8;                       // column blocks per warp the bias/dot staging holds
+constexpr int kEpiVecBytes = kEpiVecBlocks * kEpiCols * 4 * 2;   // bias + row-dot weights
 
 template <int BN1, int BN2, bool STAGED_EPI = true, bool PAIR = false>
 struct GemmCfg {
@@ -79,7 +81,7 @@ struct GemmCfg {
   // per-warp staging tile + per-warp copies of its blocks' bias / row-dot weight slices
   static constexpr int EPI_WARPS = STAGED_EPI ? kEpiWarpsNT : kEpiWarpsTN;
   static constexpr int EPI_BYTES = STAGED_EPI ? EPI_WARPS * (kEpiStageBytes + kEpiVecBytes) : 0;
-  static_assert(!STAGED_EPI || (BN + kEpiCols - 1) / kEpiCols <= 4 * (EPI_WARPS / 8), "kEpiVecBytes holds 4 blocks per warp");
+  static_assert(!STAGED_EPI || (BN + kEpiCols - 1) / kEpiCols <= kEpiVecBlocks * (EPI_WARPS / 8), "bias/dot staging too small");
   static constexpr int STAGES_RAW = (kSmemBudget - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
@@ -353,15 +355,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // bias / row-dot weights of this warp's column blocks -> smem and the first aux tile ->
         // registers while the MMAs still run: no global-load latency after the TMEM read
         if (has_bias || has_dot) {
-          const int blk = lane >> 3, c4 = (lane & 7) * 4;          // 4 blocks x 8 float4
-          const int c = n0 + (part + blk * kParts) * kEpiCols + c4;
-          uint4 bz = make_uint4(0, 0, 0, 0), wz = bz;
-          if (part + blk * kParts < kBlocks && c < p.N) {
-            if (has_bias) bz = __ldg(reinterpret_cast<const uint4*>(p.bias + c));
-            if (has_dot) wz = __ldg(reinterpret_cast<const uint4*>(p.dot_w + c));
+#pragma unroll
+          for (int pass = 0; pass < kEpiVecBlocks / 4; ++pass) {
+            const int blk = pass * 4 + (lane >> 3), c4 = (lane & 7) * 4;   // 4 blocks x 8 float4 per pass
+            const int c = n0 + (part + blk * kParts) * kEpiCols + c4;
+            uint4 bz = make_uint4(0, 0, 0, 0), wz = bz;
+            if (part + blk * kParts < kBlocks && c < p.N) {
+              if (has_bias) bz = __ldg(reinterpret_cast<const uint4*>(p.bias + c));
+              if (has_dot) wz = __ldg(reinterpret_cast<const uint4*>(p.dot_w + c));
+            }
+            if (has_bias) sts128(vec_s + (blk * kEpiCols + c4) * 4, bz);
+            if (has_dot) sts128(vec_s + kEpiVecBytes / 2 + (blk * kEpiCols + c4) * 4, wz);
           }
-          if (has_bias) sts128(vec_s + lane * 16, bz);
-          if (has_dot) sts128(vec_s + 512 + lane * 16, wz);
           __syncwarp();
         }
         if (aux_mode != AUX_NONE) aux_fetch(n0 + part * kEpiCols);
@@ -459,7 +464,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (has_dot) {
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
-                    const uint4 w = lds128(vec_s + 512 + (bi * kEpiCols + q * 16 + k4 * 4) * 4);
+                    const uint4 w = lds128(vec_s + kEpiVecBytes / 2 + (bi * kEpiCols + q * 16 + k4 * 4) * 4);
                     dot = fmaf(v[4 * k4 + 0], __uint_as_float(w.x), dot); dot = fmaf(v[4 * k4 + 1], __uint_as_float(w.y), dot);
                     dot = fmaf(v[4 * k4 + 2], __uint_as_float(w.z), dot); dot = fmaf(v[4 * k4 + 3], __uint_as_float(w.w), dot);
                   }
