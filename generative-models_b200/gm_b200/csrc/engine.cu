@@ -652,7 +652,7 @@ static int check_step_args(gm_gan* g, int batch) {
 }
 
 static int run_generator(gm_gan* g, StepPlans* sp, int B, const float* noise, uint64_t seed, uint64_t stream_id, cudaStream_t s) {
-  stage_noise_kernel<<<cdiv(B, 128), 128, 0, s>>>(noise, g->Zb, B, g->Z, g->ZP, seed, stream_id);
+  stage_noise_kernel<<<cdiv(B * (g->ZP / 8), 256), 256, 0, s>>>(noise, g->Zb, B, g->Z, g->ZP, seed, stream_id);
   g->ctx->launches++;
   int rc;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
@@ -839,7 +839,7 @@ extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* imag
   int rc;
   if ((rc = build_plans(g, B, &sp))) return rc;
   // stage n noise rows (rows n..B-1 keep whatever they held; their outputs are not read)
-  stage_noise_kernel<<<cdiv(n, 128), 128, 0, s>>>(noise, g->Zb, n, g->Z, g->ZP, 0, 0);
+  stage_noise_kernel<<<cdiv(n * (g->ZP / 8), 256), 256, 0, s>>>(noise, g->Zb, n, g->Z, g->ZP, 0, 0);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
   if ((rc = launch_plan(g->ctx, sp->g2, s))) return rc;

@@ -26,23 +26,39 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
                                     __nv_bfloat16* __restrict__ dst, int rows, int x, int ld) {
   const int groups = ld / 8;
   const long long total = (long long)rows * groups;
+  if (fmt == IMG_BITS && (x & 7) == 0) {
+    // one packed byte (MSB first) expands to 8 bf16 values; 4 independent items per thread
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+      uint32_t byte[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + u * stride;
+        byte[u] = 0;
+        if (i < total) {
+          const int r = int(i / groups), g = int(i % groups);
+          const long long sr = idx ? idx[r] : r;
+          if (g * 8 < x) byte[u] = __ldg(reinterpret_cast<const uint8_t*>(src) + sr * (x >> 3) + g);
+          else if (g * 8 == x) byte[u] = 0x80u;     // ones column
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + u * stride;
+        if (i >= total) break;
+        const uint32_t b = byte[u];
+        // bf16 1.0 = 0x3F80: build the four packed pairs without float conversions
+        auto pr = [&](int hi_bit, int lo_bit) { return ((b >> lo_bit) & 1u ? 0x3F80u : 0u) | ((b >> hi_bit) & 1u ? 0x3F800000u : 0u); };
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pr(6, 7), pr(4, 5), pr(2, 3), pr(0, 1));
+      }
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int r = int(i / groups), g = int(i % groups);
     const long long sr = idx ? idx[r] : r;
     float v[8];
-    if (fmt == IMG_BITS && (x & 7) == 0) {
-      // one packed byte (MSB first) expands to this thread's 8 bf16 values
-      const int c0 = g * 8;
-      uint32_t byte = 0;
-      if (c0 < x) byte = __ldg(reinterpret_cast<const uint8_t*>(src) + sr * (x >> 3) + g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (byte >> (7 - j)) & 1u ? 1.f : 0.f;
-      if (c0 == x) v[0] = 1.f;
-      reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      continue;
-    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
@@ -63,27 +79,33 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
 }
 
 // noise fp32 [rows, z] (or Philox N(0,1) when src == nullptr) -> bf16 [rows, ld], ones col at z.
+// One thread per (row, 8-column group); the Philox subsequence is the group index, the
+// offset the step stream, so every step / rank / group draws disjoint numbers.
 __global__ void stage_noise_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
                                    int z, int ld, unsigned long long seed, unsigned long long stream_id) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  curandStatePhilox4_32_10_t st;
-  if (src == nullptr) curand_init(seed, (unsigned long long)r, stream_id * (unsigned long long)((ld + 3) / 4), &st);
-  for (int c0 = 0; c0 < ld; c0 += 8) {
-    float v[8];
+  const int groups = ld / 8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * groups) return;
+  const int r = int(i / groups), c0 = int(i % groups) * 8;
+  float v[8];
+  if (c0 < z) {
     if (src == nullptr) {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seed, (unsigned long long)i, stream_id * 2ull, &st);
       const float4 a = curand_normal4(&st), b = curand_normal4(&st);
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      if (c < z) { if (src) v[j] = src[(long long)r * z + c]; }
-      else v[j] = (c == z) ? 1.f : 0.f;
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < z) ? src[(long long)r * z + c0 + j] : 0.f;
     }
-    reinterpret_cast<uint4*>(dst + (long long)r * ld)[c0 / 8] =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    if (c >= z) v[j] = (c == z) ? 1.f : 0.f;
+  }
+  reinterpret_cast<uint4*>(dst)[i] =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
 // ---------------------------------------------------------------- block reduction (deterministic)
