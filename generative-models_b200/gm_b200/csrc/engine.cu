@@ -78,14 +78,15 @@ struct GemmPlan {
   GemmParams p;
   int kind;
   int grid;
-  int cs;         // cluster size (1, or 2 = multicast the shared B tile to a CTA pair)
+  int cs;         // cluster size (1, or 2 = CTA pair)
+  int ew;         // epilogue warps: 8 (one more smem stage) or 16 (epilogue-bound short-K GEMMs)
   double flops;   // algorithmic 2*M*N*K of the logical problem (no padding)
 };
 
-template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T, int DOT_T, int CS>
+template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T, int DOT_T, int CS, int EW>
 static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
-  using Cfg = GemmCfg<BN1, BN2, !AMN, (CS == 2) && !AMN>;
-  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, CS>;
+  using Cfg = GemmCfg<BN1, BN2, !AMN, (CS == 2) && !AMN, EW>;
+  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, CS, EW>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -95,7 +96,7 @@ static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(pl.grid);
-  cfg.blockDim = dim3(gemm_threads(AMN));
+  cfg.blockDim = dim3(gemm_threads(EW));
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -110,8 +111,11 @@ static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
 
 template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
 static cudaError_t launch_inst(const GemmPlan& pl, cudaStream_t s) {
-  if (pl.cs == 2) return launch_cs<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, 2>(pl, s);
-  return launch_cs<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, 1>(pl, s);
+  if constexpr (!AMN && ACT_T >= 0) {   // specialised K-major kernels: pair mode, epilogue warps by plan
+    if (pl.cs == 2 && pl.ew == 16) return launch_cs<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, 2, 16>(pl, s);
+  }
+  if (pl.cs == 2) return launch_cs<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, 2, 8>(pl, s);
+  return launch_cs<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, 1, 8>(pl, s);
 }
 
 // K-major 128x208 kernel: pick the compile-time-specialised epilogue when the plan's
@@ -170,6 +174,7 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
   // single-CTA (pairing 7 m-tiles wastes an eighth of the MMAs and measured slower)
   const int cs = (mode == 0 && cdiv(M, BM) >= 2 && c->num_sms % 2 == 0 && c->use_clusters) ? 2 : 1;
   pl->cs = cs;
+  pl->ew = (mode == 0 && cs == 2 && K < 512) ? 16 : 8;
   if (mode == 0) {
     if (ncover <= 64) { pl->kind = PK_NT_64; bn = 64; boxn = 64 / cs; }
     else { pl->kind = PK_NT_208; bn = 208; boxn = 208 / cs; }

@@ -23,11 +23,11 @@ namespace gm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kUmmaK = 16;
-// epilogue warps (2 per TMEM lane quarter).  16 warps on the K-major kernels measured no
-// faster than 8 (the epilogue is issue-bound, not latency-bound) and cost a pipeline stage
-// of shared memory, so both kernel families use 8
-constexpr int kEpiWarpsNT = 8, kEpiWarpsTN = 8;
-constexpr int gemm_threads(bool a_mn) { return 64 + (a_mn ? kEpiWarpsTN : kEpiWarpsNT) * 32; }
+// epilogue warps EW (template parameter): 8 (2 per TMEM lane quarter) or 16.  Measured: the
+// feed-bound long-K GEMMs (K = 784) want the extra smem pipeline stage 8 warps leave room for
+// (D1: 83.0 -> 79.5 us), the epilogue-bound short-K ones (K <= 400, sigmoid / aux epilogues)
+// want 16 warps (dX: 96.9 -> 84.9 us); the host picks per plan
+constexpr int gemm_threads(int epi_warps) { return 64 + epi_warps * 32; }
 constexpr int kSmemBudget = 225 * 1024;
 
 enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
@@ -71,7 +71,7 @@ constexpr int kEpiStageBytes = 32 * kEpiPitch;
 constexpr int kEpiVecBlocks = 8;                       // column blocks per warp the bias/dot staging holds
 constexpr int kEpiVecBytes = kEpiVecBlocks * kEpiCols * 4 * 2;   // bias + row-dot weights
 
-template <int BN1, int BN2, bool STAGED_EPI = true, bool PAIR = false>
+template <int BN1, int BN2, bool STAGED_EPI = true, bool PAIR = false, int EW = 8>
 struct GemmCfg {
   static constexpr int BN = BN1 + BN2;
   static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;
@@ -79,7 +79,8 @@ struct GemmCfg {
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // per-warp staging tile + per-warp copies of its blocks' bias / row-dot weight slices
-  static constexpr int EPI_WARPS = STAGED_EPI ? kEpiWarpsNT : kEpiWarpsTN;
+  static constexpr int EPI_WARPS = EW;
+  static_assert(EW == 8 || (EW == 16 && STAGED_EPI), "8 or 16 epilogue warps");
   static constexpr int EPI_BYTES = STAGED_EPI ? EPI_WARPS * (kEpiStageBytes + kEpiVecBytes) : 0;
   static_assert(!STAGED_EPI || (BN + kEpiCols - 1) / kEpiCols <= kEpiVecBlocks * (EPI_WARPS / 8), "bias/dot staging too small");
   static constexpr int STAGES_RAW = (kSmemBudget - EPI_BYTES) / STAGE_BYTES;
@@ -105,12 +106,12 @@ struct GemmCfg {
 //    completions of both CTAs are signalled on the leader's full barrier, slots / accumulators
 //    are released with multicast commits, peer epilogue warps release the accumulator remotely.
 //  * MN-major kernels: each CTA TMA-multicasts half of the shared B tile to both CTAs.
-template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1, int CS = 1>
-__global__ void __launch_bounds__(gemm_threads(A_MN), 1)
+template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1, int CS = 1, int EW = 8>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   constexpr bool PAIR = (CS == 2) && !A_MN;
-  using Cfg = GemmCfg<BN1, BN2, !A_MN, PAIR>;
+  using Cfg = GemmCfg<BN1, BN2, !A_MN, PAIR, EW>;
   constexpr int BN = Cfg::BN;
   constexpr int NACC = Cfg::NACC;
   constexpr int STAGES = Cfg::STAGES;
