@@ -148,7 +148,14 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
     cudaEventRecord(rec.e0, s);
   }
   switch (pl.kind) {
-    case PK_NT_208: e = launch_nt208(pl, s); break;
+    case PK_NT_208: {
+      // long-K GEMMs with a light epilogue are TMA-feed-bound: 8 epilogue warps leave smem for a
+      // 6th pipeline stage; aux epilogues and short-K GEMMs are epilogue-bound: 16 warps
+      GemmPlan q = pl;
+      if (q.cs == 2 && q.p.K >= 512 && q.p.aux_mode == AUX_NONE) q.ew = 8;
+      e = launch_nt208(q, s);
+      break;
+    }
     case PK_NT_64: e = launch_inst<64, 0, false, false>(pl, s); break;
     case PK_TN_448: e = launch_inst<256, 192, true, true>(pl, s); break;
     default: e = launch_inst<64, 0, true, true>(pl, s); break;
@@ -174,7 +181,7 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
   // single-CTA (pairing 7 m-tiles wastes an eighth of the MMAs and measured slower)
   const int cs = (mode == 0 && cdiv(M, BM) >= 2 && c->num_sms % 2 == 0 && c->use_clusters) ? 2 : 1;
   pl->cs = cs;
-  pl->ew = (mode == 0 && cs == 2 && K < 512) ? 16 : 8;
+  pl->ew = (mode == 0 && cs == 2) ? 16 : 8;   // refined per plan once its epilogue is known (launch_plan)
   if (mode == 0) {
     if (ncover <= 64) { pl->kind = PK_NT_64; bn = 64; boxn = 64 / cs; }
     else { pl->kind = PK_NT_208; bn = 208; boxn = 208 / cs; }

@@ -416,3 +416,97 @@ def vae_train(P, x, draws, steps, lr=1e-3, wd=1e-5):
         R.append(float(recon))
         K.append(float(kl))
     return np.array(R), np.array(K)
+
+
+# ---------------------------------------------------------------- InfoGAN (src/info_gan.py)
+def info_q_step(P, noise, z_dim=20, disc_dim=10, q=_exact):
+    """InfoGANTrainer.train_Q + MI_loss.backward() (src/info_gan.py:269-304): CE on the
+    categorical code + MSE on the continuous code (both torch means, LAMBDA = 1); returns
+    the loss and the gradients for G and Q."""
+    gf = g_forward(P, noise, q=q)
+    fake = gf["out"]
+    a1 = linear(fake, q("W", P["Q.linear.weight"]), P["Q.linear.bias"])
+    hq = q("h", np.maximum(a1, 0))
+    inf = linear(hq, q("W", P["Q.inference.weight"]), P["Q.inference.bias"])
+    B = noise.shape[0]
+    disc, cont = inf[:, :disc_dim], inf[:, disc_dim:]
+    tgt = np.argmax(noise[:, z_dim:z_dim + disc_dim], axis=1)
+    m = disc.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.sum(np.exp(disc - m), axis=1))
+    ce = np.mean(lse - disc[np.arange(B), tgt])
+    ctgt = noise[:, z_dim + disc_dim:]
+    mse = np.mean((cont - ctgt) ** 2)
+    L = ce + mse
+    sm = np.exp(disc - lse[:, None])
+    sm[np.arange(B), tgt] -= 1
+    dinf = q("dinf", np.concatenate([sm / B, 2 * (cont - ctgt) / cont.size], axis=1))
+    g = {}
+    g["Q.inference.weight"] = dinf.T @ hq
+    g["Q.inference.bias"] = dinf.sum(0)
+    dhq = q("dh", (dinf @ q("W", P["Q.inference.weight"])) * (hq > 0))
+    g["Q.linear.weight"] = dhq.T @ fake
+    g["Q.linear.bias"] = dhq.sum(0)
+    dfake = dhq @ q("W", P["Q.linear.weight"])
+    g.update(g_backward(P, gf, dfake, q=q))
+    return L, g
+
+
+# ---------------------------------------------------------------- BEGAN (src/be_gan.py)
+def began_ae(P, x, q=_exact):
+    """Discriminator = autoencoder x -> relu(We x + be) -> Wd e + bd (src/be_gan.py:63-76)."""
+    a1 = linear(x, q("W", P["D.encoder.weight"]), P["D.encoder.bias"])
+    e = q("h", np.maximum(a1, 0))
+    r = linear(e, q("W", P["D.decoder.weight"]), P["D.decoder.bias"])
+    return dict(x=x, e=e, r=r)
+
+
+def began_ae_backward(P, fw, dr, q=_exact, need_dx=False):
+    dr = q("dr", dr)
+    g = {"D.decoder.weight": dr.T @ fw["e"], "D.decoder.bias": dr.sum(0)}
+    de = q("dh", (dr @ q("W", P["D.decoder.weight"])) * (fw["e"] > 0))
+    g["D.encoder.weight"] = de.T @ fw["x"]
+    g["D.encoder.bias"] = de.sum(0)
+    return g, (de @ q("W", P["D.encoder.weight"]) if need_dx else None)
+
+
+def began_d_step(P, x, z, K, q=_exact):
+    """train_D + backward (src/be_gan.py:212-238,168-169): D_loss = DX - K*DG with L1
+    reconstruction losses; only D's gradients."""
+    B = x.shape[0]
+    gf = g_forward(P, z, q=q)
+    fx, fg = began_ae(P, x, q), began_ae(P, gf["out"], q)
+    DX = np.mean(np.sum(np.abs(fx["r"] - x), axis=1))
+    DG = np.mean(np.sum(np.abs(fg["r"] - gf["out"]), axis=1))
+    gx, _ = began_ae_backward(P, fx, np.sign(fx["r"] - x) / B, q)
+    gg, _ = began_ae_backward(P, fg, -K * np.sign(fg["r"] - gf["out"]) / B, q)
+    return DX - K * DG, {k: gx[k] + gg[k] for k in gx}, DX, DG
+
+
+def began_g_step(P, z, q=_exact):
+    """train_G + backward (src/be_gan.py:240-258,177-178): G_loss = E sum |D(G(z)) - G(z)|;
+    the gradient reaches G(z) both through D and directly."""
+    B = z.shape[0]
+    gf = g_forward(P, z, q=q)
+    fg = began_ae(P, gf["out"], q)
+    s = np.sign(fg["r"] - gf["out"]) / B
+    L = np.mean(np.sum(np.abs(fg["r"] - gf["out"]), axis=1))
+    _, dx = began_ae_backward(P, fg, s, q, need_dx=True)
+    return L, g_backward(P, gf, dx - q("dr", s), q=q)
+
+
+def began_train(P, x, draws, steps, G_lr=1e-4, D_lr=1e-4, GAMMA=0.5, LAMBDA=1e-3, K=0.0):
+    """BEGANTrainer.train inner loop (src/be_gan.py:147-195) incl. the proportional control
+    of K; the two ReduceLROnPlateau schedulers (patience 5 epochs) are inert over a few steps."""
+    draws = iter(draws)
+    optG = Adam([k for k in P if k.startswith("G.")], G_lr)
+    optD = Adam([k for k in P if k.startswith("D.")], D_lr)
+    Dl, Gl = [], []
+    for _ in range(steps):
+        L, g, DX, DG = began_d_step(P, x, next(draws), K)
+        optD.step(P, g)
+        Dl.append(float(L))
+        Lg, gg = began_g_step(P, next(draws))
+        optG.step(P, gg)
+        Gl.append(float(Lg))
+        K = min(max(0.0, K + LAMBDA * (GAMMA * DX - DG)), 1.0)
+    return np.array(Dl), np.array(Gl), K

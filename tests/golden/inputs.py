@@ -11,6 +11,11 @@ STEPS = 3
 
 GAN_SHAPES = [("G.linear", (H, Z)), ("G.generate", (X, H)),
               ("D.linear", (H, X)), ("D.discriminate", (1, H))]
+INFO_SHAPES = [("G.linear", (H, Z + 20)), ("G.generate", (X, H)),
+               ("D.linear", (H, X)), ("D.discriminator", (1, H)),
+               ("Q.linear", (H, X)), ("Q.inference", (20, H))]
+BEGAN_SHAPES = [("G.linear", (H, Z)), ("G.generate", (X, H)),
+                ("D.encoder", (H, X)), ("D.decoder", (X, H))]
 VAE_SHAPES = [("encoder.linear", (H, X)), ("encoder.mu", (Z, H)), ("encoder.log_var", (Z, H)),
               ("decoder.linear", (H, Z)), ("decoder.recon", (X, H))]
 

@@ -141,6 +141,8 @@ GAN_CASES = {
     "ra":      ("ra_gan", "RaNSGAN", "RaNSGANTrainer", dict(G_lr=2e-4, D_lr=2e-4, D_steps=1)),
     "fisher":  ("fisher_gan", "FisherGAN", "FisherGANTrainer", dict(G_lr=1e-4, D_lr=1e-4, D_steps=1, RHO=1e-6)),
 }
+GAN_CASES["info"] = ("info_gan", "InfoGAN", "InfoGANTrainer", dict(G_lr=2e-4, D_lr=2e-4, D_steps=1))
+GAN_CASES["began"] = ("be_gan", "BEGAN", "BEGANTrainer", dict(G_lr=1e-4, D_lr=1e-4, D_steps=1, GAMMA=0.5, LAMBDA=1e-3, K=0.0))
 for _m in ["total_variation", "forward_kl", "reverse_kl", "pearson", "hellinger", "jensen_shannon"]:
     GAN_CASES["f_" + _m] = ("f_gan", "fGAN", "fGANTrainer",
                             dict(method=_m, G_lr=1e-4, D_lr=1e-4, D_steps=1))
@@ -150,7 +152,15 @@ def make_gan_case(case):
     modname, mcls, tcls, kw = GAN_CASES[case]
     mod = import_ref(modname)
     torch.set_num_threads(1)
-    weights = gm_init_weights(GAN_SHAPES, seed=1234)
+    from inputs import INFO_SHAPES, BEGAN_SHAPES
+    shapes = INFO_SHAPES if case == "info" else (BEGAN_SHAPES if case == "began" else GAN_SHAPES)
+    weights = gm_init_weights(shapes, seed=1234)
+
+    def build_model():
+        if case == "info":
+            return getattr(mod, mcls)(X, H, Z, 10, 10)
+        return getattr(mod, mcls)(X, H, Z)
+
     imgs = gm_images(B)
     images4d = torch.from_numpy(imgs.copy()).view(B, 1, 28, 28)
     labels = torch.zeros(B, dtype=torch.long)
@@ -158,27 +168,47 @@ def make_gan_case(case):
     out = {"images_bits": np.packbits(imgs.astype(np.uint8), axis=None)}
 
     # ---- (1) the reference's own train() ---------------------------------
-    model = getattr(mod, mcls)(X, H, Z)
+    model = build_model()
     load_weights(model, weights)
     # list iterator: next(iter(list)) == first batch every time, no RNG use;
     # len(list) fixes epoch_steps = ceil(len/D_steps) (src/ns_gan.py:114)
     it = [(images4d, labels)] * (STEPS * d_steps)
     trainer = getattr(mod, tcls)(model, it, it, it, viz=False)
     torch.manual_seed(20240923)
+    noises = []
+    if case == "info":      # structured noise z + onehot + N(0,1): record what compute_noise returns
+        orig_cn = trainer.compute_noise
+
+        def cn(*a, **k):
+            t = orig_cn(*a, **k)
+            noises.append(("randn", t.detach().clone().numpy()))
+            return t
+        trainer.compute_noise = cn
     with DrawRecorder() as rec:
         trainer.train(num_epochs=1, **kw)
     out["D_loss"] = np.asarray(trainer.Dlosses, dtype=np.float64)
     out["G_loss"] = np.asarray(trainer.Glosses, dtype=np.float64)
-    pack_draws(rec.draws, out)
+    if case == "info":
+        out["MI_loss"] = np.asarray(trainer.MIlosses, dtype=np.float64)
+    pack_draws(noises if case == "info" else rec.draws, out)
     for name, p in model.state_dict().items():
         summarise("final_" + name, p.numpy(), out)
     if case == "fisher":
         out["final_LAMBDA"] = trainer.LAMBDA.detach().numpy().astype(np.float32)
 
     # ---- (2) step-1 detail: reference train_D/train_G called by hand -----
-    model2 = getattr(mod, mcls)(X, H, Z)
+    model2 = build_model()
     load_weights(model2, weights)
     tr2 = getattr(mod, tcls)(model2, it, it, it, viz=False)
+    noises2 = []
+    if case == "info":
+        orig_cn2 = tr2.compute_noise
+
+        def cn2(*a, **k):
+            t = orig_cn2(*a, **k)
+            noises2.append(("randn", t.detach().clone().numpy()))
+            return t
+        tr2.compute_noise = cn2
     if case.startswith("f_"):
         tr2.loss_fnc = mod.Divergence(kw["method"])
     if case == "fisher":
@@ -195,7 +225,9 @@ def make_gan_case(case):
         # the *initial* weights with its own seed, stored under step1_draws.
         pass
     with DrawRecorder() as rec2:
-        D_loss = tr2.train_D(images)
+        D_loss = tr2.train_D(images, 0.3) if case == "began" else tr2.train_D(images)
+        if case == "began":
+            out["step1_DX_loss"], out["step1_DG_loss"] = np.float64(D_loss[1].item()), np.float64(D_loss[2].item())
         if isinstance(D_loss, tuple):
             D_loss = D_loss[0]
         for p in model2.parameters():
@@ -212,12 +244,22 @@ def make_gan_case(case):
         out["step1_G_loss"] = np.float64(G_loss.item())
         for name, p in model2.G.named_parameters():
             summarise("step1_Ggrad_" + name, p.grad.numpy(), out)
+        if case == "info":
+            for p in model2.parameters():
+                p.grad = None
+            MI = tr2.train_Q(images)
+            MI.backward()
+            out["step1_MI_loss"] = np.float64(MI.item())
+            for name, p in model2.G.named_parameters():
+                summarise("step1_MI_Ggrad_" + name, p.grad.numpy(), out)
+            for name, p in model2.Q.named_parameters():
+                summarise("step1_MI_Qgrad_" + name, p.grad.numpy(), out)
     hook.remove()
     for k, s in enumerate(scores):
         out["step1_score_%d" % k] = s.reshape(-1)
     out["step1_n_scores_D"] = np.int64(n_scores_d)
     d2 = {}
-    pack_draws(rec2.draws, d2)
+    pack_draws(noises2 if case == "info" else rec2.draws, d2)
     for k, v in d2.items():
         out["step1_" + k] = v
     np.savez_compressed(os.path.join(HERE, "gan_%s.npz" % case), **out)

@@ -110,3 +110,44 @@ def test_vae_step1_and_trajectory():
             upd = P[k].ravel()[idx] - P0[k].ravel()[idx]
             ref_upd = fx["final_" + k + "__samp"].astype(np.float64) - P0[k].ravel()[idx]
         assert np.linalg.norm(upd - ref_upd) / max(np.linalg.norm(ref_upd), 1e-12) < 2e-3, k
+
+
+def test_infogan_step1_and_q_step():
+    from inputs import INFO_SHAPES
+    fx = load_case("gan_info")
+    P = params_dict(gm_init_weights(INFO_SHAPES, 1234), np.float64)
+    Pn = {k.replace("D.discriminator", "D.discriminate"): v for k, v in P.items()}   # oracle uses the NS names
+    x = images_from_bits(fx).astype(np.float64)
+    d = [t.astype(np.float64) for t in unpack_draws(fx, "step1_")]
+    L, g, _ = R.gan_d_step(Pn, "info", x, d[0])
+    assert abs(L - fx["step1_D_loss"]) <= 2e-6 * abs(fx["step1_D_loss"])
+    for k, v in g.items():
+        check_summary(fx, "step1_Dgrad_" + k[2:].replace("discriminate", "discriminator"), v, rtol=3e-4, atol=1e-9)
+    Lg, gg, _ = R.gan_g_step(Pn, "info", d[1])
+    assert abs(Lg - fx["step1_G_loss"]) <= 2e-6 * abs(fx["step1_G_loss"])
+    Lq, gq = R.info_q_step(Pn, d[2])
+    assert abs(Lq - fx["step1_MI_loss"]) <= 2e-6 * abs(fx["step1_MI_loss"])
+    for k, v in gq.items():
+        pre = "step1_MI_Ggrad_" if k.startswith("G.") else "step1_MI_Qgrad_"
+        check_summary(fx, pre + k[2:], v, rtol=3e-4, atol=1e-9)
+
+
+def test_began_step1_and_trajectory():
+    from inputs import BEGAN_SHAPES
+    fx = load_case("gan_began")
+    P0 = params_dict(gm_init_weights(BEGAN_SHAPES, 1234), np.float64)
+    x = images_from_bits(fx).astype(np.float64)
+    d = [t.astype(np.float64) for t in unpack_draws(fx, "step1_")]
+    L, g, DX, DG = R.began_d_step(P0, x, d[0], 0.3)
+    assert abs(L - fx["step1_D_loss"]) <= 2e-6 * abs(fx["step1_D_loss"])
+    assert abs(DX - fx["step1_DX_loss"]) <= 2e-6 * DX and abs(DG - fx["step1_DG_loss"]) <= 2e-6 * DG
+    for k, v in g.items():
+        check_summary(fx, "step1_Dgrad_" + k[2:], v, rtol=3e-4, atol=1e-9)
+    Lg, gg = R.began_g_step(P0, d[1])
+    assert abs(Lg - fx["step1_G_loss"]) <= 2e-6 * abs(fx["step1_G_loss"])
+    for k, v in gg.items():
+        check_summary(fx, "step1_Ggrad_" + k[2:], v, rtol=3e-4, atol=1e-9)
+    P = dict(P0)
+    Dl, Gl, K = R.began_train(P, x, [t.astype(np.float64) for t in unpack_draws(fx)], STEPS)
+    np.testing.assert_allclose(Dl, fx["D_loss"], rtol=5e-5)
+    np.testing.assert_allclose(Gl, fx["G_loss"], rtol=5e-5)
