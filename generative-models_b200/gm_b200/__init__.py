@@ -5,4 +5,4 @@ declared in include/gm_b200.h.  There is no CPU or eager-PyTorch fallback: impor
 works anywhere, but creating a context without a B200 raises."""
 from ._lib import (GmError, lib, lib_path, ctx, gemm_bf16, adam_step, launch_count,  # noqa: F401
                    VARIANTS, OUT_ACTS, IMG_FMTS, AdamHP, prof_enable, prof_collect)
-from .engine import GanEngine, VaeEngine  # noqa: F401
+from .engine import GanEngine, InfoGanEngine, VaeEngine  # noqa: F401

@@ -82,6 +82,11 @@ def lib():
     L.gm_gan_apply.argtypes = [vp, i, C.POINTER(AdamHP), i, vp]
     L.gm_gan_scores.argtypes = [vp, vp, i, vp]
     L.gm_gan_generate.argtypes = [vp, vp, i, vp, vp]
+    L.gm_gan_q_param_count.argtypes = [vp]
+    L.gm_gan_bind_q.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.gm_gan_sync_shadows_q.argtypes = [vp, vp]
+    L.gm_gan_q_grad.argtypes = [vp, i, vp, i, f, vp, vp]
+    L.gm_gan_apply_mi.argtypes = [vp, C.POINTER(AdamHP), i, vp]
     L.gm_gan_discriminate.argtypes = [vp, vp, i, i, vp, vp]
     L.gm_vae_create.argtypes = [vp, C.POINTER(VaeDesc), C.POINTER(vp)]
     L.gm_vae_destroy.argtypes = [vp]

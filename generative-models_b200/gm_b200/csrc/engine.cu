@@ -391,6 +391,7 @@ struct NetLayout {
 
 struct StepPlans {
   GemmPlan g1, g2, d1_d, d1_g, d1_x, dw1d, dx, dw2g, dhg, dw1g, gp_v, gp_t;
+  GemmPlan q1, q2, gq2, dhq, gq1, dfq;   // InfoGAN Q head
 };
 
 struct gm_gan {
@@ -411,6 +412,14 @@ struct gm_gan {
   float *dw2p2 = nullptr, *dw2p3 = nullptr, *slots_v = nullptr, *coef = nullptr, *stats = nullptr;
   double *gp_part = nullptr, *mom_part = nullptr;
   int nreg = 2;                  // row regions of Xall/Aall/DHall: real, fake (, xhat, R)
+  // InfoGAN: auxiliary network Q (image -> hidden -> disc+cont codes), its own Adam state and a
+  // SECOND Adam state for G (MI_optimizer spans G and Q, src/info_gan.py:146-148)
+  NetLayout Qn;
+  int q_out = 0;
+  float *parQ = nullptr, *grdQ = nullptr, *amQ = nullptr, *avQ = nullptr, *amG2 = nullptr, *avG2 = nullptr;
+  __nv_bfloat16 *Wq1_s = nullptr, *Wq1_t = nullptr, *Wq2_s = nullptr, *Wq2_t = nullptr, *HQ = nullptr, *DINF = nullptr, *DHQ = nullptr;
+  float *INF = nullptr, *PQ1 = nullptr, *PQ2 = nullptr;
+  double* q_part = nullptr;
   double* loss_part = nullptr;   // 3 x [loss_blocks][4]
   int loss_blocks = 0;
   float *PD = nullptr, *PG2 = nullptr, *PG1 = nullptr;
@@ -449,7 +458,6 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
     return fail(c, GM_ERR_ARG, "image_size and hidden_dim must be positive multiples of 16 (got %d, %d, z=%d)",
                 d->image_size, d->hidden_dim, d->z_dim);
   if (d->max_batch <= 0) return fail(c, GM_ERR_ARG, "max_batch must be positive (got %d)", d->max_batch);
-  if (d->variant == GM_INFO) return fail(c, GM_ERR_UNSUPPORTED, "variant %d is not built yet", d->variant);
   gm_gan* g = new gm_gan();
   g->ctx = c;
   g->d = *d;
@@ -509,6 +517,21 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   TRY(dev_alloc(g, &g->PD, size_t(sp_d) * g->H * (cdiv(g->X + 1, BM) * BM)));
   TRY(dev_alloc(g, &g->PG2, size_t(sp_g2) * g->X * rup(g->H + 1, 64)));
   TRY(dev_alloc(g, &g->PG1, size_t(sp_g1) * g->H * 64 * cdiv(g->Z + 1, 64)));
+  if (d->variant == GM_INFO) {
+    g->q_out = 20;   // 10 categorical logits + 10 continuous codes (src/info_gan.py:403-407)
+    g->Qn.init(g->X, g->H, g->q_out);
+    TRY(dev_alloc(g, &g->Wq1_s, size_t(g->H) * g->X));
+    TRY(dev_alloc(g, &g->Wq1_t, size_t(g->X) * g->H));
+    TRY(dev_alloc(g, &g->Wq2_s, size_t(64) * g->H));
+    TRY(dev_alloc(g, &g->Wq2_t, size_t(g->H) * 64));
+    TRY(dev_alloc(g, &g->HQ, B * g->HP));
+    TRY(dev_alloc(g, &g->DINF, B * 64));
+    TRY(dev_alloc(g, &g->DHQ, B * g->HP));
+    TRY(dev_alloc(g, &g->INF, B * 32));
+    TRY(dev_alloc(g, &g->PQ1, size_t(sp_g1) * g->H * 896));
+    TRY(dev_alloc(g, &g->PQ2, size_t(c->num_sms) * 64 * 448));
+    TRY(dev_alloc(g, &g->q_part, size_t(c->num_sms) * 2 * 4));
+  }
 #undef TRY
   if (g->H + 1 > 448 || g->Z + 1 > 64) {
     gm_gan_destroy(g);
@@ -649,6 +672,28 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
     GemmParams& p = sp.dw1g.p;
     p.epi = EPI_F32; p.part = g->PG1; p.ldp = 64; p.part_stride = (long long)H * 64; p.transpose = 0;
     sp.dw1g.flops = 2.0 * H * Z * B;
+  }
+  if (g->d.variant == GM_INFO && g->parQ != nullptr) {
+    const float* pQ = g->parQ;
+    const int QO = g->q_out;
+    if ((rc = plan_gemm(c, &sp.q1, 0, B, H, X, Xfake, XP, g->Wq1_s, X, HP, 1))) return rc;
+    set_bf16_epi(sp.q1.p, g->HQ, HP, HP, 1, pQ + g->Qn.off_b1, ACT_RELU);
+    if ((rc = plan_gemm(c, &sp.q2, 0, B, QO, H, g->HQ, HP, g->Wq2_s, H, QO, 1))) return rc;
+    sp.q2.p.epi = EPI_F32; sp.q2.p.part = g->INF; sp.q2.p.ldp = 32; sp.q2.p.part_stride = 0; sp.q2.p.transpose = 0;
+    sp.q2.p.bias = pQ + g->Qn.off_b2;
+    if ((rc = plan_gemm(c, &sp.gq2, 1, QO, H + 1, B, g->DINF, 64, g->HQ, HP, H + 1, g->max_splits))) return rc;
+    { GemmParams& p = sp.gq2.p; p.epi = EPI_F32; p.part = g->PQ2; p.ldp = 448; p.part_stride = (long long)64 * 448; p.transpose = 0;
+      sp.gq2.flops = 2.0 * QO * H * B; }
+    if ((rc = plan_gemm(c, &sp.dhq, 0, B, H, rup(QO, 16), g->DINF, 64, g->Wq2_t, 64, H, 1))) return rc;
+    set_bf16_epi(sp.dhq.p, g->DHQ, HP, H, 0, nullptr, ACT_NONE);
+    sp.dhq.p.aux = g->HQ; sp.dhq.p.ld_aux = HP; sp.dhq.p.aux_mode = AUX_RELU_MASK;
+    sp.dhq.flops = 2.0 * B * H * QO;
+    if ((rc = plan_gemm(c, &sp.gq1, 1, H, X + 1, B, g->DHQ, HP, Xfake, XP, X + 1, g->max_splits))) return rc;
+    { GemmParams& p = sp.gq1.p; p.epi = EPI_F32; p.part = g->PQ1; p.ldp = p.n_tiles * 448; p.part_stride = (long long)H * p.ldp; p.transpose = 0;
+      sp.gq1.flops = 2.0 * H * X * B; }
+    if ((rc = plan_gemm(c, &sp.dfq, 0, B, X, H, g->DHQ, HP, g->Wq1_t, H, X, 1))) return rc;
+    set_bf16_epi(sp.dfq.p, g->DA2, XP, X, 0, nullptr, ACT_NONE);
+    sp.dfq.p.aux = Xfake; sp.dfq.p.ld_aux = XP; sp.dfq.p.aux_mode = AUX_SIGMOID_GRAD;
   }
   g->plans[B] = sp;
   *out = &g->plans[B];
@@ -822,6 +867,114 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   g->last_rows = B;
   CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}
+
+// ---- InfoGAN: auxiliary network Q and the mutual-information step (src/info_gan.py:269-304,196-205)
+extern "C" int gm_gan_bind_q(gm_gan* g, float* q_params, float* q_grads, float* q_m, float* q_v, float* g_mi_m, float* g_mi_v) {
+  if (!g || !q_params || !q_grads) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_bind_q: bad argument") : GM_ERR_ARG;
+  if (g->d.variant != GM_INFO) return fail(g->ctx, GM_ERR_STATE, "gm_gan_bind_q: engine was not created with GM_INFO");
+  g->parQ = q_params; g->grdQ = q_grads; g->amQ = q_m; g->avQ = q_v; g->amG2 = g_mi_m; g->avG2 = g_mi_v;
+  g->plans.clear();
+  return GM_OK;
+}
+extern "C" int gm_gan_q_param_count(const gm_gan* g) { return (g && g->d.variant == GM_INFO) ? g->Qn.total : GM_ERR_ARG; }
+
+static void q_adam_segs(gm_gan* g, AdamParams& a) {
+  a.total = g->Qn.total;
+  a.nseg = 2;
+  a.seg[0] = {g->Qn.off_w1, g->H * g->X, g->X, g->Wq1_s, g->X, g->Wq1_t, g->H};
+  a.seg[1] = {g->Qn.off_w2, g->q_out * g->H, g->H, g->Wq2_s, g->H, g->Wq2_t, 64};
+}
+extern "C" int gm_gan_sync_shadows_q(gm_gan* g, gm_stream stream) {
+  if (!g || !g->parQ) return g ? fail(g->ctx, GM_ERR_STATE, "Q not bound") : GM_ERR_ARG;
+  AdamParams a;
+  memset(&a, 0, sizeof a);
+  a.p = g->parQ; a.update = 0;
+  q_adam_segs(g, a);
+  adam_kernel<<<cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+// train_Q + MI_loss.backward(): writes the flat G gradient (G's grad buffer), the flat Q
+// gradient and loss_dev[0].  noise_dev [batch, z_total] fp32 is required (structured noise:
+// z, one-hot code at [zd, zd+10), continuous code at [zd+10, zd+20)).
+extern "C" int gm_gan_q_grad(gm_gan* g, int batch, const float* noise, int zd, float inv_global_batch, float* loss_dev,
+                             gm_stream stream) {
+  int rc = check_step_args(g, batch);
+  if (rc) return rc;
+  if (g->d.variant != GM_INFO || !g->parQ) return fail(g->ctx, GM_ERR_STATE, "bind Q first (GM_INFO engines only)");
+  if (!noise) return fail(g->ctx, GM_ERR_ARG, "the Q step needs the structured noise tensor");
+  if (zd + g->q_out != g->Z) return fail(g->ctx, GM_ERR_ARG, "z_dim (%d) + codes (%d) != generator input (%d)", zd, g->q_out, g->Z);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StepPlans* sp;
+  if ((rc = build_plans(g, batch, &sp))) return rc;
+  const int B = batch;
+  gm_ctx* c = g->ctx;
+  if ((rc = run_generator(g, sp, B, noise, 0, 0, s))) return rc;
+  if ((rc = launch_plan(c, sp->q1, s))) return rc;
+  if ((rc = launch_plan(c, sp->q2, s))) return rc;
+  const int nb = cdiv(B, kLossThreads) < c->num_sms * 2 ? cdiv(B, kLossThreads) : c->num_sms * 2;
+  info_loss_kernel<<<nb, kLossThreads, 0, s>>>(g->INF, 32, noise, g->Z, zd, 10, 10, B, inv_global_batch, g->DINF, 64, g->q_part);
+  info_loss_final_kernel<<<1, kLossThreads, 0, s>>>(g->q_part, nb, B, 10, g->lossbuf);
+  c->launches += 2;
+  if ((rc = launch_plan(c, sp->gq2, s))) return rc;
+  if ((rc = launch_plan(c, sp->dhq, s))) return rc;
+  if ((rc = launch_plan(c, sp->gq1, s))) return rc;
+  if ((rc = launch_plan(c, sp->dfq, s))) return rc;
+  if ((rc = launch_plan(c, sp->dw2g, s))) return rc;
+  if ((rc = launch_plan(c, sp->dhg, s))) return rc;
+  if ((rc = launch_plan(c, sp->dw1g, s))) return rc;
+  GradSegs gs;
+  memset(&gs, 0, sizeof gs);
+  const GemmParams& p2 = sp->dw2g.p;
+  const GemmParams& p1 = sp->dw1g.p;
+  gs.nseg = 4;
+  gs.total = g->G.total;
+  gs.s[0] = {g->G.off_w1, g->H * g->Z, 0, g->Z, p1.ldp, 0, p1.splits, p1.part_stride, g->PG1};
+  gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
+  gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
+  gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
+  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_G]);
+  GradSegs qs;
+  memset(&qs, 0, sizeof qs);
+  const GemmParams& q1 = sp->gq1.p;
+  const GemmParams& q2 = sp->gq2.p;
+  qs.nseg = 4;
+  qs.total = g->Qn.total;
+  qs.s[0] = {g->Qn.off_w1, g->H * g->X, 0, g->X, q1.ldp, 0, q1.splits, q1.part_stride, g->PQ1};
+  qs.s[1] = {g->Qn.off_b1, g->H, 2, 0, q1.ldp, g->X, q1.splits, q1.part_stride, g->PQ1};
+  qs.s[2] = {g->Qn.off_w2, g->q_out * g->H, 0, g->H, q2.ldp, 0, q2.splits, q2.part_stride, g->PQ2};
+  qs.s[3] = {g->Qn.off_b2, g->q_out, 2, 0, q2.ldp, g->H, q2.splits, q2.part_stride, g->PQ2};
+  finalize_grads_kernel<<<cdiv(qs.total, 256), 256, 0, s>>>(qs, g->grdQ);
+  c->launches += 2;
+  if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}
+
+// MI_optimizer.step(): Adam over G (with its OWN moment buffers, separate from G_optimizer's)
+// and over Q (src/info_gan.py:146-148,205); refreshes both nets' operand copies.
+extern "C" int gm_gan_apply_mi(gm_gan* g, const gm_adam_hp* hp, int step, gm_stream stream) {
+  if (!g || !hp || step <= 0) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_apply_mi: bad argument") : GM_ERR_ARG;
+  if (!g->parQ || !g->amQ || !g->avQ || !g->amG2 || !g->avG2) return fail(g->ctx, GM_ERR_STATE, "Q / MI optimizer state not bound");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  AdamParams a;
+  memset(&a, 0, sizeof a);
+  a.p = g->par[GM_NET_G]; a.g = g->grd[GM_NET_G]; a.m = g->amG2; a.v = g->avG2;
+  fill_adam(a, hp, step);
+  adam_segs(g, GM_NET_G, a);
+  adam_kernel<<<cdiv(a.total, 256), 256, 0, s>>>(a);
+  AdamParams q;
+  memset(&q, 0, sizeof q);
+  q.p = g->parQ; q.g = g->grdQ; q.m = g->amQ; q.v = g->avQ;
+  fill_adam(q, hp, step);
+  q_adam_segs(g, q);
+  adam_kernel<<<cdiv(q.total, 256), 256, 0, s>>>(q);
+  g->ctx->launches += 2;
+  CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
 }
 

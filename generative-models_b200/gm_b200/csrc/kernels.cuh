@@ -577,6 +577,50 @@ __global__ void vae_losses_final_kernel(const double* __restrict__ part_r, int n
   if (threadIdx.x == 0) { losses[0] = float(a); losses[1] = float(b); }
 }
 
+// ---------------------------------------------------------------- InfoGAN Q head (src/info_gan.py:290-302)
+// inf fp32 [rows, ldi]: [0,nd) categorical logits, [nd, nd+nc) continuous code.  noise fp32
+// [rows, ldn]: columns [zd, zd+nd) one-hot target, [zd+nd, zd+nd+nc) continuous target.
+// loss = mean_r CE(logits_r, argmax onehot_r) + mean_{r,c} (cont - target)^2; writes
+// d loss / d inf (x inv_b-style scaling for data parallel) as bf16 [rows, ldo] (zero padded).
+__global__ void __launch_bounds__(kLossThreads) info_loss_kernel(const float* __restrict__ inf, int ldi,
+                                                                  const float* __restrict__ noise, int ldn, int zd, int nd,
+                                                                  int nc, int rows, float inv_b,
+                                                                  __nv_bfloat16* __restrict__ dinf, int ldo,
+                                                                  double* __restrict__ part) {
+  __shared__ double sh[kLossThreads / 32];
+  double ce = 0, mse = 0;
+  for (int r = blockIdx.x * kLossThreads + threadIdx.x; r < rows; r += gridDim.x * kLossThreads) {
+    const float* v = inf + (long long)r * ldi;
+    const float* t = noise + (long long)r * ldn;
+    int tgt = 0;
+    float best = t[zd];
+    for (int c = 1; c < nd; ++c) if (t[zd + c] > best) { best = t[zd + c]; tgt = c; }   // torch.max: first maximum
+    float m = v[0];
+    for (int c = 1; c < nd; ++c) m = fmaxf(m, v[c]);
+    float se = 0.f;
+    for (int c = 0; c < nd; ++c) se += expf(v[c] - m);
+    const float lse = m + logf(se);
+    ce += lse - v[tgt];
+    __nv_bfloat16* o = dinf + (long long)r * ldo;
+    for (int c = 0; c < nd; ++c) o[c] = __float2bfloat16_rn((expf(v[c] - lse) - (c == tgt ? 1.f : 0.f)) * inv_b);
+    for (int c = 0; c < nc; ++c) {
+      const float d = v[nd + c] - t[zd + nd + c];
+      mse += (double)d * d;
+      o[nd + c] = __float2bfloat16_rn(2.f * d * inv_b / nc);
+    }
+    for (int c = nd + nc; c < ldo; ++c) o[c] = __float2bfloat16_rn(0.f);
+  }
+  ce = block_sum<kLossThreads>(ce, sh);
+  mse = block_sum<kLossThreads>(mse, sh);
+  if (threadIdx.x == 0) { part[blockIdx.x * 4] = ce; part[blockIdx.x * 4 + 1] = mse; }
+}
+__global__ void __launch_bounds__(kLossThreads) info_loss_final_kernel(const double* __restrict__ part, int nblk, int rows,
+                                                                        int nc, float* __restrict__ loss) {
+  __shared__ double sh[kLossThreads / 32];
+  const double ce = reduce_partials4(part, nblk, 0, sh), mse = reduce_partials4(part, nblk, 1, sh);
+  if (threadIdx.x == 0) loss[0] = float(ce / rows + mse / ((double)rows * nc));
+}
+
 // ---------------------------------------------------------------- gradient finalisation
 // flat_grad[dst_off + i] = sum over `nsplit` partial copies of src[map(i)]:
 //   kind 0 (matrix, rows x cols):  src[r*ld + c]        (partial stored as [rows][ld])

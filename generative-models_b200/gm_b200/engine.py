@@ -138,6 +138,70 @@ class GanEngine:
         return buf[0], buf[1]
 
 
+class InfoGanEngine(GanEngine):
+    """GanEngine + the auxiliary network Q and the mutual-information step of InfoGAN
+    (src/info_gan.py:78-94,269-304).  The generator input is z + disc_dim + cont_dim wide."""
+
+    def __init__(self, image_size=784, hidden_dim=400, z_dim=20, disc_dim=10, cont_dim=10, max_batch=64, device=None):
+        if (disc_dim, cont_dim) != (10, 10):
+            raise GmError("the fused Q head is built for disc_dim = cont_dim = 10 (the reference's setting)")
+        super().__init__(image_size, hidden_dim, z_dim + disc_dim + cont_dim, max_batch, variant="info", device=device)
+        self.noise_dim, self.code_z = z_dim + disc_dim + cont_dim, z_dim
+        nq = lib().gm_gan_q_param_count(self.g)
+        kw = dict(device=self.device, dtype=torch.float32)
+        self.q_params, self.q_grads = torch.zeros(nq, **kw), torch.zeros(nq, **kw)
+        self.q_exp_avg, self.q_exp_avg_sq = torch.zeros(nq, **kw), torch.zeros(nq, **kw)
+        self.g_mi_exp_avg, self.g_mi_exp_avg_sq = torch.zeros(self.n[G], **kw), torch.zeros(self.n[G], **kw)
+        check(self.h, lib().gm_gan_bind_q(self.g, _ptr(self.q_params), _ptr(self.q_grads), _ptr(self.q_exp_avg),
+                                          _ptr(self.q_exp_avg_sq), _ptr(self.g_mi_exp_avg), _ptr(self.g_mi_exp_avg_sq)))
+        H, X = hidden_dim, image_size
+        self.q_shapes = [(H, X), (H,), (disc_dim + cont_dim, H), (disc_dim + cont_dim,)]
+        self.mi_steps = 0
+
+    def q_views(self, flat=None):
+        flat = self.q_params if flat is None else flat
+        out, off = [], 0
+        for shp in self.q_shapes:
+            n = 1
+            for s in shp:
+                n *= s
+            out.append(flat[off:off + n].view(shp))
+            off += n
+        return out
+
+    def load_q(self, tensors):
+        for dst, src in zip(self.q_views(), tensors):
+            dst.copy_(torch.as_tensor(src, dtype=torch.float32).reshape(dst.shape))
+        self.sync_shadows_q()
+
+    def sync_shadows_q(self):
+        check(self.h, lib().gm_gan_sync_shadows_q(self.g, _stream()))
+
+    def sync_all(self):
+        super().sync_all()
+        self.sync_shadows_q()
+
+    sync_if_stale = sync_all
+
+    def reset_optimizer(self):
+        super().reset_optimizer()
+        for t in (self.q_exp_avg, self.q_exp_avg_sq, self.g_mi_exp_avg, self.g_mi_exp_avg_sq):
+            t.zero_()
+        self.mi_steps = 0
+
+    def q_grad(self, batch, noise, inv_global_batch=None):
+        """train_Q + backward (src/info_gan.py:269-304,204): G and Q gradients, MI loss."""
+        inv = 1.0 / batch if inv_global_batch is None else inv_global_batch
+        if not hasattr(self, "mi_loss_buf"):
+            self.mi_loss_buf = torch.zeros(1, device=self.device)
+        check(self.h, lib().gm_gan_q_grad(self.g, batch, _ptr(noise), self.code_z, inv, _ptr(self.mi_loss_buf), _stream()))
+        return self.mi_loss_buf[0]
+
+    def apply_mi(self, hp):
+        self.mi_steps += 1
+        check(self.h, lib().gm_gan_apply_mi(self.g, C.byref(hp), self.mi_steps, _stream()))
+
+
 class VaeEngine:
     """One MLP VAE (x -> hidden -> (mu, log_var) ; z -> hidden -> x) on one GPU.  The flat
     layout puts the two latent heads next to each other (one 400 -> 2z GEMM):

@@ -135,6 +135,19 @@ int gm_gan_scores(gm_gan* gan, float* dst_dev, int n, gm_stream stream);
 /* Generator.forward (src/ns_gan.py:43-46) for sampling: noise [n, z] fp32 -> images
  * [n, image_size] fp32. */
 int gm_gan_generate(gm_gan* gan, const float* noise_dev, int n, float* images_dev, gm_stream stream);
+/* InfoGAN (GM_INFO engines; generator input = z + 10 categorical + 10 continuous codes):
+ * the auxiliary network Q (src/info_gan.py:78-94), flat layout [linear.W | .b | inference.W | .b];
+ * g_mi_* are the G moment buffers of MI_optimizer, which spans G and Q (src/info_gan.py:146-148). */
+int gm_gan_q_param_count(const gm_gan* gan);
+int gm_gan_bind_q(gm_gan* gan, float* q_params_dev, float* q_grads_dev, float* q_exp_avg_dev, float* q_exp_avg_sq_dev,
+                  float* g_mi_exp_avg_dev, float* g_mi_exp_avg_sq_dev);
+int gm_gan_sync_shadows_q(gm_gan* gan, gm_stream stream);
+/* train_Q + MI_loss.backward() (src/info_gan.py:269-304,204): CE on the categorical code
+ * + MSE on the continuous code; writes the flat G and Q gradients and loss_dev[0]. */
+int gm_gan_q_grad(gm_gan* gan, int batch, const float* noise_dev, int z_dim, float inv_global_batch, float* loss_dev,
+                  gm_stream stream);
+/* MI_optimizer.step() (src/info_gan.py:205). */
+int gm_gan_apply_mi(gm_gan* gan, const gm_adam_hp* hp, int step, gm_stream stream);
 /* Discriminator.forward (src/ns_gan.py:57-60) for inference: images [n, image_size]
  * (gm_img_fmt) -> scores [n] fp32. */
 int gm_gan_discriminate(gm_gan* gan, const void* images_dev, int img_fmt, int n, float* scores_dev, gm_stream stream);

@@ -203,3 +203,55 @@ def test_generate_matches_reference_forward():
     Wg1, bg1, Wg2, bg2 = eng.views(0)
     ref = torch.sigmoid(torch.relu(z @ Wg1.t() + bg1) @ Wg2.t() + bg2)
     assert _nrel(out.cpu().numpy(), ref.cpu().numpy()) < 5e-3
+
+
+def test_infogan_steps_against_golden_and_oracle():
+    """InfoGAN: D and G steps are NS with a 40-wide generator input; the Q / MI step
+    (src/info_gan.py:269-304) trains G and Q."""
+    import gm_b200
+    from inputs import INFO_SHAPES
+    fx = load_case("gan_info")
+    W = gm_init_weights(INFO_SHAPES, 1234)
+    eng = gm_b200.InfoGanEngine(784, 400, 20, 10, 10, max_batch=B)
+    eng.load(0, [W["G.linear"][0], W["G.linear"][1], W["G.generate"][0], W["G.generate"][1]])
+    eng.load(1, [W["D.linear"][0], W["D.linear"][1], W["D.discriminator"][0], W["D.discriminator"][1]])
+    eng.load_q([W["Q.linear"][0], W["Q.linear"][1], W["Q.inference"][0], W["Q.inference"][1]])
+    x = torch.from_numpy(images_from_bits(fx)).cuda()
+    d1 = unpack_draws(fx, "step1_")
+    P = {k.replace("D.discriminator", "D.discriminate"): v for k, v in params_dict(W, np.float64).items()}
+    Ld = eng.d_grad(x, noise=torch.from_numpy(d1[0]).cuda()).item()
+    assert abs(Ld - float(fx["step1_D_loss"])) < TOL_LOSS * abs(float(fx["step1_D_loss"]))
+    Lg = eng.g_grad(B, noise=torch.from_numpy(d1[1]).cuda()).item()
+    assert abs(Lg - float(fx["step1_G_loss"])) < TOL_LOSS * abs(float(fx["step1_G_loss"]))
+    Lq = eng.q_grad(B, torch.from_numpy(d1[2]).cuda()).item()
+    assert abs(Lq - float(fx["step1_MI_loss"])) < TOL_LOSS * abs(float(fx["step1_MI_loss"])), (Lq, fx["step1_MI_loss"])
+    _, gq = R.info_q_step(P, d1[2].astype(np.float64), q=R.bf16_points)
+    _, gq_exact = R.info_q_step(P, d1[2].astype(np.float64))
+    names = ["G.linear.weight", "G.linear.bias", "G.generate.weight", "G.generate.bias"]
+    rep = {}
+    for nme, g in zip(names, eng.views(0, eng.grads[0])):
+        rep["gradq_" + nme] = _nrel(g.cpu().numpy(), gq[nme])
+        rep["grad_" + nme] = _nrel(g.cpu().numpy(), gq_exact[nme])
+    for nme, g in zip(["Q.linear.weight", "Q.linear.bias", "Q.inference.weight", "Q.inference.bias"], eng.q_views(eng.q_grads)):
+        rep["gradq_" + nme] = _nrel(g.cpu().numpy(), gq[nme])
+        rep["grad_" + nme] = _nrel(g.cpu().numpy(), gq_exact[nme])
+    _REPORT["step1_info_q"] = rep
+    _dump()
+    for k, v in rep.items():
+        assert v < (TOL_GRAD_Q if k.startswith("gradq_") else TOL_GRAD_BF16_B64), (k, v, rep)
+    # trajectory through the drop-in module
+    import info_gan
+    model = info_gan.InfoGAN(784, 400, 20, 10, 10)
+    sd = model.state_dict()
+    for k, (w, b) in W.items():
+        sd[k + ".weight"], sd[k + ".bias"] = torch.from_numpy(w.copy()), torch.from_numpy(b.copy())
+    model.load_state_dict(sd)
+    xi = torch.from_numpy(images_from_bits(fx)).view(B, 1, 28, 28)
+    it = [(xi, torch.zeros(B, dtype=torch.long))] * STEPS
+    tr = info_gan.InfoGANTrainer(model, it, it, it)
+    draws = iter(unpack_draws(fx))
+    tr.compute_noise = lambda *a, **k: torch.from_numpy(next(draws)).cuda()
+    tr.train(num_epochs=1, G_lr=2e-4, D_lr=2e-4, D_steps=1)
+    np.testing.assert_allclose(tr.Dlosses, fx["D_loss"], rtol=2e-3)
+    np.testing.assert_allclose(tr.Glosses, fx["G_loss"], rtol=2e-3)
+    np.testing.assert_allclose(tr.MIlosses, fx["MI_loss"], rtol=2e-3)

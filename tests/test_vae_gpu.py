@@ -109,3 +109,18 @@ def test_dropin_vae_module_trains_like_the_reference():
     out, mu, lv = model(x.view(B, -1))
     assert out.shape == (B, 784) and mu.shape == (B, 20) and lv.shape == (B, 20)
     assert trainer.sample_images(num_images=36).shape == (36, 28, 28)
+
+
+def test_forward_at_batch_512_pair_mode_fp32_head():
+    """batch 512 -> CTA-pair (cta_group::2) GEMMs, incl. the fp32-output latent head."""
+    eng = _engine(512)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.rand(512, 784, device="cuda", generator=g) < 0.13).float()
+    eps = torch.randn(512, 20, device="cuda", generator=g)
+    out, mu, lv, ls = eng.forward(x, eps=eps, want_losses=True)
+    v = eng.views()
+    h1 = torch.relu(x @ v["encoder.linear.weight"].t() + v["encoder.linear.bias"])
+    mu_r = h1 @ v["encoder.mu.weight"].t() + v["encoder.mu.bias"]
+    lv_r = h1 @ v["encoder.log_var.weight"].t() + v["encoder.log_var.bias"]
+    assert _nrel(mu.cpu().numpy(), mu_r.cpu().numpy()) < 5e-3
+    assert _nrel(lv.cpu().numpy(), lv_r.cpu().numpy()) < 5e-3
