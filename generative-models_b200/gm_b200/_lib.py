@@ -12,7 +12,7 @@ class GmError(RuntimeError):
 
 VARIANTS = {"ns": 0, "mm": 1, "w": 2, "wgp": 3, "ls": 4, "dra": 5, "ra": 6, "fisher": 7,
             "f_total_variation": 8, "f_forward_kl": 9, "f_reverse_kl": 10, "f_pearson": 11,
-            "f_hellinger": 12, "f_jensen_shannon": 13, "info": 14}
+            "f_hellinger": 12, "f_jensen_shannon": 13, "info": 14, "began": 15}
 OUT_ACTS = {"sigmoid": 0, "relu": 1, "none": 2}
 IMG_FMTS = {"f32": 0, "u8": 1, "bits": 2}
 
@@ -87,6 +87,8 @@ def lib():
     L.gm_gan_sync_shadows_q.argtypes = [vp, vp]
     L.gm_gan_q_grad.argtypes = [vp, i, vp, i, f, vp, vp]
     L.gm_gan_apply_mi.argtypes = [vp, C.POINTER(AdamHP), i, vp]
+    L.gm_gan_began_state.argtypes = [vp, C.POINTER(C.c_float), i, vp]
+    L.gm_gan_began_control.argtypes = [vp, f, f, f, vp]
     L.gm_gan_discriminate.argtypes = [vp, vp, i, i, vp, vp]
     L.gm_vae_create.argtypes = [vp, C.POINTER(VaeDesc), C.POINTER(vp)]
     L.gm_vae_destroy.argtypes = [vp]

@@ -131,6 +131,7 @@ static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
   if (bias && dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 1>(pl, s);
   if (!bias && !dot && aux == AUX_SIGMOID_GRAD && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_SIGMOID_GRAD, 0, 0>(pl, s);
   if (!bias && !dot && aux == AUX_RELU_MASK && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_RELU_MASK, 0, 0>(pl, s);
+  if (bias && !dot && aux == AUX_L1 && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_L1, 1, 0>(pl, s);
   if (bias && !dot && aux == AUX_VAE_OUT && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_VAE_OUT, 1, 0>(pl, s);
   if (!bias && !dot && aux == AUX_NONE && p.act == ACT_NONE && p.dot_sq) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONE, 0, 2>(pl, s);
   if (!bias && !dot && aux == AUX_NONE && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONE, 0, 0>(pl, s);
@@ -392,6 +393,7 @@ struct NetLayout {
 struct StepPlans {
   GemmPlan g1, g2, d1_d, d1_g, d1_x, dw1d, dx, dw2g, dhg, dw1g, gp_v, gp_t;
   GemmPlan q1, q2, gq2, dhq, gq1, dfq;   // InfoGAN Q head
+  GemmPlan be_enc_d, be_dec_d, be_gwd, be_de_d, be_enc_g, be_dec_g, be_de_g, be_dxg;   // BEGAN autoencoder-discriminator
 };
 
 struct gm_gan {
@@ -420,6 +422,10 @@ struct gm_gan {
   __nv_bfloat16 *Wq1_s = nullptr, *Wq1_t = nullptr, *Wq2_s = nullptr, *Wq2_t = nullptr, *HQ = nullptr, *DINF = nullptr, *DHQ = nullptr;
   float *INF = nullptr, *PQ1 = nullptr, *PQ2 = nullptr;
   double* q_part = nullptr;
+  // BEGAN: D is an autoencoder x -> h -> x (src/be_gan.py:63-76)
+  __nv_bfloat16 *Wd_s = nullptr, *Wd_t = nullptr, *DR = nullptr, *BT = nullptr;
+  float *slots_r = nullptr, *be_state = nullptr, *PWd = nullptr;
+  double* be_part = nullptr;
   double* loss_part = nullptr;   // 3 x [loss_blocks][4]
   int loss_blocks = 0;
   float *PD = nullptr, *PG2 = nullptr, *PG1 = nullptr;
@@ -466,7 +472,7 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   g->HP = rup(g->H + 1, 16);
   g->ZP = rup(g->Z + 1, 64);
   g->G.init(g->Z, g->H, g->X);
-  g->D.init(g->X, g->H, 1);
+  g->D.init(g->X, g->H, d->variant == GM_BEGAN ? g->X : 1);
   g->region_rows = g->Bmax;
   g->nreg = d->variant == GM_WGP ? 3 : (d->variant == GM_DRA ? 4 : 2);
   const size_t B = g->Bmax;
@@ -517,6 +523,16 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   TRY(dev_alloc(g, &g->PD, size_t(sp_d) * g->H * (cdiv(g->X + 1, BM) * BM)));
   TRY(dev_alloc(g, &g->PG2, size_t(sp_g2) * g->X * rup(g->H + 1, 64)));
   TRY(dev_alloc(g, &g->PG1, size_t(sp_g1) * g->H * 64 * cdiv(g->Z + 1, 64)));
+  if (d->variant == GM_BEGAN) {
+    TRY(dev_alloc(g, &g->Wd_s, size_t(g->X) * g->H));
+    TRY(dev_alloc(g, &g->Wd_t, size_t(g->H) * g->X));
+    TRY(dev_alloc(g, &g->DR, 2 * B * g->XP));
+    TRY(dev_alloc(g, &g->BT, B * g->XP));
+    TRY(dev_alloc(g, &g->slots_r, size_t(2 * cdiv(g->X, 208)) * 2 * B));
+    TRY(dev_alloc(g, &g->be_state, 16));
+    TRY(dev_alloc(g, &g->PWd, size_t(sp_g2) * g->X * rup(g->H + 1, 64)));
+    TRY(dev_alloc(g, &g->be_part, size_t(c->num_sms) * 2 * 2));
+  }
   if (d->variant == GM_INFO) {
     g->q_out = 20;   // 10 categorical logits + 10 continuous codes (src/info_gan.py:403-407)
     g->Qn.init(g->X, g->H, g->q_out);
@@ -565,7 +581,13 @@ static void adam_segs(gm_gan* g, int net, AdamParams& a) {
     a.total = g->D.total;
     a.nseg = 1;
     a.seg[0] = {g->D.off_w1, g->H * g->X, g->X, g->W1d_s, g->X, g->W1d_t, g->H};
+    if (g->d.variant == GM_BEGAN) {   // decoder weight [x, h]: K-major copy + transpose
+      a.nseg = 2;
+      a.seg[1] = {g->D.off_w2, g->X * g->H, g->H, g->Wd_s, g->H, g->Wd_t, g->X};
+      a.lr_scale = g->be_state + 7;
+    }
   }
+  if (net == GM_NET_G && g->d.variant == GM_BEGAN) a.lr_scale = g->be_state + 7;
 }
 
 extern "C" int gm_gan_sync_shadows(gm_gan* g, int net, gm_stream stream) {
@@ -598,7 +620,7 @@ extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, 
 
 static void set_bf16_epi(GemmParams& p, __nv_bfloat16* out, int ldo, int out_cols, int pad_one, const float* bias, int act) {
   p.epi = EPI_BF16; p.out = out; p.ldo = ldo; p.out_cols = out_cols; p.pad_one = pad_one; p.bias = bias; p.act = act;
-  p.aux = nullptr; p.aux_mode = AUX_NONE; p.dot_w = nullptr; p.dot_out = nullptr; p.dot_sq = 0;
+  p.aux = nullptr; p.aux_mode = AUX_NONE; p.dot_w = nullptr; p.dot_out = nullptr; p.dot_sq = 0; p.row_scale = nullptr; p.row_split = 0;
 }
 
 static int build_plans(gm_gan* g, int B, StepPlans** out) {
@@ -672,6 +694,36 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
     GemmParams& p = sp.dw1g.p;
     p.epi = EPI_F32; p.part = g->PG1; p.ldp = 64; p.part_stride = (long long)H * 64; p.transpose = 0;
     sp.dw1g.flops = 2.0 * H * Z * B;
+  }
+  if (g->d.variant == GM_BEGAN) {
+    const int slr = 2 * g->Bmax;
+    auto l1 = [&](GemmPlan& pl, const __nv_bfloat16* aux, float* slots, const float* rs, int split) {
+      pl.p.aux = aux; pl.p.ld_aux = XP; pl.p.aux_mode = AUX_L1; pl.p.dot_out = slots; pl.p.dot_ld = slr;
+      pl.p.row_scale = rs; pl.p.row_split = split;
+    };
+    // D step: encode / decode real and fake rows together, L1 error + its sign fused in the decoder epilogue
+    if ((rc = plan_gemm(c, &sp.be_enc_d, 0, 2 * B, H, X, g->Xall, XP, g->W1d_s, X, HP, 1))) return rc;
+    set_bf16_epi(sp.be_enc_d.p, g->Aall, HP, HP, 1, pD + g->D.off_b1, ACT_RELU);
+    if ((rc = plan_gemm(c, &sp.be_dec_d, 0, 2 * B, X, H, g->Aall, HP, g->Wd_s, H, X, 1))) return rc;
+    set_bf16_epi(sp.be_dec_d.p, g->DR, XP, X, 0, pD + g->D.off_b2, ACT_NONE);
+    l1(sp.be_dec_d, g->Xall, g->slots_r, g->be_state + 1, B);
+    if ((rc = plan_gemm(c, &sp.be_gwd, 1, X, H + 1, 2 * B, g->DR, XP, g->Aall, HP, H + 1, g->max_splits))) return rc;
+    { GemmParams& p = sp.be_gwd.p; p.epi = EPI_F32; p.part = g->PWd; p.ldp = rup(H + 1, 64); p.part_stride = (long long)X * p.ldp; p.transpose = 0;
+      sp.be_gwd.flops = 2.0 * X * H * 2.0 * B; }
+    if ((rc = plan_gemm(c, &sp.be_de_d, 0, 2 * B, H, X, g->DR, XP, g->Wd_t, X, H, 1))) return rc;
+    set_bf16_epi(sp.be_de_d.p, g->DHall, HP, H, 0, nullptr, ACT_NONE);
+    sp.be_de_d.p.aux = g->Aall; sp.be_de_d.p.ld_aux = HP; sp.be_de_d.p.aux_mode = AUX_RELU_MASK;
+    // G step: the same on the fake rows only, then back through the encoder to the images
+    if ((rc = plan_gemm(c, &sp.be_enc_g, 0, B, H, X, Xfake, XP, g->W1d_s, X, HP, 1))) return rc;
+    set_bf16_epi(sp.be_enc_g.p, Afake, HP, HP, 1, pD + g->D.off_b1, ACT_RELU);
+    if ((rc = plan_gemm(c, &sp.be_dec_g, 0, B, X, H, Afake, HP, g->Wd_s, H, X, 1))) return rc;
+    set_bf16_epi(sp.be_dec_g.p, g->DR + size_t(B) * XP, XP, X, 0, pD + g->D.off_b2, ACT_NONE);
+    l1(sp.be_dec_g, Xfake, g->slots_r + B, g->be_state + 8, 0);
+    if ((rc = plan_gemm(c, &sp.be_de_g, 0, B, H, X, g->DR + size_t(B) * XP, XP, g->Wd_t, X, H, 1))) return rc;
+    set_bf16_epi(sp.be_de_g.p, DHfake, HP, H, 0, nullptr, ACT_NONE);
+    sp.be_de_g.p.aux = Afake; sp.be_de_g.p.ld_aux = HP; sp.be_de_g.p.aux_mode = AUX_RELU_MASK;
+    if ((rc = plan_gemm(c, &sp.be_dxg, 0, B, X, H, DHfake, HP, g->W1d_t, H, X, 1))) return rc;
+    set_bf16_epi(sp.be_dxg.p, g->BT, XP, X, 0, nullptr, ACT_NONE);
   }
   if (g->d.variant == GM_INFO && g->parQ != nullptr) {
     const float* pQ = g->parQ;
@@ -747,6 +799,98 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   g->ctx->launches += 2;
 }
 
+// ---- BEGAN (src/be_gan.py:212-258): D = autoencoder, L1 reconstruction losses ----
+static int began_finalize_g(gm_gan* g, StepPlans* sp, cudaStream_t s) {
+  GradSegs gs;
+  memset(&gs, 0, sizeof gs);
+  const GemmParams& p2 = sp->dw2g.p;
+  const GemmParams& p1 = sp->dw1g.p;
+  gs.nseg = 4;
+  gs.total = g->G.total;
+  gs.s[0] = {g->G.off_w1, g->H * g->Z, 0, g->Z, p1.ldp, 0, p1.splits, p1.part_stride, g->PG1};
+  gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
+  gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
+  gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
+  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_G]);
+  g->ctx->launches++;
+  return GM_OK;
+}
+
+static int began_d_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaStream_t s) {
+  gm_ctx* c = g->ctx;
+  int rc;
+  if ((rc = launch_plan(c, sp->be_enc_d, s))) return rc;
+  if ((rc = launch_plan(c, sp->be_dec_d, s))) return rc;   // DR = scaled sign(D(.) - .), row L1 sums -> slots_r
+  const int nb = c->num_sms;
+  const int ns = 2 * cdiv(g->X, 208);
+  vae_rowsum_kernel<<<nb, 256, 0, s>>>(g->slots_r, ns, 2 * g->Bmax, B, g->be_part);
+  vae_rowsum_kernel<<<nb, 256, 0, s>>>(g->slots_r + B, ns, 2 * g->Bmax, B, g->be_part + nb);
+  began_loss_final_kernel<<<1, 256, 0, s>>>(g->be_part, g->be_part + nb, nb, B, 0, g->be_state, g->lossbuf);
+  c->launches += 3;
+  if ((rc = launch_plan(c, sp->be_gwd, s))) return rc;
+  if ((rc = launch_plan(c, sp->be_de_d, s))) return rc;
+  if ((rc = launch_plan(c, sp->dw1d, s))) return rc;
+  GradSegs gs;
+  memset(&gs, 0, sizeof gs);
+  const GemmParams& pe = sp->dw1d.p;
+  const GemmParams& pd = sp->be_gwd.p;
+  gs.nseg = 4;
+  gs.total = g->D.total;
+  gs.s[0] = {g->D.off_w1, g->H * g->X, 0, g->X, pe.ldp, 0, pe.splits, pe.part_stride, g->PD};
+  gs.s[1] = {g->D.off_b1, g->H, 2, 0, pe.ldp, g->X, pe.splits, pe.part_stride, g->PD};
+  gs.s[2] = {g->D.off_w2, g->X * g->H, 0, g->H, pd.ldp, 0, pd.splits, pd.part_stride, g->PWd};
+  gs.s[3] = {g->D.off_b2, g->X, 2, 0, pd.ldp, g->H, pd.splits, pd.part_stride, g->PWd};
+  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_D]);
+  c->launches++;
+  if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}
+
+static int began_g_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaStream_t s) {
+  gm_ctx* c = g->ctx;
+  int rc;
+  if ((rc = launch_plan(c, sp->be_enc_g, s))) return rc;
+  if ((rc = launch_plan(c, sp->be_dec_g, s))) return rc;
+  const int nb = c->num_sms;
+  vae_rowsum_kernel<<<nb, 256, 0, s>>>(g->slots_r + B, 2 * cdiv(g->X, 208), 2 * g->Bmax, B, g->be_part + nb);
+  began_loss_final_kernel<<<1, 256, 0, s>>>(g->be_part, g->be_part + nb, nb, B, 1, g->be_state, g->lossbuf);
+  c->launches += 2;
+  if ((rc = launch_plan(c, sp->be_de_g, s))) return rc;
+  if ((rc = launch_plan(c, sp->be_dxg, s))) return rc;
+  began_da2_kernel<<<c->num_sms * 8, 256, 0, s>>>(g->BT, g->DR + size_t(B) * g->XP, g->Xall + size_t(B) * g->XP, g->DA2, B, g->X, g->XP);
+  c->launches++;
+  if ((rc = launch_plan(c, sp->dw2g, s))) return rc;
+  if ((rc = launch_plan(c, sp->dhg, s))) return rc;
+  if ((rc = launch_plan(c, sp->dw1g, s))) return rc;
+  began_finalize_g(g, sp, s);
+  if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}
+
+// BEGAN device state: host get/set of [K, inv_b, -K inv_b, DX, DG, best, bad, lr_scale, inv_b, inv_b, convergence]
+extern "C" int gm_gan_began_state(gm_gan* g, float* host11, int set, gm_stream stream) {
+  if (!g || !host11) return GM_ERR_ARG;
+  if (g->d.variant != GM_BEGAN) return fail(g->ctx, GM_ERR_STATE, "not a BEGAN engine");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (set) CU_OK(g->ctx, cudaMemcpyAsync(g->be_state, host11, 11 * sizeof(float), cudaMemcpyHostToDevice, s));
+  else {
+    CU_OK(g->ctx, cudaMemcpyAsync(host11, g->be_state, 11 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU_OK(g->ctx, cudaStreamSynchronize(s));
+  }
+  return GM_OK;
+}
+// K <- clip(K + LAMBDA (GAMMA DX - DG), 0, 1) and the plateau schedulers (src/be_gan.py:186-195)
+extern "C" int gm_gan_began_control(gm_gan* g, float gamma, float lambda, float patience, gm_stream stream) {
+  if (!g) return GM_ERR_ARG;
+  if (g->d.variant != GM_BEGAN) return fail(g->ctx, GM_ERR_STATE, "not a BEGAN engine");
+  began_control_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(g->be_state, gamma, lambda, patience);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
 extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const int* gather_idx, int batch,
                              const float* noise, const float* aux, float inv_global_batch, uint64_t seed,
                              uint64_t step, float* loss_dev, gm_stream stream) {
@@ -762,6 +906,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   stage_images_kernel<<<c->num_sms * 8, 256, 0, s>>>(images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP);
   c->launches++;
   if ((rc = run_generator(g, sp, B, noise, seed, 2 * step, s))) return rc;
+  if (g->d.variant == GM_BEGAN) return began_d_grad(g, sp, B, loss_dev, s);
   const bool gp = g->nreg > 2;
   const int H = g->H, HP = g->HP, X = g->X, XP = g->XP;
   const float* w2 = g->par[GM_NET_D] + g->D.off_w2;
@@ -842,6 +987,7 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   const int B = batch;
   gm_ctx* c = g->ctx;
   if ((rc = run_generator(g, sp, B, noise, seed, 2 * step + 1, s))) return rc;
+  if (g->d.variant == GM_BEGAN) return began_g_grad(g, sp, B, loss_dev, s);
   if ((rc = launch_plan(c, sp->d1_g, s))) return rc;
   launch_loss(g, B, 1, inv_global_batch, s);
   dh_kernel<<<g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * g->HP * sizeof(float), s>>>(

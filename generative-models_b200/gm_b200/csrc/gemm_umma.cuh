@@ -32,7 +32,7 @@ constexpr int kSmemBudget = 225 * 1024;
 
 enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
-enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2, AUX_VAE_OUT = 3 };
+enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2, AUX_VAE_OUT = 3, AUX_L1 = 4 };
 
 struct GemmParams {
   int M, N, K;          // logical extents; K counts contraction elements
@@ -52,6 +52,9 @@ struct GemmParams {
   int aux_mode;
   const float* dot_w;   // nullable: row-dot of the *stored* values with dot_w[n]
   int dot_sq;           // 1: dot_out = row sum of squares instead (dot_w unused)
+  // AUX_L1 (BEGAN): out = sign(v - aux) * (row < row_split ? row_scale[0] : row_scale[1]), dot_out = sum |v - aux|
+  const float* row_scale;
+  int row_split;
   float* dot_out;       // partial slots [(n_tile*2 + half) * dot_ld + m]
   int dot_ld;
   // ---- EPI_F32: part[split*part_stride + (transpose ? n*ldp + m : m*ldp + n)] = acc
@@ -378,6 +381,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         long long t_ld = 0;
         float dot = 0.f;
         bool released = false;
+        float l1_scale = 0.f;
+        if (aux_mode == AUX_L1) l1_scale = __ldg(p.row_scale + (row < p.row_split ? 0 : 1));
 #pragma unroll 1
         for (int bi = 0; part + bi * kParts < kBlocks; ++bi) {
           const int cb = (part + bi * kParts) * kEpiCols;
@@ -445,6 +450,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (aux_mode == AUX_SIGMOID_GRAD) {
                       v[2 * k2] *= a_lo * (1.f - a_lo);
                       v[2 * k2 + 1] *= a_hi * (1.f - a_hi);
+                    } else if (aux_mode == AUX_L1) {
+                      // BEGAN: L1 reconstruction error of the autoencoder-discriminator and its
+                      // (scaled) subgradient sign(r - x)   (src/be_gan.py:225-236)
+                      const float d0 = v[2 * k2] - a_lo, d1 = v[2 * k2 + 1] - a_hi;
+                      dot += fabsf(d0) + fabsf(d1);
+                      v[2 * k2] = d0 > 0.f ? l1_scale : (d0 < 0.f ? -l1_scale : 0.f);
+                      v[2 * k2 + 1] = d1 > 0.f ? l1_scale : (d1 < 0.f ? -l1_scale : 0.f);
                     } else if (aux_mode == AUX_VAE_OUT) {
                       // v = decoder output, aux = target x: accumulate (x-v)^2 and emit
                       // d/d(pre-sigmoid) of sum (x-v)^2 = -2 (x-v) v (1-v)   (src/vae.py:203)
@@ -493,7 +505,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
         }
-        if ((has_dot || has_sq || aux_mode == AUX_VAE_OUT) && p.dot_out != nullptr && row_ok)
+        if ((has_dot || has_sq || aux_mode == AUX_VAE_OUT || aux_mode == AUX_L1) && p.dot_out != nullptr && row_ok)
           p.dot_out[size_t(n_tile * 2 + (kParts == 2 ? part : 0)) * p.dot_ld + row] = dot;
         if (!released) {
           tc_fence_before();

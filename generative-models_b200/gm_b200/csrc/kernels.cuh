@@ -12,7 +12,7 @@ namespace gm {
 // Order is the ABI (include/gm_b200.h: gm_variant).
 enum : int {
   V_NS = 0, V_MM, V_W, V_WGP, V_LS, V_DRA, V_RA, V_FISHER,
-  V_F_TV, V_F_FKL, V_F_RKL, V_F_PEARSON, V_F_HELLINGER, V_F_JS, V_INFO
+  V_F_TV, V_F_FKL, V_F_RKL, V_F_PEARSON, V_F_HELLINGER, V_F_JS, V_INFO, V_BEGAN
 };
 enum : int { OUT_SIGMOID = 0, OUT_RELU = 1, OUT_NONE = 2 };
 constexpr float kEps = 1e-8f;  // the reference's log stabiliser (src/ns_gan.py:191)
@@ -621,6 +621,63 @@ __global__ void __launch_bounds__(kLossThreads) info_loss_final_kernel(const dou
   if (threadIdx.x == 0) loss[0] = float(ce / rows + mse / ((double)rows * nc));
 }
 
+// ---------------------------------------------------------------- BEGAN (src/be_gan.py)
+// device state: [0] K  [1] scale of real rows (= inv_b)  [2] scale of fake rows (= -K inv_b)
+// [3] DX  [4] DG  [5] plateau best  [6] plateau bad count  [7] lr scale  [8],[9] inv_b (G step)
+// D step: DX = mean_i sum_k |D(x)-x|, DG likewise on fakes, loss = DX - K DG (src/be_gan.py:225-236);
+// G step: loss = DG (src/be_gan.py:256).  part_x / part_g: per-block partial row sums.
+__global__ void began_loss_final_kernel(const double* __restrict__ part_x, const double* __restrict__ part_g, int nblk,
+                                        int B, int g_step, float* __restrict__ state, float* __restrict__ loss) {
+  __shared__ double sh[256 / 32];
+  double a = 0, b = 0;
+  for (int i = threadIdx.x; i < nblk; i += 256) { if (!g_step) a += part_x[i]; b += part_g[i]; }
+  a = block_sum<256>(a, sh);
+  b = block_sum<256>(b, sh);
+  if (threadIdx.x == 0) {
+    const float DX = float(a / B), DG = float(b / B);
+    if (g_step) loss[0] = DG;
+    else { loss[0] = DX - state[0] * DG; state[3] = DX; state[4] = DG; }
+  }
+}
+// proportional control of K (src/be_gan.py:189-191) and the two identical ReduceLROnPlateau
+// schedulers (factor 0.5, rel threshold 0.01, patience given; src/be_gan.py:133-136,194-195)
+__global__ void began_control_kernel(float* __restrict__ state, float gamma, float lambda, float patience) {
+  const float DX = state[3], DG = state[4];
+  const float K = fminf(fmaxf(state[0] + lambda * (gamma * DX - DG), 0.f), 1.f);
+  const float conv = DX + fabsf(gamma * DX - DG);
+  state[0] = K;
+  state[2] = -K * state[1];
+  if (conv < state[5] * (1.f - 0.01f)) { state[5] = conv; state[6] = 0.f; }
+  else state[6] += 1.f;
+  if (state[6] > patience) { state[7] *= 0.5f; state[6] = 0.f; }
+  state[10] = conv;
+}
+// DA2 = (T - DRg) * fake (1 - fake): dL/d(pre-sigmoid) of G for BEGAN's G loss, whose gradient
+// reaches G(z) through D (T) and directly (-DRg)   (src/be_gan.py:256)
+__global__ void began_da2_kernel(const __nv_bfloat16* __restrict__ T, const __nv_bfloat16* __restrict__ DRg,
+                                 const __nv_bfloat16* __restrict__ fake, __nv_bfloat16* __restrict__ out, int rows, int x,
+                                 int ld) {
+  const int groups = ld / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)rows * groups;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = int(i % groups) * 8;
+    const uint4 t = reinterpret_cast<const uint4*>(T)[i], d = reinterpret_cast<const uint4*>(DRg)[i],
+                f = reinterpret_cast<const uint4*>(fake)[i];
+    const uint32_t tt[4] = {t.x, t.y, t.z, t.w}, dd[4] = {d.x, d.y, d.z, d.w}, ff[4] = {f.x, f.y, f.z, f.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float f0 = bf16_lo(ff[q]), f1 = bf16_hi(ff[q]);
+      float v0 = (bf16_lo(tt[q]) - bf16_lo(dd[q])) * f0 * (1.f - f0);
+      float v1 = (bf16_hi(tt[q]) - bf16_hi(dd[q])) * f1 * (1.f - f1);
+      if (c0 + 2 * q >= x) v0 = 0.f;
+      if (c0 + 2 * q + 1 >= x) v1 = 0.f;
+      o[q] = pack_bf16x2(v0, v1);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---------------------------------------------------------------- gradient finalisation
 // flat_grad[dst_off + i] = sum over `nsplit` partial copies of src[map(i)]:
 //   kind 0 (matrix, rows x cols):  src[r*ld + c]        (partial stored as [rows][ld])
@@ -669,6 +726,7 @@ struct AdamParams {
   int total;
   float lr, b1, b2, eps, wd, bc1, bc2_sqrt, clamp;   // clamp <= 0: off
   int update;                                        // 0: only refresh shadows
+  const float* lr_scale;                             // nullable device scalar multiplying lr (BEGAN's plateau scheduler)
   AdamSeg seg[6]; int nseg;
 };
 
@@ -684,7 +742,8 @@ __global__ void adam_kernel(const AdamParams a) {
     a.m[i] = m;
     a.v[i] = v;
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-    p = p - (a.lr / a.bc1) * (m / denom);
+    const float lr = a.lr_scale ? a.lr * a.lr_scale[0] : a.lr;
+    p = p - (lr / a.bc1) * (m / denom);
     if (a.clamp > 0.f) p = fminf(fmaxf(p, -a.clamp), a.clamp);
     a.p[i] = p;
   }

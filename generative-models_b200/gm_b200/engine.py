@@ -41,6 +41,8 @@ class GanEngine:
                                             _ptr(self.exp_avg[net]), _ptr(self.exp_avg_sq[net])))
         H, X, Z = hidden_dim, image_size, z_dim
         self.shapes = [[(H, Z), (H,), (X, H), (X,)], [(H, X), (H,), (1, H), (1,)]]
+        if variant == "began":      # D is an autoencoder: encoder [h, x], decoder [x, h]
+            self.shapes[1] = [(H, X), (H,), (X, H), (X,)]
         self.steps = [0, 0]
 
     def __del__(self):
@@ -127,6 +129,24 @@ class GanEngine:
         out = torch.empty(n, self.image_size, device=self.device, dtype=torch.float32)
         check(self.h, lib().gm_gan_generate(self.g, _ptr(noise.contiguous().float()), n, _ptr(out), _stream()))
         return out
+
+    def began_state(self, values=None):
+        """BEGAN device state (list of 11 floats, see include/gm_b200.h); pass values to set."""
+        buf = (C.c_float * 11)()
+        if values is not None:
+            for i, v in enumerate(values):
+                buf[i] = v
+            check(self.h, lib().gm_gan_began_state(self.g, buf, 1, _stream()))
+            return list(values)
+        check(self.h, lib().gm_gan_began_state(self.g, buf, 0, _stream()))
+        return list(buf)
+
+    def began_init(self, K, batch, world=1):
+        inv = 1.0 / (batch * world)
+        return self.began_state([K, inv, -K * inv, 0.0, 0.0, float("inf"), 0.0, 1.0, inv, inv, 0.0])
+
+    def began_control(self, gamma, lam, patience):
+        check(self.h, lib().gm_gan_began_control(self.g, gamma, lam, float(patience), _stream()))
 
     def fisher_state(self, lam=None, rho=None):
         buf = (C.c_float * 2)()

@@ -43,7 +43,8 @@ typedef enum {
   GM_RA,          /* src/ra_gan.py:183-229      */
   GM_FISHER,      /* src/fisher_gan.py:193-248  */
   GM_F_TV, GM_F_FKL, GM_F_RKL, GM_F_PEARSON, GM_F_HELLINGER, GM_F_JS, /* src/f_gan.py:99-142 */
-  GM_INFO         /* src/info_gan.py:223-304    */
+  GM_INFO,        /* src/info_gan.py:223-304    */
+  GM_BEGAN        /* src/be_gan.py:212-258 (D is an autoencoder, flat layout [encoder.W|.b|decoder.W|.b]) */
 } gm_variant;
 
 typedef enum { GM_OUT_SIGMOID = 0, GM_OUT_RELU = 1, GM_OUT_NONE = 2 } gm_out_act;
@@ -148,6 +149,11 @@ int gm_gan_q_grad(gm_gan* gan, int batch, const float* noise_dev, int z_dim, flo
                   gm_stream stream);
 /* MI_optimizer.step() (src/info_gan.py:205). */
 int gm_gan_apply_mi(gm_gan* gan, const gm_adam_hp* hp, int step, gm_stream stream);
+/* BEGAN (GM_BEGAN engines): device state [K, scale_real, scale_fake, DX, DG, plateau best,
+ * plateau bad count, lr scale, inv_b, inv_b, convergence] (src/be_gan.py:109-110,186-195);
+ * gm_gan_began_control applies the proportional control of K and the ReduceLROnPlateau pair. */
+int gm_gan_began_state(gm_gan* gan, float* host11, int set, gm_stream stream);
+int gm_gan_began_control(gm_gan* gan, float gamma, float lambda, float patience, gm_stream stream);
 /* Discriminator.forward (src/ns_gan.py:57-60) for inference: images [n, image_size]
  * (gm_img_fmt) -> scores [n] fp32. */
 int gm_gan_discriminate(gm_gan* gan, const void* images_dev, int img_fmt, int n, float* scores_dev, gm_stream stream);

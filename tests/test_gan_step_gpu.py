@@ -255,3 +255,57 @@ def test_infogan_steps_against_golden_and_oracle():
     np.testing.assert_allclose(tr.Dlosses, fx["D_loss"], rtol=2e-3)
     np.testing.assert_allclose(tr.Glosses, fx["G_loss"], rtol=2e-3)
     np.testing.assert_allclose(tr.MIlosses, fx["MI_loss"], rtol=2e-3)
+
+
+def test_began_steps_against_golden_and_oracle():
+    """BEGAN: autoencoder discriminator, L1 losses, K control (src/be_gan.py)."""
+    import gm_b200
+    from inputs import BEGAN_SHAPES
+    fx = load_case("gan_began")
+    W = gm_init_weights(BEGAN_SHAPES, 1234)
+    eng = gm_b200.GanEngine(784, 400, 20, max_batch=B, variant="began")
+    eng.load(0, [W["G.linear"][0], W["G.linear"][1], W["G.generate"][0], W["G.generate"][1]])
+    eng.load(1, [W["D.encoder"][0], W["D.encoder"][1], W["D.decoder"][0], W["D.decoder"][1]])
+    x = torch.from_numpy(images_from_bits(fx)).cuda()
+    d1 = unpack_draws(fx, "step1_")
+    P = params_dict(W, np.float64)
+    eng.began_init(0.3, B)
+    Ld = eng.d_grad(x, noise=torch.from_numpy(d1[0]).cuda()).item()
+    st = eng.began_state()
+    assert abs(Ld - float(fx["step1_D_loss"])) < TOL_LOSS * abs(float(fx["step1_D_loss"])), (Ld, fx["step1_D_loss"])
+    assert abs(st[3] - float(fx["step1_DX_loss"])) < TOL_LOSS * st[3] and abs(st[4] - float(fx["step1_DG_loss"])) < TOL_LOSS * st[4]
+    _, gq, _, _ = R.began_d_step(P, images_from_bits(fx).astype(np.float64), d1[0].astype(np.float64), 0.3, q=R.bf16_points)
+    _, ge, _, _ = R.began_d_step(P, images_from_bits(fx).astype(np.float64), d1[0].astype(np.float64), 0.3)
+    rep = {}
+    names = ["D.encoder.weight", "D.encoder.bias", "D.decoder.weight", "D.decoder.bias"]
+    for nme, g in zip(names, eng.views(1, eng.grads[1])):
+        rep["gradq_" + nme] = _nrel(g.cpu().numpy(), gq[nme])
+        rep["grad_" + nme] = _nrel(g.cpu().numpy(), ge[nme])
+    Lg = eng.g_grad(B, noise=torch.from_numpy(d1[1]).cuda()).item()
+    assert abs(Lg - float(fx["step1_G_loss"])) < TOL_LOSS * abs(float(fx["step1_G_loss"]))
+    _, ggq = R.began_g_step(P, d1[1].astype(np.float64), q=R.bf16_points)
+    _, gge = R.began_g_step(P, d1[1].astype(np.float64))
+    for nme, g in zip(["G.linear.weight", "G.linear.bias", "G.generate.weight", "G.generate.bias"], eng.views(0, eng.grads[0])):
+        rep["gradq_" + nme] = _nrel(g.cpu().numpy(), ggq[nme])
+        rep["grad_" + nme] = _nrel(g.cpu().numpy(), gge[nme])
+    _REPORT["step1_began"] = rep
+    _dump()
+    for k, v in rep.items():
+        # sign(r - x) flips where |r - x| is below the bf16 resolution of r: the L1 subgradient is
+        # discontinuous, so a handful of elements differ from the bf16-point oracle too
+        assert v < (2e-2 if k.startswith("gradq_") else TOL_GRAD_BF16_B64), (k, v, rep)
+    # trajectory (K control included) through the drop-in module
+    import be_gan
+    model = be_gan.BEGAN(784, 400, 20)
+    sd = model.state_dict()
+    for k, (w, b) in W.items():
+        sd[k + ".weight"], sd[k + ".bias"] = torch.from_numpy(w.copy()), torch.from_numpy(b.copy())
+    model.load_state_dict(sd)
+    xi = torch.from_numpy(images_from_bits(fx)).view(B, 1, 28, 28)
+    it = [(xi, torch.zeros(B, dtype=torch.long))] * STEPS
+    tr = be_gan.BEGANTrainer(model, it, it, it)
+    draws = iter(unpack_draws(fx))
+    tr.compute_noise = lambda *a, **k: torch.from_numpy(next(draws)).cuda()
+    tr.train(num_epochs=1, G_lr=1e-4, D_lr=1e-4, D_steps=1, GAMMA=0.5, LAMBDA=1e-3, K=0.0)
+    np.testing.assert_allclose(tr.Dlosses, fx["D_loss"], rtol=2e-3)
+    np.testing.assert_allclose(tr.Glosses, fx["G_loss"], rtol=2e-3)
