@@ -214,8 +214,12 @@ def run_ours(args):
     peak_tf = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
     dom_tf = dom[2] / (dom[1] * 1e-3) / 1e12 if dom[1] > 0 else 0.0
     gemm_ms_per_step = sum(r[1] for r in prof) / 3.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):      # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": dom[0], "achieved": round(dom_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": round(dom_tf / peak_tf, 4), "traffic": None, "peak_source": pk_src + ", sustained cuBLAS bf16",
+                "frac": round(dom_tf / peak_tf, 4), "traffic": traffic, "peak_source": pk_src + ", sustained cuBLAS bf16",
                 "launches_per_step": dom[3] / 3.0, "avg_launch_ms": round(dom[1] / max(dom[3], 1), 4),
                 "all_gemm_ms_per_step": round(gemm_ms_per_step, 4),
                 "step_frac_of_tensor_roofline": round(value / world * FLOP_PER_IMG / (peak_tf * 1e12), 4),
