@@ -83,6 +83,26 @@ struct GemmPlan {
   double flops;   // algorithmic 2*M*N*K of the logical problem (no padding)
 };
 
+// Every kernel of the library is launched with programmatic stream serialisation: the grid
+// may become resident while its predecessor drains, and blocks in griddepcontrol.wait (first
+// statement of every kernel, after the prologue in the GEMM) until the predecessor completed.
+static bool g_pdl = true;   // GM_NO_PDL=1 turns it off (gm_ctx_create)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T, int DOT_T, int CS, int EW>
 static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
   using Cfg = GemmCfg<BN1, BN2, !AMN, (CS == 2) && !AMN, EW>;
@@ -99,13 +119,22 @@ static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
   cfg.blockDim = dim3(gemm_threads(EW));
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CS;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (CS > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = CS;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = CS > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, pl.tmA, pl.tmB, pl.p);
 }
 
@@ -224,6 +253,7 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
 
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nsplit, long long stride, long long n,
                                        float* __restrict__ out) {
+  griddep_sync();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float t = 0.f;
@@ -256,6 +286,8 @@ extern "C" int gm_ctx_create(int device, gm_ctx** out) {
   c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
   const char* nc = getenv("GM_NO_CLUSTERS");
   c->use_clusters = !(nc && nc[0] == '1');
+  const char* np = getenv("GM_NO_PDL");
+  g_pdl = !(np && np[0] == '1');
   return GM_OK;
 }
 extern "C" int gm_ctx_destroy(gm_ctx* c) {
@@ -353,7 +385,7 @@ extern "C" int gm_gemm_bf16(gm_ctx* c, const gm_gemm_desc* d, gm_stream stream) 
   p.part_stride = per;
   rc = launch_plan(c, pl, s);
   if (rc) return rc;
-  reduce_partials_kernel<<<unsigned((per + 255) / 256), 256, 0, s>>>(c->scratch, p.splits, per, per,
+  launch_pdl(reduce_partials_kernel, unsigned((per + 255) / 256), 256, 0, s, c->scratch, p.splits, per, per,
                                                                      static_cast<float*>(d->C_dev));
   c->launches++;
   CU_OK(c, cudaGetLastError());
@@ -374,7 +406,7 @@ extern "C" int gm_adam_step(gm_ctx* c, float* p, const float* g, float* m, float
   memset(&a, 0, sizeof a);
   a.p = p; a.g = g; a.m = m; a.v = v; a.total = n; a.nseg = 0;
   fill_adam(a, hp, step);
-  adam_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(adam_kernel, cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   c->launches++;
   CU_OK(c, cudaGetLastError());
   return GM_OK;
@@ -598,7 +630,7 @@ extern "C" int gm_gan_sync_shadows(gm_gan* g, int net, gm_stream stream) {
   a.p = g->par[net];
   a.update = 0;
   adam_segs(g, net, a);
-  adam_kernel<<<cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -612,7 +644,7 @@ extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, 
   a.p = g->par[net]; a.g = g->grd[net]; a.m = g->am[net]; a.v = g->av[net];
   fill_adam(a, hp, step);
   adam_segs(g, net, a);
-  adam_kernel<<<cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -761,7 +793,7 @@ static int check_step_args(gm_gan* g, int batch) {
 }
 
 static int run_generator(gm_gan* g, StepPlans* sp, int B, const float* noise, uint64_t seed, uint64_t stream_id, cudaStream_t s) {
-  stage_noise_kernel<<<cdiv(B * (g->ZP / 8), 256), 256, 0, s>>>(noise, g->Zb, B, g->Z, g->ZP, seed, stream_id);
+  launch_pdl(stage_noise_kernel, cdiv(B * (g->ZP / 8), 256), 256, 0, s, noise, g->Zb, B, g->Z, g->ZP, seed, stream_id);
   g->ctx->launches++;
   int rc;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
@@ -787,15 +819,15 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   lp.partR = g->loss_part + size_t(g->loss_blocks) * 8;
   const int v = g->d.variant;
   if (!g_step && (v == V_RA || v == V_FISHER)) {
-    loss_pass_kernel<0><<<lp.nblk, kLossThreads, 0, s>>>(lp);
+    launch_pdl(loss_pass_kernel<0>, lp.nblk, kLossThreads, 0, s, lp);
     g->ctx->launches++;
     if (v == V_RA) {
-      loss_pass_kernel<1><<<lp.nblk, kLossThreads, 0, s>>>(lp);
+      launch_pdl(loss_pass_kernel<1>, lp.nblk, kLossThreads, 0, s, lp);
       g->ctx->launches++;
     }
   }
-  loss_pass_kernel<2><<<lp.nblk, kLossThreads, 0, s>>>(lp);
-  loss_final_kernel<<<1, kLossThreads, 0, s>>>(lp);
+  launch_pdl(loss_pass_kernel<2>, lp.nblk, kLossThreads, 0, s, lp);
+  launch_pdl(loss_final_kernel, 1, kLossThreads, 0, s, lp);
   g->ctx->launches += 2;
 }
 
@@ -811,7 +843,7 @@ static int began_finalize_g(gm_gan* g, StepPlans* sp, cudaStream_t s) {
   gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
   gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
   gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
-  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_G]);
+  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_G]);
   g->ctx->launches++;
   return GM_OK;
 }
@@ -823,9 +855,9 @@ static int began_d_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaSt
   if ((rc = launch_plan(c, sp->be_dec_d, s))) return rc;   // DR = scaled sign(D(.) - .), row L1 sums -> slots_r
   const int nb = c->num_sms;
   const int ns = 2 * cdiv(g->X, 208);
-  vae_rowsum_kernel<<<nb, 256, 0, s>>>(g->slots_r, ns, 2 * g->Bmax, B, g->be_part);
-  vae_rowsum_kernel<<<nb, 256, 0, s>>>(g->slots_r + B, ns, 2 * g->Bmax, B, g->be_part + nb);
-  began_loss_final_kernel<<<1, 256, 0, s>>>(g->be_part, g->be_part + nb, nb, B, 0, g->be_state, g->lossbuf);
+  launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r, ns, 2 * g->Bmax, B, g->be_part);
+  launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r + B, ns, 2 * g->Bmax, B, g->be_part + nb);
+  launch_pdl(began_loss_final_kernel, 1, 256, 0, s, g->be_part, g->be_part + nb, nb, B, 0, g->be_state, g->lossbuf);
   c->launches += 3;
   if ((rc = launch_plan(c, sp->be_gwd, s))) return rc;
   if ((rc = launch_plan(c, sp->be_de_d, s))) return rc;
@@ -840,7 +872,7 @@ static int began_d_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaSt
   gs.s[1] = {g->D.off_b1, g->H, 2, 0, pe.ldp, g->X, pe.splits, pe.part_stride, g->PD};
   gs.s[2] = {g->D.off_w2, g->X * g->H, 0, g->H, pd.ldp, 0, pd.splits, pd.part_stride, g->PWd};
   gs.s[3] = {g->D.off_b2, g->X, 2, 0, pd.ldp, g->H, pd.splits, pd.part_stride, g->PWd};
-  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_D]);
+  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_D]);
   c->launches++;
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   CU_OK(c, cudaGetLastError());
@@ -853,12 +885,12 @@ static int began_g_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaSt
   if ((rc = launch_plan(c, sp->be_enc_g, s))) return rc;
   if ((rc = launch_plan(c, sp->be_dec_g, s))) return rc;
   const int nb = c->num_sms;
-  vae_rowsum_kernel<<<nb, 256, 0, s>>>(g->slots_r + B, 2 * cdiv(g->X, 208), 2 * g->Bmax, B, g->be_part + nb);
-  began_loss_final_kernel<<<1, 256, 0, s>>>(g->be_part, g->be_part + nb, nb, B, 1, g->be_state, g->lossbuf);
+  launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r + B, 2 * cdiv(g->X, 208), 2 * g->Bmax, B, g->be_part + nb);
+  launch_pdl(began_loss_final_kernel, 1, 256, 0, s, g->be_part, g->be_part + nb, nb, B, 1, g->be_state, g->lossbuf);
   c->launches += 2;
   if ((rc = launch_plan(c, sp->be_de_g, s))) return rc;
   if ((rc = launch_plan(c, sp->be_dxg, s))) return rc;
-  began_da2_kernel<<<c->num_sms * 8, 256, 0, s>>>(g->BT, g->DR + size_t(B) * g->XP, g->Xall + size_t(B) * g->XP, g->DA2, B, g->X, g->XP);
+  launch_pdl(began_da2_kernel, c->num_sms * 8, 256, 0, s, g->BT, g->DR + size_t(B) * g->XP, g->Xall + size_t(B) * g->XP, g->DA2, B, g->X, g->XP);
   c->launches++;
   if ((rc = launch_plan(c, sp->dw2g, s))) return rc;
   if ((rc = launch_plan(c, sp->dhg, s))) return rc;
@@ -885,7 +917,7 @@ extern "C" int gm_gan_began_state(gm_gan* g, float* host11, int set, gm_stream s
 extern "C" int gm_gan_began_control(gm_gan* g, float gamma, float lambda, float patience, gm_stream stream) {
   if (!g) return GM_ERR_ARG;
   if (g->d.variant != GM_BEGAN) return fail(g->ctx, GM_ERR_STATE, "not a BEGAN engine");
-  began_control_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(g->be_state, gamma, lambda, patience);
+  launch_pdl(began_control_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), g->be_state, gamma, lambda, patience);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -903,7 +935,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   const int B = batch;
   gm_ctx* c = g->ctx;
   // real rows -> Xall[0:B] (bf16, ones column)
-  stage_images_kernel<<<c->num_sms * 8, 256, 0, s>>>(images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP);
+  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP);
   c->launches++;
   if ((rc = run_generator(g, sp, B, noise, seed, 2 * step, s))) return rc;
   if (g->d.variant == GM_BEGAN) return began_d_grad(g, sp, B, loss_dev, s);
@@ -915,23 +947,23 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     // interpolated rows (region 2): WGAN-GP between real and fake, DRAGAN around the real data
     const int mode = g->d.variant == GM_DRA ? 1 : 0;
     if (mode == 1) {
-      moments_kernel<<<c->num_sms * 2, 256, 0, s>>>(g->Xall, B, X, XP, g->mom_part);
-      moments_final_kernel<<<1, 256, 0, s>>>(g->mom_part, c->num_sms * 2, g->stats);
+      launch_pdl(moments_kernel, c->num_sms * 2, 256, 0, s, g->Xall, B, X, XP, g->mom_part);
+      launch_pdl(moments_final_kernel, 1, 256, 0, s, g->mom_part, c->num_sms * 2, g->stats);
       c->launches += 2;
     }
-    xhat_kernel<<<cdiv(B, 128), 128, 0, s>>>(g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
+    launch_pdl(xhat_kernel, cdiv(B, 128), 128, 0, s, g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
                                            mode, aux, g->stats, seed, 2 * step);
     c->launches++;
   }
   if ((rc = launch_plan(c, sp->d1_d, s))) return rc;
   launch_loss(g, B, 0, inv_global_batch, s);
-  dh_kernel<<<g->dh_blocks, g->dh_threads, dh_smem, s>>>(g->Aall, g->ds, w2, g->DHall, g->dw2p, 2 * B, H, HP, g->dh_rows_per_iter);
-  colsum_kernel<<<cdiv(HP * 32, 256), 256, 0, s>>>(g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
+  launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall, g->ds, w2, g->DHall, g->dw2p, 2 * B, H, HP, g->dh_rows_per_iter);
+  launch_pdl(colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
   c->launches += 2;
   if (gp) {
     const size_t rreg = size_t(g->nreg - 1) * B;
     // U = 1[a_hat > 0] * w2  -> DHall rows of the R region
-    dh_kernel<<<g->dh_blocks, g->dh_threads, dh_smem, s>>>(g->Aall + size_t(2) * B * HP, nullptr, w2, g->DHall + rreg * HP, nullptr,
+    launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, nullptr, w2, g->DHall + rreg * HP, nullptr,
                                                           B, H, HP, g->dh_rows_per_iter);
     c->launches++;
     if ((rc = launch_plan(c, sp->gp_v, s))) return rc;          // V = U W1 -> R region of Xall, ||V||^2 -> slots_v
@@ -944,18 +976,18 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     gpp.coef = g->coef; gpp.ds_gp = g->ds + 2 * B;
     gpp.part = g->gp_part; gpp.nblk = cdiv(B, kLossThreads) < c->num_sms * 2 ? cdiv(B, kLossThreads) : c->num_sms * 2;
     gpp.loss = g->lossbuf;
-    gp_rows_kernel<<<gpp.nblk, kLossThreads, 0, s>>>(gpp);
-    gp_final_kernel<<<1, kLossThreads, 0, s>>>(gpp);
-    scale_rows_kernel<<<c->num_sms * 4, 256, 0, s>>>(g->Xall + rreg * XP, g->coef, B, XP);   // R = coef * V
+    launch_pdl(gp_rows_kernel, gpp.nblk, kLossThreads, 0, s, gpp);
+    launch_pdl(gp_final_kernel, 1, kLossThreads, 0, s, gpp);
+    launch_pdl(scale_rows_kernel, c->num_sms * 4, 256, 0, s, g->Xall + rreg * XP, g->coef, B, XP);   // R = coef * V
     c->launches += 3;
     if ((rc = launch_plan(c, sp->gp_t, s))) return rc;          // T = (R W1^T) * mask -> DHg
-    dh_kernel<<<g->dh_blocks, g->dh_threads, dh_smem, s>>>(g->DHg, nullptr, w2, g->DA2, g->dw2p2, B, H, HP, g->dh_rows_per_iter);
-    colsum_kernel<<<cdiv(HP * 32, 256), 256, 0, s>>>(g->dw2p2, g->dh_blocks, HP, HP, g->dw2sum + HP);
+    launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->DHg, nullptr, w2, g->DA2, g->dw2p2, B, H, HP, g->dh_rows_per_iter);
+    launch_pdl(colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p2, g->dh_blocks, HP, HP, g->dw2sum + HP);
     c->launches += 2;
     if (g->nreg == 4) {   // DRAGAN: the penalty also back-propagates through s(xhat)
-      dh_kernel<<<g->dh_blocks, g->dh_threads, dh_smem, s>>>(g->Aall + size_t(2) * B * HP, g->ds + 2 * B, w2,
+      launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, g->ds + 2 * B, w2,
                                                             g->DHall + size_t(2) * B * HP, g->dw2p3, B, H, HP, g->dh_rows_per_iter);
-      colsum_kernel<<<cdiv(HP * 32, 256), 256, 0, s>>>(g->dw2p3, g->dh_blocks, HP, HP, g->dw2sum + 2 * HP);
+      launch_pdl(colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p3, g->dh_blocks, HP, HP, g->dw2sum + 2 * HP);
       c->launches += 2;
     }
   }
@@ -969,7 +1001,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   gs.s[1] = {g->D.off_b1, g->H, 2, 0, pw.ldp, g->X, pw.splits, pw.part_stride, g->PD};
   gs.s[2] = {g->D.off_w2, g->H, 3, 0, 0, 0, gp ? g->nreg - 1 : 1, (long long)HP, g->dw2sum};
   gs.s[3] = {g->D.off_b2, 1, 3, 0, 0, 0, gp ? 2 : 1, 2, g->lossbuf + 1};
-  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_D]);
+  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_D]);
   c->launches++;
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   g->last_rows = 2 * B;
@@ -990,7 +1022,7 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   if (g->d.variant == GM_BEGAN) return began_g_grad(g, sp, B, loss_dev, s);
   if ((rc = launch_plan(c, sp->d1_g, s))) return rc;
   launch_loss(g, B, 1, inv_global_batch, s);
-  dh_kernel<<<g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * g->HP * sizeof(float), s>>>(
+  launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * g->HP * sizeof(float), s, 
       g->Aall + size_t(B) * g->HP, g->ds + B, g->par[GM_NET_D] + g->D.off_w2, g->DHall + size_t(B) * g->HP, nullptr, B,
       g->H, g->HP, g->dh_rows_per_iter);
   c->launches++;
@@ -1008,7 +1040,7 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
   gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
   gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
-  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_G]);
+  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_G]);
   c->launches++;
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   g->last_rows = B;
@@ -1038,7 +1070,7 @@ extern "C" int gm_gan_sync_shadows_q(gm_gan* g, gm_stream stream) {
   memset(&a, 0, sizeof a);
   a.p = g->parQ; a.update = 0;
   q_adam_segs(g, a);
-  adam_kernel<<<cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -1063,8 +1095,8 @@ extern "C" int gm_gan_q_grad(gm_gan* g, int batch, const float* noise, int zd, f
   if ((rc = launch_plan(c, sp->q1, s))) return rc;
   if ((rc = launch_plan(c, sp->q2, s))) return rc;
   const int nb = cdiv(B, kLossThreads) < c->num_sms * 2 ? cdiv(B, kLossThreads) : c->num_sms * 2;
-  info_loss_kernel<<<nb, kLossThreads, 0, s>>>(g->INF, 32, noise, g->Z, zd, 10, 10, B, inv_global_batch, g->DINF, 64, g->q_part);
-  info_loss_final_kernel<<<1, kLossThreads, 0, s>>>(g->q_part, nb, B, 10, g->lossbuf);
+  launch_pdl(info_loss_kernel, nb, kLossThreads, 0, s, g->INF, 32, noise, g->Z, zd, 10, 10, B, inv_global_batch, g->DINF, 64, g->q_part);
+  launch_pdl(info_loss_final_kernel, 1, kLossThreads, 0, s, g->q_part, nb, B, 10, g->lossbuf);
   c->launches += 2;
   if ((rc = launch_plan(c, sp->gq2, s))) return rc;
   if ((rc = launch_plan(c, sp->dhq, s))) return rc;
@@ -1083,7 +1115,7 @@ extern "C" int gm_gan_q_grad(gm_gan* g, int batch, const float* noise, int zd, f
   gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
   gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
   gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
-  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd[GM_NET_G]);
+  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_G]);
   GradSegs qs;
   memset(&qs, 0, sizeof qs);
   const GemmParams& q1 = sp->gq1.p;
@@ -1094,7 +1126,7 @@ extern "C" int gm_gan_q_grad(gm_gan* g, int batch, const float* noise, int zd, f
   qs.s[1] = {g->Qn.off_b1, g->H, 2, 0, q1.ldp, g->X, q1.splits, q1.part_stride, g->PQ1};
   qs.s[2] = {g->Qn.off_w2, g->q_out * g->H, 0, g->H, q2.ldp, 0, q2.splits, q2.part_stride, g->PQ2};
   qs.s[3] = {g->Qn.off_b2, g->q_out, 2, 0, q2.ldp, g->H, q2.splits, q2.part_stride, g->PQ2};
-  finalize_grads_kernel<<<cdiv(qs.total, 256), 256, 0, s>>>(qs, g->grdQ);
+  launch_pdl(finalize_grads_kernel, cdiv(qs.total, 256), 256, 0, s, qs, g->grdQ);
   c->launches += 2;
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   CU_OK(c, cudaGetLastError());
@@ -1112,13 +1144,13 @@ extern "C" int gm_gan_apply_mi(gm_gan* g, const gm_adam_hp* hp, int step, gm_str
   a.p = g->par[GM_NET_G]; a.g = g->grd[GM_NET_G]; a.m = g->amG2; a.v = g->avG2;
   fill_adam(a, hp, step);
   adam_segs(g, GM_NET_G, a);
-  adam_kernel<<<cdiv(a.total, 256), 256, 0, s>>>(a);
+  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, s, a);
   AdamParams q;
   memset(&q, 0, sizeof q);
   q.p = g->parQ; q.g = g->grdQ; q.m = g->amQ; q.v = g->avQ;
   fill_adam(q, hp, step);
   q_adam_segs(g, q);
-  adam_kernel<<<cdiv(q.total, 256), 256, 0, s>>>(q);
+  launch_pdl(adam_kernel, cdiv(q.total, 256), 256, 0, s, q);
   g->ctx->launches += 2;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -1133,6 +1165,7 @@ extern "C" int gm_gan_scores(gm_gan* g, float* dst, int n, gm_stream stream) {
 }
 
 __global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int ld, float* __restrict__ dst, int rows, int cols) {
+  griddep_sync();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)rows * cols) return;
   const int r = int(i / cols), cidx = int(i % cols);
@@ -1150,12 +1183,12 @@ extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* imag
   int rc;
   if ((rc = build_plans(g, B, &sp))) return rc;
   // stage n noise rows (rows n..B-1 keep whatever they held; their outputs are not read)
-  stage_noise_kernel<<<cdiv(n * (g->ZP / 8), 256), 256, 0, s>>>(noise, g->Zb, n, g->Z, g->ZP, 0, 0);
+  launch_pdl(stage_noise_kernel, cdiv(n * (g->ZP / 8), 256), 256, 0, s, noise, g->Zb, n, g->Z, g->ZP, 0, 0);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
   if ((rc = launch_plan(g->ctx, sp->g2, s))) return rc;
   const long long tot = (long long)n * g->X;
-  bf16_rows_to_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, s>>>(g->Xall + size_t(B) * g->XP, g->XP, images, n, g->X);
+  launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->Xall + size_t(B) * g->XP, g->XP, images, n, g->X);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -1169,10 +1202,10 @@ extern "C" int gm_gan_discriminate(gm_gan* g, const void* images, int img_fmt, i
   StepPlans* sp;
   int rc;
   if ((rc = build_plans(g, n, &sp))) return rc;
-  stage_images_kernel<<<g->ctx->num_sms * 8, 256, 0, s>>>(images, img_fmt, nullptr, g->Xall, n, g->X, g->XP);
+  launch_pdl(stage_images_kernel, g->ctx->num_sms * 8, 256, 0, s, images, img_fmt, nullptr, g->Xall, n, g->X, g->XP);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->d1_x, s))) return rc;
-  scores_kernel<<<cdiv(n, 256), 256, 0, s>>>(g->slots, 2 * cdiv(g->H, 208), g->nreg * g->Bmax, g->par[GM_NET_D] + g->D.off_b2,
+  launch_pdl(scores_kernel, cdiv(n, 256), 256, 0, s, g->slots, 2 * cdiv(g->H, 208), g->nreg * g->Bmax, g->par[GM_NET_D] + g->D.off_b2,
                                             g->d.d_out_act, scores, n);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());

@@ -119,7 +119,7 @@ extern "C" int gm_vae_sync_shadows(gm_vae* g, gm_stream stream) {
   memset(&a, 0, sizeof a);
   a.p = g->par; a.update = 0;
   vae_adam_segs(g, a);
-  adam_kernel<<<cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -133,7 +133,7 @@ extern "C" int gm_vae_apply(gm_vae* g, const gm_adam_hp* hp, int step, gm_stream
   a.p = g->par; a.g = g->grd; a.m = g->am; a.v = g->av;
   fill_adam(a, hp, step);
   vae_adam_segs(g, a);
-  adam_kernel<<<cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -205,11 +205,11 @@ static int vae_forward_core(gm_vae* g, VaePlans* sp, const void* images, int fmt
                             uint64_t seed, uint64_t step, bool train, cudaStream_t s) {
   gm_ctx* c = g->ctx;
   int rc;
-  stage_images_kernel<<<c->num_sms * 8, 256, 0, s>>>(images, fmt, idx, g->Xin, B, g->X, g->XP);
+  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, fmt, idx, g->Xin, B, g->X, g->XP);
   c->launches++;
   if ((rc = launch_plan(c, sp->e1, s))) return rc;
   if ((rc = launch_plan(c, sp->e2, s))) return rc;
-  vae_reparam_kernel<<<cdiv(B, 256), 256, 0, s>>>(g->MULV, 64, eps, g->EPS, g->Zb, g->ZP, B, g->Z, seed, step, g->part_k);
+  launch_pdl(vae_reparam_kernel, cdiv(B, 256), 256, 0, s, g->MULV, 64, eps, g->EPS, g->Zb, g->ZP, B, g->Z, seed, step, g->part_k);
   c->launches++;
   if ((rc = launch_plan(c, sp->d1, s))) return rc;
   if ((rc = launch_plan(c, train ? sp->d2 : sp->d2_fwd, s))) return rc;
@@ -218,8 +218,8 @@ static int vae_forward_core(gm_vae* g, VaePlans* sp, const void* images, int fmt
 
 static void vae_losses(gm_vae* g, int B, cudaStream_t s) {
   const int nb = g->ctx->num_sms * 2;
-  vae_rowsum_kernel<<<nb, 256, 0, s>>>(g->slots_r, 2 * cdiv(g->X, 208), g->Bmax, B, g->part_r);
-  vae_losses_final_kernel<<<1, 256, 0, s>>>(g->part_r, nb, g->part_k, cdiv(B, 256), g->losses);
+  launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r, 2 * cdiv(g->X, 208), g->Bmax, B, g->part_r);
+  launch_pdl(vae_losses_final_kernel, 1, 256, 0, s, g->part_r, nb, g->part_k, cdiv(B, 256), g->losses);
   g->ctx->launches += 2;
 }
 
@@ -243,7 +243,7 @@ extern "C" int gm_vae_grad(gm_vae* g, const void* images, int img_fmt, const int
   if ((rc = launch_plan(c, sp->da3, s))) return rc;
   if ((rc = launch_plan(c, sp->gw3, s))) return rc;
   if ((rc = launch_plan(c, sp->dz, s))) return rc;
-  vae_dlatent_kernel<<<cdiv(B * 64, 256), 256, 0, s>>>(g->MULV, 64, g->DZ, 32, g->EPS, g->DML, 64, B, g->Z, 1.f);
+  launch_pdl(vae_dlatent_kernel, cdiv(B * 64, 256), 256, 0, s, g->MULV, 64, g->DZ, 32, g->EPS, g->DML, 64, B, g->Z, 1.f);
   c->launches++;
   if ((rc = launch_plan(c, sp->gwmv, s))) return rc;
   if ((rc = launch_plan(c, sp->da1, s))) return rc;
@@ -261,7 +261,7 @@ extern "C" int gm_vae_grad(gm_vae* g, const void* images, int img_fmt, const int
   gs.s[5] = {g->off_b3, g->H, 2, 0, p3.ldp, g->Z, p3.splits, p3.part_stride, g->P3};
   gs.s[6] = {g->off_w4, g->X * g->H, 0, g->H, p4.ldp, 0, p4.splits, p4.part_stride, g->P4};
   gs.s[7] = {g->off_b4, g->X, 2, 0, p4.ldp, g->H, p4.splits, p4.part_stride, g->P4};
-  finalize_grads_kernel<<<cdiv(gs.total, 256), 256, 0, s>>>(gs, g->grd);
+  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd);
   c->launches++;
   if (losses_dev) CU_OK(c, cudaMemcpyAsync(losses_dev, g->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   CU_OK(c, cudaGetLastError());
@@ -289,7 +289,7 @@ extern "C" int gm_vae_forward(gm_vae* g, const void* images, int img_fmt, int n,
   }
   if (out_images_dev) {
     const long long tot = (long long)n * g->X;
-    bf16_rows_to_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, s>>>(g->DA4, g->XP, out_images_dev, n, g->X);
+    launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->DA4, g->XP, out_images_dev, n, g->X);
     g->ctx->launches++;
   }
   if (mu_logvar_dev)
@@ -308,12 +308,12 @@ extern "C" int gm_vae_decode(gm_vae* g, const float* z_dev, int n, float* out_im
   VaePlans* sp;
   int rc;
   if ((rc = vae_plans(g, n, &sp))) return rc;
-  stage_noise_kernel<<<cdiv(n * (g->ZP / 8), 256), 256, 0, s>>>(z_dev, g->Zb, n, g->Z, g->ZP, 0, 0);
+  launch_pdl(stage_noise_kernel, cdiv(n * (g->ZP / 8), 256), 256, 0, s, z_dev, g->Zb, n, g->Z, g->ZP, 0, 0);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->d1, s))) return rc;
   if ((rc = launch_plan(g->ctx, sp->d2_fwd, s))) return rc;
   const long long tot = (long long)n * g->X;
-  bf16_rows_to_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, s>>>(g->DA4, g->XP, out_images_dev, n, g->X);
+  launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->DA4, g->XP, out_images_dev, n, g->X);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;

@@ -143,6 +143,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert(!PAIR || BN2 == 0, "pair mode: one MMA per k-step");
   const bool pair_leader = !PAIR || crank == 0;
 
+  griddep_launch();   // the next grid may start its prologue as soon as SMs free up
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -162,6 +163,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_wait();     // barrier init / TMEM alloc above overlapped the previous grid's tail
 
   // work items are walked per CLUSTER: item -> (split, m_super, n_tile); this CTA's m-tile is
   // m_super*CS + rank (an m-tile past the end just loads zero rows and stores nothing)
@@ -373,7 +375,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           __syncwarp();
         }
-        if (aux_mode != AUX_NONE) aux_fetch(n0 + part * kEpiCols);
+        if (aux_mode != AUX_NONE) {
+          aux_fetch(n0 + part * kEpiCols);
+          // pull the aux tile of the NEXT tile this warp will process (same accumulator stage)
+          // into L2 now: its loads are otherwise HBM-latency-bound (dX epilogue measured 12-14 k
+          // cycles per tile against 5 k for the same epilogue without aux; profiles/r1e)
+          const int nitem = item + NACC * item_step;
+          if (nitem < total) {
+            const int nrem = nitem - (nitem / tiles) * tiles;
+            const int nm0 = ((nrem / p.n_tiles) * CS + crank) * BM + quarter * 32;
+            const int nn0 = (nrem % p.n_tiles) * BN;
+            // 32 rows x 416 B: each of the kParts warps of this quarter takes every kParts-th row
+            for (int t = lane; t < (32 / kParts) * 4; t += 32) {
+              const int r = nm0 + (t >> 2) * kParts + part, c = nn0 + (t & 3) * 64;
+              if (r < p.M && c < p.out_cols)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux + size_t(r) * p.ld_aux + c));
+            }
+          }
+        }
         const long long te0 = clock64();
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();

@@ -24,6 +24,7 @@ constexpr float kEps = 1e-8f;  // the reference's log stabiliser (src/ns_gan.py:
 enum : int { IMG_F32 = 0, IMG_U8 = 1, IMG_BITS = 2, IMG_BF16PAD = 3 };
 __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const int* __restrict__ idx,
                                     __nv_bfloat16* __restrict__ dst, int rows, int x, int ld) {
+  griddep_sync();
   const int groups = ld / 8;
   const long long total = (long long)rows * groups;
   if (fmt == IMG_BITS && (x & 7) == 0) {
@@ -83,6 +84,7 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
 // offset the step stream, so every step / rank / group draws disjoint numbers.
 __global__ void stage_noise_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
                                    int z, int ld, unsigned long long seed, unsigned long long stream_id) {
+  griddep_sync();
   const int groups = ld / 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)rows * groups) return;
@@ -166,6 +168,7 @@ __device__ __forceinline__ double reduce_partials4(const double* part, int nblk,
 
 template <int PASS>
 __global__ void __launch_bounds__(kLossThreads) loss_pass_kernel(const LossParams p) {
+  griddep_sync();
   __shared__ double sh[kLossThreads / 32];
   const int rows = p.g_step ? p.B : 2 * p.B;
   const float b2 = p.b2[0];
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass_kernel(const LossParam
 }
 
 __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossParams p) {
+  griddep_sync();
   __shared__ double sh[kLossThreads / 32];
   const double lsum = reduce_partials4(p.partR, p.nblk, 0, sh);
   const double dssum = reduce_partials4(p.partR, p.nblk, 1, sh);
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossPara
 // D's output for inference: d[r] = act(sum(slots[:, r]) + b2)
 __global__ void scores_kernel(const float* __restrict__ slots, int nslots, int slot_ld, const float* __restrict__ b2,
                               int out_act, float* __restrict__ out, int rows) {
+  griddep_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float s = 0.f;
@@ -291,6 +296,7 @@ __global__ void scores_kernel(const float* __restrict__ slots, int nslots, int s
 
 // out[c] = sum_p part[p*ld + c]: one warp per column (deterministic shuffle tree)
 __global__ void colsum_kernel(const float* __restrict__ part, int nparts, int ld, int cols, float* __restrict__ out) {
+  griddep_sync();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= cols) return;
@@ -307,6 +313,7 @@ __global__ void colsum_kernel(const float* __restrict__ part, int nparts, int ld
 __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ ds,
                           const float* __restrict__ w2, __nv_bfloat16* __restrict__ dh, float* __restrict__ dw2p,
                           int rows, int h, int ld, int rows_per_iter) {
+  griddep_sync();
   extern __shared__ float sh_acc[];  // [rows_per_iter][ld]
   const int groups = ld / 8;
   const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
@@ -372,6 +379,7 @@ __global__ void xhat_kernel(const __nv_bfloat16* __restrict__ xr, const __nv_bfl
                             __nv_bfloat16* __restrict__ out, int rows, int x, int ld, int mode,
                             const float* __restrict__ rnd, const float* __restrict__ stats,
                             unsigned long long seed, unsigned long long stream_id) {
+  griddep_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   curandStatePhilox4_32_10_t st;
@@ -414,6 +422,7 @@ __global__ void xhat_kernel(const __nv_bfloat16* __restrict__ xr, const __nv_bfl
 
 // sum and sum of squares of the first x columns of `rows` bf16 rows -> per-block partials [nblk][2]
 __global__ void moments_kernel(const __nv_bfloat16* __restrict__ a, int rows, int x, int ld, double* __restrict__ part) {
+  griddep_sync();
   __shared__ double sh[256 / 32];
   const int groups = ld / 8;
   double s1 = 0, s2 = 0;
@@ -433,6 +442,7 @@ __global__ void moments_kernel(const __nv_bfloat16* __restrict__ a, int rows, in
   if (threadIdx.x == 0) { part[blockIdx.x * 2] = s1; part[blockIdx.x * 2 + 1] = s2; }
 }
 __global__ void moments_final_kernel(const double* __restrict__ part, int nblk, float* __restrict__ stats) {
+  griddep_sync();
   __shared__ double sh[256 / 32];
   double s1 = 0, s2 = 0;
   for (int i = threadIdx.x; i < nblk; i += 256) { s1 += part[2 * i]; s2 += part[2 * i + 1]; }
@@ -455,6 +465,7 @@ struct GpParams {
   float* loss;   // [0] += lam * sum (n-K)^2 / rows ;  [3] = sum ds_gp
 };
 __global__ void __launch_bounds__(kLossThreads) gp_rows_kernel(const GpParams p) {
+  griddep_sync();
   __shared__ double sh[kLossThreads / 32];
   double a0 = 0, a1 = 0;
   for (int r = blockIdx.x * kLossThreads + threadIdx.x; r < p.rows; r += gridDim.x * kLossThreads) {
@@ -478,6 +489,7 @@ __global__ void __launch_bounds__(kLossThreads) gp_rows_kernel(const GpParams p)
   if (threadIdx.x == 0) { p.part[blockIdx.x * 4] = a0; p.part[blockIdx.x * 4 + 1] = a1; }
 }
 __global__ void __launch_bounds__(kLossThreads) gp_final_kernel(const GpParams p) {
+  griddep_sync();
   __shared__ double sh[kLossThreads / 32];
   const double s0 = reduce_partials4(p.part, p.nblk, 0, sh);
   const double s1 = reduce_partials4(p.part, p.nblk, 1, sh);
@@ -489,6 +501,7 @@ __global__ void __launch_bounds__(kLossThreads) gp_final_kernel(const GpParams p
 
 // rows[r, :] *= coef[r]  (bf16, in place)
 __global__ void scale_rows_kernel(__nv_bfloat16* __restrict__ a, const float* __restrict__ coef, int rows, int ld) {
+  griddep_sync();
   const int groups = ld / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)rows * groups;
        i += (long long)gridDim.x * blockDim.x) {
@@ -509,6 +522,7 @@ __global__ void vae_reparam_kernel(const float* __restrict__ mulv, int ldm, cons
                                    float* __restrict__ eps_out, __nv_bfloat16* __restrict__ zb, int ldz, int rows,
                                    int z, unsigned long long seed, unsigned long long stream_id,
                                    double* __restrict__ part) {
+  griddep_sync();
   __shared__ double sh[256 / 32];
   double kl = 0.0;
   const int r = blockIdx.x * 256 + threadIdx.x;
@@ -542,6 +556,7 @@ __global__ void vae_reparam_kernel(const float* __restrict__ mulv, int ldm, cons
 __global__ void vae_dlatent_kernel(const float* __restrict__ mulv, int ldm, const float* __restrict__ dz, int lddz,
                                    const float* __restrict__ eps, __nv_bfloat16* __restrict__ out, int ld, int rows,
                                    int z, float scale) {
+  griddep_sync();
   const long long i = blockIdx.x * 256ll + threadIdx.x;
   if (i >= (long long)rows * ld) return;
   const int r = int(i / ld), c = int(i % ld);
@@ -559,6 +574,7 @@ __global__ void vae_dlatent_kernel(const float* __restrict__ mulv, int ldm, cons
 // recon = sum over rows of the per-row slots (sum (x-out)^2); losses[0] = recon, [1] = kl
 __global__ void vae_rowsum_kernel(const float* __restrict__ slots, int nslots, int slot_ld, int rows,
                                   double* __restrict__ part) {
+  griddep_sync();
   __shared__ double sh[256 / 32];
   double t = 0.0;
   for (int r = blockIdx.x * 256 + threadIdx.x; r < rows; r += gridDim.x * 256)
@@ -568,6 +584,7 @@ __global__ void vae_rowsum_kernel(const float* __restrict__ slots, int nslots, i
 }
 __global__ void vae_losses_final_kernel(const double* __restrict__ part_r, int nr, const double* __restrict__ part_k,
                                         int nk, float* __restrict__ losses) {
+  griddep_sync();
   __shared__ double sh[256 / 32];
   double a = 0, b = 0;
   for (int i = threadIdx.x; i < nr; i += 256) a += part_r[i];
@@ -587,6 +604,7 @@ __global__ void __launch_bounds__(kLossThreads) info_loss_kernel(const float* __
                                                                   int nc, int rows, float inv_b,
                                                                   __nv_bfloat16* __restrict__ dinf, int ldo,
                                                                   double* __restrict__ part) {
+  griddep_sync();
   __shared__ double sh[kLossThreads / 32];
   double ce = 0, mse = 0;
   for (int r = blockIdx.x * kLossThreads + threadIdx.x; r < rows; r += gridDim.x * kLossThreads) {
@@ -616,6 +634,7 @@ __global__ void __launch_bounds__(kLossThreads) info_loss_kernel(const float* __
 }
 __global__ void __launch_bounds__(kLossThreads) info_loss_final_kernel(const double* __restrict__ part, int nblk, int rows,
                                                                         int nc, float* __restrict__ loss) {
+  griddep_sync();
   __shared__ double sh[kLossThreads / 32];
   const double ce = reduce_partials4(part, nblk, 0, sh), mse = reduce_partials4(part, nblk, 1, sh);
   if (threadIdx.x == 0) loss[0] = float(ce / rows + mse / ((double)rows * nc));
@@ -628,6 +647,7 @@ __global__ void __launch_bounds__(kLossThreads) info_loss_final_kernel(const dou
 // G step: loss = DG (src/be_gan.py:256).  part_x / part_g: per-block partial row sums.
 __global__ void began_loss_final_kernel(const double* __restrict__ part_x, const double* __restrict__ part_g, int nblk,
                                         int B, int g_step, float* __restrict__ state, float* __restrict__ loss) {
+  griddep_sync();
   __shared__ double sh[256 / 32];
   double a = 0, b = 0;
   for (int i = threadIdx.x; i < nblk; i += 256) { if (!g_step) a += part_x[i]; b += part_g[i]; }
@@ -642,6 +662,7 @@ __global__ void began_loss_final_kernel(const double* __restrict__ part_x, const
 // proportional control of K (src/be_gan.py:189-191) and the two identical ReduceLROnPlateau
 // schedulers (factor 0.5, rel threshold 0.01, patience given; src/be_gan.py:133-136,194-195)
 __global__ void began_control_kernel(float* __restrict__ state, float gamma, float lambda, float patience) {
+  griddep_sync();
   const float DX = state[3], DG = state[4];
   const float K = fminf(fmaxf(state[0] + lambda * (gamma * DX - DG), 0.f), 1.f);
   const float conv = DX + fabsf(gamma * DX - DG);
@@ -657,6 +678,7 @@ __global__ void began_control_kernel(float* __restrict__ state, float gamma, flo
 __global__ void began_da2_kernel(const __nv_bfloat16* __restrict__ T, const __nv_bfloat16* __restrict__ DRg,
                                  const __nv_bfloat16* __restrict__ fake, __nv_bfloat16* __restrict__ out, int rows, int x,
                                  int ld) {
+  griddep_sync();
   const int groups = ld / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)rows * groups;
        i += (long long)gridDim.x * blockDim.x) {
@@ -693,6 +715,7 @@ struct GradSeg {
 struct GradSegs { GradSeg s[8]; int nseg; int total; };
 
 __global__ void finalize_grads_kernel(const GradSegs segs, float* __restrict__ flat) {
+  griddep_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= segs.total) return;
 #pragma unroll 1
@@ -731,6 +754,7 @@ struct AdamParams {
 };
 
 __global__ void adam_kernel(const AdamParams a) {
+  griddep_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total) return;
   float p = a.p[i];

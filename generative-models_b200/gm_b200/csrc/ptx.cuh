@@ -235,6 +235,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn_m
 // ~2^-11): the GEMM epilogue is MUFU-bound with the 2-op exp + rcp form.  The result is
 // stored as bf16 (half-ulp 2^-9 relative), so the approximation stays below the storage
 // rounding.  fp32 outputs (losses, scores) use expf-based sigmoids instead.
+// Programmatic dependent launch: every kernel of the step lets the next grid start its
+// prologue early (launch_dependents) and orders its own global accesses after the previous
+// grid's completion (wait).  EVERY kernel in the chain must execute the wait, otherwise
+// completion is no longer transitive along the stream.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_sync() { griddep_launch(); griddep_wait(); }
+
 __device__ __forceinline__ float fast_sigmoid(float x) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));

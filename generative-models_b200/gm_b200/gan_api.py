@@ -90,6 +90,48 @@ class GANBase(nn.Module):
         self.shape = int(image_size ** 0.5)
 
 
+class DeviceDataset:
+    """Device-resident, bit-packed copy of a binarised image dataset + on-device batch sampling.
+
+    The reference fetches every batch with `next(iter(DataLoader(shuffle=True)))`
+    (src/ns_gan.py:222-226): a fresh random permutation of the whole dataset and a host
+    `stack` + H2D copy per step — 27-34 % of its CPU step.  When the
+    Trainer is handed a DataLoader over a TensorDataset of {0,1} images, the images are
+    packed once to 1 bit/pixel (98 B/image) in HBM; a batch is then `batch_size` distinct
+    random row indices drawn on the device and gathered + unpacked by the staging kernel."""
+
+    def __init__(self, images, batch_size, drop_last=False):
+        n = images.shape[0]
+        flat = images.reshape(n, -1)
+        if not bool(((flat == 0) | (flat == 1)).all()):
+            raise ValueError("DeviceDataset needs binarised {0,1} images")
+        self.n, self.x, self.batch_size = n, flat.shape[1], batch_size
+        if self.x % 8:
+            raise ValueError("image_size must be a multiple of 8")
+        bits = np.packbits(flat.to(torch.uint8).cpu().numpy(), axis=1)      # MSB first, row-aligned
+        self.bits = to_cuda(torch.from_numpy(bits).contiguous())
+        self.num_batches = n // batch_size if drop_last else -(-n // batch_size)
+
+    def __len__(self):
+        return self.num_batches
+
+    def sample(self):
+        """indices of one shuffled batch (what the first batch of a fresh shuffling iterator holds)"""
+        b = min(self.batch_size, self.n)
+        return torch.randperm(self.n, device=self.bits.device)[:b].to(torch.int32)
+
+    @staticmethod
+    def from_loader(loader):
+        ds = getattr(loader, "dataset", None)
+        tensors = getattr(ds, "tensors", None)
+        if tensors is None or getattr(loader, "batch_size", None) is None:
+            return None
+        try:
+            return DeviceDataset(tensors[0], loader.batch_size, getattr(loader, "drop_last", False))
+        except ValueError:
+            return None
+
+
 class _FusedLoss(torch.autograd.Function):
     """0-dim loss whose backward() hands the gradients the fused kernels already
     computed to the parameters' .grad (the reference calls loss.backward() then
@@ -115,6 +157,7 @@ class GANTrainerBase:
     """Object to hold data iterators, train a GAN variant (src/ns_gan.py:77-290)."""
     variant = "ns"
     d_out_act = "sigmoid"
+    device_dataset = True     # keep a bit-packed copy of train_iter's dataset in HBM when possible
 
     def __init__(self, model, train_iter, val_iter, test_iter, viz=False):
         self.model = model
@@ -178,6 +221,7 @@ class GANTrainerBase:
         back once per epoch instead of once per step."""
         hpG, hpD = AdamHP.make(G_lr), AdamHP.make(D_lr, clamp=float(extra.get("clip", 0.0) or 0.0))
         epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
+        self._resident = DeviceDataset.from_loader(self.train_iter) if self.device_dataset else None
         self._pre_train(num_epochs, hpG, hpD, D_steps, extra)
         for epoch in range(1, num_epochs + 1):
             self.model.train()
@@ -185,8 +229,12 @@ class GANTrainerBase:
             for _ in range(epoch_steps):
                 dstep = []
                 for _ in range(D_steps):
-                    images = self.process_batch(self.train_iter)
-                    dstep.append(self._fused_D(images, hpD))
+                    if self._resident is not None:          # on-device shuffle + gather, no host work
+                        images = self._resident.sample()
+                        dstep.append(self._fused_D(self._resident.bits, hpD, gather_idx=images))
+                    else:
+                        images = self.process_batch(self.train_iter)
+                        dstep.append(self._fused_D(images, hpD))
                 dl.append(torch.stack(dstep).mean())
                 gl.append(self._fused_G(images.shape[0], hpG))
             G_losses = torch.stack(gl).tolist()     # one device->host read per epoch
@@ -210,11 +258,17 @@ class GANTrainerBase:
             eng.sync_all()
             self._needs_sync = False
 
-    def _fused_D(self, images, hp):
-        eng = self._ensure_engine(images.shape[0])
+    def _fused_D(self, images, hp, gather_idx=None):
+        batch = images.shape[0] if gather_idx is None else gather_idx.shape[0]
+        eng = self._ensure_engine(batch)
         self._sync_once(eng)
-        noise = self.compute_noise(images.shape[0], self.model.z_dim)
-        loss = eng.d_grad(images, noise=noise, aux=self._draw_aux(images), seed=self._seed, step=self._step).clone()
+        noise = self.compute_noise(batch, self.model.z_dim)
+        if gather_idx is None:
+            loss = eng.d_grad(images, noise=noise, aux=self._draw_aux(images), seed=self._seed, step=self._step).clone()
+        else:
+            loss = eng.d_grad(images, fmt="bits", gather_idx=gather_idx, batch=batch, noise=noise,
+                              aux=self._draw_aux(torch.empty(batch, self.model.image_size, device="meta")),
+                              seed=self._seed, step=self._step).clone()
         eng.apply(D_NET, hp)
         return loss
 

@@ -127,3 +127,31 @@ def test_modules_forward_and_checkpoint_roundtrip(tmp_path):
             p.zero_()
     trainer.load_model(path)
     assert float((model.G(z) - before).abs().max()) < 1e-6
+
+
+def test_device_resident_dataset_path():
+    """train() over a real DataLoader(TensorDataset): images are packed to 1 bit/pixel in HBM
+    once and batches are sampled on the device (the reference's per-step DataLoader fetch)."""
+    import ns_gan
+    from gm_b200.gan_api import DeviceDataset
+    g = torch.Generator().manual_seed(0)
+    imgs = (torch.rand(1000, 1, 28, 28, generator=g) < 0.13).float()
+    ds = torch.utils.data.TensorDataset(imgs, torch.zeros(1000, dtype=torch.long))
+    loader = torch.utils.data.DataLoader(ds, batch_size=100, shuffle=True)
+    dd = DeviceDataset.from_loader(loader)
+    assert dd is not None and len(dd) == 10 and dd.bits.shape == (1000, 98)
+    idx = dd.sample()
+    assert idx.shape == (100,) and idx.unique().numel() == 100          # distinct rows, like a shuffled batch
+    # unpack on the GPU through the staging kernel and compare with the source rows
+    model = ns_gan.NSGAN(784, 400, 20)
+    tr = ns_gan.NSGANTrainer(model, loader, loader, loader)
+    tr.train(num_epochs=1, G_lr=2e-4, D_lr=2e-4, D_steps=1)
+    assert len(tr.Dlosses) == 10 and all(np.isfinite(tr.Dlosses)) and all(np.isfinite(tr.Glosses))
+    eng = tr._engine
+    eng.d_grad(dd.bits, fmt="bits", gather_idx=idx, batch=100, noise=torch.randn(100, 20, device="cuda"))
+    sc = eng.scores(100)
+    ref = model.D(imgs.view(1000, -1)[idx.long().cpu()])
+    assert float((sc - ref.view(-1)).abs().max()) < 2e-3
+    # a non-binary dataset falls back to process_batch
+    loader2 = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(torch.rand(200, 1, 28, 28), torch.zeros(200)), batch_size=100)
+    assert DeviceDataset.from_loader(loader2) is None

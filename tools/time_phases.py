@@ -47,3 +47,9 @@ out2 = torch.zeros(2 * B, 416, device=dev, dtype=torch.bfloat16)
 w2 = torch.randn(400, device=dev)
 slots = torch.zeros(4, 2 * B, device=dev)
 run("d1 (K=784)", lambda: gm_b200.gemm_bf16(A2, W2, out2, "nt", K=784, bias=bias, act=1, dot_w=w2, dot_out=slots))
+A3, W3 = bf(B, 416), bf(784, 400, scale=0.05)
+out3 = torch.zeros(B, 800, device=dev, dtype=torch.bfloat16)
+bias3 = torch.randn(784, device=dev)
+run("g2 (K=400, sigmoid+bias)", lambda: gm_b200.gemm_bf16(A3, W3, out3, "nt", K=400, bias=bias3, act=2, pad_one=True, out_cols=800))
+aux3 = torch.rand(B, 800, device=dev).to(torch.bfloat16)
+run("dx (K=400, aux sigmoid-grad)", lambda: gm_b200.gemm_bf16(A3, W3, out3, "nt", K=400, aux=aux3, aux_mode=1))
