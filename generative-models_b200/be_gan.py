@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from utils import *  # noqa: F401,F403
 from gm_b200 import AdamHP, GmError
-from gm_b200.gan_api import Generator, GANTrainerBase, _EngineBacked, to_cuda, G_NET, D_NET
+from gm_b200.gan_api import builtin_step, Generator, GANTrainerBase, _EngineBacked, to_cuda, G_NET, D_NET
 
 
 class Discriminator(_EngineBacked):
@@ -81,6 +81,7 @@ class BEGANTrainer(GANTrainerBase):
             self._began_pending = None
         return eng
 
+    @builtin_step
     def train_D(self, images, K):
         """ returns (D_loss, DX_loss, DG_loss) like src/be_gan.py:212-238 """
         images = to_cuda(images)

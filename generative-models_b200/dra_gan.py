@@ -8,7 +8,7 @@ import torch.nn as nn  # noqa: F401
 import numpy as np  # noqa: F401
 
 from utils import *  # noqa: F401,F403  (to_var, to_cuda, get_data — src/utils.py)
-from gm_b200.gan_api import Generator, Discriminator, GANBase, GANTrainerBase, G_NET, D_NET
+from gm_b200.gan_api import builtin_step, Generator, Discriminator, GANBase, GANTrainerBase, G_NET, D_NET
 from gm_b200 import AdamHP
 
 
@@ -23,6 +23,7 @@ class DRAGANTrainer(GANTrainerBase):
     def train(self, num_epochs, G_lr=1e-4, D_lr=1e-4, D_steps=5):
         super().train(num_epochs, G_lr=G_lr, D_lr=D_lr, D_steps=D_steps)
 
+    @builtin_step
     def train_D(self, images, LAMBDA=10, K=1, C=1):
         if (LAMBDA, K, C) != (10, 1, 1):
             raise ValueError("the fused penalty is built for the reference defaults LAMBDA=10, K=1, C=1")

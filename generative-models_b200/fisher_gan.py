@@ -7,7 +7,7 @@ import torch.nn as nn  # noqa: F401
 import numpy as np  # noqa: F401
 
 from utils import *  # noqa: F401,F403  (to_var, to_cuda, get_data — src/utils.py)
-from gm_b200.gan_api import Generator, Discriminator, GANBase, GANTrainerBase, G_NET, D_NET
+from gm_b200.gan_api import builtin_step, Generator, Discriminator, GANBase, GANTrainerBase, G_NET, D_NET
 from gm_b200 import AdamHP
 
 
@@ -38,6 +38,7 @@ class FisherGANTrainer(GANTrainerBase):
         eng.fisher_state(*(pend if pend else (0.0, getattr(self, "_rho", 1e-6))))
         self._fisher_pending = None
 
+    @builtin_step
     def train_D(self, images):
         """ returns (D_loss, IPM_ratio) like src/fisher_gan.py:193-229; the IPM ratio is a
         logging-only quantity (with the reference's operator-precedence quirk) and is not

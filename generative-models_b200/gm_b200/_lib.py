@@ -90,6 +90,11 @@ def lib():
     L.gm_gan_began_state.argtypes = [vp, C.POINTER(C.c_float), i, vp]
     L.gm_gan_began_control.argtypes = [vp, f, f, f, vp]
     L.gm_gan_discriminate.argtypes = [vp, vp, i, i, vp, vp]
+    L.gm_gan_num_slots.argtypes = [vp]
+    L.gm_gan_d_forward.argtypes = [vp, i, vp, i, vp, vp]
+    L.gm_gan_d_backward.argtypes = [vp, i, i, vp, vp, vp]
+    L.gm_gan_g_forward.argtypes = [vp, vp, i, vp, vp]
+    L.gm_gan_g_backward.argtypes = [vp, i, vp, vp]
     L.gm_vae_create.argtypes = [vp, C.POINTER(VaeDesc), C.POINTER(vp)]
     L.gm_vae_destroy.argtypes = [vp]
     L.gm_vae_param_count.argtypes = [vp]

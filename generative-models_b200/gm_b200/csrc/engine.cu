@@ -428,6 +428,10 @@ struct StepPlans {
   GemmPlan be_enc_d, be_dec_d, be_gwd, be_de_d, be_enc_g, be_dec_g, be_de_g, be_dxg;   // BEGAN autoencoder-discriminator
 };
 
+struct CustomPlans {   // custom-loss path (engine_custom.inl): per-slot D forward / backward, G output kept in DA2
+  GemmPlan d1[4], dw1[4], dx[4], g2;
+};
+
 struct gm_gan {
   gm_ctx* ctx;
   gm_gan_desc d;
@@ -466,6 +470,7 @@ struct gm_gan {
   int last_rows = 0;
   int region_rows = 0;   // rows per region of Xall/Aall/DHall (3 regions)
   std::map<int, StepPlans> plans;
+  std::map<int, CustomPlans> cplans;
   std::vector<void*> allocs;
 };
 
@@ -599,7 +604,7 @@ extern "C" int gm_gan_bind(gm_gan* g, int net, float* p, float* gr, float* m, fl
   if (reinterpret_cast<uintptr_t>(p) & 15)
     return fail(g->ctx, GM_ERR_ARG, "parameter buffer must be 16-byte aligned");
   g->par[net] = p; g->grd[net] = gr; g->am[net] = m; g->av[net] = v;
-  g->plans.clear();
+  g->plans.clear(); g->cplans.clear();
   return GM_OK;
 }
 
@@ -1053,7 +1058,7 @@ extern "C" int gm_gan_bind_q(gm_gan* g, float* q_params, float* q_grads, float* 
   if (!g || !q_params || !q_grads) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_bind_q: bad argument") : GM_ERR_ARG;
   if (g->d.variant != GM_INFO) return fail(g->ctx, GM_ERR_STATE, "gm_gan_bind_q: engine was not created with GM_INFO");
   g->parQ = q_params; g->grdQ = q_grads; g->amQ = q_m; g->avQ = q_v; g->amG2 = g_mi_m; g->avG2 = g_mi_v;
-  g->plans.clear();
+  g->plans.clear(); g->cplans.clear();
   return GM_OK;
 }
 extern "C" int gm_gan_q_param_count(const gm_gan* g) { return (g && g->d.variant == GM_INFO) ? g->Qn.total : GM_ERR_ARG; }
@@ -1223,4 +1228,5 @@ extern "C" int gm_gan_fisher_state(gm_gan* g, float* lambda_rho_host, int set, g
   return GM_OK;
 }
 
+#include "engine_custom.inl"
 #include "engine_vae.inl"

@@ -130,6 +130,46 @@ class GanEngine:
         check(self.h, lib().gm_gan_generate(self.g, _ptr(noise.contiguous().float()), n, _ptr(out), _stream()))
         return out
 
+    # ---- custom-loss path (README.md:31): forward / backward halves as separate calls
+    g_generation = 0
+    d_calls = 0
+
+    @property
+    def supports_custom_loss(self):
+        return self.variant not in ("began",)        # BEGAN's D is an autoencoder (src/be_gan.py:63-76)
+
+    @property
+    def d_generation(self):
+        if not hasattr(self, "_d_generation"):
+            self._d_generation = [0] * self.num_slots()
+        return self._d_generation
+
+    def num_slots(self):
+        return lib().gm_gan_num_slots(self.g)
+
+    def d_forward(self, slot, x):
+        n = x.shape[0]
+        out = torch.empty(n, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_gan_d_forward(self.g, slot, _ptr(x), n, _ptr(out), _stream()))
+        return out
+
+    def d_backward(self, slot, dscore, need_dx):
+        """-> (flat D gradient (engine buffer, overwritten by the next call), dL/dx or None)"""
+        n = dscore.shape[0]
+        dx = torch.empty(n, self.image_size, device=self.device, dtype=torch.float32) if need_dx else None
+        check(self.h, lib().gm_gan_d_backward(self.g, slot, n, _ptr(dscore), _ptr(dx), _stream()))
+        return self.grads[1], dx
+
+    def g_forward(self, noise):
+        n = noise.shape[0]
+        out = torch.empty(n, self.image_size, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_gan_g_forward(self.g, _ptr(noise), n, _ptr(out), _stream()))
+        return out
+
+    def g_backward(self, dimages):
+        check(self.h, lib().gm_gan_g_backward(self.g, dimages.shape[0], _ptr(dimages), _stream()))
+        return self.grads[0]
+
     def began_state(self, values=None):
         """BEGAN device state (list of 11 floats, see include/gm_b200.h); pass values to set."""
         buf = (C.c_float * 11)()

@@ -10,6 +10,7 @@ become views into the engine's flat fp32 buffers and every forward / loss / back
 Adam is a hand-written sm_100a kernel behind the C ABI.  No autograd on the hot path.
 """
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -39,10 +40,23 @@ class _EngineBacked(nn.Module):
     Trainer has attached it; forward runs the CUDA kernels (inference, no autograd)."""
     _engine = None
     _net = None
+    _owner = None      # weakref to the Trainer that creates / grows the engine on demand
 
     def _attach(self, engine, net):
         object.__setattr__(self, "_engine", engine)
         object.__setattr__(self, "_net", net)
+
+    def _engine_for(self, batch, what):
+        """The engine able to hold `batch` rows; the owning Trainer creates or grows it lazily
+        (the reference moves the model to the GPU in Trainer.__init__, src/ns_gan.py:81)."""
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None and (self._engine is None or batch > (owner._max_batch or 0)):
+            owner._ensure_engine(batch)
+        if self._engine is None:
+            raise GmError(what + " is not attached to a CUDA engine yet: construct the Trainer first "
+                          "(there is no eager/CPU path)")
+        self._engine.sync_if_stale()
+        return self._engine
 
 
 class Generator(_EngineBacked):
@@ -54,11 +68,11 @@ class Generator(_EngineBacked):
         self.generate = nn.Linear(hidden_dim, image_size)
 
     def forward(self, x):
-        if self._engine is None:
-            raise GmError("Generator is not attached to a CUDA engine yet: construct the Trainer first "
-                          "(there is no eager/CPU path)")
-        self._engine.sync_if_stale()
-        return self._engine.generate(to_cuda(x))
+        x = to_cuda(x).float().contiguous()
+        eng = self._engine_for(x.shape[0], "Generator")
+        if torch.is_grad_enabled() and eng.supports_custom_loss:
+            return _GForward.apply(x, eng, *self.parameters())     # custom-loss path (README.md:31)
+        return eng.generate(x)
 
 
 class Discriminator(_EngineBacked):
@@ -72,10 +86,11 @@ class Discriminator(_EngineBacked):
         self.discriminate = nn.Linear(hidden_dim, output_dim)
 
     def forward(self, x):
-        if self._engine is None:
-            raise GmError("Discriminator is not attached to a CUDA engine yet: construct the Trainer first")
-        self._engine.sync_if_stale()
-        return self._engine.discriminate(to_cuda(x))
+        x = to_cuda(x).float().contiguous()
+        eng = self._engine_for(x.shape[0], "Discriminator")
+        if torch.is_grad_enabled() and eng.supports_custom_loss:
+            return _DForward.apply(x, eng, *self.parameters())     # custom-loss path (README.md:31)
+        return eng.discriminate(x)
 
 
 class GANBase(nn.Module):
@@ -132,6 +147,89 @@ class DeviceDataset:
             return None
 
 
+def builtin_step(fn):
+    """Marks a train_D / train_G implementation as one of the fused built-in losses.  A
+    Trainer whose train_D / train_G is NOT marked (a user override, README.md:31) is trained
+    by the reference loop over the custom-loss path instead of the fused step."""
+    fn._gm_builtin = True
+    return fn
+
+
+def _split_like(flat, params):
+    out, off = [], 0
+    for p in params:
+        n = p.numel()
+        out.append(flat[off:off + n].view_as(p).clone())
+        off += n
+    return out
+
+
+class _GForward(torch.autograd.Function):
+    """Generator.forward with a backward (src/ns_gan.py:43-46): both halves are the CUDA
+    kernels; autograd only routes dL/dG(z) in and the parameter gradients out."""
+
+    @staticmethod
+    def forward(ctx, noise, engine, *params):
+        ctx.engine, ctx.params = engine, params
+        engine.g_generation += 1
+        ctx.generation = engine.g_generation
+        return engine.g_forward(noise)
+
+    @staticmethod
+    def backward(ctx, dimages):
+        eng = ctx.engine
+        if eng.g_generation != ctx.generation:
+            raise RuntimeError("Generator activations were overwritten by a later Generator.forward: "
+                               "back-propagate a G output before calling G again")
+        flat = eng.g_backward(dimages.float().contiguous())
+        return (None, None, *_split_like(flat, ctx.params))
+
+
+class _DForward(torch.autograd.Function):
+    """Discriminator.forward with a backward (src/ns_gan.py:57-60).  Each call keeps its
+    activations in one of the engine's row regions until its backward ran."""
+
+    @staticmethod
+    def forward(ctx, x, engine, *params):
+        ctx.engine, ctx.params = engine, params
+        ctx.slot = engine.d_calls % engine.num_slots()
+        engine.d_calls += 1
+        engine.d_generation[ctx.slot] = engine.d_calls
+        ctx.generation = engine.d_calls
+        return engine.d_forward(ctx.slot, x).view(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dscore):
+        eng = ctx.engine
+        if eng.d_generation[ctx.slot] != ctx.generation:
+            raise RuntimeError("Discriminator activations were overwritten: at most %d Discriminator.forward "
+                               "results can await their backward (construct the engine with a gradient-penalty "
+                               "variant for more)" % eng.num_slots())
+        flat, dx = eng.d_backward(ctx.slot, dscore.reshape(-1).float().contiguous(), ctx.needs_input_grad[0])
+        return (dx, None, *_split_like(flat, ctx.params))
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (src/ns_gan.py:107-110) with the update done by
+    gm_adam_step; used by the reference loop when train_D / train_G are user overrides."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, clamp=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clamp=clamp))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            hp = AdamHP.make(group["lr"], group["betas"], group["eps"], group["weight_decay"], group["clamp"])
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"], st["exp_avg"], st["exp_avg_sq"] = 0, torch.zeros_like(p.data), torch.zeros_like(p.data)
+                st["step"] += 1
+                _lib.adam_step(p.data, p.grad.contiguous(), st["exp_avg"], st["exp_avg_sq"], hp, st["step"])
+
+
 class _FusedLoss(torch.autograd.Function):
     """0-dim loss whose backward() hands the gradients the fused kernels already
     computed to the parameters' .grad (the reference calls loss.backward() then
@@ -171,6 +269,9 @@ class GANTrainerBase:
         self._step = 0
         self._seed = int(torch.initial_seed() & 0x7FFFFFFF)
         self._needs_sync = True
+        for mod in (getattr(model, "G", None), getattr(model, "D", None)):
+            if isinstance(mod, _EngineBacked):
+                object.__setattr__(mod, "_owner", weakref.ref(self))
 
     # ------------------------------------------------------------------ engine plumbing
     def _ensure_engine(self, batch):
@@ -219,6 +320,8 @@ class GANTrainerBase:
         """Trainer.train (src/ns_gan.py:94-170): same loop, same logging; each train_D /
         train_G + backward + Adam step is one fused kernel sequence and losses are read
         back once per epoch instead of once per step."""
+        if self._has_custom_step():
+            return self._train_reference_loop(num_epochs, G_lr, D_lr, D_steps, float(extra.get("clip", 0.0) or 0.0))
         hpG, hpD = AdamHP.make(G_lr), AdamHP.make(D_lr, clamp=float(extra.get("clip", 0.0) or 0.0))
         epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
         self._resident = DeviceDataset.from_loader(self.train_iter) if self.device_dataset else None
@@ -239,6 +342,44 @@ class GANTrainerBase:
                 gl.append(self._fused_G(images.shape[0], hpG))
             G_losses = torch.stack(gl).tolist()     # one device->host read per epoch
             D_losses = torch.stack(dl).tolist()
+            self.Glosses.extend(G_losses)
+            self.Dlosses.extend(D_losses)
+            print("Epoch[%d/%d], G Loss: %.4f, D Loss: %.4f" % (epoch, num_epochs, np.mean(G_losses), np.mean(D_losses)))
+            self.num_epochs += 1
+            if self.viz:
+                self.generate_images(epoch)
+
+    def _has_custom_step(self):
+        return not (getattr(type(self).train_D, "_gm_builtin", False) and getattr(type(self).train_G, "_gm_builtin", False))
+
+    def _train_reference_loop(self, num_epochs, G_lr, D_lr, D_steps, clip):
+        """The reference's loop verbatim (src/ns_gan.py:107-156) for Trainers whose train_D /
+        train_G were overridden: the override's torch loss drives the CUDA forward / backward
+        kernels through Generator.forward / Discriminator.forward and their autograd nodes."""
+        bs = getattr(self.train_iter, "batch_size", None) or next(iter(self.train_iter))[0].shape[0]
+        self._ensure_engine(bs)
+        G_optimizer = FusedAdam(self.model.G.parameters(), lr=G_lr)
+        D_optimizer = FusedAdam(self.model.D.parameters(), lr=D_lr, clamp=clip)
+        epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
+        for epoch in range(1, num_epochs + 1):
+            self.model.train()
+            G_losses, D_losses = [], []
+            for _ in range(epoch_steps):
+                D_step_loss = []
+                for _ in range(D_steps):
+                    images = self.process_batch(self.train_iter)
+                    D_optimizer.zero_grad()
+                    D_loss = self.train_D(images)
+                    D_loss.backward()
+                    D_optimizer.step()
+                    D_step_loss.append(D_loss.detach())
+                D_losses.append(torch.stack(D_step_loss).mean())
+                G_optimizer.zero_grad()
+                G_loss = self.train_G(images)
+                G_losses.append(G_loss.detach())
+                G_loss.backward()
+                G_optimizer.step()
+            G_losses, D_losses = torch.stack(G_losses).tolist(), torch.stack(D_losses).tolist()
             self.Glosses.extend(G_losses)
             self.Dlosses.extend(D_losses)
             print("Epoch[%d/%d], G Loss: %.4f, D Loss: %.4f" % (epoch, num_epochs, np.mean(G_losses), np.mean(D_losses)))
@@ -281,6 +422,7 @@ class GANTrainerBase:
         self._step += 1
         return loss
 
+    @builtin_step
     def train_D(self, images):
         """Run 1 step of training for the discriminator (src/ns_gan.py:172-194): returns
         the loss; `.backward()` delivers the D gradients to model.D's parameters."""
@@ -292,6 +434,7 @@ class GANTrainerBase:
                           seed=self._seed, step=self._step)
         return self._loss_tensor(D_NET, loss)
 
+    @builtin_step
     def train_G(self, images):
         """Run 1 step of training for the generator (src/ns_gan.py:196-216)."""
         batch = images.shape[0]

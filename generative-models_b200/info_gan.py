@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from utils import *  # noqa: F401,F403
 from gm_b200 import AdamHP, GmError, InfoGanEngine
-from gm_b200.gan_api import Generator as _Generator, Discriminator as _Discriminator, GANTrainerBase, _FusedLoss, to_cuda, G_NET, D_NET
+from gm_b200.gan_api import builtin_step, Generator as _Generator, Discriminator as _Discriminator, GANTrainerBase, _FusedLoss, to_cuda, G_NET, D_NET
 
 
 class Generator(_Generator):
@@ -141,6 +141,7 @@ class InfoGANTrainer(GANTrainerBase):
         eng.apply(G_NET, hp)
         return loss
 
+    @builtin_step
     def train_D(self, images):
         images = to_cuda(images)
         eng = self._ensure_engine(images.shape[0])
@@ -150,6 +151,7 @@ class InfoGANTrainer(GANTrainerBase):
         loss = eng.d_grad(images.float().contiguous(), noise=noise.float().contiguous())
         return self._loss_tensor(D_NET, loss)
 
+    @builtin_step
     def train_G(self, images):
         eng = self._ensure_engine(images.shape[0])
         eng.sync_all()

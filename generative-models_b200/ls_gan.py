@@ -7,7 +7,7 @@ import torch.nn as nn  # noqa: F401
 import numpy as np  # noqa: F401
 
 from utils import *  # noqa: F401,F403  (to_var, to_cuda, get_data — src/utils.py)
-from gm_b200.gan_api import Generator, Discriminator, GANBase, GANTrainerBase, G_NET, D_NET
+from gm_b200.gan_api import builtin_step, Generator, Discriminator, GANBase, GANTrainerBase, G_NET, D_NET
 from gm_b200 import AdamHP
 
 
@@ -21,11 +21,13 @@ class LSGANTrainer(GANTrainerBase):
     def train(self, num_epochs, G_lr=1e-4, D_lr=1e-4, D_steps=1):
         super().train(num_epochs, G_lr=G_lr, D_lr=D_lr, D_steps=D_steps)
 
+    @builtin_step
     def train_D(self, images, a=0, b=1):
         if (a, b) != (0, 1):
             raise ValueError("the fused LSGAN loss is built for the reference defaults a=0, b=1")
         return super().train_D(images)
 
+    @builtin_step
     def train_G(self, images, c=1):
         if c != 1:
             raise ValueError("the fused LSGAN loss is built for the reference default c=1")

@@ -133,6 +133,24 @@ int gm_gan_apply(gm_gan* gan, int net, const gm_adam_hp* hp, int step, gm_stream
 /* D outputs of the last *_grad call (D step: batch real then batch fake; G step:
  * batch fake) -> dst_dev; what the reference names DX_score / DG_score. */
 int gm_gan_scores(gm_gan* gan, float* dst_dev, int n, gm_stream stream);
+/* ---- custom-loss path --------------------------------------------------------
+ * README.md:31 tells users to "edit train_D and train_G": a loss written in torch on
+ * DX_score / DG_score must still train.  These four calls are Generator.forward /
+ * Discriminator.forward (src/ns_gan.py:43-46,57-60) and their backward halves as
+ * separate entry points; the host wraps them in torch.autograd.Function objects
+ * (gm_b200/gan_api.py).  `slot` in [0, gm_gan_num_slots) picks the row region that keeps
+ * one D forward's activations alive until its backward.  Gradients are written to the
+ * bound flat gradient buffers (overwritten per call; the host accumulates). */
+int gm_gan_num_slots(const gm_gan* gan);
+/* scores_dev[batch] = D(x_dev[batch, image_size]) (fp32 in, fp32 out, final activation applied) */
+int gm_gan_d_forward(gm_gan* gan, int slot, const float* x_dev, int batch, float* scores_dev, gm_stream stream);
+/* dscore_dev[batch] = dL/dscore -> flat D gradient; dx_dev (nullable) [batch, image_size] = dL/dx */
+int gm_gan_d_backward(gm_gan* gan, int slot, int batch, const float* dscore_dev, float* dx_dev, gm_stream stream);
+/* images_dev[batch, image_size] = G(noise_dev[batch, z]) keeping the activations for one backward */
+int gm_gan_g_forward(gm_gan* gan, const float* noise_dev, int batch, float* images_dev, gm_stream stream);
+/* dimages_dev[batch, image_size] = dL/dG(z) -> flat G gradient */
+int gm_gan_g_backward(gm_gan* gan, int batch, const float* dimages_dev, gm_stream stream);
+
 /* Generator.forward (src/ns_gan.py:43-46) for sampling: noise [n, z] fp32 -> images
  * [n, image_size] fp32. */
 int gm_gan_generate(gm_gan* gan, const float* noise_dev, int n, float* images_dev, gm_stream stream);

