@@ -74,6 +74,16 @@ constexpr int kEpiStageBytes = 32 * kEpiPitch;
 constexpr int kEpiVecBlocks = 8;                       // column blocks per warp the bias/dot staging holds
 constexpr int kEpiVecBytes = kEpiVecBlocks * kEpiCols * 4 * 2;   // bias + row-dot weights
 
+// Phase timing (tools/time_phases.py) is compiled in only with -DGM_PHASE_TIMING: the clock
+// reads cost 8+ registers and CS2R stalls in the 96-register epilogue (profiles/r1e).
+#ifdef GM_PHASE_TIMING
+__device__ __forceinline__ long long phase_clock() { return phase_clock(); }
+constexpr bool kPhaseTiming = true;
+#else
+__device__ __forceinline__ long long phase_clock() { return 0; }
+constexpr bool kPhaseTiming = false;
+#endif
+
 template <int BN1, int BN2, bool STAGED_EPI = true, bool PAIR = false, int EW = 8>
 struct GemmCfg {
   static constexpr int BN = BN1 + BN2;
@@ -258,17 +268,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
       const int as = acc_iter % NACC;
       const uint32_t aphase = (acc_iter / NACC) & 1;
-      const long long tm0 = clock64();
+      const long long tm0 = phase_clock();
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tc_fence_after();
-      const long long tm1 = clock64();
+      const long long tm1 = phase_clock();
       long long full_wait = 0;
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = kb0; kb < kb1; ++kb) {
-        const long long tw0 = clock64();
+        const long long tw0 = phase_clock();
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        full_wait += clock64() - tw0;
+        full_wait += phase_clock() - tw0;
         const uint32_t a_src = smem_base + stage * Cfg::STAGE_BYTES;
         const uint32_t b_src = a_src + Cfg::A_BYTES;
         const int krem = p.K - kb * BK;
@@ -302,9 +312,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         else umma_commit(tfull_bar(as));
       }
       __syncwarp();
-      if (p.dbg != nullptr && blockIdx.x == 0 && acc_iter < 16 && leader) {
+      if (kPhaseTiming && p.dbg != nullptr && blockIdx.x == 0 && acc_iter < 16 && leader) {
         long long* d = p.dbg + acc_iter * 4;   // [tile][wait accumulator free, issue loop, of which waiting for TMA, start stamp]
-        d[0] = tm1 - tm0; d[1] = clock64() - tm1; d[2] = full_wait; d[3] = tm0;
+        d[0] = tm1 - tm0; d[1] = phase_clock() - tm1; d[2] = full_wait; d[3] = tm0;
       }
     }
   } else {
@@ -348,15 +358,31 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // row segment, 8 rows per pass, 4 passes
         const int lr = lane >> 2, lc = lane & 3;
         constexpr int kBlocks = (BN + kEpiCols - 1) / kEpiCols;
-        uint4 pre[4];
+        // aux tile (32 rows x 32 columns of the warp's next block):
+        //  * kernels without bias / row-dot (dX, dHg, penalty T): cp.async straight into the
+        //    warp's (otherwise unused) bias staging area, 64-byte rows with the 16-byte chunks
+        //    XOR-swizzled by (row >> 1) & 3 so that the row-per-lane reads are conflict-free.
+        //    No registers held across the block, no STS (the 96-register budget of the
+        //    16-warp epilogue was spilling / re-reading S2R and constants, profiles/r1e);
+        //  * otherwise: coalesced LDG into registers, transposed through the staging tile.
+        constexpr bool kAuxAsync = (AUX_T > 0) && (BIAS_T == 0) && (DOT_T == 0);
+        uint4 pre[kAuxAsync ? 1 : 4];
         auto aux_fetch = [&](int c_first) {
           const int c = c_first + lc * 8;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            const int r = wrow0 + it * 8 + lr;
-            pre[it] = make_uint4(0, 0, 0, 0);
-            if (r < p.M && c < p.out_cols) pre[it] = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(r) * p.ld_aux + c));
+            const int rl = it * 8 + lr;
+            const int r = wrow0 + rl;
+            const bool ok = r < p.M && c < p.out_cols;
+            if constexpr (kAuxAsync) {
+              const __nv_bfloat16* src = ok ? p.aux + size_t(r) * p.ld_aux + c : p.aux;
+              cp_async16_zfill(vec_s + rl * 64 + ((lc ^ ((rl >> 1) & 3)) << 4), src, ok ? 16u : 0u);
+            } else {
+              pre[it] = make_uint4(0, 0, 0, 0);
+              if (ok) pre[it] = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(r) * p.ld_aux + c));
+            }
           }
+          if constexpr (kAuxAsync) cp_async_commit();
         };
         // bias / row-dot weights of this warp's column blocks -> smem and the first aux tile ->
         // registers while the MMAs still run: no global-load latency after the TMEM read
@@ -393,10 +419,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        const long long te0 = clock64();
+        const long long te0 = phase_clock();
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
-        const long long te1 = clock64();
+        const long long te1 = phase_clock();
         long long t_ld = 0;
         float dot = 0.f;
         bool released = false;
@@ -412,22 +438,29 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool last_block = (cb_next >= BN) || (n0 + cb_next >= p.out_cols);
           uint4 ax[4];
           if (aux_mode != AUX_NONE) {   // prefetched aux (coalesced mapping) -> smem -> own row
+            if constexpr (kAuxAsync) {
+              cp_async_wait_all();
+              __syncwarp();
 #pragma unroll
-            for (int it = 0; it < 4; ++it) sts128(stage_s + (it * 8 + lr) * kEpiPitch + lc * 16, pre[it]);
-            __syncwarp();
+              for (int q = 0; q < 4; ++q) ax[q] = lds128(vec_s + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ax[q] = lds128(stage_s + lane * kEpiPitch + q * 16);
+              for (int it = 0; it < 4; ++it) sts128(stage_s + (it * 8 + lr) * kEpiPitch + lc * 16, pre[it]);
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) ax[q] = lds128(stage_s + lane * kEpiPitch + q * 16);
+            }
             __syncwarp();
             if (!last_block) aux_fetch(n0 + cb_next);   // overlaps with this block's math + stores
           }
           // accumulator columns -> registers: both chunks in flight, one wait
           uint32_t raw[2][16];
-          const long long tl0 = clock64();
+          const long long tl0 = phase_clock();
 #pragma unroll
           for (int q = 0; q < 2; ++q)
             if (q < nch && col0 + q * 16 < p.N) tmem_ld16_issue(t_row + cb + q * 16, raw[q]);
           tmem_ld_wait();
-          t_ld += clock64() - tl0;
+          t_ld += phase_clock() - tl0;
           if (last_block) {   // accumulator stage fully read by this warp: hand it back to the MMA warp
             released = true;
             tc_fence_before();
@@ -534,9 +567,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else mbar_arrive(tempty_bar(as));
           }
         }
-        if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (e & 3) == 0 && part == 0 && acc_iter < 16) {
+        if (kPhaseTiming && p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (e & 3) == 0 && part == 0 && acc_iter < 16) {
           long long* d = p.dbg + 64 + acc_iter * 4;   // [tile][wait accumulator ready, epilogue work, of which TMEM ld+wait, start stamp]
-          d[0] = te1 - te0; d[1] = clock64() - te1; d[2] = t_ld; d[3] = te0;
+          d[0] = te1 - te0; d[1] = phase_clock() - te1; d[2] = t_ld; d[3] = te0;
         }
        }
       } else {

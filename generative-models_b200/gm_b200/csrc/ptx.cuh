@@ -235,6 +235,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn_m
 // ~2^-11): the GEMM epilogue is MUFU-bound with the 2-op exp + rcp form.  The result is
 // stored as bf16 (half-ulp 2^-9 relative), so the approximation stays below the storage
 // rounding.  fp32 outputs (losses, scores) use expf-based sigmoids instead.
+// Ampere-style asynchronous 16-byte global->shared copy (zero-fills when src_bytes == 0)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Programmatic dependent launch: every kernel of the step lets the next grid start its
 // prologue early (launch_dependents) and orders its own global accesses after the previous
 // grid's completion (wait).  EVERY kernel in the chain must execute the wait, otherwise

@@ -52,3 +52,9 @@ if "dx" in which:
     out = torch.zeros(B, 800, device=dev, dtype=torch.bfloat16)
     t = timeit(lambda: gm_b200.gemm_bf16(A, W, out, "nt", K=400, aux=aux, aux_mode=1))
     print("dx %.1f us  %.0f TFLOP/s" % (t, 2 * B * 400 * 784 / t / 1e6))
+if "g2" in which:
+    A, W = bf(B, 416), bf(784, 400, scale=0.05)
+    out = torch.zeros(B, 832, device=dev, dtype=torch.bfloat16)
+    bias = torch.randn(784, device=dev)
+    t = timeit(lambda: gm_b200.gemm_bf16(A, W, out, "nt", K=400, bias=bias, act=2, pad_one=True, out_cols=832))
+    print("g2 %.1f us  %.0f TFLOP/s" % (t, 2 * B * 400 * 784 / t / 1e6))
