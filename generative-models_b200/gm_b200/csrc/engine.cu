@@ -157,6 +157,8 @@ static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
   if (p.dot_sq && (bias || dot || aux != AUX_NONE || p.act != ACT_NONE)) return launch_inst<208, 0, false, false>(pl, s);
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 0>(pl, s);
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_NONE, 1, 0>(pl, s);
+  if (bias && dot && p.dot_mask && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 3>(pl, s);
+  if (p.dot_mask) return launch_inst<208, 0, false, false>(pl, s);
   if (bias && dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 1>(pl, s);
   if (!bias && !dot && aux == AUX_SIGMOID_GRAD && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_SIGMOID_GRAD, 0, 0>(pl, s);
   if (!bias && !dot && aux == AUX_RELU_MASK && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_RELU_MASK, 0, 0>(pl, s);
@@ -657,7 +659,7 @@ extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, 
 
 static void set_bf16_epi(GemmParams& p, __nv_bfloat16* out, int ldo, int out_cols, int pad_one, const float* bias, int act) {
   p.epi = EPI_BF16; p.out = out; p.ldo = ldo; p.out_cols = out_cols; p.pad_one = pad_one; p.bias = bias; p.act = act;
-  p.aux = nullptr; p.aux_mode = AUX_NONE; p.dot_w = nullptr; p.dot_out = nullptr; p.dot_sq = 0; p.row_scale = nullptr; p.row_split = 0;
+  p.aux = nullptr; p.aux_mode = AUX_NONE; p.dot_w = nullptr; p.dot_out = nullptr; p.dot_sq = 0; p.row_scale = nullptr; p.row_split = 0; p.dot_mask = 0; p.row_vec = nullptr;
 }
 
 static int build_plans(gm_gan* g, int B, StepPlans** out) {
@@ -688,6 +690,9 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   if ((rc = plan_gemm(c, &sp.d1_g, 0, B, H, X, Xfake, XP, g->W1d_s, X, H, 1))) return rc;
   set_bf16_epi(sp.d1_g.p, Afake, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
   sp.d1_g.p.dot_w = pD + g->D.off_w2; sp.d1_g.p.dot_out = g->slots + B; sp.d1_g.p.dot_ld = slot_ld;
+  // the G step does not update D: instead of the hidden activations it stores M = w2 * 1[a1 > 0]
+  // (what dL/dfake = ds * (M W1d) needs) and so skips the dh pass over the fake rows
+  sp.d1_g.p.dot_mask = g->d.variant != GM_BEGAN;
   // D layer 1 on the real rows only (inference: gm_gan_discriminate)
   if ((rc = plan_gemm(c, &sp.d1_x, 0, B, H, X, g->Xall, XP, g->W1d_s, X, H, 1))) return rc;
   set_bf16_epi(sp.d1_x.p, g->Aall, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
@@ -711,9 +716,10 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
     sp.gp_t.p.aux = g->Aall + size_t(2) * B * HP; sp.gp_t.p.ld_aux = HP; sp.gp_t.p.aux_mode = AUX_RELU_MASK;
   }
   // dX of D w.r.t. fake, times sigmoid'(fake): DA2 = (DHfake W1d) * fake(1-fake)
-  if ((rc = plan_gemm(c, &sp.dx, 0, B, X, H, DHfake, HP, g->W1d_t, H, X, 1))) return rc;
+  if ((rc = plan_gemm(c, &sp.dx, 0, B, X, H, Afake, HP, g->W1d_t, H, X, 1))) return rc;
   set_bf16_epi(sp.dx.p, g->DA2, XP, X, 0, nullptr, ACT_NONE);
   sp.dx.p.aux = Xfake; sp.dx.p.ld_aux = XP; sp.dx.p.aux_mode = AUX_SIGMOID_GRAD;
+  sp.dx.p.row_vec = g->ds + B;     // dL/ds of the fake rows (launch_loss, G step)
   // [dW2g | db2g] = DA2^T [Hg | 1]
   if ((rc = plan_gemm(c, &sp.dw2g, 1, X, H + 1, B, g->DA2, XP, g->Hg, HP, H + 1, g->max_splits))) return rc;
   {
@@ -798,7 +804,7 @@ static int check_step_args(gm_gan* g, int batch) {
 }
 
 static int run_generator(gm_gan* g, StepPlans* sp, int B, const float* noise, uint64_t seed, uint64_t stream_id, cudaStream_t s) {
-  launch_pdl(stage_noise_kernel, cdiv(B * (g->ZP / 8), 256), 256, 0, s, noise, g->Zb, B, g->Z, g->ZP, seed, stream_id);
+  launch_pdl(stage_noise_kernel, cdiv(B * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, B, g->Z, g->ZP, seed, stream_id);
   g->ctx->launches++;
   int rc;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
@@ -1027,10 +1033,6 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   if (g->d.variant == GM_BEGAN) return began_g_grad(g, sp, B, loss_dev, s);
   if ((rc = launch_plan(c, sp->d1_g, s))) return rc;
   launch_loss(g, B, 1, inv_global_batch, s);
-  launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * g->HP * sizeof(float), s, 
-      g->Aall + size_t(B) * g->HP, g->ds + B, g->par[GM_NET_D] + g->D.off_w2, g->DHall + size_t(B) * g->HP, nullptr, B,
-      g->H, g->HP, g->dh_rows_per_iter);
-  c->launches++;
   if ((rc = launch_plan(c, sp->dx, s))) return rc;
   if ((rc = launch_plan(c, sp->dw2g, s))) return rc;
   if ((rc = launch_plan(c, sp->dhg, s))) return rc;
@@ -1188,7 +1190,7 @@ extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* imag
   int rc;
   if ((rc = build_plans(g, B, &sp))) return rc;
   // stage n noise rows (rows n..B-1 keep whatever they held; their outputs are not read)
-  launch_pdl(stage_noise_kernel, cdiv(n * (g->ZP / 8), 256), 256, 0, s, noise, g->Zb, n, g->Z, g->ZP, 0, 0);
+  launch_pdl(stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, n, g->Z, g->ZP, 0, 0);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
   if ((rc = launch_plan(g->ctx, sp->g2, s))) return rc;

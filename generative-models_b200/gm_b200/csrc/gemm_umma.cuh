@@ -55,6 +55,11 @@ struct GemmParams {
   // AUX_L1 (BEGAN): out = sign(v - aux) * (row < row_split ? row_scale[0] : row_scale[1]), dot_out = sum |v - aux|
   const float* row_scale;
   int row_split;
+  // dot_mask: with the row-dot, store dot_w[n] * 1[v > 0] instead of v (the G step needs only
+  // M = w2 * relu'(a1) of D's hidden layer: dL/dx = ds * (M W1), src/ns_gan.py:57-60 backward)
+  int dot_mask;
+  // row_vec (AUX_SIGMOID_GRAD): additional per-row factor, out = v * row_vec[m] * aux (1 - aux)
+  const float* row_vec;
   float* dot_out;       // partial slots [(n_tile*2 + half) * dot_ld + m]
   int dot_ld;
   // ---- EPI_F32: part[split*part_stride + (transpose ? n*ldp + m : m*ldp + n)] = acc
@@ -333,7 +338,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int act = ACT_T >= 0 ? ACT_T : p.act;
     const int aux_mode = AUX_T >= 0 ? AUX_T : p.aux_mode;
     const bool has_bias = BIAS_T >= 0 ? (BIAS_T != 0) : (p.bias != nullptr);
-    const bool has_dot = DOT_T >= 0 ? (DOT_T == 1) : (p.dot_w != nullptr);
+    const bool has_dot = DOT_T >= 0 ? (DOT_T == 1 || DOT_T == 3) : (p.dot_w != nullptr);
+    const bool mask_out = DOT_T >= 0 ? (DOT_T == 3) : (p.dot_mask != 0);
     const bool has_sq = DOT_T >= 0 ? (DOT_T == 2) : (p.dot_sq != 0);
     int acc_iter = 0;
 #pragma unroll 1
@@ -393,7 +399,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int c = n0 + (part + blk * kParts) * kEpiCols + c4;
             uint4 bz = make_uint4(0, 0, 0, 0), wz = bz;
             if (part + blk * kParts < kBlocks && c < p.N) {
-              if (has_bias) bz = __ldg(reinterpret_cast<const uint4*>(p.bias + c));
+              if (has_bias) {
+                bz = __ldg(reinterpret_cast<const uint4*>(p.bias + c));
+                if (act == ACT_SIGMOID) {   // sigmoid(x + b) = 0.5 tanh(0.5 x + 0.5 b) + 0.5: stage 0.5 b, one FFMA later
+                  bz.x = __float_as_uint(0.5f * __uint_as_float(bz.x)); bz.y = __float_as_uint(0.5f * __uint_as_float(bz.y));
+                  bz.z = __float_as_uint(0.5f * __uint_as_float(bz.z)); bz.w = __float_as_uint(0.5f * __uint_as_float(bz.w));
+                }
+              }
               if (has_dot) wz = __ldg(reinterpret_cast<const uint4*>(p.dot_w + c));
             }
             if (has_bias) sts128(vec_s + (blk * kEpiCols + c4) * 4, bz);
@@ -428,6 +440,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bool released = false;
         float l1_scale = 0.f;
         if (aux_mode == AUX_L1) l1_scale = __ldg(p.row_scale + (row < p.row_split ? 0 : 1));
+        if (aux_mode == AUX_SIGMOID_GRAD) l1_scale = (p.row_vec != nullptr && row_ok) ? __ldg(p.row_vec + row) : 1.f;
 #pragma unroll 1
         for (int bi = 0; part + bi * kParts < kBlocks; ++bi) {
           const int cb = (part + bi * kParts) * kEpiCols;
@@ -482,8 +495,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
                     const uint4 b = lds128(vec_s + (bi * kEpiCols + q * 16 + k4 * 4) * 4);
-                    v[4 * k4 + 0] += __uint_as_float(b.x); v[4 * k4 + 1] += __uint_as_float(b.y);
-                    v[4 * k4 + 2] += __uint_as_float(b.z); v[4 * k4 + 3] += __uint_as_float(b.w);
+                    if (act == ACT_SIGMOID) {   // staged bias is 0.5 b: v = 0.5 (acc + b), exact
+                      v[4 * k4 + 0] = fmaf(v[4 * k4 + 0], 0.5f, __uint_as_float(b.x)); v[4 * k4 + 1] = fmaf(v[4 * k4 + 1], 0.5f, __uint_as_float(b.y));
+                      v[4 * k4 + 2] = fmaf(v[4 * k4 + 2], 0.5f, __uint_as_float(b.z)); v[4 * k4 + 3] = fmaf(v[4 * k4 + 3], 0.5f, __uint_as_float(b.w));
+                    } else {
+                      v[4 * k4 + 0] += __uint_as_float(b.x); v[4 * k4 + 1] += __uint_as_float(b.y);
+                      v[4 * k4 + 2] += __uint_as_float(b.z); v[4 * k4 + 3] += __uint_as_float(b.w);
+                    }
                   }
                 }
                 if (act == ACT_RELU) {
@@ -491,7 +509,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 } else if (act == ACT_SIGMOID) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = fast_sigmoid(v[j]);
+                  for (int j = 0; j < 16; ++j) v[j] = has_bias ? fast_sigmoid_half(v[j]) : fast_sigmoid(v[j]);
                 }
                 if (aux_mode != AUX_NONE) {
                   const uint32_t w[8] = {ax[2 * q].x, ax[2 * q].y, ax[2 * q].z, ax[2 * q].w,
@@ -500,8 +518,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int k2 = 0; k2 < 8; ++k2) {
                     const float a_lo = bf16_lo(w[k2]), a_hi = bf16_hi(w[k2]);
                     if (aux_mode == AUX_SIGMOID_GRAD) {
-                      v[2 * k2] *= a_lo * (1.f - a_lo);
-                      v[2 * k2 + 1] *= a_hi * (1.f - a_hi);
+                      v[2 * k2] *= (l1_scale * a_lo) * (1.f - a_lo);
+                      v[2 * k2 + 1] *= (l1_scale * a_hi) * (1.f - a_hi);
                     } else if (aux_mode == AUX_L1) {
                       // BEGAN: L1 reconstruction error of the autoencoder-discriminator and its
                       // (scaled) subgradient sign(r - x)   (src/be_gan.py:225-236)
@@ -532,6 +550,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint4 w = lds128(vec_s + kEpiVecBytes / 2 + (bi * kEpiCols + q * 16 + k4 * 4) * 4);
                     dot = fmaf(v[4 * k4 + 0], __uint_as_float(w.x), dot); dot = fmaf(v[4 * k4 + 1], __uint_as_float(w.y), dot);
                     dot = fmaf(v[4 * k4 + 2], __uint_as_float(w.z), dot); dot = fmaf(v[4 * k4 + 3], __uint_as_float(w.w), dot);
+                    if (mask_out) {
+                      v[4 * k4 + 0] = v[4 * k4 + 0] > 0.f ? __uint_as_float(w.x) : 0.f;
+                      v[4 * k4 + 1] = v[4 * k4 + 1] > 0.f ? __uint_as_float(w.y) : 0.f;
+                      v[4 * k4 + 2] = v[4 * k4 + 2] > 0.f ? __uint_as_float(w.z) : 0.f;
+                      v[4 * k4 + 3] = v[4 * k4 + 3] > 0.f ? __uint_as_float(w.w) : 0.f;
+                    }
                   }
                 }
               } else {

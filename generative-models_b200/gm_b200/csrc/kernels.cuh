@@ -28,29 +28,34 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
   const int groups = ld / 8;
   const long long total = (long long)rows * groups;
   if (fmt == IMG_BITS && (x & 7) == 0) {
-    // one packed byte (MSB first) expands to 8 bf16 values; 4 independent items per thread
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
-      uint32_t byte[4];
+    // One warp per row: lanes walk the row's 8-pixel groups (one packed byte, MSB first, expands
+    // to 8 bf16 = one 16-byte store), 4 passes in flight; no index divisions, the gather index
+    // of the next row is fetched while this row is expanded.  Bound by the 16-byte stores.
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int xb = x >> 3;   // source bytes per row; group xb holds the ones column
+    long long sr_next = w < rows ? (idx ? (long long)idx[w] : (long long)w) : 0;
+    for (int r = w; r < rows; r += nwarps) {
+      const long long sr = sr_next;
+      if (r + nwarps < rows) sr_next = idx ? (long long)idx[r + nwarps] : (long long)(r + nwarps);
+      const uint8_t* srow = reinterpret_cast<const uint8_t*>(src) + sr * xb;
+      uint4* drow = reinterpret_cast<uint4*>(dst) + (long long)r * groups;
+      for (int g0 = 0; g0 < groups; g0 += 128) {
+        uint32_t byte[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        byte[u] = 0;
-        if (i < total) {
-          const int r = int(i / groups), g = int(i % groups);
-          const long long sr = idx ? idx[r] : r;
-          if (g * 8 < x) byte[u] = __ldg(reinterpret_cast<const uint8_t*>(src) + sr * (x >> 3) + g);
-          else if (g * 8 == x) byte[u] = 0x80u;     // ones column
+        for (int u = 0; u < 4; ++u) {
+          const int g = g0 + u * 32 + lane;
+          byte[u] = g < xb ? uint32_t(__ldg(srow + g)) : (g == xb ? 0x80u : 0u);
         }
-      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + u * stride;
-        if (i >= total) break;
-        const uint32_t b = byte[u];
-        // bf16 1.0 = 0x3F80: build the four packed pairs without float conversions
-        auto pr = [&](int hi_bit, int lo_bit) { return ((b >> lo_bit) & 1u ? 0x3F80u : 0u) | ((b >> hi_bit) & 1u ? 0x3F800000u : 0u); };
-        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pr(6, 7), pr(4, 5), pr(2, 3), pr(0, 1));
+        for (int u = 0; u < 4; ++u) {
+          const int g = g0 + u * 32 + lane;
+          if (g >= groups) break;
+          const uint32_t b = byte[u];
+          // bf16 1.0 = 0x3F80: build the four packed pairs without float conversions
+          auto pr = [&](int hi_bit, int lo_bit) { return ((b >> lo_bit) & 1u ? 0x3F80u : 0u) | ((b >> hi_bit) & 1u ? 0x3F800000u : 0u); };
+          drow[g] = make_uint4(pr(6, 7), pr(4, 5), pr(2, 3), pr(0, 1));
+        }
       }
     }
     return;
@@ -85,10 +90,14 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
 __global__ void stage_noise_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
                                    int z, int ld, unsigned long long seed, unsigned long long stream_id) {
   griddep_sync();
-  const int groups = ld / 8;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= (long long)rows * groups) return;
-  const int r = int(i / groups), c0 = int(i % groups) * 8;
+  // One thread per (row, 8-column group that holds noise): every lane runs the Philox /
+  // Box-Muller path (a thread per group of the padded row left 5 of 8 lanes idle in it).
+  // The thread also writes its share of the row's zero padding groups.
+  const int groups = ld / 8, gz = (z + 8) / 8;   // gz: groups holding noise or the ones column
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)rows * gz) return;
+  const int r = int(t / gz), g = int(t % gz), c0 = g * 8;
+  const long long i = (long long)r * groups + g;   // cell index = Philox subsequence
   float v[8];
   if (c0 < z) {
     if (src == nullptr) {
@@ -106,8 +115,9 @@ __global__ void stage_noise_kernel(const float* __restrict__ src, __nv_bfloat16*
     const int c = c0 + j;
     if (c >= z) v[j] = (c == z) ? 1.f : 0.f;
   }
-  reinterpret_cast<uint4*>(dst)[i] =
-      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  uint4* row = reinterpret_cast<uint4*>(dst) + (long long)r * groups;
+  row[g] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  for (int pg = gz + g; pg < groups; pg += gz) row[pg] = make_uint4(0, 0, 0, 0);
 }
 
 // ---------------------------------------------------------------- block reduction (deterministic)

@@ -250,6 +250,12 @@ __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_sync() { griddep_launch(); griddep_wait(); }
 
+// sigmoid(2 h) from h = x / 2 (the epilogue folds the halving into its bias FFMA)
+__device__ __forceinline__ float fast_sigmoid_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(t, 0.5f, 0.5f);
+}
 __device__ __forceinline__ float fast_sigmoid(float x) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));

@@ -95,7 +95,9 @@ def d_backward(P, fw, ds, need_dx=False, pre="D.", q=_exact):
     dh = q("dh", (ds @ w2) * (fw["hq"] > 0))
     g[pre + "linear.weight"] = dh.T @ fw["x"]
     g[pre + "linear.bias"] = dh.sum(0)
-    dx = dh @ q("W", W1) if need_dx else None
+    # dL/dx: the CUDA G step forms M = w2 * relu'(a1) as the bf16 GEMM operand and applies
+    # the per-row factor ds in fp32 after the product (same value; different rounding point)
+    dx = ds * (q("mw", w2 * (fw["hq"] > 0)) @ q("W", W1)) if need_dx else None
     return g, dx
 
 
