@@ -113,6 +113,7 @@ def run_ours(args):
     init_weights_like_reference(eng)
     hpG, hpD = gm_b200.AdamHP.make(2e-4), gm_b200.AdamHP.make(2e-4)
     inv = par.inv_global_batch(B, world)
+    eng.set_lazy_grads(world == 1)    # no all-reduce on one GPU: gather + Adam in one kernel
     # device-resident synthetic dataset, 1 bit per pixel (binarised MNIST carries exactly
     # that: src/utils.py:31); pool of 4*B images = 412 MB as bf16 rows, > 126 MB L2
     N = 4 * B

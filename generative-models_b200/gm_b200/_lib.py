@@ -91,6 +91,8 @@ def lib():
     L.gm_gan_began_control.argtypes = [vp, f, f, f, vp]
     L.gm_gan_discriminate.argtypes = [vp, vp, i, i, vp, vp]
     L.gm_gan_num_slots.argtypes = [vp]
+    L.gm_gan_set_lazy_grads.argtypes = [vp, i, vp]
+    L.gm_gan_materialize_grads.argtypes = [vp, vp]
     L.gm_gan_d_forward.argtypes = [vp, i, vp, i, vp, vp]
     L.gm_gan_d_backward.argtypes = [vp, i, i, vp, vp, vp]
     L.gm_gan_g_forward.argtypes = [vp, vp, i, vp, vp]

@@ -471,6 +471,10 @@ struct gm_gan {
   int max_splits = 0;
   int last_rows = 0;
   int region_rows = 0;   // rows per region of Xall/Aall/DHall (3 regions)
+  // lazy gradients: *_grad leaves the split-K partials, gm_gan_apply gathers + updates in one kernel
+  bool lazy = false;
+  bool pend[2] = {false, false};
+  GradSegs pend_segs[2];
   std::map<int, StepPlans> plans;
   std::map<int, CustomPlans> cplans;
   std::vector<void*> allocs;
@@ -643,6 +647,8 @@ extern "C" int gm_gan_sync_shadows(gm_gan* g, int net, gm_stream stream) {
   return GM_OK;
 }
 
+static void flush_pending(gm_gan* g, cudaStream_t s);
+
 extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, gm_stream stream) {
   if (!g || net < 0 || net > 1 || !hp || step <= 0) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_apply: bad argument") : GM_ERR_ARG;
   if (!g->par[net] || !g->am[net] || !g->av[net]) return fail(g->ctx, GM_ERR_STATE, "net %d not fully bound", net);
@@ -651,8 +657,25 @@ extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, 
   a.p = g->par[net]; a.g = g->grd[net]; a.m = g->am[net]; a.v = g->av[net];
   fill_adam(a, hp, step);
   adam_segs(g, net, a);
+  if (g->pend[net]) {   // lazy gradients: gather from the partials inside the update
+    a.gather = 1; a.gout = g->grd[net]; a.gsegs = g->pend_segs[net];
+    g->pend[net] = false;
+  }
   launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+extern "C" int gm_gan_set_lazy_grads(gm_gan* g, int on, gm_stream stream) {
+  if (!g) return GM_ERR_ARG;
+  if (!on) flush_pending(g, static_cast<cudaStream_t>(stream));
+  g->lazy = on != 0;
+  return GM_OK;
+}
+extern "C" int gm_gan_materialize_grads(gm_gan* g, gm_stream stream) {
+  if (!g) return GM_ERR_ARG;
+  flush_pending(g, static_cast<cudaStream_t>(stream));
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
 }
@@ -842,8 +865,26 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   g->ctx->launches += 2;
 }
 
+// The flat gradient of `net` from its partials: now (finalize kernel), or - with lazy gradients -
+// inside the next gm_gan_apply(net).
+static void emit_grads(gm_gan* g, int net, const GradSegs& gs, cudaStream_t s, bool force_now = false) {
+  if (g->lazy && !force_now) {
+    g->pend_segs[net] = gs;
+    g->pend[net] = true;
+    return;
+  }
+  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[net]);
+  g->ctx->launches++;
+  g->pend[net] = false;
+}
+// Partials are only valid until the next *_grad call reuses the buffers: form pending gradients first.
+static void flush_pending(gm_gan* g, cudaStream_t s) {
+  for (int net = 0; net < 2; ++net)
+    if (g->pend[net]) emit_grads(g, net, g->pend_segs[net], s, true);
+}
+
 // ---- BEGAN (src/be_gan.py:212-258): D = autoencoder, L1 reconstruction losses ----
-static int began_finalize_g(gm_gan* g, StepPlans* sp, cudaStream_t s) {
+static int began_finalize_g(gm_gan* g, StepPlans* sp, cudaStream_t s, bool force_now = false) {
   GradSegs gs;
   memset(&gs, 0, sizeof gs);
   const GemmParams& p2 = sp->dw2g.p;
@@ -854,8 +895,7 @@ static int began_finalize_g(gm_gan* g, StepPlans* sp, cudaStream_t s) {
   gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
   gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
   gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
-  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_G]);
-  g->ctx->launches++;
+  emit_grads(g, GM_NET_G, gs, s, force_now);
   return GM_OK;
 }
 
@@ -883,8 +923,7 @@ static int began_d_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaSt
   gs.s[1] = {g->D.off_b1, g->H, 2, 0, pe.ldp, g->X, pe.splits, pe.part_stride, g->PD};
   gs.s[2] = {g->D.off_w2, g->X * g->H, 0, g->H, pd.ldp, 0, pd.splits, pd.part_stride, g->PWd};
   gs.s[3] = {g->D.off_b2, g->X, 2, 0, pd.ldp, g->H, pd.splits, pd.part_stride, g->PWd};
-  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_D]);
-  c->launches++;
+  emit_grads(g, GM_NET_D, gs, s);
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   CU_OK(c, cudaGetLastError());
   return GM_OK;
@@ -945,6 +984,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   if ((rc = build_plans(g, batch, &sp))) return rc;
   const int B = batch;
   gm_ctx* c = g->ctx;
+  flush_pending(g, s);
   // real rows -> Xall[0:B] (bf16, ones column)
   launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP);
   c->launches++;
@@ -1012,8 +1052,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   gs.s[1] = {g->D.off_b1, g->H, 2, 0, pw.ldp, g->X, pw.splits, pw.part_stride, g->PD};
   gs.s[2] = {g->D.off_w2, g->H, 3, 0, 0, 0, gp ? g->nreg - 1 : 1, (long long)HP, g->dw2sum};
   gs.s[3] = {g->D.off_b2, 1, 3, 0, 0, 0, gp ? 2 : 1, 2, g->lossbuf + 1};
-  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_D]);
-  c->launches++;
+  emit_grads(g, GM_NET_D, gs, s);
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   g->last_rows = 2 * B;
   CU_OK(c, cudaGetLastError());
@@ -1029,6 +1068,7 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   if ((rc = build_plans(g, batch, &sp))) return rc;
   const int B = batch;
   gm_ctx* c = g->ctx;
+  flush_pending(g, s);
   if ((rc = run_generator(g, sp, B, noise, seed, 2 * step + 1, s))) return rc;
   if (g->d.variant == GM_BEGAN) return began_g_grad(g, sp, B, loss_dev, s);
   if ((rc = launch_plan(c, sp->d1_g, s))) return rc;
@@ -1047,8 +1087,7 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
   gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
   gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
-  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_G]);
-  c->launches++;
+  emit_grads(g, GM_NET_G, gs, s);
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   g->last_rows = B;
   CU_OK(c, cudaGetLastError());
@@ -1094,6 +1133,7 @@ extern "C" int gm_gan_q_grad(gm_gan* g, int batch, const float* noise, int zd, f
   if (!noise) return fail(g->ctx, GM_ERR_ARG, "the Q step needs the structured noise tensor");
   if (zd + g->q_out != g->Z) return fail(g->ctx, GM_ERR_ARG, "z_dim (%d) + codes (%d) != generator input (%d)", zd, g->q_out, g->Z);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  flush_pending(g, s);
   StepPlans* sp;
   if ((rc = build_plans(g, batch, &sp))) return rc;
   const int B = batch;
@@ -1122,7 +1162,7 @@ extern "C" int gm_gan_q_grad(gm_gan* g, int batch, const float* noise, int zd, f
   gs.s[1] = {g->G.off_b1, g->H, 2, 0, p1.ldp, g->Z, p1.splits, p1.part_stride, g->PG1};
   gs.s[2] = {g->G.off_w2, g->X * g->H, 0, g->H, p2.ldp, 0, p2.splits, p2.part_stride, g->PG2};
   gs.s[3] = {g->G.off_b2, g->X, 2, 0, p2.ldp, g->H, p2.splits, p2.part_stride, g->PG2};
-  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_G]);
+  emit_grads(g, GM_NET_G, gs, s, true);   // consumed by gm_gan_apply_mi, which reads the flat buffer
   GradSegs qs;
   memset(&qs, 0, sizeof qs);
   const GemmParams& q1 = sp->gq1.p;
@@ -1146,6 +1186,7 @@ extern "C" int gm_gan_apply_mi(gm_gan* g, const gm_adam_hp* hp, int step, gm_str
   if (!g || !hp || step <= 0) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_apply_mi: bad argument") : GM_ERR_ARG;
   if (!g->parQ || !g->amQ || !g->avQ || !g->amG2 || !g->avG2) return fail(g->ctx, GM_ERR_STATE, "Q / MI optimizer state not bound");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  flush_pending(g, s);
   AdamParams a;
   memset(&a, 0, sizeof a);
   a.p = g->par[GM_NET_G]; a.g = g->grd[GM_NET_G]; a.m = g->amG2; a.v = g->avG2;

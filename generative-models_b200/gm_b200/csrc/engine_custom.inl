@@ -87,9 +87,10 @@ static int build_custom_plans(gm_gan* g, int B, CustomPlans** out) {
   return GM_OK;
 }
 
-static int check_custom(gm_gan* g, int batch) {
+static int check_custom(gm_gan* g, int batch, gm_stream stream) {
   int rc = check_step_args(g, batch);
   if (rc) return rc;
+  flush_pending(g, static_cast<cudaStream_t>(stream));   // lazy gradients of the fused step are formed before their partial buffers are reused
   if (g->d.variant == GM_BEGAN)
     return fail(g->ctx, GM_ERR_UNSUPPORTED, "the custom-loss path needs a scalar-output discriminator (BEGAN's D is an autoencoder)");
   return GM_OK;
@@ -98,7 +99,7 @@ static int check_custom(gm_gan* g, int batch) {
 extern "C" int gm_gan_num_slots(const gm_gan* g) { return g ? g->nreg : 0; }
 
 extern "C" int gm_gan_d_forward(gm_gan* g, int slot, const float* x, int batch, float* scores, gm_stream stream) {
-  int rc = check_custom(g, batch);
+  int rc = check_custom(g, batch, stream);
   if (rc) return rc;
   if (!x || !scores) return fail(g->ctx, GM_ERR_ARG, "x / scores is null");
   if (slot < 0 || slot >= g->nreg) return fail(g->ctx, GM_ERR_ARG, "slot must be in [0, %d)", g->nreg);
@@ -118,7 +119,7 @@ extern "C" int gm_gan_d_forward(gm_gan* g, int slot, const float* x, int batch, 
 }
 
 extern "C" int gm_gan_d_backward(gm_gan* g, int slot, int batch, const float* dscore, float* dx, gm_stream stream) {
-  int rc = check_custom(g, batch);
+  int rc = check_custom(g, batch, stream);
   if (rc) return rc;
   if (!dscore) return fail(g->ctx, GM_ERR_ARG, "dscore is null");
   if (slot < 0 || slot >= g->nreg) return fail(g->ctx, GM_ERR_ARG, "slot must be in [0, %d)", g->nreg);
@@ -158,7 +159,7 @@ extern "C" int gm_gan_d_backward(gm_gan* g, int slot, int batch, const float* ds
 }
 
 extern "C" int gm_gan_g_forward(gm_gan* g, const float* noise, int batch, float* images, gm_stream stream) {
-  int rc = check_custom(g, batch);
+  int rc = check_custom(g, batch, stream);
   if (rc) return rc;
   if (!noise || !images) return fail(g->ctx, GM_ERR_ARG, "noise / images is null");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -179,7 +180,7 @@ extern "C" int gm_gan_g_forward(gm_gan* g, const float* noise, int batch, float*
 }
 
 extern "C" int gm_gan_g_backward(gm_gan* g, int batch, const float* dimages, gm_stream stream) {
-  int rc = check_custom(g, batch);
+  int rc = check_custom(g, batch, stream);
   if (rc) return rc;
   if (!dimages) return fail(g->ctx, GM_ERR_ARG, "dimages is null");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -192,7 +193,7 @@ extern "C" int gm_gan_g_backward(gm_gan* g, int batch, const float* dimages, gm_
   if ((rc = launch_plan(c, sp->dw2g, s))) return rc;
   if ((rc = launch_plan(c, sp->dhg, s))) return rc;
   if ((rc = launch_plan(c, sp->dw1g, s))) return rc;
-  began_finalize_g(g, sp, s);   // flat G gradient from the dW2g / dW1g partials (same layout for every variant)
+  began_finalize_g(g, sp, s, true);   // flat G gradient from the dW2g / dW1g partials (same layout for every variant)
   CU_OK(c, cudaGetLastError());
   return GM_OK;
 }

@@ -724,10 +724,8 @@ struct GradSeg {
 };
 struct GradSegs { GradSeg s[8]; int nseg; int total; };
 
-__global__ void finalize_grads_kernel(const GradSegs segs, float* __restrict__ flat) {
-  griddep_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= segs.total) return;
+// element i of the flat gradient: sum of its split-K partials (fixed order -> deterministic)
+__device__ __forceinline__ float gather_grad(const GradSegs& segs, int i) {
 #pragma unroll 1
   for (int k = 0; k < segs.nseg; ++k) {
     const GradSeg& s = segs.s[k];
@@ -739,9 +737,16 @@ __global__ void finalize_grads_kernel(const GradSegs segs, float* __restrict__ f
     else off = j;
     float t = 0.f;
     for (int q = 0; q < s.nsplit; ++q) t += s.src[off + q * s.split_stride];
-    flat[i] = t;
-    return;
+    return t;
   }
+  return 0.f;
+}
+
+__global__ void finalize_grads_kernel(const GradSegs segs, float* __restrict__ flat) {
+  griddep_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= segs.total) return;
+  flat[i] = gather_grad(segs, i);
 }
 
 // ---------------------------------------------------------------- fused Adam + operand shadows
@@ -761,6 +766,9 @@ struct AdamParams {
   int update;                                        // 0: only refresh shadows
   const float* lr_scale;                             // nullable device scalar multiplying lr (BEGAN's plateau scheduler)
   AdamSeg seg[6]; int nseg;
+  // lazy gradients (gm_gan_set_lazy_grads): the flat gradient has not been formed yet; the
+  // update gathers each element from the split-K partials itself and stores it to gout
+  int gather; float* gout; GradSegs gsegs;
 };
 
 __global__ void adam_kernel(const AdamParams a) {
@@ -769,7 +777,9 @@ __global__ void adam_kernel(const AdamParams a) {
   if (i >= a.total) return;
   float p = a.p[i];
   if (a.update) {
-    float g = a.g[i];
+    float g;
+    if (a.gather) { g = gather_grad(a.gsegs, i); a.gout[i] = g; }
+    else g = a.g[i];
     if (a.wd != 0.f) g = fmaf(a.wd, p, g);
     const float m = a.b1 * a.m[i] + (1.f - a.b1) * g;
     const float v = a.b2 * a.v[i] + (1.f - a.b2) * g * g;

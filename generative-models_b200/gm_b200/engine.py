@@ -130,6 +130,14 @@ class GanEngine:
         check(self.h, lib().gm_gan_generate(self.g, _ptr(noise.contiguous().float()), n, _ptr(out), _stream()))
         return out
 
+    def set_lazy_grads(self, on=True):
+        """Single-GPU fast path: d_grad / g_grad leave split-K partials and apply() gathers + updates
+        in one kernel; self.grads[net] is then valid only after apply() (or materialize_grads())."""
+        check(self.h, lib().gm_gan_set_lazy_grads(self.g, 1 if on else 0, _stream()))
+
+    def materialize_grads(self):
+        check(self.h, lib().gm_gan_materialize_grads(self.g, _stream()))
+
     # ---- custom-loss path (README.md:31): forward / backward halves as separate calls
     g_generation = 0
     d_calls = 0

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import parallel as par
 from ._lib import AdamHP, GmError
 from .engine import GanEngine
 
@@ -126,6 +127,11 @@ class DeviceDataset:
         bits = np.packbits(flat.to(torch.uint8).cpu().numpy(), axis=1)      # MSB first, row-aligned
         self.bits = to_cuda(torch.from_numpy(bits).contiguous())
         self.num_batches = n // batch_size if drop_last else -(-n // batch_size)
+        self._gen = None
+
+    def seed(self, value):
+        """Own device generator (data-parallel ranks must draw different batches)."""
+        self._gen = torch.Generator(device=self.bits.device).manual_seed(int(value) & 0x7FFFFFFFFFFFFFFF)
 
     def __len__(self):
         return self.num_batches
@@ -133,7 +139,7 @@ class DeviceDataset:
     def sample(self):
         """indices of one shuffled batch (what the first batch of a fresh shuffling iterator holds)"""
         b = min(self.batch_size, self.n)
-        return torch.randperm(self.n, device=self.bits.device)[:b].to(torch.int32)
+        return torch.randperm(self.n, device=self.bits.device, generator=self._gen)[:b].to(torch.int32)
 
     @staticmethod
     def from_loader(loader):
@@ -325,6 +331,13 @@ class GANTrainerBase:
         hpG, hpD = AdamHP.make(G_lr), AdamHP.make(D_lr, clamp=float(extra.get("clip", 0.0) or 0.0))
         epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
         self._resident = DeviceDataset.from_loader(self.train_iter) if self.device_dataset else None
+        # data parallel when launched under torchrun with an initialised process group:
+        # per-rank batches, upstream gradients scaled by 1/(global batch), SUM all-reduce of the flat
+        # D / G gradients.  On one GPU the gradient gather is fused into the Adam kernel instead.
+        self._world = par.world_size()
+        self._lazy = self._world == 1
+        if self._resident is not None and self._world > 1:
+            self._resident.seed(int(torch.initial_seed()) + par.rank_of())
         self._pre_train(num_epochs, hpG, hpD, D_steps, extra)
         for epoch in range(1, num_epochs + 1):
             self.model.train()
@@ -348,6 +361,9 @@ class GANTrainerBase:
             self.num_epochs += 1
             if self.viz:
                 self.generate_images(epoch)
+        self._lazy = False
+        if self._engine is not None:
+            self._engine.set_lazy_grads(False)
 
     def _has_custom_step(self):
         return not (getattr(type(self).train_D, "_gm_builtin", False) and getattr(type(self).train_G, "_gm_builtin", False))
@@ -403,13 +419,19 @@ class GANTrainerBase:
         batch = images.shape[0] if gather_idx is None else gather_idx.shape[0]
         eng = self._ensure_engine(batch)
         self._sync_once(eng)
+        world = getattr(self, "_world", 1)
+        eng.set_lazy_grads(getattr(self, "_lazy", False))
+        inv = par.inv_global_batch(batch, world)
         noise = self.compute_noise(batch, self.model.z_dim)
         if gather_idx is None:
-            loss = eng.d_grad(images, noise=noise, aux=self._draw_aux(images), seed=self._seed, step=self._step).clone()
+            loss = eng.d_grad(images, noise=noise, aux=self._draw_aux(images), inv_global_batch=inv, seed=self._seed,
+                              step=self._step).clone()
         else:
             loss = eng.d_grad(images, fmt="bits", gather_idx=gather_idx, batch=batch, noise=noise,
                               aux=self._draw_aux(torch.empty(batch, self.model.image_size, device="meta")),
-                              seed=self._seed, step=self._step).clone()
+                              inv_global_batch=inv, seed=self._seed, step=self._step).clone()
+        if world > 1:
+            par.sum_gradients(eng.grads[D_NET])
         eng.apply(D_NET, hp)
         return loss
 
@@ -417,7 +439,11 @@ class GANTrainerBase:
         eng = self._ensure_engine(batch)
         self._sync_once(eng)
         noise = self.compute_noise(batch, self.model.z_dim)
-        loss = eng.g_grad(batch, noise=noise, seed=self._seed, step=self._step).clone()
+        world = getattr(self, "_world", 1)
+        loss = eng.g_grad(batch, noise=noise, inv_global_batch=par.inv_global_batch(batch, world), seed=self._seed,
+                          step=self._step).clone()
+        if world > 1:
+            par.sum_gradients(eng.grads[G_NET])
         eng.apply(G_NET, hp)
         self._step += 1
         return loss

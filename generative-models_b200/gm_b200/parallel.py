@@ -27,6 +27,15 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def world_size(group=None):
+    """Ranks in the (default) process group; 1 when torch.distributed is not initialised."""
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank_of(group=None):
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
 def inv_global_batch(local_batch, world):
     """Scale for per-sample upstream gradients so that SUM over ranks == mean over the
     global batch (the reference's losses are batch means, src/ns_gan.py:191-192)."""

@@ -130,6 +130,14 @@ int gm_gan_g_grad(gm_gan* gan, int batch, const float* noise_dev, float inv_glob
                   uint64_t step, float* loss_dev, gm_stream stream);
 /* optimizer.step() on one net (src/ns_gan.py:139,156) + operand-copy refresh. */
 int gm_gan_apply(gm_gan* gan, int net, const gm_adam_hp* hp, int step, gm_stream stream);
+/* Lazy gradients (single-GPU fast path): with on != 0, *_grad leaves the gradient as split-K
+ * partials and the following gm_gan_apply(net) gathers, stores the flat gradient AND applies
+ * Adam in one kernel (one launch and one pass over the partials less per update).  The flat
+ * gradient buffer is then valid only after gm_gan_apply; call gm_gan_materialize_grads to
+ * form it earlier (e.g. before an all-reduce).  Any later *_grad call materialises pending
+ * gradients first, so results never depend on the mode. */
+int gm_gan_set_lazy_grads(gm_gan* gan, int on, gm_stream stream);
+int gm_gan_materialize_grads(gm_gan* gan, gm_stream stream);
 /* D outputs of the last *_grad call (D step: batch real then batch fake; G step:
  * batch fake) -> dst_dev; what the reference names DX_score / DG_score. */
 int gm_gan_scores(gm_gan* gan, float* dst_dev, int n, gm_stream stream);

@@ -126,7 +126,7 @@ def test_modules_forward_and_checkpoint_roundtrip(tmp_path):
         for p in model.parameters():
             p.zero_()
     trainer.load_model(path)
-    assert float((model.G(z) - before).abs().max()) < 1e-6
+    assert float((model.G(z).detach() - before).abs().max()) < 1e-6
 
 
 def test_device_resident_dataset_path():

@@ -309,3 +309,45 @@ def test_began_steps_against_golden_and_oracle():
     tr.train(num_epochs=1, G_lr=1e-4, D_lr=1e-4, D_steps=1, GAMMA=0.5, LAMBDA=1e-3, K=0.0)
     np.testing.assert_allclose(tr.Dlosses, fx["D_loss"], rtol=2e-3)
     np.testing.assert_allclose(tr.Glosses, fx["G_loss"], rtol=2e-3)
+
+
+@pytest.mark.parametrize("case", ["ns", "wgp"])
+def test_lazy_gradients_are_bit_identical(case):
+    """gm_gan_set_lazy_grads: gathering the split-K partials inside the Adam kernel gives exactly
+    the parameters, moments and flat gradients of the finalize-then-Adam path; an out-of-order
+    call sequence (G gradient requested while D's is pending) materialises D's first."""
+    import gm_b200
+    fx = load_case("gan_" + case)
+    x = torch.from_numpy(images_from_bits(fx)).cuda()
+    g = torch.Generator().manual_seed(7)
+    zs = [torch.randn(B, 20, generator=g).cuda() for _ in range(6)]
+    aux = [torch.rand(B, generator=g).cuda() for _ in range(3)] if case == "wgp" else [None] * 3
+    hp = gm_b200.AdamHP.make(2e-4)
+
+    def run(lazy, out_of_order=False):
+        eng = _engine(case)
+        eng.set_lazy_grads(lazy)
+        grads = []
+        for t in range(3):
+            eng.d_grad(x, noise=zs[2 * t], aux=aux[t], step=t)
+            if out_of_order and t == 1:
+                eng.g_grad(B, noise=zs[2 * t + 1], step=t)      # D's partials would be clobbered: flushed first
+                eng.apply(1, hp)
+                eng.apply(0, hp)
+            else:
+                eng.apply(1, hp)
+                eng.g_grad(B, noise=zs[2 * t + 1], step=t)
+                eng.apply(0, hp)
+            grads.append([eng.grads[n].clone() for n in (0, 1)])
+        return [eng.params[n].clone() for n in (0, 1)], [eng.exp_avg_sq[n].clone() for n in (0, 1)], grads
+
+    p0, v0, g0 = run(False)
+    p1, v1, g1 = run(True)
+    for n in (0, 1):
+        assert torch.equal(p0[n], p1[n]) and torch.equal(v0[n], v1[n])
+        for t in range(3):
+            assert torch.equal(g0[t][n], g1[t][n])
+    pa, _, _ = run(False, out_of_order=True)
+    pb, _, _ = run(True, out_of_order=True)
+    for n in (0, 1):
+        assert torch.equal(pa[n], pb[n])
