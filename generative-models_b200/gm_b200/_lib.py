@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "lib", "libgm_b200.so")
+# GM_B200_LIB: load an alternative build of the same library (kernel A/B experiments, tools/)
+lib_path = os.environ.get("GM_B200_LIB") or os.path.join(_HERE, "lib", "libgm_b200.so")
 
 
 class GmError(RuntimeError):

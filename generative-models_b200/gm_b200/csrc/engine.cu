@@ -56,7 +56,7 @@ static inline int rup(int a, int b) { return cdiv(a, b) * b; }
 // 2-D bf16 row-major matrix: `inner` contiguous elements per row (logical extent, may
 // be smaller than ld), `outer` rows, 128-byte swizzle, OOB elements read as zero.
 static int make_tmap(gm_ctx* c, CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                     uint32_t box_inner, uint32_t box_outer) {
+                     uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16 != 0)
     return fail(c, GM_ERR_ARG, "tensor map: pointer/ld must be 16-byte aligned (ptr=%p ld=%llu)", ptr, (unsigned long long)ld);
   cuuint64_t dims[2] = {inner, outer};
@@ -64,7 +64,7 @@ static int make_tmap(gm_ctx* c, CUtensorMap* tm, const void* ptr, uint64_t inner
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(c, GM_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", int(r));
   return GM_OK;
@@ -75,6 +75,10 @@ enum PlanKind { PK_NT_208 = 0, PK_NT_64, PK_TN_448, PK_TN_64 };
 
 struct GemmPlan {
   CUtensorMap tmA, tmB;
+  // output map of the K-major bf16 kernels (32 x 32 box, 64-byte swizzle), encoded at the first
+  // launch because the epilogue (output pointer / leading dimension) is set after plan_gemm
+  mutable CUtensorMap tmC;
+  mutable int tmc_state;   // 0: not encoded yet, 1: in use, 2: output not eligible (STG path)
   GemmParams p;
   int kind;
   int grid;
@@ -87,6 +91,7 @@ struct GemmPlan {
 // may become resident while its predecessor drains, and blocks in griddepcontrol.wait (first
 // statement of every kernel, after the prologue in the GEMM) until the predecessor completed.
 static bool g_pdl = true;   // GM_NO_PDL=1 turns it off (gm_ctx_create)
+static bool g_tma_store = true;   // GM_NO_TMA_STORE=1: epilogue stores through LDS + STG only
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -135,7 +140,9 @@ static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, kern, pl.tmA, pl.tmB, pl.p);
+  GemmParams prm = pl.p;
+  prm.tma_store = pl.tmc_state == 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, pl.tmA, pl.tmB, pl.tmC, prm);
 }
 
 template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
@@ -170,6 +177,21 @@ static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
 }
 
 static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
+  if (pl.tmc_state == 0) {
+    const GemmParams& p = pl.p;
+    const bool nt = pl.kind == PK_NT_208 || pl.kind == PK_NT_64;
+    pl.tmc_state = 2;
+    // measured (profiles/r1e): the bulk store helps the pure activation epilogues (G1 22.4 -> 20.7 us,
+    // G2 52.0 -> 49.4 us) and costs ~2-5 % on the aux / row-dot epilogues (fence + wait in their longer
+    // per-block dependency chain), so only the former use it
+    const bool plain = p.aux_mode == AUX_NONE && p.dot_w == nullptr && p.dot_sq == 0;
+    if (g_tma_store && nt && plain && p.epi == EPI_BF16 && p.out != nullptr && !(reinterpret_cast<uintptr_t>(p.out) & 15) &&
+        (p.ldo * 2) % 16 == 0 && p.out_cols > 0) {
+      int rc = make_tmap(c, &pl.tmC, p.out, uint64_t(p.out_cols), uint64_t(p.M), uint64_t(p.ldo), kEpiCols, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+      pl.tmc_state = 1;
+    }
+  }
   cudaError_t e;
   gm_ctx::ProfRec rec;
   if (c->prof) {
@@ -290,6 +312,8 @@ extern "C" int gm_ctx_create(int device, gm_ctx** out) {
   c->use_clusters = !(nc && nc[0] == '1');
   const char* np = getenv("GM_NO_PDL");
   g_pdl = !(np && np[0] == '1');
+  const char* nts = getenv("GM_NO_TMA_STORE");
+  g_tma_store = !(nts && nts[0] == '1');
   return GM_OK;
 }
 extern "C" int gm_ctx_destroy(gm_ctx* c) {

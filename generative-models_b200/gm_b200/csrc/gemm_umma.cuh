@@ -58,6 +58,9 @@ struct GemmParams {
   // dot_mask: with the row-dot, store dot_w[n] * 1[v > 0] instead of v (the G step needs only
   // M = w2 * relu'(a1) of D's hidden layer: dL/dx = ds * (M W1), src/ns_gan.py:57-60 backward)
   int dot_mask;
+  // tma_store: full 32-column blocks of the bf16 output leave through the output tensor map
+  // (cp.async.bulk.tensor store of the warp's swizzled staging tile) instead of LDS + STG
+  int tma_store;
   // row_vec (AUX_SIGMOID_GRAD): additional per-row factor, out = v * row_vec[m] * aux (1 - aux)
   const float* row_vec;
   float* dot_out;       // partial slots [(n_tile*2 + half) * dot_ld + m]
@@ -103,7 +106,7 @@ struct GemmCfg {
   static_assert(!STAGED_EPI || (BN + kEpiCols - 1) / kEpiCols <= kEpiVecBlocks * (EPI_WARPS / 8), "bias/dot staging too small");
   static constexpr int STAGES_RAW = (kSmemBudget - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + EPI_BYTES;   // 512: barriers; staging tiles stay 512-B aligned (TMA 64B swizzle)
   // K-major B is loaded with boxes of BOXN rows (<= 256, divides BN1 and BN2)
   static constexpr int gcd(int a, int b) { return b == 0 ? a : gcd(b, a % b); }
   static constexpr int BOXN = (BN2 == 0) ? BN1 : gcd(BN1, BN2);
@@ -127,7 +130,7 @@ struct GemmCfg {
 template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1, int CS = 1, int EW = 8>
 __global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr bool PAIR = (CS == 2) && !A_MN;
   using Cfg = GemmCfg<BN1, BN2, !A_MN, PAIR, EW>;
   constexpr int BN = Cfg::BN;
@@ -162,6 +165,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), PAIR ? 2 : 1);          // pair: both producers arrive on the leader's barrier
       mbar_init(empty_bar(s), PAIR ? 1 : CS);        // multicast mode: every CTA releases the slot
@@ -333,14 +337,23 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int grp = e >> 2;         // 0..kEpiWarps/4-1
     const int my_stage = grp & 1;   // accumulator stage this warp serves when NACC == 2
     const int part = A_MN ? 0 : (grp >> 1);   // which interleaved set of 32-column blocks (K-major kernels)
-    const uint32_t stage_s = bar_base + 256u + uint32_t(e) * kEpiStageBytes;  // staging tile (NT kernels)
-    const uint32_t vec_s = bar_base + 256u + kEpiWarps * kEpiStageBytes + uint32_t(e) * kEpiVecBytes;
+    const uint32_t stage_s = bar_base + 512u + uint32_t(e) * kEpiStageBytes;  // staging tile (NT kernels)
+    const uint32_t vec_s = bar_base + 512u + kEpiWarps * kEpiStageBytes + uint32_t(e) * kEpiVecBytes;
     const int act = ACT_T >= 0 ? ACT_T : p.act;
     const int aux_mode = AUX_T >= 0 ? AUX_T : p.aux_mode;
     const bool has_bias = BIAS_T >= 0 ? (BIAS_T != 0) : (p.bias != nullptr);
     const bool has_dot = DOT_T >= 0 ? (DOT_T == 1 || DOT_T == 3) : (p.dot_w != nullptr);
     const bool mask_out = DOT_T >= 0 ? (DOT_T == 3) : (p.dot_mask != 0);
     const bool has_sq = DOT_T >= 0 ? (DOT_T == 2) : (p.dot_sq != 0);
+    const bool tma_st = !A_MN && p.tma_store != 0;
+    bool st_pending = false;   // a bulk store may still be reading this warp's staging tile
+    auto stage_acquire = [&]() {
+      if (st_pending) {
+        if (lane == 0) bulk_wait_read();
+        __syncwarp();
+        st_pending = false;
+      }
+    };
     int acc_iter = 0;
 #pragma unroll 1
     for (int item = first_item; item < total; item += item_step, ++acc_iter) {
@@ -457,6 +470,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int q = 0; q < 4; ++q) ax[q] = lds128(vec_s + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
             } else {
+              stage_acquire();
 #pragma unroll
               for (int it = 0; it < 4; ++it) sts128(stage_s + (it * 8 + lr) * kEpiPitch + lc * 16, pre[it]);
               __syncwarp();
@@ -483,6 +497,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               else mbar_arrive(tempty_bar(as));
             }
           }
+          // full 32-column block -> one bulk tensor store of the (64-byte rows, XOR-swizzled) tile
+          const bool blk_tma = tma_st && nch == 2 && wrow0 < p.M;
+          stage_acquire();
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             if (q < nch) {
@@ -563,11 +580,29 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < 16; ++j) v[j] = 0.f;
                 if (c0 == p.N && p.pad_one) v[0] = 1.f;
               }
-              sts128(stage_s + lane * kEpiPitch + q * 32,
-                     make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
-              sts128(stage_s + lane * kEpiPitch + q * 32 + 16,
-                     make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15])));
+              {
+                const uint4 lo = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                const uint4 hi = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                if (blk_tma) {
+                  const uint32_t sw = (lane >> 1) & 3, rowb = stage_s + lane * 64;
+                  sts128(rowb + (((2 * q) ^ sw) << 4), lo);
+                  sts128(rowb + (((2 * q + 1) ^ sw) << 4), hi);
+                } else {
+                  sts128(stage_s + lane * kEpiPitch + q * 32, lo);
+                  sts128(stage_s + lane * kEpiPitch + q * 32 + 16, hi);
+                }
+              }
             }
+          }
+          if (blk_tma) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, stage_s, col0, wrow0);
+              bulk_commit();
+            }
+            st_pending = true;
+            continue;
           }
           __syncwarp();
           // coalesced store: 4 lanes cover 64 contiguous bytes of one row, 8 rows per pass
@@ -638,6 +673,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+    stage_acquire();   // the last bulk store has read its staging tile before shared memory goes away
   }
 
   tc_fence_before();
