@@ -92,6 +92,11 @@ def lib():
     L.gm_gan_began_control.argtypes = [vp, f, f, f, vp]
     L.gm_gan_discriminate.argtypes = [vp, vp, i, i, vp, vp]
     L.gm_gan_num_slots.argtypes = [vp]
+    L.gm_comm_create.argtypes = [vp, i, C.POINTER(vp)]
+    L.gm_comm_handle.argtypes = [vp, vp]
+    L.gm_comm_open.argtypes = [vp, i, i, vp]
+    L.gm_comm_destroy.argtypes = [vp]
+    L.gm_gan_apply_allreduce.argtypes = [vp, i, C.POINTER(AdamHP), i, vp, vp]
     L.gm_gan_set_lazy_grads.argtypes = [vp, i, vp]
     L.gm_gan_materialize_grads.argtypes = [vp, vp]
     L.gm_gan_d_forward.argtypes = [vp, i, vp, i, vp, vp]

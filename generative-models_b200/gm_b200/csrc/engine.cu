@@ -1296,4 +1296,5 @@ extern "C" int gm_gan_fisher_state(gm_gan* g, float* lambda_rho_host, int set, g
 }
 
 #include "engine_custom.inl"
+#include "engine_comm.inl"
 #include "engine_vae.inl"

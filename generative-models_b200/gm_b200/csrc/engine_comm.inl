@@ -1,0 +1,96 @@
+// Peer exchange for the fused all-reduce + Adam kernel (kernels.cuh: adam_allreduce_kernel).
+// One cudaMalloc'ed region per rank = [2][nfloats] exchange buffer + flag array, exported with
+// cudaIpcGetMemHandle; the host (gm_b200/parallel.py) gathers the 64-byte handles of all ranks
+// through torch.distributed and gm_comm_open maps them (NVLink peer access on the B200 box).
+
+struct gm_comm {
+  gm_ctx* ctx = nullptr;
+  int rank = 0, world = 1, nblocks = 0;
+  long long nfloats = 0;
+  void* base = nullptr;
+  size_t flag_off = 0;
+  void* peer[kCommMaxWorld] = {};
+  bool opened = false;
+  unsigned long long seq = 0;
+};
+
+extern "C" int gm_comm_create(gm_ctx* c, int nfloats, gm_comm** out) {
+  if (!c || !out || nfloats <= 0) return GM_ERR_ARG;
+  gm_comm* m = new gm_comm();
+  m->ctx = c;
+  m->nfloats = (long long)rup(nfloats, kCommChunk);
+  m->nblocks = int(m->nfloats / kCommChunk);
+  m->flag_off = size_t(2) * m->nfloats * sizeof(float);
+  const size_t bytes = m->flag_off + size_t(2) * kCommMaxWorld * m->nblocks * sizeof(unsigned long long);
+  cudaError_t e = cudaMalloc(&m->base, bytes);
+  if (e != cudaSuccess) { delete m; return fail(c, GM_ERR_CUDA, "gm_comm_create: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  CU_OK(c, cudaMemset(m->base, 0, bytes));
+  CU_OK(c, cudaDeviceSynchronize());
+  *out = m;
+  return GM_OK;
+}
+
+extern "C" int gm_comm_handle(gm_comm* m, void* out64) {
+  if (!m || !out64) return GM_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CU_OK(m->ctx, cudaIpcGetMemHandle(&h, m->base));
+  memcpy(out64, &h, 64);
+  return GM_OK;
+}
+
+extern "C" int gm_comm_open(gm_comm* m, int rank, int world, const void* handles) {
+  if (!m || !handles) return GM_ERR_ARG;
+  if (world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world)
+    return fail(m->ctx, GM_ERR_ARG, "gm_comm_open: rank %d / world %d (max %d ranks)", rank, world, kCommMaxWorld);
+  m->rank = rank; m->world = world;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { m->peer[r] = m->base; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + size_t(r) * 64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&m->peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+      return fail(m->ctx, GM_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (no peer access between the GPUs?)", r, cudaGetErrorString(e));
+  }
+  m->opened = true;
+  return GM_OK;
+}
+
+extern "C" int gm_comm_destroy(gm_comm* m) {
+  if (!m) return GM_OK;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < m->world; ++r)
+    if (r != m->rank && m->peer[r]) cudaIpcCloseMemHandle(m->peer[r]);
+  if (m->base) cudaFree(m->base);
+  delete m;
+  return GM_OK;
+}
+
+// optimizer.step() of one net on every rank at once: SUM all-reduce of the flat gradient over the
+// peer mappings fused with Adam (replaces dist.all_reduce + gm_gan_apply).  Every rank must call it
+// with the same net / step, in the same order.
+extern "C" int gm_gan_apply_allreduce(gm_gan* g, int net, const gm_adam_hp* hp, int step, gm_comm* m, gm_stream stream) {
+  if (!g || net < 0 || net > 1 || !hp || step <= 0 || !m) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_apply_allreduce: bad argument") : GM_ERR_ARG;
+  if (!m->opened) return fail(g->ctx, GM_ERR_STATE, "gm_comm_open has not been called");
+  if (!g->par[net] || !g->am[net] || !g->av[net] || !g->grd[net]) return fail(g->ctx, GM_ERR_STATE, "net %d not fully bound", net);
+  AdamParams a;
+  memset(&a, 0, sizeof a);
+  a.p = g->par[net]; a.g = g->grd[net]; a.m = g->am[net]; a.v = g->av[net];
+  fill_adam(a, hp, step);
+  adam_segs(g, net, a);
+  if (a.total > m->nfloats) return fail(g->ctx, GM_ERR_ARG, "exchange buffer too small (%lld < %d)", m->nfloats, a.total);
+  a.gout = g->grd[net];
+  if (g->pend[net]) { a.gather = 1; a.gsegs = g->pend_segs[net]; g->pend[net] = false; }
+  CommDev cm;
+  memset(&cm, 0, sizeof cm);
+  for (int r = 0; r < m->world; ++r) {
+    cm.x[r] = static_cast<float*>(m->peer[r]);
+    cm.f[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(m->peer[r]) + m->flag_off);
+  }
+  cm.rank = m->rank; cm.world = m->world; cm.nblocks = m->nblocks; cm.nfloats = m->nfloats;
+  cm.seq = ++m->seq;
+  launch_pdl(adam_allreduce_kernel, cdiv(a.total, kCommChunk), 256, 0, static_cast<cudaStream_t>(stream), a, cm);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}

@@ -771,15 +771,10 @@ struct AdamParams {
   int gather; float* gout; GradSegs gsegs;
 };
 
-__global__ void adam_kernel(const AdamParams a) {
-  griddep_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.total) return;
+// one element of the update: p, m, v and the bf16 operand copies
+__device__ __forceinline__ void adam_element(const AdamParams& a, int i, float g) {
   float p = a.p[i];
   if (a.update) {
-    float g;
-    if (a.gather) { g = gather_grad(a.gsegs, i); a.gout[i] = g; }
-    else g = a.g[i];
     if (a.wd != 0.f) g = fmaf(a.wd, p, g);
     const float m = a.b1 * a.m[i] + (1.f - a.b1) * g;
     const float v = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
@@ -803,6 +798,91 @@ __global__ void adam_kernel(const AdamParams a) {
       if (s.shadow_t) s.shadow_t[(long long)c * s.ld_t + r] = b;
     }
     return;
+  }
+}
+
+__global__ void adam_kernel(const AdamParams a) {
+  griddep_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  float g = 0.f;
+  if (a.update) {
+    if (a.gather) { g = gather_grad(a.gsegs, i); a.gout[i] = g; }
+    else g = a.g[i];
+  }
+  adam_element(a, i, g);
+}
+
+// ---------------------------------------------------------------- gradient all-reduce fused into Adam
+// Data-parallel optimizer step in ONE kernel per rank (the only exchange of the
+// path is the SUM of the flat D / G gradient): block b
+//   1. forms its 1024-element chunk of the local gradient (split-K gather or the flat buffer)
+//      and stores it in this rank's exchange buffer (peer-mapped device memory, CUDA IPC);
+//   2. publishes "chunk b of step seq is in place" into every peer's flag array (release.sys
+//      stores through NVLink peer mappings);
+//   3. waits until every peer's chunk b has arrived (local polling, acquire.sys);
+//   4. reads chunk b of every rank through the peer mappings, sums in rank order (bitwise the
+//      same on every rank) and applies Adam + the bf16 operand refresh.
+// No grid-wide or cross-rank barrier: a block only ever waits for the same-numbered block of its
+// peers, whose steps 1-2 never block.  Exchange buffers are double-buffered by seq parity.
+constexpr int kCommMaxWorld = 16;
+constexpr int kCommChunk = 1024;
+struct CommDev {
+  float* x[kCommMaxWorld];                    // exchange buffers [2][nfloats] of every rank (own = local pointer)
+  unsigned long long* f[kCommMaxWorld];       // flag arrays [2][kCommMaxWorld][nblocks] of every rank
+  int rank, world, nblocks;
+  long long nfloats;
+  unsigned long long seq;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) adam_allreduce_kernel(const AdamParams a, const CommDev cm) {
+  griddep_sync();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int par = int(cm.seq & 1ull);
+  const int base = b * kCommChunk;
+  float* mine = cm.x[cm.rank] + (long long)par * cm.nfloats;
+#pragma unroll
+  for (int k = 0; k < kCommChunk / 256; ++k) {
+    const int i = base + k * 256 + tid;
+    if (i < a.total) mine[i] = a.gather ? gather_grad(a.gsegs, i) : a.g[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < cm.world && tid != cm.rank)
+    st_release_sys(cm.f[tid] + ((long long)par * kCommMaxWorld + cm.rank) * cm.nblocks + b, cm.seq);
+  if (tid < cm.world && tid != cm.rank) {
+    const unsigned long long* flag = cm.f[cm.rank] + ((long long)par * kCommMaxWorld + tid) * cm.nblocks + b;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < cm.seq) {
+      if (clock64() - t0 > 40000000000ll) __trap();   // ~20 s: a peer died
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kCommChunk / 256; ++k) {
+    const int i = base + k * 256 + tid;
+    if (i >= a.total) continue;
+    float g = 0.f;
+    for (int r = 0; r < cm.world; ++r) {
+      const float* src = cm.x[r] + (long long)par * cm.nfloats + i;
+      g += (r == cm.rank) ? mine[i] : ld_relaxed_sys(src);
+    }
+    a.gout[i] = g;
+    adam_element(a, i, g);
   }
 }
 

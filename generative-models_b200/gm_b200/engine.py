@@ -130,6 +130,12 @@ class GanEngine:
         check(self.h, lib().gm_gan_generate(self.g, _ptr(noise.contiguous().float()), n, _ptr(out), _stream()))
         return out
 
+    def apply_allreduce(self, net, hp, comm):
+        """Data-parallel optimizer.step(): SUM all-reduce of the gradient over the peer mappings of
+        `comm` (parallel.PeerComm) fused with Adam, one kernel per rank."""
+        self.steps[net] += 1
+        check(self.h, lib().gm_gan_apply_allreduce(self.g, net, C.byref(hp), self.steps[net], comm.c, _stream()))
+
     def set_lazy_grads(self, on=True):
         """Single-GPU fast path: d_grad / g_grad leave split-K partials and apply() gathers + updates
         in one kernel; self.grads[net] is then valid only after apply() (or materialize_grads())."""

@@ -335,7 +335,11 @@ class GANTrainerBase:
         # per-rank batches, upstream gradients scaled by 1/(global batch), SUM all-reduce of the flat
         # D / G gradients.  On one GPU the gradient gather is fused into the Adam kernel instead.
         self._world = par.world_size()
-        self._lazy = self._world == 1
+        self._comm = None
+        if self._world > 1:
+            n = sum(p.numel() for p in self.model.G.parameters()), sum(p.numel() for p in self.model.D.parameters())
+            self._comm = par.make_peer_comm(max(n))
+        self._lazy = self._world == 1 or self._comm is not None
         if self._resident is not None and self._world > 1:
             self._resident.seed(int(torch.initial_seed()) + par.rank_of())
         self._pre_train(num_epochs, hpG, hpD, D_steps, extra)
@@ -430,9 +434,7 @@ class GANTrainerBase:
             loss = eng.d_grad(images, fmt="bits", gather_idx=gather_idx, batch=batch, noise=noise,
                               aux=self._draw_aux(torch.empty(batch, self.model.image_size, device="meta")),
                               inv_global_batch=inv, seed=self._seed, step=self._step).clone()
-        if world > 1:
-            par.sum_gradients(eng.grads[D_NET])
-        eng.apply(D_NET, hp)
+        self._dp_apply(eng, D_NET, hp)
         return loss
 
     def _fused_G(self, batch, hp):
@@ -442,11 +444,20 @@ class GANTrainerBase:
         world = getattr(self, "_world", 1)
         loss = eng.g_grad(batch, noise=noise, inv_global_batch=par.inv_global_batch(batch, world), seed=self._seed,
                           step=self._step).clone()
-        if world > 1:
-            par.sum_gradients(eng.grads[G_NET])
-        eng.apply(G_NET, hp)
+        self._dp_apply(eng, G_NET, hp)
         self._step += 1
         return loss
+
+    def _dp_apply(self, eng, net, hp):
+        """optimizer.step(); under data parallelism preceded by the SUM of the flat gradient - fused into
+        the Adam kernel over peer mappings when available, else NCCL all-reduce."""
+        comm = getattr(self, "_comm", None)
+        if comm is not None:
+            eng.apply_allreduce(net, hp, comm)
+            return
+        if getattr(self, "_world", 1) > 1:
+            par.sum_gradients(eng.grads[net])
+        eng.apply(net, hp)
 
     @builtin_step
     def train_D(self, images):

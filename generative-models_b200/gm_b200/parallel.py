@@ -66,3 +66,61 @@ def shard_slice(n, rank, world):
     """Rows [lo, hi) of a global batch of n that rank owns (contiguous, equal shards)."""
     per = n // world
     return rank * per, (rank + 1) * per
+
+
+class PeerComm:
+    """Peer-mapped exchange buffers for the fused all-reduce + Adam kernel
+    (include/gm_b200.h: gm_comm_*, gm_gan_apply_allreduce).  Every rank allocates one buffer,
+    the 64-byte CUDA IPC handles travel through torch.distributed (all_gather on the
+    default group), and each rank maps its peers' buffers: afterwards the gradient exchange
+    never leaves the kernel.  `nfloats` = the larger of the two nets' parameter counts."""
+
+    def __init__(self, nfloats, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.h = _lib.ctx()
+        self.rank, self.world = rank_of(group), world_size(group)
+        self.c = C.c_void_p()
+        _lib.check(self.h, _lib.lib().gm_comm_create(self.h, int(nfloats), C.byref(self.c)))
+        mine = (C.c_ubyte * 64)()
+        _lib.check(self.h, _lib.lib().gm_comm_handle(self.c, mine))
+        backend = dist.get_backend(group) if self.world > 1 else "none"
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        local = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        if self.world > 1:
+            allh = [torch.empty_like(local) for _ in range(self.world)]
+            dist.all_gather(allh, local, group=group)
+        else:
+            allh = [local]
+        blob = bytes(torch.cat([t.cpu() for t in allh]).tolist())
+        _lib.check(self.h, _lib.lib().gm_comm_open(self.c, self.rank, self.world, C.c_char_p(blob)))
+        if self.world > 1:
+            dist.barrier(group=group)      # every rank has mapped every buffer before the first kernel uses them
+
+    def close(self):
+        if self.c is not None:
+            self._lib.lib().gm_comm_destroy(self.c)
+            self.c = None
+
+
+def make_peer_comm(nfloats, group=None):
+    """PeerComm on every rank, or None everywhere if any rank could not map its peers (no CUDA IPC /
+    peer access): callers then use sum_gradients (NCCL) + apply.  GM_DP=nccl forces the fallback."""
+    if world_size(group) == 1 or os.environ.get("GM_DP", "peer") != "peer":
+        return None
+    comm, ok = None, 1
+    try:
+        comm = PeerComm(nfloats, group)
+    except Exception as exc:           # noqa: BLE001  (any failure -> collective fallback)
+        ok = 0
+        print("[gm_b200] peer all-reduce unavailable on rank %d: %s" % (rank_of(group), exc), flush=True)
+    backend = dist.get_backend(group)
+    flag = torch.tensor([ok], dtype=torch.int32,
+                        device=torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        if comm is not None:
+            comm.close()
+        return None
+    return comm

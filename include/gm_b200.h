@@ -138,6 +138,21 @@ int gm_gan_apply(gm_gan* gan, int net, const gm_adam_hp* hp, int step, gm_stream
  * gradients first, so results never depend on the mode. */
 int gm_gan_set_lazy_grads(gm_gan* gan, int on, gm_stream stream);
 int gm_gan_materialize_grads(gm_gan* gan, gm_stream stream);
+/* ---- data-parallel optimizer step: gradient all-reduce fused into Adam --------
+ * The only exchange of the path is the SUM of the flat D / G gradient (one process per GPU).
+ * gm_comm owns a peer-mapped exchange buffer: create one per process, exchange the 64-byte
+ * gm_comm_handle of every rank (the host uses torch.distributed for that), gm_comm_open them.
+ * gm_gan_apply_allreduce then replaces `all_reduce(grad); optimizer.step()` (src/ns_gan.py:139,156
+ * under data parallelism) by ONE kernel per rank that publishes its gradient chunk by chunk,
+ * sums the peers' chunks over NVLink in rank order and applies Adam.  Collective: every rank
+ * calls it with the same net and step, in the same order. */
+typedef struct gm_comm gm_comm;
+int gm_comm_create(gm_ctx* ctx, int nfloats, gm_comm** out);
+int gm_comm_handle(gm_comm* comm, void* out64);
+int gm_comm_open(gm_comm* comm, int rank, int world, const void* handles /* world x 64 bytes, rank order */);
+int gm_comm_destroy(gm_comm* comm);
+int gm_gan_apply_allreduce(gm_gan* gan, int net, const gm_adam_hp* hp, int step, gm_comm* comm, gm_stream stream);
+
 /* D outputs of the last *_grad call (D step: batch real then batch fake; G step:
  * batch fake) -> dst_dev; what the reference names DX_score / DG_score. */
 int gm_gan_scores(gm_gan* gan, float* dst_dev, int n, gm_stream stream);

@@ -351,3 +351,17 @@ def test_lazy_gradients_are_bit_identical(case):
     pb, _, _ = run(True, out_of_order=True)
     for n in (0, 1):
         assert torch.equal(pa[n], pb[n])
+
+
+def test_fused_peer_allreduce_adam_two_ranks():
+    """gm_gan_apply_allreduce (gradient SUM over CUDA-IPC peer mappings fused into Adam) against
+    all_reduce + gm_gan_apply, two ranks.  On a one-GPU box both ranks share cuda:0."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if torch.cuda.device_count() < 2:
+        env["GM_PEER_SAME_GPU"] = "1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "peer_allreduce_check.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "PEER_ALLREDUCE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -1,0 +1,87 @@
+"""Correctness of the fused all-reduce + Adam kernel (gm_gan_apply_allreduce) against
+torch.distributed.all_reduce + gm_gan_apply.  Launch one process per rank:
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/peer_allreduce_check.py
+With GM_PEER_SAME_GPU=1 every rank uses cuda:0 (CUDA IPC works between processes on one GPU, the
+two kernels then take turns through context time-slicing) and the rendezvous runs over gloo."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "generative-models_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import gm_b200  # noqa: E402
+from gm_b200 import parallel as par  # noqa: E402
+from inputs import GAN_SHAPES, gm_init_weights  # noqa: E402
+
+same_gpu = os.environ.get("GM_PEER_SAME_GPU") == "1"
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = 0 if same_gpu else int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("gloo" if same_gpu else "nccl")
+B, STEPS = 256, 3
+
+
+def engine():
+    eng = gm_b200.GanEngine(784, 400, 20, max_batch=B, variant="ns")
+    W = gm_init_weights(GAN_SHAPES, 1234)
+    eng.load(0, [W["G.linear"][0], W["G.linear"][1], W["G.generate"][0], W["G.generate"][1]])
+    eng.load(1, [W["D.linear"][0], W["D.linear"][1], W["D.discriminate"][0], W["D.discriminate"][1]])
+    return eng
+
+
+g = torch.Generator().manual_seed(100 + rank)          # every rank its own batch and noise
+xs = [(torch.rand(B, 784, generator=g) < 0.13).float().cuda() for _ in range(STEPS)]
+zs = [torch.randn(B, 20, generator=g).cuda() for _ in range(2 * STEPS)]
+hp = gm_b200.AdamHP.make(2e-4)
+inv = par.inv_global_batch(B, world)
+
+
+def reduce_ref(t):
+    if same_gpu:
+        c = t.cpu()
+        dist.all_reduce(c)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t)
+
+
+ref = engine()
+for s in range(STEPS):
+    ref.d_grad(xs[s], noise=zs[2 * s], inv_global_batch=inv, step=s)
+    reduce_ref(ref.grads[1])
+    ref.apply(1, hp)
+    ref.g_grad(B, noise=zs[2 * s + 1], inv_global_batch=inv, step=s)
+    reduce_ref(ref.grads[0])
+    ref.apply(0, hp)
+torch.cuda.synchronize()
+
+eng = engine()
+eng.set_lazy_grads(True)
+comm = par.PeerComm(max(eng.n))
+for s in range(STEPS):
+    eng.d_grad(xs[s], noise=zs[2 * s], inv_global_batch=inv, step=s)
+    eng.apply_allreduce(1, hp, comm)
+    eng.g_grad(B, noise=zs[2 * s + 1], inv_global_batch=inv, step=s)
+    eng.apply_allreduce(0, hp, comm)
+torch.cuda.synchronize()
+
+worst = 0.0
+for net in (0, 1):
+    a, b = eng.params[net], ref.params[net]
+    worst = max(worst, float((a - b).abs().max() / b.abs().max()))
+    ga, gb = eng.grads[net], ref.grads[net]
+    worst = max(worst, float((ga - gb).abs().max() / gb.abs().max()))
+    # replicas stay bitwise identical: every rank sums the chunks in rank order
+    mine = eng.params[net].cpu() if same_gpu else eng.params[net].clone()
+    allp = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allp, mine)
+    assert all(torch.equal(allp[0], t) for t in allp), "replicas diverged"
+assert worst < 1e-5, worst
+comm.close()
+if rank == 0:
+    print("PEER_ALLREDUCE_OK world=%d worst_rel=%.3g" % (world, worst))
+dist.destroy_process_group()
