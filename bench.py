@@ -153,12 +153,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host_ms[0] = (time.perf_counter() - t_host) * 1e3 / steps    # CPU time to enqueue one step
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -171,6 +175,7 @@ def run_ours(args):
     gm_b200.launch_count(reset=True)
     sampler = ClockSampler(local) if rank == 0 else None
     ms = timed(lambda i: resident_step(), args.steps)
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if sampler else None
     launches = gm_b200.launch_count(reset=True)
     value = B * world * args.steps / (ms * 1e-3)
@@ -257,7 +262,7 @@ def run_ours(args):
            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / e2e_steps, 4),
                    "h2d_bytes_per_step": B * X // 8, "d2h_bytes_per_step": 8,
                    "input_format": "1 bit/pixel packed rows in pinned host memory, double-buffered H2D"},
-           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+           "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 4), "clocks": clocks, "roofline": roofline,
            "losses_last_step": {"D": loss_d, "G": loss_g}}
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline()

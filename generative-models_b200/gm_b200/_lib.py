@@ -96,6 +96,7 @@ def lib():
     L.gm_comm_handle.argtypes = [vp, vp]
     L.gm_comm_open.argtypes = [vp, i, i, vp]
     L.gm_comm_destroy.argtypes = [vp]
+    L.gm_gan_attach_comm.argtypes = [vp, vp]
     L.gm_gan_apply_allreduce.argtypes = [vp, i, C.POINTER(AdamHP), i, vp, vp]
     L.gm_gan_set_lazy_grads.argtypes = [vp, i, vp]
     L.gm_gan_materialize_grads.argtypes = [vp, vp]

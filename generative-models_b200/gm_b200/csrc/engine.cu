@@ -454,6 +454,18 @@ struct StepPlans {
   GemmPlan be_enc_d, be_dec_d, be_gwd, be_de_d, be_enc_g, be_dec_g, be_de_g, be_dxg;   // BEGAN autoencoder-discriminator
 };
 
+struct gm_comm {
+  gm_ctx* ctx = nullptr;
+  int rank = 0, world = 1, nblocks = 0;
+  long long nfloats = 0;
+  void* base = nullptr;
+  size_t flag_off = 0, stat_off = 0, sflag_off = 0;
+  void* peer[kCommMaxWorld] = {};
+  bool opened = false;
+  unsigned long long seq = 0, seq_stats = 0;
+};
+
+
 struct CustomPlans {   // custom-loss path (engine_custom.inl): per-slot D forward / backward, G output kept in DA2
   GemmPlan d1[4], dw1[4], dx[4], g2;
 };
@@ -495,6 +507,7 @@ struct gm_gan {
   int max_splits = 0;
   int last_rows = 0;
   int region_rows = 0;   // rows per region of Xall/Aall/DHall (3 regions)
+  gm_comm* comm = nullptr;   // attached communicator: batch statistics run over the global batch
   // lazy gradients: *_grad leaves the split-K partials, gm_gan_apply gathers + updates in one kernel
   bool lazy = false;
   bool pend[2] = {false, false};
@@ -859,12 +872,29 @@ static int run_generator(gm_gan* g, StepPlans* sp, int B, const float* noise, ui
   return GM_OK;
 }
 
+// replace per-block partial sums by their sum over all ranks (no-op without an attached communicator)
+static void exchange_stats(gm_gan* g, double* part, int nblk, int stride, int nvals, cudaStream_t s) {
+  gm_comm* m = g->comm;
+  if (!m || m->world <= 1) return;
+  CommStats cs;
+  memset(&cs, 0, sizeof cs);
+  for (int r = 0; r < m->world; ++r) {
+    cs.v[r] = reinterpret_cast<double*>(static_cast<char*>(m->peer[r]) + m->stat_off);
+    cs.f[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(m->peer[r]) + m->sflag_off);
+  }
+  cs.rank = m->rank; cs.world = m->world; cs.seq = ++m->seq_stats;
+  launch_pdl(stats_exchange_kernel, 1, 256, 0, s, part, nblk, stride, nvals, cs);
+  g->ctx->launches++;
+}
+static int stat_world(const gm_gan* g) { return (g->comm && g->comm->world > 1) ? g->comm->world : 1; }
+
 static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t s) {
   LossParams lp;
   lp.slots = g->slots + (g_step ? B : 0);
   lp.nslots = 2 * cdiv(g->H, 208);
   lp.slot_ld = g->nreg * g->Bmax;
   lp.b2 = g->par[GM_NET_D] + g->D.off_b2;
+  lp.Bstat = B * stat_world(g);
   lp.B = B; lp.g_step = g_step; lp.variant = g->d.variant; lp.out_act = g->d.d_out_act; lp.inv_b = inv_b;
   lp.ds = g->ds + (g_step ? B : 0);
   lp.d_out = g->scores + (g_step ? B : 0);
@@ -879,9 +909,11 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   if (!g_step && (v == V_RA || v == V_FISHER)) {
     launch_pdl(loss_pass_kernel<0>, lp.nblk, kLossThreads, 0, s, lp);
     g->ctx->launches++;
+    exchange_stats(g, lp.partA, lp.nblk, 4, 4, s);       // sum d, d^2 per branch over all ranks
     if (v == V_RA) {
       launch_pdl(loss_pass_kernel<1>, lp.nblk, kLossThreads, 0, s, lp);
       g->ctx->launches++;
+      exchange_stats(g, lp.partB, lp.nblk, 4, 1, s);     // sum q(1-q)/(q+eps) over all ranks' real rows
     }
   }
   launch_pdl(loss_pass_kernel<2>, lp.nblk, kLossThreads, 0, s, lp);
@@ -932,7 +964,9 @@ static int began_d_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaSt
   const int ns = 2 * cdiv(g->X, 208);
   launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r, ns, 2 * g->Bmax, B, g->be_part);
   launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r + B, ns, 2 * g->Bmax, B, g->be_part + nb);
-  launch_pdl(began_loss_final_kernel, 1, 256, 0, s, g->be_part, g->be_part + nb, nb, B, 0, g->be_state, g->lossbuf);
+  exchange_stats(g, g->be_part, nb, 1, 1, s);          // DX, DG of the K controller over the global batch
+  exchange_stats(g, g->be_part + nb, nb, 1, 1, s);
+  launch_pdl(began_loss_final_kernel, 1, 256, 0, s, g->be_part, g->be_part + nb, nb, B * stat_world(g), 0, g->be_state, g->lossbuf);
   c->launches += 3;
   if ((rc = launch_plan(c, sp->be_gwd, s))) return rc;
   if ((rc = launch_plan(c, sp->be_de_d, s))) return rc;
@@ -1023,7 +1057,8 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     const int mode = g->d.variant == GM_DRA ? 1 : 0;
     if (mode == 1) {
       launch_pdl(moments_kernel, c->num_sms * 2, 256, 0, s, g->Xall, B, X, XP, g->mom_part);
-      launch_pdl(moments_final_kernel, 1, 256, 0, s, g->mom_part, c->num_sms * 2, g->stats);
+      exchange_stats(g, g->mom_part, c->num_sms * 2, 2, 2, s);     // images.std() over the global batch
+      launch_pdl(moments_final_kernel, 1, 256, 0, s, g->mom_part, c->num_sms * 2, float(double(B) * X * stat_world(g)), g->stats);
       c->launches += 2;
     }
     launch_pdl(xhat_kernel, cdiv(B, 128), 128, 0, s, g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,

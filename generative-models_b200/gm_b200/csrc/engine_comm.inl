@@ -3,17 +3,6 @@
 // cudaIpcGetMemHandle; the host (gm_b200/parallel.py) gathers the 64-byte handles of all ranks
 // through torch.distributed and gm_comm_open maps them (NVLink peer access on the B200 box).
 
-struct gm_comm {
-  gm_ctx* ctx = nullptr;
-  int rank = 0, world = 1, nblocks = 0;
-  long long nfloats = 0;
-  void* base = nullptr;
-  size_t flag_off = 0;
-  void* peer[kCommMaxWorld] = {};
-  bool opened = false;
-  unsigned long long seq = 0;
-};
-
 extern "C" int gm_comm_create(gm_ctx* c, int nfloats, gm_comm** out) {
   if (!c || !out || nfloats <= 0) return GM_ERR_ARG;
   gm_comm* m = new gm_comm();
@@ -21,7 +10,9 @@ extern "C" int gm_comm_create(gm_ctx* c, int nfloats, gm_comm** out) {
   m->nfloats = (long long)rup(nfloats, kCommChunk);
   m->nblocks = int(m->nfloats / kCommChunk);
   m->flag_off = size_t(2) * m->nfloats * sizeof(float);
-  const size_t bytes = m->flag_off + size_t(2) * kCommMaxWorld * m->nblocks * sizeof(unsigned long long);
+  m->stat_off = m->flag_off + size_t(2) * kCommMaxWorld * m->nblocks * sizeof(unsigned long long);
+  m->sflag_off = m->stat_off + size_t(2) * kCommMaxWorld * kCommStatVals * sizeof(double);
+  const size_t bytes = m->sflag_off + size_t(2) * kCommMaxWorld * sizeof(unsigned long long);
   cudaError_t e = cudaMalloc(&m->base, bytes);
   if (e != cudaSuccess) { delete m; return fail(c, GM_ERR_CUDA, "gm_comm_create: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
   CU_OK(c, cudaMemset(m->base, 0, bytes));
@@ -92,5 +83,15 @@ extern "C" int gm_gan_apply_allreduce(gm_gan* g, int net, const gm_adam_hp* hp, 
   launch_pdl(adam_allreduce_kernel, cdiv(a.total, kCommChunk), 256, 0, static_cast<cudaStream_t>(stream), a, cm);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+// Batch statistics over the global batch: attach the communicator to the engine; gm_gan_d_grad then
+// exchanges the RaNS / Fisher / DRAGAN / BEGAN partial sums between the ranks on the device
+// (stats_exchange_kernel).  comm == NULL detaches (per-rank statistics).
+extern "C" int gm_gan_attach_comm(gm_gan* g, gm_comm* m) {
+  if (!g) return GM_ERR_ARG;
+  if (m && !m->opened) return fail(g->ctx, GM_ERR_STATE, "gm_comm_open has not been called");
+  g->comm = m;
   return GM_OK;
 }

@@ -143,6 +143,7 @@ struct LossParams {
   const float* slots; int nslots; int slot_ld;   // slots[k*slot_ld + row]
   const float* b2;
   int B;                 // local batch
+  int Bstat;             // batch the statistics (RaNS mean, Fisher moments) run over: B x world when ranks exchange them
   int g_step;            // 0: D step (2B rows), 1: G step (B rows, all fake)
   int variant, out_act;
   float inv_b;
@@ -190,13 +191,13 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass_kernel(const LossParam
   float mg = 0.f, gq_mean = 0.f, c_f = 0.f;
   if (PASS >= 1 && !p.g_step && (p.variant == V_RA || p.variant == V_FISHER)) {
     const double s1 = reduce_partials4(p.partA, p.nblk, 1, sh);
-    mg = float(s1 / p.B);
+    mg = float(s1 / p.Bstat);
     if (p.variant == V_FISHER) {
       const double s2 = reduce_partials4(p.partA, p.nblk, 2, sh), s3 = reduce_partials4(p.partA, p.nblk, 3, sh);
-      const float omega = 1.f - (0.5f * float(s2 / p.B) + 0.5f * float(s3 / p.B));
+      const float omega = 1.f - (0.5f * float(s2 / p.Bstat) + 0.5f * float(s3 / p.Bstat));
       c_f = p.fisher[0] - p.fisher[1] * omega;
     } else if (PASS == 2) {
-      gq_mean = float(reduce_partials4(p.partB, p.nblk, 0, sh) / p.B);
+      gq_mean = float(reduce_partials4(p.partB, p.nblk, 0, sh) / p.Bstat);
     }
   }
   double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossPara
     float L = float(lsum / p.B);
     if (fisher) {
       const float lam = p.fisher[0], rho = p.fisher[1];
-      const float omega = 1.f - (0.5f * float(s2 / p.B) + 0.5f * float(s3 / p.B));
+      const float omega = 1.f - (0.5f * float(s2 / p.Bstat) + 0.5f * float(s3 / p.Bstat));
       L = L - lam * omega + 0.5f * rho * omega * omega;   // src/fisher_gan.py:221-223
       p.fisher[0] = lam + rho * (-omega);                 // src/fisher_gan.py:155: lambda += rho * dL/dlambda
       p.loss[2] = omega;
@@ -397,7 +398,7 @@ __global__ void xhat_kernel(const __nv_bfloat16* __restrict__ xr, const __nv_bfl
   const float e = rnd ? rnd[r] : curand_uniform(&st);   // (0,1]; the reference's rand is [0,1)
   float sd = 0.f;
   if (mode == 1) {
-    const double n = double(rows) * x, s1 = stats[0], s2 = stats[1];
+    const double n = stats[2], s1 = stats[0], s2 = stats[1];
     sd = float(sqrt(fmax((s2 - s1 * s1 / n) / (n - 1.0), 0.0)));   // images.std(): unbiased, global
   }
   for (int c0 = 0; c0 < ld; c0 += 8) {
@@ -451,14 +452,14 @@ __global__ void moments_kernel(const __nv_bfloat16* __restrict__ a, int rows, in
   s2 = block_sum<256>(s2, sh);
   if (threadIdx.x == 0) { part[blockIdx.x * 2] = s1; part[blockIdx.x * 2 + 1] = s2; }
 }
-__global__ void moments_final_kernel(const double* __restrict__ part, int nblk, float* __restrict__ stats) {
+__global__ void moments_final_kernel(const double* __restrict__ part, int nblk, float count, float* __restrict__ stats) {
   griddep_sync();
   __shared__ double sh[256 / 32];
   double s1 = 0, s2 = 0;
   for (int i = threadIdx.x; i < nblk; i += 256) { s1 += part[2 * i]; s2 += part[2 * i + 1]; }
   s1 = block_sum<256>(s1, sh);
   s2 = block_sum<256>(s2, sh);
-  if (threadIdx.x == 0) { stats[0] = float(s1); stats[1] = float(s2); }
+  if (threadIdx.x == 0) { stats[0] = float(s1); stats[1] = float(s2); stats[2] = count; }   // count: elements behind the sums
 }
 
 // Per xhat row: nv = ||V|| from the sum-of-squares slots of the V GEMM, q = 1[s>0] (ReLU D)
@@ -827,6 +828,7 @@ __global__ void adam_kernel(const AdamParams a) {
 // peers, whose steps 1-2 never block.  Exchange buffers are double-buffered by seq parity.
 constexpr int kCommMaxWorld = 16;
 constexpr int kCommChunk = 1024;
+constexpr int kCommStatVals = 4;
 struct CommDev {
   float* x[kCommMaxWorld];                    // exchange buffers [2][nfloats] of every rank (own = local pointer)
   unsigned long long* f[kCommMaxWorld];       // flag arrays [2][kCommMaxWorld][nblocks] of every rank
@@ -847,6 +849,59 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   float v;
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
+}
+
+// Batch statistics over the GLOBAL batch (SURVEY.md 8e caveats: RaNS mean(DG) and sum q(1-q)/(q+eps),
+// Fisher moments, DRAGAN images.std(), BEGAN DX / DG): one block reduces the per-block partial sums
+// part[blk*stride + v] (v < nvals <= 4), pushes them into every peer's statistics area, waits for the
+// peers' values, and replaces the partials by the rank-ordered global sums (entry 0 = sum, rest 0), so
+// the passes that re-reduce `part` afterwards see global statistics without knowing about ranks.
+struct CommStats {
+  double* v[kCommMaxWorld];                   // [2][kCommMaxWorld][kCommStatVals] per rank
+  unsigned long long* f[kCommMaxWorld];       // [2][kCommMaxWorld] per rank
+  int rank, world;
+  unsigned long long seq;
+};
+__global__ void __launch_bounds__(256) stats_exchange_kernel(double* __restrict__ part, int nblk, int stride, int nvals,
+                                                             const CommStats cs) {
+  griddep_sync();
+  __shared__ double sh[256 / 32];
+  __shared__ double tot[kCommStatVals];
+  const int tid = threadIdx.x, par = int(cs.seq & 1ull);
+  for (int v = 0; v < nvals; ++v) {
+    double t = 0.0;
+    for (int i = tid; i < nblk; i += 256) t += part[(long long)i * stride + v];
+    t = block_sum<256>(t, sh);
+    if (tid == 0) tot[v] = t;
+  }
+  __syncthreads();
+  if (tid < cs.world && tid != cs.rank) {
+    double* dst = cs.v[tid] + ((long long)par * kCommMaxWorld + cs.rank) * kCommStatVals;
+    for (int v = 0; v < nvals; ++v) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + v), "d"(tot[v]) : "memory");
+    st_release_sys(cs.f[tid] + par * kCommMaxWorld + cs.rank, cs.seq);
+  }
+  if (tid < cs.world && tid != cs.rank) {
+    const unsigned long long* flag = cs.f[cs.rank] + par * kCommMaxWorld + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < cs.seq) {
+      if (clock64() - t0 > 40000000000ll) __trap();
+    }
+  }
+  __syncthreads();
+  if (tid < nvals) {
+    double g = 0.0;
+    for (int r = 0; r < cs.world; ++r) {
+      if (r == cs.rank) { g += tot[tid]; continue; }
+      const double* src = cs.v[cs.rank] + ((long long)par * kCommMaxWorld + r) * kCommStatVals + tid;
+      double x;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(src) : "memory");
+      g += x;
+    }
+    tot[tid] = g;
+  }
+  __syncthreads();
+  for (int i = tid; i < nblk; i += 256)
+    for (int v = 0; v < nvals; ++v) part[(long long)i * stride + v] = (i == 0) ? tot[v] : 0.0;
 }
 
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(const AdamParams a, const CommDev cm) {

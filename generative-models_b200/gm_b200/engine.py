@@ -136,6 +136,11 @@ class GanEngine:
         self.steps[net] += 1
         check(self.h, lib().gm_gan_apply_allreduce(self.g, net, C.byref(hp), self.steps[net], comm.c, _stream()))
 
+    def attach_comm(self, comm):
+        """Batch statistics (RaNS / Fisher / DRAGAN / BEGAN) over the global batch of all ranks of `comm`
+        (parallel.PeerComm); None detaches."""
+        check(self.h, lib().gm_gan_attach_comm(self.g, comm.c if comm is not None else None))
+
     def set_lazy_grads(self, on=True):
         """Single-GPU fast path: d_grad / g_grad leave split-K partials and apply() gathers + updates
         in one kernel; self.grads[net] is then valid only after apply() (or materialize_grads())."""

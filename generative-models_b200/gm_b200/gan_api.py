@@ -425,6 +425,9 @@ class GANTrainerBase:
         self._sync_once(eng)
         world = getattr(self, "_world", 1)
         eng.set_lazy_grads(getattr(self, "_lazy", False))
+        if getattr(self, "_comm", None) is not None and getattr(eng, "_comm_attached", None) is not self._comm:
+            eng.attach_comm(self._comm)          # batch statistics over the global batch
+            eng._comm_attached = self._comm
         inv = par.inv_global_batch(batch, world)
         noise = self.compute_noise(batch, self.model.z_dim)
         if gather_idx is None:

@@ -152,6 +152,12 @@ int gm_comm_handle(gm_comm* comm, void* out64);
 int gm_comm_open(gm_comm* comm, int rank, int world, const void* handles /* world x 64 bytes, rank order */);
 int gm_comm_destroy(gm_comm* comm);
 int gm_gan_apply_allreduce(gm_gan* gan, int net, const gm_adam_hp* hp, int step, gm_comm* comm, gm_stream stream);
+/* Batch statistics over the GLOBAL batch under data parallelism (RaNS mean(DG) src/ra_gan.py:204, Fisher
+ * moments src/fisher_gan.py:214-218, DRAGAN images.std() src/dra_gan.py:204, BEGAN DX / DG of the K
+ * controller src/be_gan.py:189-190): with a communicator attached, gm_gan_d_grad exchanges the partial
+ * sums between the ranks on the device, so N ranks x B samples reproduce one process with N*B samples.
+ * comm == NULL detaches (per-rank statistics). */
+int gm_gan_attach_comm(gm_gan* gan, gm_comm* comm);
 
 /* D outputs of the last *_grad call (D step: batch real then batch fake; G step:
  * batch fake) -> dst_dev; what the reference names DX_score / DG_score. */

@@ -84,4 +84,57 @@ assert worst < 1e-5, worst
 comm.close()
 if rank == 0:
     print("PEER_ALLREDUCE_OK world=%d worst_rel=%.3g" % (world, worst))
+
+
+# ---- global-batch equivalence: `world` ranks x Bl rows == one engine with world*Bl rows ----------
+def global_batch_check(variant):
+    comm2 = par.PeerComm(400000)
+    Bl = 128
+    Bg = Bl * world
+    gg = torch.Generator().manual_seed(4242)              # same global tensors on every rank
+    X = (torch.rand(Bg, 784, generator=gg) < 0.13).float().cuda()
+    Z1, Z2 = torch.randn(Bg, 20, generator=gg).cuda(), torch.randn(Bg, 20, generator=gg).cuda()
+    delta, u = torch.rand(Bg, generator=gg).cuda(), torch.rand(Bg, 784, generator=gg).cuda()
+    lo, hi = rank * Bl, (rank + 1) * Bl
+
+    def mk(batch):
+        e = gm_b200.GanEngine(784, 400, 20, max_batch=batch, variant=variant, d_out_act="relu" if variant == "wgp" else "sigmoid")
+        W = gm_init_weights(GAN_SHAPES, 1234)
+        e.load(0, [W["G.linear"][0], W["G.linear"][1], W["G.generate"][0], W["G.generate"][1]])
+        e.load(1, [W["D.linear"][0], W["D.linear"][1], W["D.discriminate"][0], W["D.discriminate"][1]])
+        if variant == "fisher":
+            e.fisher_state(0.3, 1e-2)
+        return e
+
+    def aux(a, b):
+        if variant == "dra":
+            return torch.cat([delta[a:b].reshape(-1), u[a:b].reshape(-1)]).contiguous()
+        if variant == "wgp":
+            return delta[a:b].contiguous()
+        return None
+
+    one = mk(Bg)                                           # the single-process run over the global batch
+    one.d_grad(X, noise=Z1, aux=aux(0, Bg), inv_global_batch=1.0 / Bg)
+    gD_one = one.grads[1].clone()
+    loss_one = float(one.loss_buf[0])
+    dp = mk(Bl)
+    dp.attach_comm(comm2)
+    dp.set_lazy_grads(True)
+    dp.d_grad(X[lo:hi].contiguous(), noise=Z1[lo:hi].contiguous(), aux=aux(lo, hi), inv_global_batch=1.0 / Bg)
+    hp0 = gm_b200.AdamHP.make(0.0)                         # lr 0: only the summed gradient is of interest
+    dp.apply_allreduce(1, hp0, comm2)
+    torch.cuda.synchronize()
+    rel = float((dp.grads[1] - gD_one).norm() / gD_one.norm())
+    # per-rank statistics (no communicator) must NOT reproduce it for the batch-statistic variants
+    assert rel < 2e-4, (variant, rel)
+    if variant == "fisher":
+        lam_dp, lam_one = dp.fisher_state()[0], one.fisher_state()[0]
+        assert abs(lam_dp - lam_one) < 1e-6 * max(1.0, abs(lam_one)), (lam_dp, lam_one)
+    comm2.close()
+    return rel
+
+
+rels = {v: global_batch_check(v) for v in os.environ.get("GM_CHECK_VARIANTS", "ns,ra,fisher,dra").split(",") if v}
+if rank == 0:
+    print("GLOBAL_BATCH_OK " + " ".join("%s=%.2g" % kv for kv in rels.items()))
 dist.destroy_process_group()
