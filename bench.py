@@ -289,20 +289,31 @@ def cpu_baseline():
     steps = int(max(50, min(782, best[0] * 10.0 / 64)))
     ips64, dt64, _ = TP.time_cpu_steps(64, steps=steps, warmup=5, threads=th, with_loader=True, pool=pool)
     ips64c, _, _ = TP.time_cpu_steps(64, steps=max(50, steps // 3), warmup=5, threads=th, with_loader=False, pool=pool)
-    big = 16384
-    ipsb, dtb, _ = TP.time_cpu_steps(big, steps=3, warmup=1, threads=cores, with_loader=False)
+    _, thb, big = _best_cpu_config(TP, cores, [16384, 4096], 4, 20.0)
+    ipsb, dtb, _ = TP.time_cpu_steps(big, steps=3, warmup=1, threads=thb, with_loader=False)
     return {"value": round(ips64, 1), "unit": "images/s", "cores": th, "host_cores": cores, "kind": "port",
             "sample": "BASELINE configs[0]: B=64, %d of the 782 steps of one N=50000 epoch, incl. the reference's "
                       "per-step shuffling DataLoader fetch, %.1f s" % (steps, dt64),
             "compute_only_b64": round(ips64c, 1),
             "large_batch": {"batch": big, "value": round(ipsb, 1), "seconds": round(dtb, 2), "steps": 3,
-                            "threads": cores}}
+                            "threads": thb}}
 
 
 def _pool(n):
     import torch
     g = torch.Generator().manual_seed(3435)
     return (torch.rand(n, X, generator=g) < 0.1307).float()
+
+
+def _best_cpu_config(TP, cores, batches, n_steps, budget):
+    """(images/s, threads, batch) of the fastest (threads, batch) probe whose n_steps fit the budget."""
+    best = None
+    for batch in sorted(set(batches), reverse=True):
+        for th in sorted({cores, max(cores // 2, 1), max(cores // 4, 1), max(cores // 8, 1), min(cores, 8)}, reverse=True):
+            ips, _, _ = TP.time_cpu_steps(batch, steps=1, warmup=1, threads=th)
+            if (batch / ips) * n_steps <= budget and (best is None or ips > best[0]):
+                best = (ips, th, batch)
+    return best or (1.0, cores, min(min(batches), 1024))
 
 
 def run_reference(args):
@@ -314,14 +325,13 @@ def run_reference(args):
         return
     from oracle import torch_port as TP
     cores = os.cpu_count() or 1
-    # calibrate so the whole run stays within a few minutes
-    ips, dt, th = TP.time_cpu_steps(4096, steps=2, warmup=1, threads=cores)
+    # the reference gets its best configuration: probe (threads, batch) pairs briefly, keep the fastest one
+    # whose K + W steps still end within the time budget (a 65536-image step is ~7 s on this class of host)
     budget = 150.0
     n_steps = args.steps + args.warmup
-    batch = args.batch
-    while batch > 4096 and (batch / ips) * n_steps > budget:
-        batch //= 2
-    ips, dt, th = TP.time_cpu_steps(batch, steps=args.steps, warmup=args.warmup, threads=cores)
+    best = _best_cpu_config(TP, cores, [min(args.batch, 16384), min(args.batch, 4096)], n_steps, budget)
+    _, th, batch = best
+    ips, dt, th = TP.time_cpu_steps(batch, steps=args.steps, warmup=args.warmup, threads=th)
     out = {"impl": "reference", "metric": METRIC, "value": round(ips, 1), "unit": "images/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
