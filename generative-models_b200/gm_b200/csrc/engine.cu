@@ -501,6 +501,7 @@ struct gm_gan {
   float *slots_r = nullptr, *be_state = nullptr, *PWd = nullptr;
   double* be_part = nullptr;
   double* loss_part = nullptr;   // 3 x [loss_blocks][4]
+  unsigned int* loss_done = nullptr;
   int loss_blocks = 0;
   float *PD = nullptr, *PG2 = nullptr, *PG1 = nullptr;
   int dh_blocks = 0, dh_rows_per_iter = 0, dh_threads = 0;
@@ -595,6 +596,7 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   }
   g->loss_blocks = c->num_sms * 2;
   TRY(dev_alloc(g, &g->loss_part, size_t(3) * g->loss_blocks * 4));
+  TRY(dev_alloc(g, &g->loss_done, 4));
   // split-K partials
   g->max_splits = c->num_sms;
   const int sp_d = c->num_sms / cdiv(g->X + 1, BM) > 0 ? c->num_sms / cdiv(g->X + 1, BM) : 1;
@@ -895,6 +897,7 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   lp.slot_ld = g->nreg * g->Bmax;
   lp.b2 = g->par[GM_NET_D] + g->D.off_b2;
   lp.Bstat = B * stat_world(g);
+  lp.done = g->loss_done;
   lp.B = B; lp.g_step = g_step; lp.variant = g->d.variant; lp.out_act = g->d.d_out_act; lp.inv_b = inv_b;
   lp.ds = g->ds + (g_step ? B : 0);
   lp.d_out = g->scores + (g_step ? B : 0);
@@ -916,9 +919,8 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
       exchange_stats(g, lp.partB, lp.nblk, 4, 1, s);     // sum q(1-q)/(q+eps) over all ranks' real rows
     }
   }
-  launch_pdl(loss_pass_kernel<2>, lp.nblk, kLossThreads, 0, s, lp);
-  launch_pdl(loss_final_kernel, 1, kLossThreads, 0, s, lp);
-  g->ctx->launches += 2;
+  launch_pdl(loss_pass_kernel<2>, lp.nblk, kLossThreads, 0, s, lp);   // its last block writes loss[0..1]
+  g->ctx->launches += 1;
 }
 
 // The flat gradient of `net` from its partials: now (finalize kernel), or - with lazy gradients -

@@ -153,6 +153,7 @@ struct LossParams {
   float* fisher;         // [0] LAMBDA  [1] RHO  (device state, V_FISHER only)
   double* partA; double* partB; double* partR;   // per-block partials [nblk][4]
   int nblk;
+  unsigned int* done;    // block-completion counter of PASS 2 (self-resetting): the last block finalises
 };
 
 __device__ __forceinline__ float act_out(float s, int a) {
@@ -167,7 +168,7 @@ __device__ __forceinline__ float act_grad(float s, float d, int a) {
 //   PASS 0 (RA, Fisher): sum d, d^2 per branch            -> partA[blk][4]
 //   PASS 1 (RA):         sum q(1-q)/(q+eps) over real rows -> partB[blk][4] (slot 0)
 //   PASS 2 (all):        per-row loss term + dL/ds         -> partR[blk][4] (loss, sum ds)
-// loss_final_kernel (1 block) reduces partR into loss[0..1] and applies the Fisher
+// The last PASS 2 block to finish (loss_finalize) reduces partR into loss[0..1] and applies the Fisher
 // lambda update (src/fisher_gan.py:155).
 constexpr int kLossThreads = 256;
 
@@ -175,6 +176,27 @@ __device__ __forceinline__ double reduce_partials4(const double* part, int nblk,
   double t = 0.0;
   for (int i = threadIdx.x; i < nblk; i += kLossThreads) t += part[(long long)i * 4 + slot];
   return block_sum<kLossThreads>(t, sh);
+}
+
+// loss[0..1] from the PASS 2 partials (+ the Fisher lambda update, src/fisher_gan.py:155); one block
+__device__ __forceinline__ void loss_finalize(const LossParams& p, double* sh) {
+  const double lsum = reduce_partials4(p.partR, p.nblk, 0, sh);
+  const double dssum = reduce_partials4(p.partR, p.nblk, 1, sh);
+  double s2 = 0, s3 = 0;
+  const bool fisher = !p.g_step && p.variant == V_FISHER;
+  if (fisher) { s2 = reduce_partials4(p.partA, p.nblk, 2, sh); s3 = reduce_partials4(p.partA, p.nblk, 3, sh); }
+  if (threadIdx.x == 0) {
+    float L = float(lsum / p.B);
+    if (fisher) {
+      const float lam = p.fisher[0], rho = p.fisher[1];
+      const float omega = 1.f - (0.5f * float(s2 / p.Bstat) + 0.5f * float(s3 / p.Bstat));
+      L = L - lam * omega + 0.5f * rho * omega * omega;   // src/fisher_gan.py:221-223
+      p.fisher[0] = lam + rho * (-omega);                 // src/fisher_gan.py:155: lambda += rho * dL/dlambda
+      p.loss[2] = omega;
+    }
+    p.loss[0] = L;
+    p.loss[1] = float(dssum);
+  }
 }
 
 template <int PASS>
@@ -270,27 +292,20 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass_kernel(const LossParam
     double* out = (PASS == 0 ? p.partA : (PASS == 1 ? p.partB : p.partR)) + (long long)blockIdx.x * 4;
     out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
   }
-}
-
-__global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossParams p) {
-  griddep_sync();
-  __shared__ double sh[kLossThreads / 32];
-  const double lsum = reduce_partials4(p.partR, p.nblk, 0, sh);
-  const double dssum = reduce_partials4(p.partR, p.nblk, 1, sh);
-  double s2 = 0, s3 = 0;
-  const bool fisher = !p.g_step && p.variant == V_FISHER;
-  if (fisher) { s2 = reduce_partials4(p.partA, p.nblk, 2, sh); s3 = reduce_partials4(p.partA, p.nblk, 3, sh); }
-  if (threadIdx.x == 0) {
-    float L = float(lsum / p.B);
-    if (fisher) {
-      const float lam = p.fisher[0], rho = p.fisher[1];
-      const float omega = 1.f - (0.5f * float(s2 / p.Bstat) + 0.5f * float(s3 / p.Bstat));
-      L = L - lam * omega + 0.5f * rho * omega * omega;   // src/fisher_gan.py:221-223
-      p.fisher[0] = lam + rho * (-omega);                 // src/fisher_gan.py:155: lambda += rho * dL/dlambda
-      p.loss[2] = omega;
+  if (PASS == 2) {
+    // the last block to finish reduces every block's partials (fixed order -> deterministic) instead
+    // of a separate one-block launch
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      last = atomicAdd(p.done, 1u) == gridDim.x - 1;
     }
-    p.loss[0] = L;
-    p.loss[1] = float(dssum);
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      loss_finalize(p, sh);
+      if (threadIdx.x == 0) *p.done = 0u;
+    }
   }
 }
 
@@ -736,9 +751,18 @@ __device__ __forceinline__ float gather_grad(const GradSegs& segs, int i) {
     if (s.kind <= 1) off = (long long)(j / s.cols) * s.ld + (j % s.cols);
     else if (s.kind == 2) off = (long long)j * s.ld + s.col;
     else off = j;
-    float t = 0.f;
-    for (int q = 0; q < s.nsplit; ++q) t += s.src[off + q * s.split_stride];
-    return t;
+    // four independent partial sums (loads in flight), combined in a fixed order -> deterministic
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    const float* src = s.src + off;
+    int q = 0;
+    for (; q + 4 <= s.nsplit; q += 4) {
+      t0 += src[(long long)q * s.split_stride];
+      t1 += src[(long long)(q + 1) * s.split_stride];
+      t2 += src[(long long)(q + 2) * s.split_stride];
+      t3 += src[(long long)(q + 3) * s.split_stride];
+    }
+    for (; q < s.nsplit; ++q) t0 += src[(long long)q * s.split_stride];
+    return (t0 + t1) + (t2 + t3);
   }
   return 0.f;
 }
