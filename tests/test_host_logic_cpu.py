@@ -1,0 +1,67 @@
+"""Host-side logic of the drop-in layer that needs no GPU: override detection for the README's
+extension mechanism, the bit-packed resident dataset, and the C header / ctypes agreement."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_builtin_losses_are_marked_and_overrides_detected():
+    import ns_gan, mm_gan, w_gan, w_gp_gan, ls_gan, dra_gan, be_gan, ra_gan, f_gan, fisher_gan, info_gan
+    for m, t in ((ns_gan, "NSGANTrainer"), (mm_gan, "MMGANTrainer"), (w_gan, "WGANTrainer"), (w_gp_gan, "WGPGANTrainer"),
+                 (ls_gan, "LSGANTrainer"), (dra_gan, "DRAGANTrainer"), (be_gan, "BEGANTrainer"), (ra_gan, "RaNSGANTrainer"),
+                 (f_gan, "fGANTrainer"), (fisher_gan, "FisherGANTrainer"), (info_gan, "InfoGANTrainer")):
+        T = getattr(m, t)
+        assert getattr(T.train_D, "_gm_builtin", False) and getattr(T.train_G, "_gm_builtin", False), t
+
+    class Mine(ns_gan.NSGANTrainer):                      # README.md:31: "edit train_D and train_G"
+        def train_D(self, images):
+            return torch.zeros(())
+
+    model = ns_gan.NSGAN(784, 400, 20)
+    assert not ns_gan.NSGANTrainer(model, [], [], [])._has_custom_step()
+    assert Mine(model, [], [], [])._has_custom_step()
+
+
+def test_forward_without_engine_fails_loudly():
+    """No eager / CPU path: the modules refuse to run until a CUDA engine exists."""
+    import ns_gan
+    from gm_b200 import GmError
+    model = ns_gan.NSGAN(784, 400, 20)
+    with pytest.raises(GmError, match="CUDA engine"):
+        model.G(torch.randn(4, 20))
+
+
+def test_device_dataset_bit_packing_matches_numpy():
+    from gm_b200.gan_api import DeviceDataset
+    g = torch.Generator().manual_seed(1)
+    imgs = (torch.rand(37, 1, 28, 28, generator=g) < 0.13).float()
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(imgs, torch.zeros(37)), batch_size=10, shuffle=True)
+    dd = DeviceDataset.from_loader(loader)
+    assert dd is not None and len(dd) == 4 and dd.bits.shape == (37, 98) and dd.bits.dtype == torch.uint8
+    back = np.unpackbits(dd.bits.cpu().numpy(), axis=1)[:, :784]        # MSB first, row-aligned: the kernel's layout
+    assert np.array_equal(back, imgs.view(37, -1).numpy().astype(np.uint8))
+    dd.seed(5)
+    a = dd.sample()
+    dd.seed(5)
+    b = dd.sample()
+    assert torch.equal(a, b) and a.unique().numel() == 10 and int(a.max()) < 37
+    # grey-level data cannot be packed: the Trainer then keeps the reference's process_batch path
+    loader2 = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(torch.rand(8, 1, 28, 28), torch.zeros(8)), batch_size=4)
+    assert DeviceDataset.from_loader(loader2) is None
+    assert DeviceDataset.from_loader([(imgs, None)]) is None               # plain list iterators: nothing to cache
+
+
+def test_every_header_function_has_ctypes_argtypes():
+    """include/gm_b200.h and gm_b200/_lib.py stay in step: each declared entry point gets its argument
+    types declared (a missing declaration would pass Python ints as 32-bit C ints)."""
+    hdr = open(os.path.join(ROOT, "include", "gm_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(gm_[a-z0-9_]+)\s*\(", hdr)))
+    src = open(os.path.join(ROOT, "generative-models_b200", "gm_b200", "_lib.py")).read()
+    no_args = {"gm_version"}
+    missing = [n for n in names if n not in no_args and ("L.%s.argtypes" % n) not in src]
+    assert not missing, missing
