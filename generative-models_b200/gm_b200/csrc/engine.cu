@@ -207,6 +207,8 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
       // 6th pipeline stage; aux epilogues and short-K GEMMs are epilogue-bound: 16 warps
       GemmPlan q = pl;
       if (q.cs == 2 && q.p.K >= 512 && q.p.aux_mode == AUX_NONE) q.ew = 8;
+      static const int force_ew = getenv("GM_FORCE_EW") ? atoi(getenv("GM_FORCE_EW")) : 0;   // tuning knob (tools/prof_gemm.py)
+      if (q.cs == 2 && (force_ew == 8 || force_ew == 16)) q.ew = force_ew;
       e = launch_nt208(q, s);
       break;
     }

@@ -368,6 +368,13 @@ class GANTrainerBase:
         self._lazy = False
         if self._engine is not None:
             self._engine.set_lazy_grads(False)
+            if getattr(self._engine, "_comm_attached", None) is not None:
+                self._engine.attach_comm(None)
+                self._engine._comm_attached = None
+        if self._comm is not None:          # the exchange buffers live for one train() call
+            torch.cuda.synchronize()
+            self._comm.close()
+            self._comm = None
 
     def _has_custom_step(self):
         return not (getattr(type(self).train_D, "_gm_builtin", False) and getattr(type(self).train_G, "_gm_builtin", False))

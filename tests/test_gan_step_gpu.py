@@ -368,3 +368,5 @@ def test_fused_peer_allreduce_adam_two_ranks():
     # RaNS / Fisher / DRAGAN batch statistics are exchanged on the device: 2 ranks x B rows reproduce the
     # gradients (and Fisher's lambda update) of one process with 2B rows
     assert "GLOBAL_BATCH_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+    # NSGANTrainer.train itself under a process group: replicas stay bitwise identical
+    assert "TRAINER_DP_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

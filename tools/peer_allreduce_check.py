@@ -137,4 +137,31 @@ def global_batch_check(variant):
 rels = {v: global_batch_check(v) for v in os.environ.get("GM_CHECK_VARIANTS", "ns,ra,fisher,dra").split(",") if v}
 if rank == 0:
     print("GLOBAL_BATCH_OK " + " ".join("%s=%.2g" % kv for kv in rels.items()))
+
+
+# ---- Trainer.train under data parallelism: the drop-in class itself exchanges gradients ----------
+def trainer_check():
+    sys.path.insert(0, os.path.join(ROOT, "generative-models_b200"))
+    import ns_gan
+    torch.manual_seed(11)                                   # same initial weights on every rank
+    model = ns_gan.NSGAN(784, 400, 20)
+    g2 = torch.Generator().manual_seed(5)
+    imgs = (torch.rand(512, 1, 28, 28, generator=g2) < 0.13).float()
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(imgs, torch.zeros(512)), batch_size=128, shuffle=True)
+    trainer = ns_gan.NSGANTrainer(model, loader, loader, loader)
+    torch.manual_seed(1000 + rank)                          # ... but different noise per rank
+    trainer.train(num_epochs=2, G_lr=2e-4, D_lr=2e-4, D_steps=1)
+    assert len(trainer.Dlosses) == 8 and all(np.isfinite(trainer.Dlosses)) and all(np.isfinite(trainer.Glosses))
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    mine = flat.cpu() if same_gpu else flat.clone()
+    allp = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allp, mine)
+    assert all(torch.equal(allp[0], t) for t in allp), "Trainer replicas diverged"
+    assert trainer._comm is not None or os.environ.get("GM_DP") == "nccl"
+    return float(trainer.Dlosses[-1])
+
+
+dl = trainer_check()
+if rank == 0:
+    print("TRAINER_DP_OK last_D_loss=%.4f" % dl)
 dist.destroy_process_group()

@@ -58,3 +58,9 @@ if "g2" in which:
     bias = torch.randn(784, device=dev)
     t = timeit(lambda: gm_b200.gemm_bf16(A, W, out, "nt", K=400, bias=bias, act=2, pad_one=True, out_cols=832))
     print("g2 %.1f us  %.0f TFLOP/s" % (t, 2 * B * 400 * 784 / t / 1e6))
+if "dhg" in which:
+    A, W = bf(B, 800), bf(400, 784, scale=0.05)
+    aux = torch.randn(B, 416, device=dev).to(torch.bfloat16)
+    out = torch.zeros(B, 416, device=dev, dtype=torch.bfloat16)
+    t = timeit(lambda: gm_b200.gemm_bf16(A, W, out, "nt", K=784, aux=aux, aux_mode=2))
+    print("dhg %.1f us  %.0f TFLOP/s" % (t, 2 * B * 400 * 784 / t / 1e6))
