@@ -340,6 +340,7 @@ class GANTrainerBase:
             n = sum(p.numel() for p in self.model.G.parameters()), sum(p.numel() for p in self.model.D.parameters())
             self._comm = par.make_peer_comm(max(n))
         self._lazy = self._world == 1 or self._comm is not None
+        self.gradient_exchange = "none" if self._world == 1 else ("peer" if self._comm is not None else "nccl")
         if self._resident is not None and self._world > 1:
             self._resident.seed(int(torch.initial_seed()) + par.rank_of())
         self._pre_train(num_epochs, hpG, hpD, D_steps, extra)

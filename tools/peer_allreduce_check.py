@@ -157,7 +157,7 @@ def trainer_check():
     allp = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allp, mine)
     assert all(torch.equal(allp[0], t) for t in allp), "Trainer replicas diverged"
-    assert trainer._comm is not None or os.environ.get("GM_DP") == "nccl"
+    assert trainer.gradient_exchange == ("nccl" if os.environ.get("GM_DP") == "nccl" else "peer"), trainer.gradient_exchange
     return float(trainer.Dlosses[-1])
 
 
