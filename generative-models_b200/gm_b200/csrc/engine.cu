@@ -112,11 +112,14 @@ template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T
 static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
   using Cfg = GemmCfg<BN1, BN2, !AMN, (CS == 2) && !AMN, EW>;
   auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, CS, EW>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 KB dynamic shared memory is per (function, device)
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);

@@ -150,7 +150,7 @@ def test_device_resident_dataset_path():
     eng = tr._engine
     eng.d_grad(dd.bits, fmt="bits", gather_idx=idx, batch=100, noise=torch.randn(100, 20, device="cuda"))
     sc = eng.scores(100)
-    ref = model.D(imgs.view(1000, -1)[idx.long().cpu()])
+    ref = model.D(imgs.view(1000, -1)[idx.long().cpu()]).detach()
     assert float((sc - ref.view(-1)).abs().max()) < 2e-3
     # a non-binary dataset falls back to process_batch
     loader2 = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(torch.rand(200, 1, 28, 28), torch.zeros(200)), batch_size=100)
