@@ -370,3 +370,49 @@ def test_fused_peer_allreduce_adam_two_ranks():
     assert "GLOBAL_BATCH_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
     # NSGANTrainer.train itself under a process group: replicas stay bitwise identical
     assert "TRAINER_DP_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("batch", [1, 37, 129, 200])
+def test_ragged_batches_match_the_oracle(batch):
+    """Batches that are not multiples of the 128-row / 64-deep tiles (TMA zero-fill and store clipping do
+    the bounds work), down to a single sample: losses, scores and the D / G gradients of one NSGAN step
+    against the bf16-point oracle.  One engine (max_batch 256) serves every size."""
+    eng = _engine("ns", 256)
+    rng = np.random.default_rng(100 + batch)
+    x = (rng.random((batch, 784)) < 0.1307).astype(np.float32)
+    z1, z2 = rng.standard_normal((batch, 20)).astype(np.float32), rng.standard_normal((batch, 20)).astype(np.float32)
+    P = params_dict(gm_init_weights(GAN_SHAPES, 1234), np.float64)
+    Lo, goq, info = R.gan_d_step(P, "ns", x.astype(np.float64), z1.astype(np.float64), q=R.bf16_points)
+    Ld = eng.d_grad(torch.from_numpy(x).cuda(), noise=torch.from_numpy(z1).cuda()).item()
+    sc = eng.scores(2 * batch).cpu().numpy()
+    assert abs(Ld - Lo) < TOL_LOSS * max(abs(Lo), 1e-3)
+    assert _nrel(sc[:batch], info["dx"]) < TOL_SCORE and _nrel(sc[batch:], info["dg"]) < TOL_SCORE
+    names = ["D.linear.weight", "D.linear.bias", "D.discriminate.weight", "D.discriminate.bias"]
+    for nme, g in zip(names, [v.cpu().numpy() for v in eng.views(1, eng.grads[1])]):
+        assert _nrel(g, goq[nme]) < TOL_GRAD_Q, (nme, batch)
+    Lgo, ggq, _ = R.gan_g_step(P, "ns", z2.astype(np.float64), q=R.bf16_points)
+    Lg = eng.g_grad(batch, noise=torch.from_numpy(z2).cuda()).item()
+    assert abs(Lg - Lgo) < TOL_LOSS * max(abs(Lgo), 1e-3)
+    for nme, g in zip(["G.linear.weight", "G.linear.bias", "G.generate.weight", "G.generate.bias"],
+                      [v.cpu().numpy() for v in eng.views(0, eng.grads[0])]):
+        assert _nrel(g, ggq[nme]) < TOL_GRAD_Q, (nme, batch)
+
+
+def test_argument_errors_are_reported_not_executed():
+    """The C ABI validates on the host and returns error codes (raised as GmError): empty and oversized
+    batches, missing inputs, bad slots; nothing is launched for them."""
+    import gm_b200
+    eng = _engine("ns", 64)
+    x = torch.zeros(64, 784, device="cuda")
+    n0 = gm_b200.launch_count(reset=True)
+    with pytest.raises(gm_b200.GmError, match="batch"):
+        eng.d_grad(x[:0], batch=0, inv_global_batch=1.0)
+    with pytest.raises(gm_b200.GmError, match="batch"):
+        eng.d_grad(torch.zeros(65, 784, device="cuda"))
+    with pytest.raises(gm_b200.GmError, match="batch"):
+        eng.g_grad(1000)
+    with pytest.raises(gm_b200.GmError, match="slot"):
+        eng.d_forward(7, x)
+    with pytest.raises(gm_b200.GmError):
+        eng.generate(torch.zeros(65, 20, device="cuda"))
+    assert gm_b200.launch_count() == 0
