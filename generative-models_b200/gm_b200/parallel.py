@@ -81,6 +81,7 @@ class PeerComm:
         self._lib, self._C = _lib, C
         self.h = _lib.ctx()
         self.rank, self.world = rank_of(group), world_size(group)
+        self._group = group
         self.c = C.c_void_p()
         _lib.check(self.h, _lib.lib().gm_comm_create(self.h, int(nfloats), C.byref(self.c)))
         mine = (C.c_ubyte * 64)()
@@ -99,7 +100,11 @@ class PeerComm:
             dist.barrier(group=group)      # every rank has mapped every buffer before the first kernel uses them
 
     def close(self):
+        """Collective: a rank may only free its buffer when no peer kernel can still be reading it."""
         if self.c is not None:
+            torch.cuda.synchronize()
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self._group)
             self._lib.lib().gm_comm_destroy(self.c)
             self.c = None
 

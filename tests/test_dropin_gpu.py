@@ -223,7 +223,7 @@ def test_custom_path_gradients_match_oracle():
     P = params_dict(W, np.float64)
     Lo, go, _ = R.gan_d_step(P, "ns", xb.astype(np.float64), draws[0].astype(np.float64))
     _, goq, _ = R.gan_d_step(P, "ns", xb.astype(np.float64), draws[0].astype(np.float64), q=R.bf16_points)
-    assert abs(float(loss) - Lo) < 1e-3 * max(abs(Lo), 1e-3)
+    assert abs(float(loss.detach()) - Lo) < 1e-3 * max(abs(Lo), 1e-3)
     for name, prm in model.D.named_parameters():
         g = prm.grad.detach().cpu().numpy().astype(np.float64).ravel()
         for ref, tol in ((goq["D." + name], 1e-3), (go["D." + name], 6e-2)):
