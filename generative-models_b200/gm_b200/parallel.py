@@ -99,11 +99,11 @@ class PeerComm:
         if self.world > 1:
             dist.barrier(group=group)      # every rank has mapped every buffer before the first kernel uses them
 
-    def close(self):
-        """Collective: a rank may only free its buffer when no peer kernel can still be reading it."""
+    def close(self, collective=True):
+        """Collective by default: a rank may only free its buffer when no peer kernel can still be reading it."""
         if self.c is not None:
             torch.cuda.synchronize()
-            if self.world > 1 and dist.is_initialized():
+            if collective and self.world > 1 and dist.is_initialized():
                 dist.barrier(group=self._group)
             self._lib.lib().gm_comm_destroy(self.c)
             self.c = None
@@ -126,6 +126,6 @@ def make_peer_comm(nfloats, group=None):
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     if int(flag.item()) == 0:
         if comm is not None:
-            comm.close()
+            comm.close(collective=False)     # some rank has no communicator: nothing ran on it yet
         return None
     return comm
