@@ -1,4 +1,10 @@
-"""Per-tile phase timing of the GEMM kernel (CTA 0): MMA issuer and one epilogue warp."""
+"""Per-tile phase timing of the GEMM kernel (CTA 0): MMA issuer and one epilogue warp.
+
+The clock reads are compiled out of the shipped library (they cost registers in the 96-register
+epilogue): build an instrumented copy and point GM_B200_LIB at it, e.g.
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared -I include \
+       -DGM_PHASE_TIMING -o build_variants/lib_timing.so generative-models_b200/gm_b200/csrc/engine.cu
+  GM_B200_LIB=$PWD/build_variants/lib_timing.so python tools/time_phases.py"""
 import ctypes as C
 import os
 import sys
