@@ -117,6 +117,9 @@ def run_ours(args):
     # (gm_gan_apply_allreduce); GM_DP=nccl (or no peer access) falls back to dist.all_reduce + gm_gan_apply
     comm = par.make_peer_comm(max(eng.n))
     eng.set_lazy_grads(world == 1 or comm is not None)    # split-K gather fused into the update kernel
+    overlap = comm is not None and os.environ.get("GM_DP_OVERLAP") == "1"
+    side = torch.cuda.Stream(device=dev) if overlap else None
+    ev_d, ev_a = (torch.cuda.Event(), torch.cuda.Event()) if overlap else (None, None)
     # device-resident synthetic dataset, 1 bit per pixel (binarised MNIST carries exactly
     # that: src/utils.py:31); pool of 4*B images = 412 MB as bf16 rows, > 126 MB L2
     N = 4 * B
@@ -132,6 +135,19 @@ def run_ours(args):
         s = step_no[0]
         step_no[0] += 1
         eng.d_grad(images, fmt=fmt, gather_idx=idx, batch=B, inv_global_batch=inv, seed=par.rank_seed(1000, rank), step=s)
+        if comm is not None and overlap:
+            # experimental (GM_DP_OVERLAP=1, off by default until measured): the D-gradient exchange + Adam runs on a
+            # side stream while this stream already computes the G step's generator forward (independent of D)
+            ev_d.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev_d)
+                eng.apply_allreduce(1, hpD, comm)
+                ev_a.record(side)
+            eng.g_forward_stage(B, seed=par.rank_seed(1000, rank), step=s)
+            torch.cuda.current_stream().wait_event(ev_a)
+            eng.g_grad_staged(B, inv_global_batch=inv)
+            eng.apply_allreduce(0, hpG, comm)
+            return
         if comm is not None:
             eng.apply_allreduce(1, hpD, comm)   # D gradient only: publish, sum over NVLink, Adam - one kernel
         else:
@@ -254,7 +270,8 @@ def run_ours(args):
                                   "1 D update + 1 G update per step, Adam lr 2e-4" % B,
                       "global_batch": B * world, "parallelism": "dp%d" % world,
                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
-                                            "fused peer all-reduce + Adam kernel (CUDA IPC over NVLink)" if comm is not None
+                                            "fused peer all-reduce + Adam kernel (CUDA IPC over NVLink)%s" % (
+                                                ", D exchange overlapped with the G forward" if overlap else "") if comm is not None
                                             else "NCCL all-reduce"),
                       "inputs": "device-resident 1-bit synthetic images, pool 4*B (412 MB as bf16 rows) > L2; "
                                 "per-step working set ~1.5 GB, no L2 flush needed",

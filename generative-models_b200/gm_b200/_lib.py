@@ -80,6 +80,8 @@ def lib():
     L.gm_gan_sync_shadows.argtypes = [vp, i, vp]
     L.gm_gan_d_grad.argtypes = [vp, vp, i, vp, i, vp, vp, f, u64, u64, vp, vp]
     L.gm_gan_g_grad.argtypes = [vp, i, vp, f, u64, u64, vp, vp]
+    L.gm_gan_g_forward_stage.argtypes = [vp, i, vp, u64, u64, vp]
+    L.gm_gan_g_grad_staged.argtypes = [vp, i, f, vp, vp]
     L.gm_gan_apply.argtypes = [vp, i, C.POINTER(AdamHP), i, vp]
     L.gm_gan_scores.argtypes = [vp, vp, i, vp]
     L.gm_gan_generate.argtypes = [vp, vp, i, vp, vp]

@@ -1125,8 +1125,11 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   return GM_OK;
 }
 
-extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv_global_batch, uint64_t seed,
-                             uint64_t step, float* loss_dev, gm_stream stream) {
+// train_G + backward; `staged`: the generator forward of this step was already enqueued by
+// gm_gan_g_forward_stage (it does not depend on the D update, so a data-parallel host can run it
+// while the D-gradient exchange is still in flight on another stream)
+static int g_grad_impl(gm_gan* g, int batch, const float* noise, float inv_global_batch, uint64_t seed, uint64_t step,
+                       float* loss_dev, gm_stream stream, bool staged) {
   int rc = check_step_args(g, batch);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1135,7 +1138,7 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   const int B = batch;
   gm_ctx* c = g->ctx;
   flush_pending(g, s);
-  if ((rc = run_generator(g, sp, B, noise, seed, 2 * step + 1, s))) return rc;
+  if (!staged && (rc = run_generator(g, sp, B, noise, seed, 2 * step + 1, s))) return rc;
   if (g->d.variant == GM_BEGAN) return began_g_grad(g, sp, B, loss_dev, s);
   if ((rc = launch_plan(c, sp->d1_g, s))) return rc;
   launch_loss(g, B, 1, inv_global_batch, s);
@@ -1158,6 +1161,23 @@ extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv
   g->last_rows = B;
   CU_OK(c, cudaGetLastError());
   return GM_OK;
+}
+
+extern "C" int gm_gan_g_grad(gm_gan* g, int batch, const float* noise, float inv_global_batch, uint64_t seed,
+                             uint64_t step, float* loss_dev, gm_stream stream) {
+  return g_grad_impl(g, batch, noise, inv_global_batch, seed, step, loss_dev, stream, false);
+}
+extern "C" int gm_gan_g_forward_stage(gm_gan* g, int batch, const float* noise, uint64_t seed, uint64_t step, gm_stream stream) {
+  int rc = check_step_args(g, batch);
+  if (rc) return rc;
+  StepPlans* sp;
+  if ((rc = build_plans(g, batch, &sp))) return rc;
+  if ((rc = run_generator(g, sp, batch, noise, seed, 2 * step + 1, static_cast<cudaStream_t>(stream)))) return rc;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+extern "C" int gm_gan_g_grad_staged(gm_gan* g, int batch, float inv_global_batch, float* loss_dev, gm_stream stream) {
+  return g_grad_impl(g, batch, nullptr, inv_global_batch, 0, 0, loss_dev, stream, true);
 }
 
 // ---- InfoGAN: auxiliary network Q and the mutual-information step (src/info_gan.py:269-304,196-205)

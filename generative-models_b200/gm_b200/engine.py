@@ -114,6 +114,17 @@ class GanEngine:
                                           C.c_void_p(self.loss_buf.data_ptr() + 4), _stream()))
         return self.loss_buf[1]
 
+    def g_forward_stage(self, batch, noise=None, seed=0, step=0):
+        """First half of g_grad: the generator forward only (independent of the D update; lets a data-parallel
+        host overlap it with the D-gradient exchange running on another stream)."""
+        check(self.h, lib().gm_gan_g_forward_stage(self.g, batch, _ptr(noise), seed, step, _stream()))
+
+    def g_grad_staged(self, batch, inv_global_batch=None):
+        """Second half of g_grad after g_forward_stage: D on the fake rows, loss, backward through D and G."""
+        inv = 1.0 / batch if inv_global_batch is None else inv_global_batch
+        check(self.h, lib().gm_gan_g_grad_staged(self.g, batch, inv, C.c_void_p(self.loss_buf.data_ptr() + 4), _stream()))
+        return self.loss_buf[1]
+
     def apply(self, net, hp):
         """optimizer.step() (src/ns_gan.py:139,156)."""
         self.steps[net] += 1

@@ -128,6 +128,11 @@ int gm_gan_d_grad(gm_gan* gan, const void* images_dev, int img_fmt, const int* g
 /* train_G + G_loss.backward() (src/ns_gan.py:196-216,155), G gradients only. */
 int gm_gan_g_grad(gm_gan* gan, int batch, const float* noise_dev, float inv_global_batch, uint64_t seed,
                   uint64_t step, float* loss_dev, gm_stream stream);
+/* gm_gan_g_grad in two halves: the generator forward G(z) of train_G (src/ns_gan.py:207-208) does not depend
+ * on the D update that precedes it, so a data-parallel host may enqueue it while the D-gradient exchange
+ * (gm_gan_apply_allreduce on another stream) is still in flight, then wait for that stream and run the rest. */
+int gm_gan_g_forward_stage(gm_gan* gan, int batch, const float* noise_dev, uint64_t seed, uint64_t step, gm_stream stream);
+int gm_gan_g_grad_staged(gm_gan* gan, int batch, float inv_global_batch, float* loss_dev, gm_stream stream);
 /* optimizer.step() on one net (src/ns_gan.py:139,156) + operand-copy refresh. */
 int gm_gan_apply(gm_gan* gan, int net, const gm_adam_hp* hp, int step, gm_stream stream);
 /* Lazy gradients (single-GPU fast path): with on != 0, *_grad leaves the gradient as split-K
