@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from utils import *  # noqa: F401,F403
+from gm_b200 import parallel as par
 from gm_b200 import AdamHP, GmError
 from gm_b200.gan_api import builtin_step, Generator, GANTrainerBase, _EngineBacked, to_cuda, G_NET, D_NET
 
@@ -44,6 +45,7 @@ class BEGANTrainer(GANTrainerBase):
     variant = "began"
 
     def train(self, num_epochs, G_lr=1e-4, D_lr=1e-4, D_steps=1, GAMMA=0.50, LAMBDA=1e-3, K=0.00):
+        par.require_single_process(self.name + "Trainer")
         hpG, hpD = AdamHP.make(G_lr), AdamHP.make(D_lr)
         epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
         patience = 5 * len(self.train_iter)                      # src/be_gan.py:133-136

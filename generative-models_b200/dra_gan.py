@@ -30,8 +30,9 @@ class DRAGANTrainer(GANTrainerBase):
         return super().train_D(images)
 
     def _draw_aux(self, images):
-        delta = torch.rand(images.shape[0], 1)                    # src/dra_gan.py:200
-        u = torch.rand(images.shape[0], images.shape[1])           # src/dra_gan.py:205
+        gen = getattr(self, "_noise_gen", None)
+        delta = torch.rand(images.shape[0], 1, generator=gen)                    # src/dra_gan.py:200
+        u = torch.rand(images.shape[0], images.shape[1], generator=gen)           # src/dra_gan.py:205
         return to_cuda(torch.cat([delta.reshape(-1), u.reshape(-1)])).contiguous()
 
 

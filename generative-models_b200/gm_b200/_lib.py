@@ -16,6 +16,7 @@ VARIANTS = {"ns": 0, "mm": 1, "w": 2, "wgp": 3, "ls": 4, "dra": 5, "ra": 6, "fis
             "f_hellinger": 12, "f_jensen_shannon": 13, "info": 14, "began": 15}
 OUT_ACTS = {"sigmoid": 0, "relu": 1, "none": 2}
 IMG_FMTS = {"f32": 0, "u8": 1, "bits": 2}
+PRECISIONS = {"bf16": 0, "split": 1}      # include/gm_b200.h: gm_prec
 
 
 class AdamHP(C.Structure):
@@ -39,12 +40,13 @@ class GemmDesc(C.Structure):
 
 
 class VaeDesc(C.Structure):
-    _fields_ = [("image_size", C.c_int), ("hidden_dim", C.c_int), ("z_dim", C.c_int), ("max_batch", C.c_int)]
+    _fields_ = [("image_size", C.c_int), ("hidden_dim", C.c_int), ("z_dim", C.c_int), ("max_batch", C.c_int),
+                ("dtype_mode", C.c_int)]
 
 
 class GanDesc(C.Structure):
     _fields_ = [("image_size", C.c_int), ("hidden_dim", C.c_int), ("z_dim", C.c_int),
-                ("max_batch", C.c_int), ("variant", C.c_int), ("d_out_act", C.c_int)]
+                ("max_batch", C.c_int), ("variant", C.c_int), ("d_out_act", C.c_int), ("dtype_mode", C.c_int)]
 
 
 _lib = None
@@ -115,6 +117,12 @@ def lib():
     L.gm_vae_apply.argtypes = [vp, C.POINTER(AdamHP), i, vp]
     L.gm_vae_forward.argtypes = [vp, vp, i, i, vp, u64, u64, vp, vp, vp, vp]
     L.gm_vae_decode.argtypes = [vp, vp, i, vp, vp]
+    L.gm_gan_set_sampler.argtypes = [vp, C.c_longlong, u64]
+    L.gm_sampler_indices_host.argtypes = [C.c_longlong, u64, u64, u64, i, vp]
+    L.gm_gan_sample_indices.argtypes = [vp, i, u64, vp, vp]
+    L.gm_gan_debug_noise.argtypes = [vp, i, u64, u64, i, vp, vp]
+    L.gm_vae_last_eps.argtypes = [vp, vp, i, vp]
+    L.gm_vae_set_sampler.argtypes = [vp, C.c_longlong, C.c_longlong, u64]
     L.gm_gan_fisher_state.argtypes = [vp, C.POINTER(C.c_float), i, vp]
     _lib = L
     return L

@@ -52,6 +52,24 @@ static int fail(gm_ctx* c, int code, const char* fmt, ...) {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int rup(int a, int b) { return cdiv(a, b) * b; }
 
+// on-device batch sampler (kernels.cuh: Sampler): permutation of [0, n) keyed by (seed, epoch-or-step)
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+static Sampler make_sampler(long long n, uint64_t seed, uint64_t round, uint64_t offset) {
+  Sampler sp;
+  sp.n = n > 0 ? unsigned(n) : 0u;
+  int bits = 2;
+  while (bits < 32 && (1ull << bits) < (unsigned long long)(n > 0 ? n : 1)) ++bits;
+  if (bits & 1) ++bits;
+  sp.half_bits = unsigned(bits / 2);
+  sp.key = splitmix64(splitmix64(seed) ^ (round * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull));
+  sp.offset = offset;
+  return sp;
+}
+static const Sampler kNoSampler = {0u, 1u, 0ull, 0ull};
+
 // ------------------------------------------------------------------ tensor maps
 // 2-D bf16 row-major matrix: `inner` contiguous elements per row (logical extent, may
 // be smaller than ld), `outer` rows, 128-byte swizzle, OOB elements read as zero.
@@ -514,6 +532,8 @@ struct gm_gan {
   int last_rows = 0;
   int region_rows = 0;   // rows per region of Xall/Aall/DHall (3 regions)
   gm_comm* comm = nullptr;   // attached communicator: batch statistics run over the global batch
+  long long pool_n = 0;      // on-device batch sampling over a resident pool of pool_n images (gm_gan_set_sampler)
+  uint64_t pool_seed = 0;
   // lazy gradients: *_grad leaves the split-K partials, gm_gan_apply gathers + updates in one kernel
   bool lazy = false;
   bool pend[2] = {false, false};
@@ -550,6 +570,7 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
     return fail(c, GM_ERR_ARG, "image_size and hidden_dim must be positive multiples of 16 (got %d, %d, z=%d)",
                 d->image_size, d->hidden_dim, d->z_dim);
   if (d->max_batch <= 0) return fail(c, GM_ERR_ARG, "max_batch must be positive (got %d)", d->max_batch);
+  if (d->dtype_mode != GM_PREC_BF16) return fail(c, GM_ERR_UNSUPPORTED, "dtype_mode %d is not built", d->dtype_mode);
   gm_gan* g = new gm_gan();
   g->ctx = c;
   g->d = *d;
@@ -1051,7 +1072,12 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   gm_ctx* c = g->ctx;
   flush_pending(g, s);
   // real rows -> Xall[0:B] (bf16, ones column)
-  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP);
+  Sampler smp = kNoSampler;
+  if (!gather_idx && g->pool_n > 0) {
+    if (B > g->pool_n) return fail(c, GM_ERR_ARG, "batch (%d) exceeds the sampler's pool (%lld)", B, g->pool_n);
+    smp = make_sampler(g->pool_n, g->pool_seed, step, 0);     // a fresh permutation every step (src/ns_gan.py:224)
+  }
+  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP, smp);
   c->launches++;
   if ((rc = run_generator(g, sp, B, noise, seed, 2 * step, s))) return rc;
   if (g->d.variant == GM_BEGAN) return began_d_grad(g, sp, B, loss_dev, s);
@@ -1336,12 +1362,53 @@ extern "C" int gm_gan_discriminate(gm_gan* g, const void* images, int img_fmt, i
   StepPlans* sp;
   int rc;
   if ((rc = build_plans(g, n, &sp))) return rc;
-  launch_pdl(stage_images_kernel, g->ctx->num_sms * 8, 256, 0, s, images, img_fmt, nullptr, g->Xall, n, g->X, g->XP);
+  launch_pdl(stage_images_kernel, g->ctx->num_sms * 8, 256, 0, s, images, img_fmt, nullptr, g->Xall, n, g->X, g->XP, kNoSampler);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->d1_x, s))) return rc;
   launch_pdl(scores_kernel, cdiv(n, 256), 256, 0, s, g->slots, 2 * cdiv(g->H, 208), g->nreg * g->Bmax, g->par[GM_NET_D] + g->D.off_b2,
                                             g->d.d_out_act, scores, n);
   g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+// On-device batch sampling: with a pool set (and gather_idx == NULL) gm_gan_d_grad reads row
+// perm_{seed,step}(r) of images_dev for batch row r - the first `batch` entries of a fresh pseudo-random
+// permutation of the pool per step, i.e. next(iter(DataLoader(shuffle=True))) (src/ns_gan.py:222-226).
+extern "C" int gm_gan_set_sampler(gm_gan* g, long long n_pool, uint64_t seed) {
+  if (!g || n_pool < 0 || n_pool > 0x7FFFFFFFll) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_set_sampler: bad pool size") : GM_ERR_ARG;
+  g->pool_n = n_pool; g->pool_seed = seed;
+  return GM_OK;
+}
+// host evaluation of the same permutation (CPU tests of the sampler; no device needed)
+extern "C" int gm_sampler_indices_host(long long n_pool, uint64_t seed, uint64_t round, uint64_t offset, int count, int* out_host) {
+  if (n_pool <= 0 || n_pool > 0x7FFFFFFFll || count < 0 || !out_host) return GM_ERR_ARG;
+  const Sampler sp = make_sampler(n_pool, seed, round, offset);
+  for (int r = 0; r < count; ++r) out_host[r] = int(sampler_index(sp, sp.offset + (unsigned long long)r));
+  return GM_OK;
+}
+// the source-row indices gm_gan_d_grad(step) draws for a batch (tests / logging)
+extern "C" int gm_gan_sample_indices(gm_gan* g, int batch, uint64_t step, int* idx_dev, gm_stream stream) {
+  if (!g || !idx_dev || batch <= 0) return GM_ERR_ARG;
+  if (g->pool_n > 0 && batch > g->pool_n) return fail(g->ctx, GM_ERR_ARG, "batch exceeds the pool");
+  const Sampler smp = g->pool_n > 0 ? make_sampler(g->pool_n, g->pool_seed, step, 0) : kNoSampler;
+  launch_pdl(sample_indices_kernel, cdiv(batch, 256), 256, 0, static_cast<cudaStream_t>(stream), smp, batch, idx_dev);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+// the generator noise of a step as the train step draws it (net_step = 2*step for train_D, 2*step+1 for
+// train_G): Philox N(0,1) rounded to the bf16 operand the GEMM reads -> out_dev [batch, z] fp32
+extern "C" int gm_gan_debug_noise(gm_gan* g, int batch, uint64_t seed, uint64_t step, int g_step, float* out_dev, gm_stream stream) {
+  int rc = check_step_args(g, batch);
+  if (rc) return rc;
+  if (!out_dev) return GM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  launch_pdl(stage_noise_kernel, cdiv(batch * ((g->Z + 8) / 8), 256), 256, 0, s, static_cast<const float*>(nullptr), g->Zb, batch, g->Z, g->ZP,
+                                                   (unsigned long long)seed, (unsigned long long)(2 * step + (g_step ? 1 : 0)));
+  const long long tot = (long long)batch * g->Z;
+  launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->Zb, g->ZP, out_dev, batch, g->Z);
+  g->ctx->launches += 2;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
 }

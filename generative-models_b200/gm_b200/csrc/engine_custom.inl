@@ -58,13 +58,13 @@ static int build_custom_plans(gm_gan* g, int B, CustomPlans** out) {
   const float* pG = g->par[GM_NET_G];
   int rc;
   for (int r = 0; r < g->nreg; ++r) {
-    __nv_bfloat16* Xr = g->Xall + size_t(r) * B * XP;
-    __nv_bfloat16* Ar = g->Aall + size_t(r) * B * HP;
-    __nv_bfloat16* DHr = g->DHall + size_t(r) * B * HP;
+    __nv_bfloat16* Xr = g->Xall + size_t(r) * g->Bmax * XP;
+    __nv_bfloat16* Ar = g->Aall + size_t(r) * g->Bmax * HP;
+    __nv_bfloat16* DHr = g->DHall + size_t(r) * g->Bmax * HP;
     // a = relu(x W1^T + b1), row-dot with w2 -> slots of this region (Discriminator.forward, src/ns_gan.py:57-60)
     if ((rc = plan_gemm(c, &cp.d1[r], 0, B, H, X, Xr, XP, g->W1d_s, X, H, 1))) return rc;
     set_bf16_epi(cp.d1[r].p, Ar, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
-    cp.d1[r].p.dot_w = pD + g->D.off_w2; cp.d1[r].p.dot_out = g->slots + size_t(r) * B; cp.d1[r].p.dot_ld = g->nreg * g->Bmax;
+    cp.d1[r].p.dot_w = pD + g->D.off_w2; cp.d1[r].p.dot_out = g->slots + size_t(r) * g->Bmax; cp.d1[r].p.dot_ld = g->nreg * g->Bmax;
     // [dW1 | db1]^T = [x | 1]^T dh over this region's rows
     if ((rc = plan_gemm(c, &cp.dw1[r], 1, X + 1, H, B, Xr, XP, DHr, HP, H, g->max_splits))) return rc;
     {
@@ -108,10 +108,10 @@ extern "C" int gm_gan_d_forward(gm_gan* g, int slot, const float* x, int batch, 
   if ((rc = build_custom_plans(g, batch, &cp))) return rc;
   gm_ctx* c = g->ctx;
   launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, static_cast<const void*>(x), int(GM_IMG_F32), static_cast<const int*>(nullptr),
-             g->Xall + size_t(slot) * batch * g->XP, batch, g->X, g->XP);
+             g->Xall + size_t(slot) * g->Bmax * g->XP, batch, g->X, g->XP, kNoSampler);
   c->launches++;
   if ((rc = launch_plan(c, cp->d1[slot], s))) return rc;
-  launch_pdl(scores_kernel, cdiv(batch, 256), 256, 0, s, g->slots + size_t(slot) * batch, 2 * cdiv(g->H, 208), g->nreg * g->Bmax,
+  launch_pdl(scores_kernel, cdiv(batch, 256), 256, 0, s, g->slots + size_t(slot) * g->Bmax, 2 * cdiv(g->H, 208), g->nreg * g->Bmax,
              g->par[GM_NET_D] + g->D.off_b2, g->d.d_out_act, scores, batch);
   c->launches++;
   CU_OK(c, cudaGetLastError());
@@ -129,11 +129,11 @@ extern "C" int gm_gan_d_backward(gm_gan* g, int slot, int batch, const float* ds
   gm_ctx* c = g->ctx;
   const int B = batch, H = g->H, HP = g->HP;
   const float* w2 = g->par[GM_NET_D] + g->D.off_w2;
-  float* ds = g->ds + size_t(slot) * B;
-  launch_pdl(custom_ds_kernel, 1, 1024, 0, s, g->slots + size_t(slot) * B, 2 * cdiv(H, 208), g->nreg * g->Bmax,
+  float* ds = g->ds + size_t(slot) * g->Bmax;
+  launch_pdl(custom_ds_kernel, 1, 1024, 0, s, g->slots + size_t(slot) * g->Bmax, 2 * cdiv(H, 208), g->nreg * g->Bmax,
              g->par[GM_NET_D] + g->D.off_b2, g->d.d_out_act, dscore, ds, g->lossbuf + 1, B);
   launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * HP * sizeof(float), s,
-             g->Aall + size_t(slot) * B * HP, static_cast<const float*>(ds), w2, g->DHall + size_t(slot) * B * HP, g->dw2p, B, H, HP,
+             g->Aall + size_t(slot) * g->Bmax * HP, static_cast<const float*>(ds), w2, g->DHall + size_t(slot) * g->Bmax * HP, g->dw2p, B, H, HP,
              g->dh_rows_per_iter);
   launch_pdl(colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
   c->launches += 3;

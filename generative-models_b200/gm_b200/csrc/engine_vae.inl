@@ -20,6 +20,8 @@ struct gm_vae {
   float *MULV = nullptr, *DZ = nullptr, *EPS = nullptr, *slots_r = nullptr, *losses = nullptr;
   float *P1 = nullptr, *Pmv = nullptr, *P3 = nullptr, *P4 = nullptr;
   double *part_r = nullptr, *part_k = nullptr;
+  long long pool_n = 0, pool_bpe = 0;   // on-device epoch sampler (gm_vae_set_sampler)
+  uint64_t pool_seed = 0;
   std::map<int, VaePlans> plans;
   std::vector<void*> allocs;
 };
@@ -50,6 +52,7 @@ extern "C" int gm_vae_create(gm_ctx* c, const gm_vae_desc* d, gm_vae** out) {
     return fail(c, GM_ERR_ARG, "image_size and hidden_dim must be positive multiples of 16");
   if (d->hidden_dim + 1 > 448 || 2 * d->z_dim > 64)
     return fail(c, GM_ERR_UNSUPPORTED, "hidden_dim <= 447 and z_dim <= 32 in this build (got %d, %d)", d->hidden_dim, d->z_dim);
+  if (d->dtype_mode != GM_PREC_BF16) return fail(c, GM_ERR_UNSUPPORTED, "dtype_mode %d is not built", d->dtype_mode);
   gm_vae* g = new gm_vae();
   g->ctx = c; g->d = *d;
   const int X = g->X = d->image_size, H = g->H = d->hidden_dim, Z = g->Z = d->z_dim;
@@ -93,6 +96,14 @@ extern "C" int gm_vae_create(gm_ctx* c, const gm_vae_desc* d, gm_vae** out) {
   return GM_OK;
 }
 
+// On-device epoch shuffling: gm_vae_grad(step) with gather_idx == NULL reads batch (step % batches_per_epoch)
+// of the pseudo-random permutation of epoch (step / batches_per_epoch) over a resident pool (src/vae.py:150).
+extern "C" int gm_vae_set_sampler(gm_vae* g, long long n_pool, long long batches_per_epoch, uint64_t seed) {
+  if (!g || n_pool < 0 || n_pool > 0x7FFFFFFFll || batches_per_epoch < 0) return g ? fail(g->ctx, GM_ERR_ARG, "gm_vae_set_sampler: bad argument") : GM_ERR_ARG;
+  g->pool_n = n_pool; g->pool_bpe = batches_per_epoch; g->pool_seed = seed;
+  return GM_OK;
+}
+
 extern "C" int gm_vae_param_count(const gm_vae* g) { return g ? g->total : GM_ERR_ARG; }
 
 extern "C" int gm_vae_bind(gm_vae* g, float* p, float* gr, float* m, float* v) {
@@ -122,6 +133,13 @@ extern "C" int gm_vae_sync_shadows(gm_vae* g, gm_stream stream) {
   launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+// the eps of the last gm_vae_grad / gm_vae_forward (caller tensor or in-kernel Philox, src/vae.py:104) -> out_dev [batch, z]
+extern "C" int gm_vae_last_eps(gm_vae* g, float* out_dev, int batch, gm_stream stream) {
+  if (!g || !out_dev || batch <= 0 || batch > g->Bmax) return g ? fail(g->ctx, GM_ERR_ARG, "gm_vae_last_eps: bad argument") : GM_ERR_ARG;
+  CU_OK(g->ctx, cudaMemcpyAsync(out_dev, g->EPS, size_t(batch) * g->Z * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return GM_OK;
 }
 
@@ -205,7 +223,13 @@ static int vae_forward_core(gm_vae* g, VaePlans* sp, const void* images, int fmt
                             uint64_t seed, uint64_t step, bool train, cudaStream_t s) {
   gm_ctx* c = g->ctx;
   int rc;
-  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, fmt, idx, g->Xin, B, g->X, g->XP);
+  Sampler smp = kNoSampler;
+  if (!idx && g->pool_n > 0) {
+    // batch (step mod batches_per_epoch) of this epoch's permutation: a true epoch like `for batch in train_iter` (src/vae.py:150)
+    const uint64_t bpe = g->pool_bpe > 0 ? uint64_t(g->pool_bpe) : 1;
+    smp = make_sampler(g->pool_n, g->pool_seed, step / bpe, (step % bpe) * uint64_t(B));
+  }
+  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, fmt, idx, g->Xin, B, g->X, g->XP, smp);
   c->launches++;
   if ((rc = launch_plan(c, sp->e1, s))) return rc;
   if ((rc = launch_plan(c, sp->e2, s))) return rc;

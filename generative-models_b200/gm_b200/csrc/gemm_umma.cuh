@@ -85,7 +85,7 @@ constexpr int kEpiVecBytes = kEpiVecBlocks * kEpiCols * 4 * 2;   // bias + row-d
 // Phase timing (tools/time_phases.py) is compiled in only with -DGM_PHASE_TIMING: the clock
 // reads cost 8+ registers and CS2R stalls in the 96-register epilogue (profiles/r1e).
 #ifdef GM_PHASE_TIMING
-__device__ __forceinline__ long long phase_clock() { return phase_clock(); }
+__device__ __forceinline__ long long phase_clock() { return clock64(); }
 constexpr bool kPhaseTiming = true;
 #else
 __device__ __forceinline__ long long phase_clock() { return 0; }

@@ -22,11 +22,48 @@ constexpr float kEps = 1e-8f;  // the reference's log stabiliser (src/ns_gan.py:
 // `x` (bias-gradient trick: dW GEMMs then produce db as one extra row) and zero pad.
 // Optional row gather (idx != nullptr): row r reads source row idx[r].
 enum : int { IMG_F32 = 0, IMG_U8 = 1, IMG_BITS = 2, IMG_BF16PAD = 3 };
+
+// On-device batch sampling (the DataLoader shuffle of src/ns_gan.py:222-226, src/vae.py:150): row r of
+// the batch reads source row perm_key(offset + r), perm_key a pseudo-random PERMUTATION of [0, n) - a
+// 4-round Feistel network over the next even power of two, cycle-walked back into range - so the rows
+// of one batch are distinct, exactly like the first batch of a freshly shuffled DataLoader (GANs: a new
+// key every step, offset 0) or like batch k of one epoch's permutation (VAE: key per epoch, offset k*B).
+// n == 0 switches sampling off.
+struct Sampler {
+  unsigned int n, half_bits;
+  unsigned long long key, offset;
+};
+__host__ __device__ __forceinline__ unsigned int sampler_mix(unsigned int x, unsigned int k) {
+  x ^= k; x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ unsigned int sampler_index(const Sampler& sp, unsigned long long pos) {
+  const unsigned int mask = (1u << sp.half_bits) - 1u;
+  const unsigned int k0 = (unsigned int)sp.key, k1 = (unsigned int)(sp.key >> 32);
+  unsigned int i = (unsigned int)(pos % sp.n);
+  do {
+    unsigned int L = i >> sp.half_bits, R = i & mask;
+#pragma unroll
+    for (int rnd = 0; rnd < 4; ++rnd) {
+      const unsigned int F = sampler_mix(R, (rnd & 1 ? k1 : k0) + 0x632BE5ABu * (unsigned int)(rnd + 1)) & mask;
+      const unsigned int t = L ^ F;
+      L = R; R = t;
+    }
+    i = (L << sp.half_bits) | R;
+  } while (i >= sp.n);
+  return i;
+}
+
 __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const int* __restrict__ idx,
-                                    __nv_bfloat16* __restrict__ dst, int rows, int x, int ld) {
+                                    __nv_bfloat16* __restrict__ dst, int rows, int x, int ld, const Sampler smp) {
   griddep_sync();
   const int groups = ld / 8;
   const long long total = (long long)rows * groups;
+  auto src_row = [&](int r) -> long long {
+    if (idx) return (long long)idx[r];
+    if (smp.n) return (long long)sampler_index(smp, smp.offset + (unsigned long long)r);
+    return (long long)r;
+  };
   if (fmt == IMG_BITS && (x & 7) == 0) {
     // One warp per row: lanes walk the row's 8-pixel groups (one packed byte, MSB first, expands
     // to 8 bf16 = one 16-byte store), 4 passes in flight; no index divisions, the gather index
@@ -34,10 +71,10 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int xb = x >> 3;   // source bytes per row; group xb holds the ones column
-    long long sr_next = w < rows ? (idx ? (long long)idx[w] : (long long)w) : 0;
+    long long sr_next = w < rows ? src_row(w) : 0;
     for (int r = w; r < rows; r += nwarps) {
       const long long sr = sr_next;
-      if (r + nwarps < rows) sr_next = idx ? (long long)idx[r + nwarps] : (long long)(r + nwarps);
+      if (r + nwarps < rows) sr_next = src_row(r + nwarps);
       const uint8_t* srow = reinterpret_cast<const uint8_t*>(src) + sr * xb;
       uint4* drow = reinterpret_cast<uint4*>(dst) + (long long)r * groups;
       for (int g0 = 0; g0 < groups; g0 += 128) {
@@ -63,7 +100,7 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int r = int(i / groups), g = int(i % groups);
-    const long long sr = idx ? idx[r] : r;
+    const long long sr = src_row(r);
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -82,6 +119,13 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
     reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                   pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
+}
+
+// the batch's source-row indices as the staging kernel draws them (tests, gm_sample_indices)
+__global__ void sample_indices_kernel(const Sampler smp, int rows, int* __restrict__ out) {
+  griddep_sync();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) out[r] = smp.n ? int(sampler_index(smp, smp.offset + (unsigned long long)r)) : r;
 }
 
 // noise fp32 [rows, z] (or Philox N(0,1) when src == nullptr) -> bf16 [rows, ld], ones col at z.

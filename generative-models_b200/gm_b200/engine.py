@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AdamHP, GanDesc, VaeDesc, GmError, VARIANTS, OUT_ACTS, IMG_FMTS, check, lib, _ptr, _stream
+from ._lib import AdamHP, GanDesc, VaeDesc, GmError, VARIANTS, OUT_ACTS, IMG_FMTS, PRECISIONS, check, lib, _ptr, _stream
 
 G, D = 0, 1
 
@@ -18,7 +18,7 @@ class GanEngine:
     """
 
     def __init__(self, image_size=784, hidden_dim=400, z_dim=20, max_batch=64, variant="ns",
-                 d_out_act="sigmoid", device=None):
+                 d_out_act="sigmoid", device=None, precision="bf16"):
         if not torch.cuda.is_available():
             raise GmError("gm_b200 needs a CUDA (B200) device; there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -26,7 +26,8 @@ class GanEngine:
         self.image_size, self.hidden_dim, self.z_dim = image_size, hidden_dim, z_dim
         self.max_batch = max_batch
         self.variant = variant
-        d = GanDesc(image_size, hidden_dim, z_dim, max_batch, VARIANTS[variant], OUT_ACTS[d_out_act])
+        self.precision = precision
+        d = GanDesc(image_size, hidden_dim, z_dim, max_batch, VARIANTS[variant], OUT_ACTS[d_out_act], PRECISIONS[precision])
         self.g = C.c_void_p()
         check(self.h, lib().gm_gan_create(self.h, C.byref(d), C.byref(self.g)))
         self.n = [lib().gm_gan_param_count(self.g, G), lib().gm_gan_param_count(self.g, D)]
@@ -99,20 +100,22 @@ class GanEngine:
 
     # ---- the hot path ----------------------------------------------------
     def d_grad(self, images, noise=None, aux=None, fmt="f32", gather_idx=None, batch=None, inv_global_batch=None,
-               seed=0, step=0):
-        """train_D + backward (src/ns_gan.py:172-194,138). Returns the device loss (0-dim view)."""
+               seed=0, step=0, loss_out=None):
+        """train_D + backward (src/ns_gan.py:172-194,138). Returns the device loss (0-dim view of loss_buf, or
+        of `loss_out`, a 0-dim fp32 device tensor the kernel writes instead: per-epoch loss logs without a copy)."""
         B = batch if batch is not None else (gather_idx.numel() if gather_idx is not None else images.shape[0])
         inv = 1.0 / B if inv_global_batch is None else inv_global_batch
+        dst = self.loss_buf[0] if loss_out is None else loss_out
         check(self.h, lib().gm_gan_d_grad(self.g, _ptr(images), IMG_FMTS[fmt], _ptr(gather_idx), B, _ptr(noise),
-                                          _ptr(aux), inv, seed, step, _ptr(self.loss_buf), _stream()))
-        return self.loss_buf[0]
+                                          _ptr(aux), inv, seed, step, _ptr(dst), _stream()))
+        return dst
 
-    def g_grad(self, batch, noise=None, inv_global_batch=None, seed=0, step=0):
+    def g_grad(self, batch, noise=None, inv_global_batch=None, seed=0, step=0, loss_out=None):
         """train_G + backward (src/ns_gan.py:196-216,155)."""
         inv = 1.0 / batch if inv_global_batch is None else inv_global_batch
-        check(self.h, lib().gm_gan_g_grad(self.g, batch, _ptr(noise), inv, seed, step,
-                                          C.c_void_p(self.loss_buf.data_ptr() + 4), _stream()))
-        return self.loss_buf[1]
+        dst = self.loss_buf[1] if loss_out is None else loss_out
+        check(self.h, lib().gm_gan_g_grad(self.g, batch, _ptr(noise), inv, seed, step, _ptr(dst), _stream()))
+        return dst
 
     def g_forward_stage(self, batch, noise=None, seed=0, step=0):
         """First half of g_grad: the generator forward only (independent of the D update; lets a data-parallel
@@ -124,6 +127,22 @@ class GanEngine:
         inv = 1.0 / batch if inv_global_batch is None else inv_global_batch
         check(self.h, lib().gm_gan_g_grad_staged(self.g, batch, inv, C.c_void_p(self.loss_buf.data_ptr() + 4), _stream()))
         return self.loss_buf[1]
+
+    def set_sampler(self, n_pool, seed=0):
+        """On-device batch sampling: d_grad(images=pool, gather_idx=None, batch=B, step=s) then reads the first B
+        rows of a fresh pseudo-random permutation of the pool per step (src/ns_gan.py:222-226)."""
+        check(self.h, lib().gm_gan_set_sampler(self.g, int(n_pool), int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def sample_indices(self, batch, step):
+        out = torch.empty(batch, device=self.device, dtype=torch.int32)
+        check(self.h, lib().gm_gan_sample_indices(self.g, batch, int(step), _ptr(out), _stream()))
+        return out
+
+    def debug_noise(self, batch, seed, step, g_step=False):
+        """The on-device Philox noise of (seed, step) as the bf16 operand values, [batch, z] fp32."""
+        out = torch.empty(batch, self.z_dim, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_gan_debug_noise(self.g, batch, int(seed), int(step), 1 if g_step else 0, _ptr(out), _stream()))
+        return out
 
     def apply(self, net, hp):
         """optimizer.step() (src/ns_gan.py:139,156)."""
@@ -232,10 +251,12 @@ class InfoGanEngine(GanEngine):
     """GanEngine + the auxiliary network Q and the mutual-information step of InfoGAN
     (src/info_gan.py:78-94,269-304).  The generator input is z + disc_dim + cont_dim wide."""
 
-    def __init__(self, image_size=784, hidden_dim=400, z_dim=20, disc_dim=10, cont_dim=10, max_batch=64, device=None):
+    def __init__(self, image_size=784, hidden_dim=400, z_dim=20, disc_dim=10, cont_dim=10, max_batch=64, device=None,
+                 precision="bf16"):
         if (disc_dim, cont_dim) != (10, 10):
             raise GmError("the fused Q head is built for disc_dim = cont_dim = 10 (the reference's setting)")
-        super().__init__(image_size, hidden_dim, z_dim + disc_dim + cont_dim, max_batch, variant="info", device=device)
+        super().__init__(image_size, hidden_dim, z_dim + disc_dim + cont_dim, max_batch, variant="info", device=device,
+                         precision=precision)
         self.noise_dim, self.code_z = z_dim + disc_dim + cont_dim, z_dim
         nq = lib().gm_gan_q_param_count(self.g)
         kw = dict(device=self.device, dtype=torch.float32)
@@ -300,13 +321,14 @@ class VaeEngine:
              "encoder.mu.bias", "encoder.log_var.bias", "decoder.linear.weight", "decoder.linear.bias",
              "decoder.recon.weight", "decoder.recon.bias"]
 
-    def __init__(self, image_size=784, hidden_dim=400, z_dim=20, max_batch=64, device=None):
+    def __init__(self, image_size=784, hidden_dim=400, z_dim=20, max_batch=64, device=None, precision="bf16"):
         if not torch.cuda.is_available():
             raise GmError("gm_b200 needs a CUDA (B200) device; there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.h = _lib.ctx(self.device.index)
         self.image_size, self.hidden_dim, self.z_dim, self.max_batch = image_size, hidden_dim, z_dim, max_batch
-        d = VaeDesc(image_size, hidden_dim, z_dim, max_batch)
+        self.precision = precision
+        d = VaeDesc(image_size, hidden_dim, z_dim, max_batch, PRECISIONS[precision])
         self.g = C.c_void_p()
         check(self.h, lib().gm_vae_create(self.h, C.byref(d), C.byref(self.g)))
         n = lib().gm_vae_param_count(self.g)
@@ -361,6 +383,25 @@ class VaeEngine:
         check(self.h, lib().gm_vae_grad(self.g, _ptr(images), IMG_FMTS[fmt], _ptr(gather_idx), B, _ptr(eps), 1.0, seed, step,
                                         _ptr(self.loss_buf), _stream()))
         return self.loss_buf
+
+    def set_sampler(self, n_pool, batches_per_epoch, seed=0):
+        """On-device epoch shuffling: grad(images=pool, gather_idx=None, batch=B, step=s) reads batch
+        s % batches_per_epoch of the permutation of epoch s // batches_per_epoch (src/vae.py:150)."""
+        check(self.h, lib().gm_vae_set_sampler(self.g, int(n_pool), int(batches_per_epoch), int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def last_eps(self, batch):
+        out = torch.empty(batch, self.z_dim, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_vae_last_eps(self.g, _ptr(out), batch, _stream()))
+        return out
+
+    def sample_indices(self, batch, step, batches_per_epoch, n_pool, seed):
+        """host evaluation of the epoch sampler's draw for `step` (tests)"""
+        import numpy as np
+        out = np.empty(batch, dtype=np.int32)
+        bpe = max(int(batches_per_epoch), 1)
+        check(self.h, lib().gm_sampler_indices_host(int(n_pool), int(seed), int(step) // bpe, (int(step) % bpe) * batch, batch,
+                                                    C.c_void_p(out.ctypes.data)))
+        return torch.from_numpy(out).to(self.device)
 
     def apply(self, hp):
         self.steps += 1

@@ -119,15 +119,29 @@ class DeviceDataset:
     def __init__(self, images, batch_size, drop_last=False):
         n = images.shape[0]
         flat = images.reshape(n, -1)
-        if not bool(((flat == 0) | (flat == 1)).all()):
-            raise ValueError("DeviceDataset needs binarised {0,1} images")
         self.n, self.x, self.batch_size = n, flat.shape[1], batch_size
         if self.x % 8:
             raise ValueError("image_size must be a multiple of 8")
-        bits = np.packbits(flat.to(torch.uint8).cpu().numpy(), axis=1)      # MSB first, row-aligned
-        self.bits = to_cuda(torch.from_numpy(bits).contiguous())
+        self.bits = self._pack(flat)            # [n, x/8] uint8 on the device, MSB first (np.packbits order)
         self.num_batches = n // batch_size if drop_last else -(-n // batch_size)
         self._gen = None
+        self._source = images
+
+    @staticmethod
+    def _pack(flat, chunk_rows=32768):
+        """{0,1} images -> 1 bit/pixel, packed ON the device chunk by chunk (a 262144-image fp32 dataset
+        packs in ~0.1 s instead of seconds of host numpy); raises ValueError for non-binary data."""
+        n, x = flat.shape
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else flat.device
+        w = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.int32, device=dev)
+        out = torch.empty(n, x // 8, dtype=torch.uint8, device=dev)
+        for i in range(0, n, chunk_rows):
+            c = flat[i:i + chunk_rows].to(dev, non_blocking=True)
+            one = c == 1
+            if not bool((one | (c == 0)).all()):
+                raise ValueError("DeviceDataset needs binarised {0,1} images")
+            out[i:i + chunk_rows] = (one.view(-1, x // 8, 8).to(torch.int32) * w).sum(dim=2).to(torch.uint8)
+        return out
 
     def seed(self, value):
         """Own device generator (data-parallel ranks must draw different batches)."""
@@ -142,13 +156,19 @@ class DeviceDataset:
         return torch.randperm(self.n, device=self.bits.device, generator=self._gen)[:b].to(torch.int32)
 
     @staticmethod
-    def from_loader(loader):
+    def from_loader(loader, cached=None):
+        """`cached`: the DeviceDataset of an earlier train() call - reused when the loader still serves the
+        same image tensor with the same batching (packing runs once per dataset, not once per train())."""
         ds = getattr(loader, "dataset", None)
         tensors = getattr(ds, "tensors", None)
         if tensors is None or getattr(loader, "batch_size", None) is None:
             return None
+        drop = getattr(loader, "drop_last", False)
+        if cached is not None and cached._source is tensors[0] and cached.batch_size == loader.batch_size and \
+                cached.num_batches == (tensors[0].shape[0] // loader.batch_size if drop else -(-tensors[0].shape[0] // loader.batch_size)):
+            return cached
         try:
-            return DeviceDataset(tensors[0], loader.batch_size, getattr(loader, "drop_last", False))
+            return DeviceDataset(tensors[0], loader.batch_size, drop)
         except ValueError:
             return None
 
@@ -272,7 +292,8 @@ class GANTrainerBase:
         self.num_epochs = 0
         self._engine = None
         self._max_batch = None
-        self._step = 0
+        self._step = 0          # G updates so far / D updates so far: the Philox streams of train_G / train_D
+        self._dcount = 0
         self._seed = int(torch.initial_seed() & 0x7FFFFFFF)
         self._needs_sync = True
         for mod in (getattr(model, "G", None), getattr(model, "D", None)):
@@ -330,52 +351,86 @@ class GANTrainerBase:
             return self._train_reference_loop(num_epochs, G_lr, D_lr, D_steps, float(extra.get("clip", 0.0) or 0.0))
         hpG, hpD = AdamHP.make(G_lr), AdamHP.make(D_lr, clamp=float(extra.get("clip", 0.0) or 0.0))
         epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
-        self._resident = DeviceDataset.from_loader(self.train_iter) if self.device_dataset else None
-        # data parallel when launched under torchrun with an initialised process group:
-        # per-rank batches, upstream gradients scaled by 1/(global batch), SUM all-reduce of the flat
-        # D / G gradients.  On one GPU the gradient gather is fused into the Adam kernel instead.
-        self._world = par.world_size()
+        self._resident = DeviceDataset.from_loader(self.train_iter, getattr(self, "_resident", None)) if self.device_dataset else None
+        self._dp_begin()
+        try:
+            self._pre_train(num_epochs, hpG, hpD, D_steps, extra)
+            for epoch in range(1, num_epochs + 1):
+                self.model.train()
+                # the kernels write each step's loss straight into this epoch's device log
+                ring = torch.zeros(D_steps + 1, epoch_steps, device="cuda")
+                done = 0
+                try:
+                    for i in range(epoch_steps):
+                        for k in range(D_steps):
+                            if self._resident is not None:          # on-device shuffle + gather, no host work
+                                batch = min(self._resident.batch_size, self._resident.n)
+                                self._fused_D(self._resident.bits, hpD, batch=batch, loss_out=ring[k, i])
+                            else:
+                                images = self.process_batch(self.train_iter)
+                                batch = images.shape[0]
+                                self._fused_D(images, hpD, loss_out=ring[k, i])
+                        self._fused_G(batch, hpG, loss_out=ring[D_steps, i])
+                        done = i + 1
+                finally:
+                    # an interrupted epoch (KeyboardInterrupt in a notebook) still logs the steps it ran;
+                    # one device->host read per epoch
+                    G_losses = ring[D_steps, :done].tolist()
+                    D_losses = ring[:D_steps, :done].mean(dim=0).tolist()
+                    self.Glosses.extend(G_losses)
+                    self.Dlosses.extend(D_losses)
+                print("Epoch[%d/%d], G Loss: %.4f, D Loss: %.4f" % (epoch, num_epochs, np.mean(G_losses), np.mean(D_losses)))
+                self.num_epochs += 1
+                if self.viz:
+                    self.generate_images(epoch)
+        finally:
+            self._dp_end()
+
+    # ------------------------------------------------------------------ data-parallel / fast-path state of one train() call
+    def _dp_begin(self):
+        """Data parallel when launched under torchrun with an initialised process group: per-rank
+        batches and noise, upstream gradients scaled by 1/(global batch), SUM of the flat D / G gradients fused
+        into the Adam kernel.  Replicas start from rank 0's parameters.  On one GPU the split-K gradient gather
+        is fused into the Adam kernel instead ("lazy gradients")."""
+        self._world, self._rank = par.world_size(), par.rank_of()
         self._comm = None
+        self._noise_gen = None
         if self._world > 1:
+            bs = getattr(self.train_iter, "batch_size", None) or 64
+            eng = self._ensure_engine(bs)
+            self._broadcast_parameters(eng)
             n = sum(p.numel() for p in self.model.G.parameters()), sum(p.numel() for p in self.model.D.parameters())
             self._comm = par.make_peer_comm(max(n))
+            # host-side draws (compute_noise overrides, the DataLoader fallback) must differ per rank
+            self._noise_gen = torch.Generator().manual_seed((int(torch.initial_seed()) + 7919 * (self._rank + 1)) & 0x7FFFFFFFFFFFFFFF)
         self._lazy = self._world == 1 or self._comm is not None
         self.gradient_exchange = "none" if self._world == 1 else ("peer" if self._comm is not None else "nccl")
-        if self._resident is not None and self._world > 1:
-            self._resident.seed(int(torch.initial_seed()) + par.rank_of())
-        self._pre_train(num_epochs, hpG, hpD, D_steps, extra)
-        for epoch in range(1, num_epochs + 1):
-            self.model.train()
-            dl, gl = [], []
-            for _ in range(epoch_steps):
-                dstep = []
-                for _ in range(D_steps):
-                    if self._resident is not None:          # on-device shuffle + gather, no host work
-                        images = self._resident.sample()
-                        dstep.append(self._fused_D(self._resident.bits, hpD, gather_idx=images))
-                    else:
-                        images = self.process_batch(self.train_iter)
-                        dstep.append(self._fused_D(images, hpD))
-                dl.append(torch.stack(dstep).mean())
-                gl.append(self._fused_G(images.shape[0], hpG))
-            G_losses = torch.stack(gl).tolist()     # one device->host read per epoch
-            D_losses = torch.stack(dl).tolist()
-            self.Glosses.extend(G_losses)
-            self.Dlosses.extend(D_losses)
-            print("Epoch[%d/%d], G Loss: %.4f, D Loss: %.4f" % (epoch, num_epochs, np.mean(G_losses), np.mean(D_losses)))
-            self.num_epochs += 1
-            if self.viz:
-                self.generate_images(epoch)
+
+    def _broadcast_parameters(self, eng):
+        import torch.distributed as dist
+        for net in (G_NET, D_NET):
+            dist.broadcast(eng.params[net], src=0)
+        eng.sync_all()
+
+    def _dp_end(self):
+        """Always runs (try/finally): leave the engine with materialised gradients and no dangling communicator."""
         self._lazy = False
-        if self._engine is not None:
-            self._engine.set_lazy_grads(False)
-            if getattr(self._engine, "_comm_attached", None) is not None:
-                self._engine.attach_comm(None)
-                self._engine._comm_attached = None
+        self._noise_gen = None
+        eng = self._engine
+        if eng is not None:
+            try:
+                eng.set_lazy_grads(False)
+                if getattr(eng, "_comm_attached", None) is not None:
+                    eng.attach_comm(None)
+                    eng._comm_attached = None
+            except GmError:      # pragma: no cover  (a CUDA error is already propagating)
+                pass
         if self._comm is not None:          # the exchange buffers live for one train() call
-            torch.cuda.synchronize()
-            self._comm.close()
-            self._comm = None
+            try:
+                torch.cuda.synchronize()
+                self._comm.close()
+            finally:
+                self._comm = None
 
     def _has_custom_step(self):
         return not (getattr(type(self).train_D, "_gm_builtin", False) and getattr(type(self).train_G, "_gm_builtin", False))
@@ -427,8 +482,25 @@ class GANTrainerBase:
             eng.sync_all()
             self._needs_sync = False
 
-    def _fused_D(self, images, hp, gather_idx=None):
-        batch = images.shape[0] if gather_idx is None else gather_idx.shape[0]
+    # in-kernel Philox noise unless the user wants the reference's CPU stream (torch.manual_seed replay):
+    # set `trainer.device_noise = False`, or override / replace compute_noise (always honoured)
+    device_noise = True
+
+    def _use_device_noise(self):
+        if not self.device_noise:
+            return False
+        return getattr(self.compute_noise, "__func__", None) is GANTrainerBase.compute_noise and \
+            getattr(self._draw_aux, "__func__", None) in (GANTrainerBase._draw_aux, type(self)._draw_aux)
+
+    def _philox_seed(self):
+        return par.rank_seed(self._seed, getattr(self, "_rank", 0))
+
+    def _fused_D(self, images, hp, gather_idx=None, batch=None, loss_out=None):
+        """One D update.  `images`: a [B, x] batch, or (with `batch`) the resident bit-packed pool the engine
+        samples from on the device, or (with gather_idx) pool + explicit row indices."""
+        pool = batch is not None and gather_idx is None
+        if batch is None:
+            batch = images.shape[0] if gather_idx is None else gather_idx.shape[0]
         eng = self._ensure_engine(batch)
         self._sync_once(eng)
         world = getattr(self, "_world", 1)
@@ -437,24 +509,32 @@ class GANTrainerBase:
             eng.attach_comm(self._comm)          # batch statistics over the global batch
             eng._comm_attached = self._comm
         inv = par.inv_global_batch(batch, world)
-        noise = self.compute_noise(batch, self.model.z_dim)
-        if gather_idx is None:
-            loss = eng.d_grad(images, noise=noise, aux=self._draw_aux(images), inv_global_batch=inv, seed=self._seed,
-                              step=self._step).clone()
+        dev = self._use_device_noise()
+        noise = None if dev else self.compute_noise(batch, self.model.z_dim)
+        kw = dict(noise=noise, inv_global_batch=inv, seed=self._philox_seed(), step=self._dcount, loss_out=loss_out)
+        if pool or gather_idx is not None:
+            if pool:
+                eng.set_sampler(self._resident.n, self._philox_seed() ^ 0x5DEECE66D)
+            aux = None if dev else self._draw_aux(torch.empty(batch, self.model.image_size, device="meta"))
+            loss = eng.d_grad(images, fmt="bits", gather_idx=gather_idx, batch=batch, aux=aux, **kw)
         else:
-            loss = eng.d_grad(images, fmt="bits", gather_idx=gather_idx, batch=batch, noise=noise,
-                              aux=self._draw_aux(torch.empty(batch, self.model.image_size, device="meta")),
-                              inv_global_batch=inv, seed=self._seed, step=self._step).clone()
+            eng.set_sampler(0)
+            loss = eng.d_grad(images, aux=None if dev else self._draw_aux(images), **kw)
+        if loss_out is None:
+            loss = loss.clone()
+        self._dcount += 1
         self._dp_apply(eng, D_NET, hp)
         return loss
 
-    def _fused_G(self, batch, hp):
+    def _fused_G(self, batch, hp, loss_out=None):
         eng = self._ensure_engine(batch)
         self._sync_once(eng)
-        noise = self.compute_noise(batch, self.model.z_dim)
+        noise = None if self._use_device_noise() else self.compute_noise(batch, self.model.z_dim)
         world = getattr(self, "_world", 1)
-        loss = eng.g_grad(batch, noise=noise, inv_global_batch=par.inv_global_batch(batch, world), seed=self._seed,
-                          step=self._step).clone()
+        loss = eng.g_grad(batch, noise=noise, inv_global_batch=par.inv_global_batch(batch, world), seed=self._philox_seed(),
+                          step=self._step, loss_out=loss_out)
+        if loss_out is None:
+            loss = loss.clone()
         self._dp_apply(eng, G_NET, hp)
         self._step += 1
         return loss
@@ -477,6 +557,8 @@ class GANTrainerBase:
         images = to_cuda(images)
         eng = self._ensure_engine(images.shape[0])
         eng.sync_if_stale()
+        eng.set_lazy_grads(False)       # .backward() reads the flat gradient: it must be formed by d_grad itself
+        eng.set_sampler(0)
         noise = self.compute_noise(images.shape[0], self.model.z_dim)
         loss = eng.d_grad(images.float().contiguous(), noise=noise.float().contiguous(), aux=self._draw_aux(images),
                           seed=self._seed, step=self._step)
@@ -488,6 +570,7 @@ class GANTrainerBase:
         batch = images.shape[0]
         eng = self._ensure_engine(batch)
         eng.sync_if_stale()
+        eng.set_lazy_grads(False)
         noise = self.compute_noise(batch, self.model.z_dim)
         loss = eng.g_grad(batch, noise=noise.float().contiguous(), seed=self._seed, step=self._step)
         self._step += 1
@@ -496,7 +579,7 @@ class GANTrainerBase:
     def compute_noise(self, batch_size, z_dim):
         """Compute random noise for the generator (src/ns_gan.py:218-220): CPU RNG then
         H2D, so a torch.manual_seed run draws the same numbers as the reference."""
-        return to_cuda(torch.randn(batch_size, z_dim))
+        return to_cuda(torch.randn(batch_size, z_dim, generator=getattr(self, "_noise_gen", None)))
 
     def process_batch(self, iterator):
         """Generate a processed batch for D (src/ns_gan.py:222-226)."""

@@ -36,6 +36,14 @@ def rank_of(group=None):
     return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
 
 
+def require_single_process(what):
+    """Trainers whose train() has no gradient exchange (InfoGAN's three optimizers, BEGAN's K controller loop)
+    refuse to run as silently independent replicas under torchrun."""
+    if world_size() > 1:
+        raise RuntimeError("%s.train is not data-parallel: run it in one process (the engine-level statistics "
+                           "exchange exists, the Trainer loop does not drive it)" % what)
+
+
 def inv_global_batch(local_batch, world):
     """Scale for per-sample upstream gradients so that SUM over ranks == mean over the
     global batch (the reference's losses are batch means, src/ns_gan.py:191-192)."""

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from utils import *  # noqa: F401,F403
+from gm_b200 import parallel as par
 from gm_b200 import AdamHP, GmError, InfoGanEngine
 from gm_b200.gan_api import builtin_step, Generator as _Generator, Discriminator as _Discriminator, GANTrainerBase, _FusedLoss, to_cuda, G_NET, D_NET
 
@@ -98,6 +99,7 @@ class InfoGANTrainer(GANTrainerBase):
 
     def train(self, num_epochs, G_lr=2e-4, D_lr=2e-4, D_steps=1):
         """ src/info_gan.py:130-221: per outer step D update(s), G update, then the Q / MI update """
+        par.require_single_process(self.name + "Trainer")
         hpG, hpD = AdamHP.make(G_lr), AdamHP.make(D_lr)
         epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
         self._pre_train(num_epochs, hpG, hpD, D_steps, {})

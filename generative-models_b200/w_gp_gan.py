@@ -31,7 +31,7 @@ class WGPGANTrainer(GANTrainerBase):
         return super().train_D(images)
 
     def _draw_aux(self, images):
-        return to_cuda(torch.rand(images.shape[0], 1)).reshape(-1).contiguous()     # src/w_gp_gan.py:197
+        return to_cuda(torch.rand(images.shape[0], 1, generator=getattr(self, "_noise_gen", None))).reshape(-1).contiguous()     # src/w_gp_gan.py:197
 
 
 # the reference notebook 04 uses these names

@@ -50,6 +50,12 @@ typedef enum {
 typedef enum { GM_OUT_SIGMOID = 0, GM_OUT_RELU = 1, GM_OUT_NONE = 2 } gm_out_act;
 typedef enum { GM_IMG_F32 = 0, GM_IMG_U8 = 1, GM_IMG_BITS = 2 } gm_img_fmt;
 typedef enum { GM_NET_G = 0, GM_NET_D = 1 } gm_net;
+/* arithmetic of the tensor-core GEMM operands (SURVEY.md 8b dtype_mode):
+ *   GM_PREC_BF16  : bf16 operands (8-bit mantissa), fp32 accumulation — the speed mode (BASELINE configs[1..3]);
+ *   GM_PREC_SPLIT : every operand is carried as a bf16 pair hi + lo (16-bit mantissa) and each product runs as
+ *                   three tensor-core passes hi*hi + hi*lo + lo*hi into the same fp32 accumulator: fp32-grade
+ *                   gradients (north_star's 1e-3 bound against the reference's fp32 CPU autograd) at ~1/3 speed. */
+typedef enum { GM_PREC_BF16 = 0, GM_PREC_SPLIT = 1 } gm_prec;
 
 /* torch.optim.Adam hyper-parameters (src/ns_gan.py:107-110, src/vae.py:139-142);
  * clamp > 0 applies WGAN weight clipping after the update (src/w_gan.py:158). */
@@ -105,6 +111,7 @@ typedef struct {
   int max_batch;                     /* largest local batch */
   int variant;                       /* gm_variant */
   int d_out_act;                     /* gm_out_act: sigmoid, or relu for src/w_gp_gan.py:61 */
+  int dtype_mode;                    /* gm_prec */
 } gm_gan_desc;
 
 int gm_gan_create(gm_ctx* ctx, const gm_gan_desc* desc, gm_gan** out);
@@ -164,6 +171,20 @@ int gm_gan_apply_allreduce(gm_gan* gan, int net, const gm_adam_hp* hp, int step,
  * comm == NULL detaches (per-rank statistics). */
 int gm_gan_attach_comm(gm_gan* gan, gm_comm* comm);
 
+/* On-device batch sampling — replaces `next(iter(DataLoader(shuffle=True)))` (src/ns_gan.py:222-226): with a
+ * resident pool of n_pool images (images_dev of gm_gan_d_grad) and gather_idx_dev == NULL, batch row r of step
+ * `step` reads pool row perm_{seed,step}(r), perm a pseudo-random permutation of [0, n_pool) drawn per step
+ * (distinct rows inside a batch, like the first batch of a freshly shuffled loader).  n_pool == 0: off. */
+int gm_gan_set_sampler(gm_gan* gan, long long n_pool, uint64_t seed);
+/* the same permutation evaluated on the host: out_host[r] = perm_{seed,round}(offset + r), r < count */
+int gm_sampler_indices_host(long long n_pool, uint64_t seed, uint64_t round, uint64_t offset, int count, int* out_host);
+/* the indices that draw produces (tests, logging): idx_dev[batch] */
+int gm_gan_sample_indices(gm_gan* gan, int batch, uint64_t step, int* idx_dev, gm_stream stream);
+/* the N(0,1) generator noise gm_gan_d_grad (g_step 0) / gm_gan_g_grad (g_step 1) draw on the device for
+ * (seed, step) when noise_dev == NULL — compute_noise of src/ns_gan.py:218-220 as in-kernel Philox —
+ * as the bf16-rounded operand values, out_dev [batch, z] fp32 (tests). */
+int gm_gan_debug_noise(gm_gan* gan, int batch, uint64_t seed, uint64_t step, int g_step, float* out_dev, gm_stream stream);
+
 /* D outputs of the last *_grad call (D step: batch real then batch fake; G step:
  * batch fake) -> dst_dev; what the reference names DX_score / DG_score. */
 int gm_gan_scores(gm_gan* gan, float* dst_dev, int n, gm_stream stream);
@@ -216,7 +237,7 @@ int gm_gan_fisher_state(gm_gan* gan, float* lambda_rho_host, int set, gm_stream 
  * hidden -> x (sigmoid) (src/vae.py:47-106).  Flat fp32 layout:
  * [enc.linear.W | .b | enc.mu.W | enc.log_var.W | enc.mu.b | enc.log_var.b |
  *  dec.linear.W | .b | dec.recon.W | .b]. */
-typedef struct { int image_size, hidden_dim, z_dim, max_batch; } gm_vae_desc;
+typedef struct { int image_size, hidden_dim, z_dim, max_batch; int dtype_mode; /* gm_prec */ } gm_vae_desc;
 int gm_vae_create(gm_ctx* ctx, const gm_vae_desc* desc, gm_vae** out);
 int gm_vae_destroy(gm_vae* vae);
 int gm_vae_param_count(const gm_vae* vae);
@@ -228,6 +249,12 @@ int gm_vae_sync_shadows(gm_vae* vae, gm_stream stream);
 int gm_vae_grad(gm_vae* vae, const void* images_dev, int img_fmt, const int* gather_idx_dev, int batch,
                 const float* eps_dev, float grad_scale, uint64_t seed, uint64_t step, float* losses_dev,
                 gm_stream stream);
+/* On-device epoch shuffling for gm_vae_grad (gather_idx_dev == NULL): step s reads batch (s mod
+ * batches_per_epoch) of the permutation of epoch (s / batches_per_epoch) over the resident pool — the
+ * `for batch in self.train_iter` of src/vae.py:150 without host work.  n_pool == 0: off. */
+int gm_vae_set_sampler(gm_vae* vae, long long n_pool, long long batches_per_epoch, uint64_t seed);
+/* eps of the last gm_vae_grad / gm_vae_forward call (src/vae.py:104; the Philox draw when eps_dev was NULL) -> out_dev [batch, z] */
+int gm_vae_last_eps(gm_vae* vae, float* out_dev, int batch, gm_stream stream);
 /* optimizer.step() with coupled weight decay (src/vae.py:139-142,162). */
 int gm_vae_apply(gm_vae* vae, const gm_adam_hp* hp, int step, gm_stream stream);
 /* VAE.forward (+ losses) without gradients: evaluate / reconstruct (src/vae.py:214-252).
