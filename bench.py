@@ -133,6 +133,7 @@ class Workload:
         self.par, self.torch = par, torch
         self.seed = par.rank_seed(1000, rank)
         self.s = 0
+        self.overlap = False
         self.inv = par.inv_global_batch(B, world)
         if name == "vae":
             self.eng = gm_b200.VaeEngine(X, H, Z, max_batch=B, precision=prec)
@@ -149,6 +150,12 @@ class Workload:
             # N > 1: the SUM of the flat D / G gradients runs inside the Adam kernel over CUDA-IPC peer mappings
             self.eng.set_lazy_grads(world == 1 or comm is not None)
             self.loss_buf = self.eng.loss_buf
+            # GM_DP_OVERLAP=1: the D-gradient exchange + Adam runs on a side stream under the G step's generator
+            # forward, which does not depend on the D update (gm_gan_g_forward_stage / gm_gan_g_grad_staged)
+            self.overlap = comm is not None and os.environ.get("GM_DP_OVERLAP", "0") == "1"
+            if self.overlap:
+                self.side = torch.cuda.Stream()
+                self.ev_d, self.ev_a = torch.cuda.Event(), torch.cuda.Event()
 
     def step(self, batch_bits=None):
         eng, B, s = self.eng, self.B, self.s
@@ -170,6 +177,18 @@ class Workload:
         else:
             eng.set_sampler(0, 0)
             eng.d_grad(batch_bits, fmt="bits", batch=B, inv_global_batch=self.inv, seed=self.seed, step=s)
+        if self.overlap:
+            torch = self.torch
+            self.ev_d.record()
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.ev_d)
+                eng.apply_allreduce(1, self.hpD, self.comm)
+                self.ev_a.record(self.side)
+            eng.g_forward_stage(B, seed=self.seed, step=s)
+            torch.cuda.current_stream().wait_event(self.ev_a)
+            eng.g_grad_staged(B, inv_global_batch=self.inv)
+            self._apply(0, self.hpG)
+            return
         self._apply(1, self.hpD)
         eng.g_grad(B, inv_global_batch=self.inv, seed=self.seed, step=s)
         self._apply(0, self.hpG)
@@ -355,7 +374,9 @@ def run_ours(args):
                                                            "1 D update + 1 G update per step, Adam"),
                       "global_batch": B * world, "parallelism": "dp%d" % world,
                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
-                                            "fused peer all-reduce + Adam kernel (CUDA IPC over NVLink)" if comm is not None
+                                            "fused peer all-reduce + Adam kernel (push over CUDA-IPC NVLink mappings)%s" % (
+                                                ", D exchange overlapped with the G forward" if os.environ.get("GM_DP_OVERLAP") == "1" else "")
+                                            if comm is not None
                                             else "NCCL all-reduce"),
                       "inputs": "device-resident 1-bit synthetic images, pool %d (25.7 MB packed, 412 MB as bf16 rows), batch rows drawn "
                                 "by the in-kernel permutation sampler; per-step working set ~1.5 GB > L2, no L2 flush needed" % N,

@@ -71,6 +71,7 @@ def lib():
     L.gm_launch_count.argtypes = [vp, i]
     L.gm_launch_count.restype = C.c_longlong
     L.gm_prof_enable.argtypes = [vp, i]
+    L.gm_prof_report.argtypes = [vp, C.c_char_p, i]
     L.gm_debug_phase_buffer.argtypes = [vp, vp]
     L.gm_prof_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.gm_gemm_bf16.argtypes = [vp, C.POINTER(GemmDesc), vp]
@@ -171,7 +172,21 @@ GEMM_KINDS = ["gemm_umma<208,0,K-major>", "gemm_umma<64,0,K-major>", "gemm_umma<
 
 
 def prof_enable(on=True):
-    check(ctx(), lib().gm_prof_enable(ctx(), 1 if on else 0))
+    """True / 1: events around GEMM launches by kind (prof_collect); 2: around every launch by name (prof_report)."""
+    check(ctx(), lib().gm_prof_enable(ctx(), int(on)))
+
+
+def prof_report():
+    """-> list of (kernel name, launches, total ms) in first-launch order (after prof_enable(2))."""
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().gm_prof_report(ctx(), buf, len(buf))
+    if n < 0:
+        check(ctx(), n)
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(",", 2)
+        out.append((name, int(cnt), float(ms)))
+    return out
 
 
 def prof_collect():

@@ -29,6 +29,7 @@ struct gm_ctx {
   bool prof = false;
   long long* dbg = nullptr;   // phase-timing buffer handed to the next generic GEMM (tools/time_phases.py)
   bool use_clusters = true;   // GM_NO_CLUSTERS=1 disables the CTA-pair multicast path (debug)
+  long long plan_lo = 0;      // > 0 while an engine in split-operand mode builds its plans: element offset of the lo planes
   struct ProfRec { cudaEvent_t e0, e1; int kind; double flops; };
   std::vector<ProfRec> prof_recs;
 };
@@ -93,6 +94,7 @@ enum PlanKind { PK_NT_208 = 0, PK_NT_64, PK_TN_448, PK_TN_64 };
 
 struct GemmPlan {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmA2, tmB2;   // residual (lo) planes of the operands in split mode, else copies of tmA / tmB
   // output map of the K-major bf16 kernels (32 x 32 box, 64-byte swizzle), encoded at the first
   // launch because the epilogue (output pointer / leading dimension) is set after plan_gemm
   mutable CUtensorMap tmC;
@@ -110,8 +112,20 @@ struct GemmPlan {
 // statement of every kernel, after the prologue in the GEMM) until the predecessor completed.
 static bool g_pdl = true;   // GM_NO_PDL=1 turns it off (gm_ctx_create)
 static bool g_tma_store = true;   // GM_NO_TMA_STORE=1: epilogue stores through LDS + STG only
+// GM_PROF_ALL / gm_prof_enable(ctx, 2): CUDA events around EVERY launch on its stream, aggregated per kernel name by
+// gm_prof_report (in-stream durations including the launch gaps ncu's serialised per-kernel times cannot show)
+struct ProfAll { const char* name; cudaEvent_t e0, e1; };
+static bool g_prof_all = false;
+static std::vector<ProfAll> g_prof_all_recs;
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+static cudaError_t launch_pdl(const char* name, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  struct Scope {
+    cudaStream_t s; ProfAll r; bool on;
+    Scope(const char* n, cudaStream_t s_) : s(s_), on(g_prof_all) {
+      if (on) { r.name = n; cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); cudaEventRecord(r.e0, s); }
+    }
+    ~Scope() { if (on) { cudaEventRecord(r.e1, s); g_prof_all_recs.push_back(r); } }
+  } scope(name, s);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid;
@@ -126,10 +140,10 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T, int DOT_T, int CS, int EW>
+template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T, int DOT_T, int CS, int EW, bool SPLIT = false>
 static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
   using Cfg = GemmCfg<BN1, BN2, !AMN, (CS == 2) && !AMN, EW>;
-  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, CS, EW>;
+  auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, CS, EW, SPLIT>;
   // the opt-in to > 48 KB dynamic shared memory is per (function, device)
   static bool configured[64] = {};
   int dev = 0;
@@ -163,7 +177,14 @@ static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
   cfg.numAttrs = na;
   GemmParams prm = pl.p;
   prm.tma_store = pl.tmc_state == 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, pl.tmA, pl.tmB, pl.tmC, prm);
+  return cudaLaunchKernelEx(&cfg, kern, pl.tmA, pl.tmB, pl.tmC, pl.tmA2, pl.tmB2, prm);
+}
+
+// split-operand plans (gm_prec GM_PREC_SPLIT): the universal epilogue with the residual-plane paths compiled in
+template <int BN1, int BN2, bool AMN, bool BMN>
+static cudaError_t launch_split(const GemmPlan& pl, cudaStream_t s) {
+  if (pl.cs == 2) return launch_cs<BN1, BN2, AMN, BMN, -1, -1, -1, -1, 2, 8, true>(pl, s);
+  return launch_cs<BN1, BN2, AMN, BMN, -1, -1, -1, -1, 1, 8, true>(pl, s);
 }
 
 template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1>
@@ -206,7 +227,7 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
     // G2 52.0 -> 49.4 us) and costs ~2-5 % on the aux / row-dot epilogues (fence + wait in their longer
     // per-block dependency chain), so only the former use it
     const bool plain = p.aux_mode == AUX_NONE && p.dot_w == nullptr && p.dot_sq == 0;
-    if (g_tma_store && nt && plain && p.epi == EPI_BF16 && p.out != nullptr && !(reinterpret_cast<uintptr_t>(p.out) & 15) &&
+    if (g_tma_store && nt && plain && p.nparts == 1 && p.epi == EPI_BF16 && p.out != nullptr && !(reinterpret_cast<uintptr_t>(p.out) & 15) &&
         (p.ldo * 2) % 16 == 0 && p.out_cols > 0) {
       int rc = make_tmap(c, &pl.tmC, p.out, uint64_t(p.out_cols), uint64_t(p.M), uint64_t(p.ldo), kEpiCols, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
@@ -215,6 +236,24 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
   }
   cudaError_t e;
   gm_ctx::ProfRec rec;
+  ProfAll pa;
+  if (g_prof_all) {
+    static const char* kKind[4] = {"gemm_nt208", "gemm_nt64", "gemm_tn448", "gemm_tn64"};
+    static std::map<int, std::string> names;   // interned: kind + epilogue signature
+    const GemmParams& q = pl.p;
+    const int key = pl.kind | (q.act << 4) | (q.aux_mode << 8) | ((q.dot_w != nullptr) << 12) | (q.dot_mask << 13) | (q.dot_sq << 14) |
+                    ((q.bias != nullptr) << 15) | ((q.epi == EPI_F32) << 16) | ((q.K >= 512) << 17) | ((q.nparts == 3) << 18);
+    auto it = names.find(key);
+    if (it == names.end()) {
+      char buf[128];
+      snprintf(buf, sizeof buf, "%s[act%d aux%d%s%s%s%s%s K%s%s]", kKind[pl.kind], q.act, q.aux_mode, q.bias ? " bias" : "", q.dot_w ? " dot" : "",
+               q.dot_mask ? " mask" : "", q.dot_sq ? " sq" : "", q.epi == EPI_F32 ? " f32" : "", q.K >= 512 ? "long" : "short", q.nparts == 3 ? " split" : "");
+      it = names.emplace(key, buf).first;
+    }
+    pa.name = it->second.c_str();
+    cudaEventCreate(&pa.e0); cudaEventCreate(&pa.e1);
+    cudaEventRecord(pa.e0, s);
+  }
   if (c->prof) {
     cudaEventCreate(&rec.e0);
     cudaEventCreate(&rec.e1);
@@ -222,6 +261,14 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
     rec.flops = pl.flops;
     cudaEventRecord(rec.e0, s);
   }
+  if (pl.p.nparts == 3) {
+    switch (pl.kind) {
+      case PK_NT_208: e = launch_split<208, 0, false, false>(pl, s); break;
+      case PK_NT_64: e = launch_split<64, 0, false, false>(pl, s); break;
+      case PK_TN_448: e = launch_split<256, 192, true, true>(pl, s); break;
+      default: e = launch_split<64, 0, true, true>(pl, s); break;
+    }
+  } else
   switch (pl.kind) {
     case PK_NT_208: {
       // long-K GEMMs with a light epilogue are TMA-feed-bound: 8 epilogue warps leave smem for a
@@ -242,6 +289,7 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
     cudaEventRecord(rec.e1, s);
     c->prof_recs.push_back(rec);
   }
+  if (g_prof_all) { cudaEventRecord(pa.e1, s); g_prof_all_recs.push_back(pa); }
   if (e != cudaSuccess) return fail(c, GM_ERR_CUDA, "GEMM launch failed: %s", cudaGetErrorString(e));
   return GM_OK;
 }
@@ -253,7 +301,7 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
                      int ldb, int ncover, int max_splits) {
   memset(pl, 0, sizeof *pl);
   if (M <= 0 || N <= 0 || K <= 0) return fail(c, GM_ERR_ARG, "gemm: bad extents %d %d %d", M, N, K);
-  int bn, boxn;
+  int bn, boxn = 0;
   // CTA pairs (cta_group::2 MMA) for the K-major kernels; the MN-major split-K kernels stay
   // single-CTA (pairing 7 m-tiles wastes an eighth of the MMAs and measured slower)
   const int cs = (mode == 0 && cdiv(M, BM) >= 2 && c->num_sms % 2 == 0 && c->use_clusters) ? 2 : 1;
@@ -281,6 +329,22 @@ static int plan_gemm(gm_ctx* c, GemmPlan* pl, int mode, int M, int N, int K, con
   p.m_tiles = cdiv(M, BM);
   p.n_tiles = cdiv(ncover, bn);
   p.kblocks = cdiv(K, BK);
+  p.nparts = 1; p.kb_part = p.kblocks; p.lo_off = 0;
+  pl->tmA2 = pl->tmA; pl->tmB2 = pl->tmB;
+  if (c->plan_lo > 0) {
+    // split operands: second tensor maps on the residual planes, contraction over (hi,hi), (hi,lo), (lo,hi)
+    const __nv_bfloat16* A2 = static_cast<const __nv_bfloat16*>(A) + c->plan_lo;
+    const __nv_bfloat16* B2 = static_cast<const __nv_bfloat16*>(B) + c->plan_lo;
+    int rc;
+    if (mode == 0) {
+      if ((rc = make_tmap(c, &pl->tmA2, A2, K, M, lda, BK, BM))) return rc;
+      if ((rc = make_tmap(c, &pl->tmB2, B2, K, N, ldb, BK, boxn))) return rc;
+    } else {
+      if ((rc = make_tmap(c, &pl->tmA2, A2, M, K, lda, 64, BK))) return rc;
+      if ((rc = make_tmap(c, &pl->tmB2, B2, N, K, ldb, 64, BK))) return rc;
+    }
+    p.nparts = 3; p.kblocks = 3 * p.kb_part; p.lo_off = c->plan_lo;
+  }
   p.m_supers = cdiv(p.m_tiles, cs);
   const int tiles = p.m_supers * p.n_tiles;   // work items per split, one per cluster
   const int slots = c->num_sms / cs;          // clusters resident at once
@@ -363,8 +427,34 @@ extern "C" int gm_debug_phase_buffer(gm_ctx* c, long long* dbg_dev) {
 
 extern "C" int gm_prof_enable(gm_ctx* c, int on) {
   if (!c) return GM_ERR_ARG;
-  c->prof = on != 0;
+  c->prof = on == 1;
+  g_prof_all = on == 2;
   return GM_OK;
+}
+// level-2 profile (gm_prof_enable(ctx, 2)): synchronises, then writes "name,launches,total_ms\n" lines (one per kernel
+// name, GEMMs named by plan kind + epilogue) into buf; returns the number of bytes needed (0 if nothing was recorded)
+extern "C" int gm_prof_report(gm_ctx* c, char* buf, int buflen) {
+  if (!c) return GM_ERR_ARG;
+  CU_OK(c, cudaDeviceSynchronize());
+  std::map<std::string, std::pair<long long, double>> agg;
+  std::vector<std::string> order;
+  for (auto& r : g_prof_all_recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    auto it = agg.find(r.name);
+    if (it == agg.end()) { order.push_back(r.name); it = agg.emplace(r.name, std::make_pair(0ll, 0.0)).first; }
+    it->second.first++; it->second.second += t;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof_all_recs.clear();
+  std::string out;
+  for (auto& n : order) {
+    char line[256];
+    snprintf(line, sizeof line, "%s,%lld,%.6f\n", n.c_str(), agg[n].first, agg[n].second);
+    out += line;
+  }
+  if (buf && buflen > 0) { strncpy(buf, out.c_str(), size_t(buflen) - 1); buf[buflen - 1] = 0; }
+  return int(out.size()) + 1;
 }
 // Synchronises the device, then sums per plan kind (0: NT 128x208, 1: NT 128x64,
 // 2: TN 128x448 split-K, 3: TN 128x64 split-K) the launch durations (ms), algorithmic
@@ -434,7 +524,7 @@ extern "C" int gm_gemm_bf16(gm_ctx* c, const gm_gemm_desc* d, gm_stream stream) 
   p.part_stride = per;
   rc = launch_plan(c, pl, s);
   if (rc) return rc;
-  launch_pdl(reduce_partials_kernel, unsigned((per + 255) / 256), 256, 0, s, c->scratch, p.splits, per, per,
+  launch_pdl("reduce_partials_kernel", reduce_partials_kernel, unsigned((per + 255) / 256), 256, 0, s, c->scratch, p.splits, per, per,
                                                                      static_cast<float*>(d->C_dev));
   c->launches++;
   CU_OK(c, cudaGetLastError());
@@ -455,11 +545,44 @@ extern "C" int gm_adam_step(gm_ctx* c, float* p, const float* g, float* m, float
   memset(&a, 0, sizeof a);
   a.p = p; a.g = g; a.m = m; a.v = v; a.total = n; a.nseg = 0;
   fill_adam(a, hp, step);
-  launch_pdl(adam_kernel, cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
+  launch_pdl("adam_kernel", adam_kernel, cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   c->launches++;
   CU_OK(c, cudaGetLastError());
   return GM_OK;
 }
+
+// ------------------------------------------------------------------ bf16 arena
+// Every bf16 buffer of an engine (activations, hidden gradients, operand copies of the weights) is carved from ONE
+// allocation; in split-operand mode (gm_prec GM_PREC_SPLIT) the allocation is twice as large and the second half
+// holds the residual (lo) planes, so the lo twin of ANY bf16 pointer p of the engine is p + lo_off.
+struct BfArena {
+  std::vector<std::pair<__nv_bfloat16**, size_t>> reqs;
+  __nv_bfloat16* base = nullptr;
+  size_t total = 0;        // elements of one plane
+  long long lo_off = 0;    // 0 in bf16 mode
+  void request(__nv_bfloat16** p, size_t n) { reqs.push_back({p, (n + 511) / 512 * 512}); }   // 1 KB granules (TMA alignment)
+  cudaError_t finalize(bool split) {
+    total = 0;
+    for (auto& r : reqs) total += r.second;
+    total += 512;
+    const size_t bytes = total * sizeof(__nv_bfloat16) * (split ? 2 : 1);
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(q, 0, bytes);
+    if (e != cudaSuccess) { cudaFree(q); return e; }
+    base = static_cast<__nv_bfloat16*>(q);
+    size_t off = 0;
+    for (auto& r : reqs) { *r.first = base + off; off += r.second; }
+    lo_off = split ? (long long)total : 0;
+    return cudaSuccess;
+  }
+};
+struct PlanLoScope {   // plans built inside the scope get the engine's residual-plane offset (plan_gemm)
+  gm_ctx* c;
+  PlanLoScope(gm_ctx* c_, long long lo) : c(c_) { c->plan_lo = lo; }
+  ~PlanLoScope() { c->plan_lo = 0; }
+};
 
 // ------------------------------------------------------------------ GAN engine
 struct NetLayout {
@@ -541,7 +664,14 @@ struct gm_gan {
   std::map<int, StepPlans> plans;
   std::map<int, CustomPlans> cplans;
   std::vector<void*> allocs;
+  BfArena arena;
+  long long lo = 0;          // arena.lo_off: > 0 in split-operand mode
 };
+
+static int dev_alloc(gm_gan* g, __nv_bfloat16** p, size_t count) {   // bf16 buffers come from the arena (finalised at the end of create)
+  g->arena.request(p, count);
+  return GM_OK;
+}
 
 template <typename T>
 static int dev_alloc(gm_gan* g, T** p, size_t count) {
@@ -570,7 +700,7 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
     return fail(c, GM_ERR_ARG, "image_size and hidden_dim must be positive multiples of 16 (got %d, %d, z=%d)",
                 d->image_size, d->hidden_dim, d->z_dim);
   if (d->max_batch <= 0) return fail(c, GM_ERR_ARG, "max_batch must be positive (got %d)", d->max_batch);
-  if (d->dtype_mode != GM_PREC_BF16) return fail(c, GM_ERR_UNSUPPORTED, "dtype_mode %d is not built", d->dtype_mode);
+  if (d->dtype_mode != GM_PREC_BF16 && d->dtype_mode != GM_PREC_SPLIT) return fail(c, GM_ERR_ARG, "unknown dtype_mode %d", d->dtype_mode);
   gm_gan* g = new gm_gan();
   g->ctx = c;
   g->d = *d;
@@ -656,6 +786,12 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
     TRY(dev_alloc(g, &g->PQ2, size_t(c->num_sms) * 64 * 448));
     TRY(dev_alloc(g, &g->q_part, size_t(c->num_sms) * 2 * 4));
   }
+  {
+    cudaError_t e = g->arena.finalize(d->dtype_mode == GM_PREC_SPLIT);
+    if (e != cudaSuccess) { rc = fail(c, GM_ERR_CUDA, "bf16 arena allocation failed: %s", cudaGetErrorString(e)); gm_gan_destroy(g); return rc; }
+    g->allocs.push_back(g->arena.base);
+    g->lo = g->arena.lo_off;
+  }
 #undef TRY
   if (g->H + 1 > 448 || g->Z + 1 > 64) {
     gm_gan_destroy(g);
@@ -680,6 +816,7 @@ extern "C" int gm_gan_bind(gm_gan* g, int net, float* p, float* gr, float* m, fl
 }
 
 static void adam_segs(gm_gan* g, int net, AdamParams& a) {
+  a.lo_off = g->lo;
   if (net == GM_NET_G) {
     a.total = g->G.total;
     a.nseg = 2;
@@ -706,7 +843,7 @@ extern "C" int gm_gan_sync_shadows(gm_gan* g, int net, gm_stream stream) {
   a.p = g->par[net];
   a.update = 0;
   adam_segs(g, net, a);
-  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
+  launch_pdl("adam_kernel", adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -726,7 +863,7 @@ extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, 
     a.gather = 1; a.gout = g->grd[net]; a.gsegs = g->pend_segs[net];
     g->pend[net] = false;
   }
-  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
+  launch_pdl("adam_kernel", adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -754,6 +891,7 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   auto it = g->plans.find(B);
   if (it != g->plans.end()) { *out = &it->second; return GM_OK; }
   gm_ctx* c = g->ctx;
+  PlanLoScope lo_scope(c, g->lo);
   StepPlans sp;
   const int X = g->X, H = g->H, Z = g->Z, XP = g->XP, HP = g->HP, ZP = g->ZP;
   const float* pG = g->par[GM_NET_G];
@@ -892,7 +1030,7 @@ static int check_step_args(gm_gan* g, int batch) {
 }
 
 static int run_generator(gm_gan* g, StepPlans* sp, int B, const float* noise, uint64_t seed, uint64_t stream_id, cudaStream_t s) {
-  launch_pdl(stage_noise_kernel, cdiv(B * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, B, g->Z, g->ZP, seed, stream_id);
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(B * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, B, g->Z, g->ZP, seed, stream_id, g->lo);
   g->ctx->launches++;
   int rc;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
@@ -911,7 +1049,7 @@ static void exchange_stats(gm_gan* g, double* part, int nblk, int stride, int nv
     cs.f[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(m->peer[r]) + m->sflag_off);
   }
   cs.rank = m->rank; cs.world = m->world; cs.seq = ++m->seq_stats;
-  launch_pdl(stats_exchange_kernel, 1, 256, 0, s, part, nblk, stride, nvals, cs);
+  launch_pdl("stats_exchange_kernel", stats_exchange_kernel, 1, 256, 0, s, part, nblk, stride, nvals, cs);
   g->ctx->launches++;
 }
 static int stat_world(const gm_gan* g) { return (g->comm && g->comm->world > 1) ? g->comm->world : 1; }
@@ -936,16 +1074,16 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   lp.partR = g->loss_part + size_t(g->loss_blocks) * 8;
   const int v = g->d.variant;
   if (!g_step && (v == V_RA || v == V_FISHER)) {
-    launch_pdl(loss_pass_kernel<0>, lp.nblk, kLossThreads, 0, s, lp);
+    launch_pdl("loss_pass_kernel<0>", loss_pass_kernel<0>, lp.nblk, kLossThreads, 0, s, lp);
     g->ctx->launches++;
     exchange_stats(g, lp.partA, lp.nblk, 4, 4, s);       // sum d, d^2 per branch over all ranks
     if (v == V_RA) {
-      launch_pdl(loss_pass_kernel<1>, lp.nblk, kLossThreads, 0, s, lp);
+      launch_pdl("loss_pass_kernel<1>", loss_pass_kernel<1>, lp.nblk, kLossThreads, 0, s, lp);
       g->ctx->launches++;
       exchange_stats(g, lp.partB, lp.nblk, 4, 1, s);     // sum q(1-q)/(q+eps) over all ranks' real rows
     }
   }
-  launch_pdl(loss_pass_kernel<2>, lp.nblk, kLossThreads, 0, s, lp);   // its last block writes loss[0..1]
+  launch_pdl("loss_pass_kernel<2>", loss_pass_kernel<2>, lp.nblk, kLossThreads, 0, s, lp);   // its last block writes loss[0..1]
   g->ctx->launches += 1;
 }
 
@@ -957,7 +1095,7 @@ static void emit_grads(gm_gan* g, int net, const GradSegs& gs, cudaStream_t s, b
     g->pend[net] = true;
     return;
   }
-  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[net]);
+  launch_pdl("finalize_grads_kernel", finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[net]);
   g->ctx->launches++;
   g->pend[net] = false;
 }
@@ -990,11 +1128,11 @@ static int began_d_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaSt
   if ((rc = launch_plan(c, sp->be_dec_d, s))) return rc;   // DR = scaled sign(D(.) - .), row L1 sums -> slots_r
   const int nb = c->num_sms;
   const int ns = 2 * cdiv(g->X, 208);
-  launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r, ns, 2 * g->Bmax, B, g->be_part);
-  launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r + B, ns, 2 * g->Bmax, B, g->be_part + nb);
+  launch_pdl("vae_rowsum_kernel", vae_rowsum_kernel, nb, 256, 0, s, g->slots_r, ns, 2 * g->Bmax, B, g->be_part);
+  launch_pdl("vae_rowsum_kernel", vae_rowsum_kernel, nb, 256, 0, s, g->slots_r + B, ns, 2 * g->Bmax, B, g->be_part + nb);
   exchange_stats(g, g->be_part, nb, 1, 1, s);          // DX, DG of the K controller over the global batch
   exchange_stats(g, g->be_part + nb, nb, 1, 1, s);
-  launch_pdl(began_loss_final_kernel, 1, 256, 0, s, g->be_part, g->be_part + nb, nb, B * stat_world(g), 0, g->be_state, g->lossbuf);
+  launch_pdl("began_loss_final_kernel", began_loss_final_kernel, 1, 256, 0, s, g->be_part, g->be_part + nb, nb, B * stat_world(g), 0, g->be_state, g->lossbuf);
   c->launches += 3;
   if ((rc = launch_plan(c, sp->be_gwd, s))) return rc;
   if ((rc = launch_plan(c, sp->be_de_d, s))) return rc;
@@ -1021,12 +1159,12 @@ static int began_g_grad(gm_gan* g, StepPlans* sp, int B, float* loss_dev, cudaSt
   if ((rc = launch_plan(c, sp->be_enc_g, s))) return rc;
   if ((rc = launch_plan(c, sp->be_dec_g, s))) return rc;
   const int nb = c->num_sms;
-  launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r + B, 2 * cdiv(g->X, 208), 2 * g->Bmax, B, g->be_part + nb);
-  launch_pdl(began_loss_final_kernel, 1, 256, 0, s, g->be_part, g->be_part + nb, nb, B, 1, g->be_state, g->lossbuf);
+  launch_pdl("vae_rowsum_kernel", vae_rowsum_kernel, nb, 256, 0, s, g->slots_r + B, 2 * cdiv(g->X, 208), 2 * g->Bmax, B, g->be_part + nb);
+  launch_pdl("began_loss_final_kernel", began_loss_final_kernel, 1, 256, 0, s, g->be_part, g->be_part + nb, nb, B, 1, g->be_state, g->lossbuf);
   c->launches += 2;
   if ((rc = launch_plan(c, sp->be_de_g, s))) return rc;
   if ((rc = launch_plan(c, sp->be_dxg, s))) return rc;
-  launch_pdl(began_da2_kernel, c->num_sms * 8, 256, 0, s, g->BT, g->DR + size_t(B) * g->XP, g->Xall + size_t(B) * g->XP, g->DA2, B, g->X, g->XP);
+  launch_pdl("began_da2_kernel", began_da2_kernel, c->num_sms * 8, 256, 0, s, g->BT, g->DR + size_t(B) * g->XP, g->Xall + size_t(B) * g->XP, g->DA2, B, g->X, g->XP, g->lo);
   c->launches++;
   if ((rc = launch_plan(c, sp->dw2g, s))) return rc;
   if ((rc = launch_plan(c, sp->dhg, s))) return rc;
@@ -1053,7 +1191,7 @@ extern "C" int gm_gan_began_state(gm_gan* g, float* host11, int set, gm_stream s
 extern "C" int gm_gan_began_control(gm_gan* g, float gamma, float lambda, float patience, gm_stream stream) {
   if (!g) return GM_ERR_ARG;
   if (g->d.variant != GM_BEGAN) return fail(g->ctx, GM_ERR_STATE, "not a BEGAN engine");
-  launch_pdl(began_control_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), g->be_state, gamma, lambda, patience);
+  launch_pdl("began_control_kernel", began_control_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), g->be_state, gamma, lambda, patience);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -1077,7 +1215,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     if (B > g->pool_n) return fail(c, GM_ERR_ARG, "batch (%d) exceeds the sampler's pool (%lld)", B, g->pool_n);
     smp = make_sampler(g->pool_n, g->pool_seed, step, 0);     // a fresh permutation every step (src/ns_gan.py:224)
   }
-  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP, smp);
+  launch_pdl("stage_images_kernel", stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP, smp, g->lo);
   c->launches++;
   if ((rc = run_generator(g, sp, B, noise, seed, 2 * step, s))) return rc;
   if (g->d.variant == GM_BEGAN) return began_d_grad(g, sp, B, loss_dev, s);
@@ -1089,25 +1227,25 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     // interpolated rows (region 2): WGAN-GP between real and fake, DRAGAN around the real data
     const int mode = g->d.variant == GM_DRA ? 1 : 0;
     if (mode == 1) {
-      launch_pdl(moments_kernel, c->num_sms * 2, 256, 0, s, g->Xall, B, X, XP, g->mom_part);
+      launch_pdl("moments_kernel", moments_kernel, c->num_sms * 2, 256, 0, s, g->Xall, B, X, XP, g->mom_part);
       exchange_stats(g, g->mom_part, c->num_sms * 2, 2, 2, s);     // images.std() over the global batch
-      launch_pdl(moments_final_kernel, 1, 256, 0, s, g->mom_part, c->num_sms * 2, float(double(B) * X * stat_world(g)), g->stats);
+      launch_pdl("moments_final_kernel", moments_final_kernel, 1, 256, 0, s, g->mom_part, c->num_sms * 2, float(double(B) * X * stat_world(g)), g->stats);
       c->launches += 2;
     }
-    launch_pdl(xhat_kernel, cdiv(B, 128), 128, 0, s, g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
-                                           mode, aux, g->stats, seed, 2 * step);
+    launch_pdl("xhat_kernel", xhat_kernel, cdiv(B, 128), 128, 0, s, g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
+                                           mode, aux, g->stats, seed, 2 * step, 1.f, g->lo);
     c->launches++;
   }
   if ((rc = launch_plan(c, sp->d1_d, s))) return rc;
   launch_loss(g, B, 0, inv_global_batch, s);
-  launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall, g->ds, w2, g->DHall, g->dw2p, 2 * B, H, HP, g->dh_rows_per_iter);
-  launch_pdl(colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
+  launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall, g->ds, w2, g->DHall, g->dw2p, 2 * B, H, HP, g->dh_rows_per_iter, g->lo);
+  launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
   c->launches += 2;
   if (gp) {
     const size_t rreg = size_t(g->nreg - 1) * B;
     // U = 1[a_hat > 0] * w2  -> DHall rows of the R region
-    launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, nullptr, w2, g->DHall + rreg * HP, nullptr,
-                                                          B, H, HP, g->dh_rows_per_iter);
+    launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, nullptr, w2, g->DHall + rreg * HP, nullptr,
+                                                          B, H, HP, g->dh_rows_per_iter, g->lo);
     c->launches++;
     if ((rc = launch_plan(c, sp->gp_v, s))) return rc;          // V = U W1 -> R region of Xall, ||V||^2 -> slots_v
     GpParams gpp;
@@ -1119,18 +1257,18 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     gpp.coef = g->coef; gpp.ds_gp = g->ds + 2 * B;
     gpp.part = g->gp_part; gpp.nblk = cdiv(B, kLossThreads) < c->num_sms * 2 ? cdiv(B, kLossThreads) : c->num_sms * 2;
     gpp.loss = g->lossbuf;
-    launch_pdl(gp_rows_kernel, gpp.nblk, kLossThreads, 0, s, gpp);
-    launch_pdl(gp_final_kernel, 1, kLossThreads, 0, s, gpp);
-    launch_pdl(scale_rows_kernel, c->num_sms * 4, 256, 0, s, g->Xall + rreg * XP, g->coef, B, XP);   // R = coef * V
+    launch_pdl("gp_rows_kernel", gp_rows_kernel, gpp.nblk, kLossThreads, 0, s, gpp);
+    launch_pdl("gp_final_kernel", gp_final_kernel, 1, kLossThreads, 0, s, gpp);
+    launch_pdl("scale_rows_kernel", scale_rows_kernel, c->num_sms * 4, 256, 0, s, g->Xall + rreg * XP, g->coef, B, XP, g->lo);   // R = coef * V
     c->launches += 3;
     if ((rc = launch_plan(c, sp->gp_t, s))) return rc;          // T = (R W1^T) * mask -> DHg
-    launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->DHg, nullptr, w2, g->DA2, g->dw2p2, B, H, HP, g->dh_rows_per_iter);
-    launch_pdl(colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p2, g->dh_blocks, HP, HP, g->dw2sum + HP);
+    launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->DHg, nullptr, w2, g->DA2, g->dw2p2, B, H, HP, g->dh_rows_per_iter, g->lo);
+    launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p2, g->dh_blocks, HP, HP, g->dw2sum + HP);
     c->launches += 2;
     if (g->nreg == 4) {   // DRAGAN: the penalty also back-propagates through s(xhat)
-      launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, g->ds + 2 * B, w2,
-                                                            g->DHall + size_t(2) * B * HP, g->dw2p3, B, H, HP, g->dh_rows_per_iter);
-      launch_pdl(colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p3, g->dh_blocks, HP, HP, g->dw2sum + 2 * HP);
+      launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, g->ds + 2 * B, w2,
+                                                            g->DHall + size_t(2) * B * HP, g->dw2p3, B, H, HP, g->dh_rows_per_iter, g->lo);
+      launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p3, g->dh_blocks, HP, HP, g->dw2sum + 2 * HP);
       c->launches += 2;
     }
   }
@@ -1217,6 +1355,7 @@ extern "C" int gm_gan_bind_q(gm_gan* g, float* q_params, float* q_grads, float* 
 extern "C" int gm_gan_q_param_count(const gm_gan* g) { return (g && g->d.variant == GM_INFO) ? g->Qn.total : GM_ERR_ARG; }
 
 static void q_adam_segs(gm_gan* g, AdamParams& a) {
+  a.lo_off = g->lo;
   a.total = g->Qn.total;
   a.nseg = 2;
   a.seg[0] = {g->Qn.off_w1, g->H * g->X, g->X, g->Wq1_s, g->X, g->Wq1_t, g->H};
@@ -1228,7 +1367,7 @@ extern "C" int gm_gan_sync_shadows_q(gm_gan* g, gm_stream stream) {
   memset(&a, 0, sizeof a);
   a.p = g->parQ; a.update = 0;
   q_adam_segs(g, a);
-  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
+  launch_pdl("adam_kernel", adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -1254,8 +1393,8 @@ extern "C" int gm_gan_q_grad(gm_gan* g, int batch, const float* noise, int zd, f
   if ((rc = launch_plan(c, sp->q1, s))) return rc;
   if ((rc = launch_plan(c, sp->q2, s))) return rc;
   const int nb = cdiv(B, kLossThreads) < c->num_sms * 2 ? cdiv(B, kLossThreads) : c->num_sms * 2;
-  launch_pdl(info_loss_kernel, nb, kLossThreads, 0, s, g->INF, 32, noise, g->Z, zd, 10, 10, B, inv_global_batch, g->DINF, 64, g->q_part);
-  launch_pdl(info_loss_final_kernel, 1, kLossThreads, 0, s, g->q_part, nb, B, 10, g->lossbuf);
+  launch_pdl("info_loss_kernel", info_loss_kernel, nb, kLossThreads, 0, s, g->INF, 32, noise, g->Z, zd, 10, 10, B, inv_global_batch, g->DINF, 64, g->q_part, g->lo);
+  launch_pdl("info_loss_final_kernel", info_loss_final_kernel, 1, kLossThreads, 0, s, g->q_part, nb, B, 10, g->lossbuf);
   c->launches += 2;
   if ((rc = launch_plan(c, sp->gq2, s))) return rc;
   if ((rc = launch_plan(c, sp->dhq, s))) return rc;
@@ -1285,7 +1424,7 @@ extern "C" int gm_gan_q_grad(gm_gan* g, int batch, const float* noise, int zd, f
   qs.s[1] = {g->Qn.off_b1, g->H, 2, 0, q1.ldp, g->X, q1.splits, q1.part_stride, g->PQ1};
   qs.s[2] = {g->Qn.off_w2, g->q_out * g->H, 0, g->H, q2.ldp, 0, q2.splits, q2.part_stride, g->PQ2};
   qs.s[3] = {g->Qn.off_b2, g->q_out, 2, 0, q2.ldp, g->H, q2.splits, q2.part_stride, g->PQ2};
-  launch_pdl(finalize_grads_kernel, cdiv(qs.total, 256), 256, 0, s, qs, g->grdQ);
+  launch_pdl("finalize_grads_kernel", finalize_grads_kernel, cdiv(qs.total, 256), 256, 0, s, qs, g->grdQ);
   c->launches += 2;
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   CU_OK(c, cudaGetLastError());
@@ -1304,13 +1443,13 @@ extern "C" int gm_gan_apply_mi(gm_gan* g, const gm_adam_hp* hp, int step, gm_str
   a.p = g->par[GM_NET_G]; a.g = g->grd[GM_NET_G]; a.m = g->amG2; a.v = g->avG2;
   fill_adam(a, hp, step);
   adam_segs(g, GM_NET_G, a);
-  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, s, a);
+  launch_pdl("adam_kernel", adam_kernel, cdiv(a.total, 256), 256, 0, s, a);
   AdamParams q;
   memset(&q, 0, sizeof q);
   q.p = g->parQ; q.g = g->grdQ; q.m = g->amQ; q.v = g->avQ;
   fill_adam(q, hp, step);
   q_adam_segs(g, q);
-  launch_pdl(adam_kernel, cdiv(q.total, 256), 256, 0, s, q);
+  launch_pdl("adam_kernel", adam_kernel, cdiv(q.total, 256), 256, 0, s, q);
   g->ctx->launches += 2;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -1324,12 +1463,15 @@ extern "C" int gm_gan_scores(gm_gan* g, float* dst, int n, gm_stream stream) {
   return GM_OK;
 }
 
-__global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int ld, float* __restrict__ dst, int rows, int cols) {
+__global__ void bf16_rows_to_f32_kernel(const __nv_bfloat16* __restrict__ src, int ld, float* __restrict__ dst, int rows, int cols,
+                                        long long lo_off) {
   griddep_sync();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)rows * cols) return;
   const int r = int(i / cols), cidx = int(i % cols);
-  dst[i] = __bfloat162float(src[(long long)r * ld + cidx]);
+  float v = __bfloat162float(src[(long long)r * ld + cidx]);
+  if (lo_off) v += __bfloat162float(src[(long long)r * ld + cidx + lo_off]);
+  dst[i] = v;
 }
 
 extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* images, gm_stream stream) {
@@ -1343,12 +1485,12 @@ extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* imag
   int rc;
   if ((rc = build_plans(g, B, &sp))) return rc;
   // stage n noise rows (rows n..B-1 keep whatever they held; their outputs are not read)
-  launch_pdl(stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, n, g->Z, g->ZP, 0, 0);
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, n, g->Z, g->ZP, 0, 0, g->lo);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
   if ((rc = launch_plan(g->ctx, sp->g2, s))) return rc;
   const long long tot = (long long)n * g->X;
-  launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->Xall + size_t(B) * g->XP, g->XP, images, n, g->X);
+  launch_pdl("bf16_rows_to_f32_kernel", bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->Xall + size_t(B) * g->XP, g->XP, images, n, g->X, g->lo);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -1362,10 +1504,10 @@ extern "C" int gm_gan_discriminate(gm_gan* g, const void* images, int img_fmt, i
   StepPlans* sp;
   int rc;
   if ((rc = build_plans(g, n, &sp))) return rc;
-  launch_pdl(stage_images_kernel, g->ctx->num_sms * 8, 256, 0, s, images, img_fmt, nullptr, g->Xall, n, g->X, g->XP, kNoSampler);
+  launch_pdl("stage_images_kernel", stage_images_kernel, g->ctx->num_sms * 8, 256, 0, s, images, img_fmt, nullptr, g->Xall, n, g->X, g->XP, kNoSampler, g->lo);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->d1_x, s))) return rc;
-  launch_pdl(scores_kernel, cdiv(n, 256), 256, 0, s, g->slots, 2 * cdiv(g->H, 208), g->nreg * g->Bmax, g->par[GM_NET_D] + g->D.off_b2,
+  launch_pdl("scores_kernel", scores_kernel, cdiv(n, 256), 256, 0, s, g->slots, 2 * cdiv(g->H, 208), g->nreg * g->Bmax, g->par[GM_NET_D] + g->D.off_b2,
                                             g->d.d_out_act, scores, n);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
@@ -1392,7 +1534,7 @@ extern "C" int gm_gan_sample_indices(gm_gan* g, int batch, uint64_t step, int* i
   if (!g || !idx_dev || batch <= 0) return GM_ERR_ARG;
   if (g->pool_n > 0 && batch > g->pool_n) return fail(g->ctx, GM_ERR_ARG, "batch exceeds the pool");
   const Sampler smp = g->pool_n > 0 ? make_sampler(g->pool_n, g->pool_seed, step, 0) : kNoSampler;
-  launch_pdl(sample_indices_kernel, cdiv(batch, 256), 256, 0, static_cast<cudaStream_t>(stream), smp, batch, idx_dev);
+  launch_pdl("sample_indices_kernel", sample_indices_kernel, cdiv(batch, 256), 256, 0, static_cast<cudaStream_t>(stream), smp, batch, idx_dev);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -1404,10 +1546,10 @@ extern "C" int gm_gan_debug_noise(gm_gan* g, int batch, uint64_t seed, uint64_t 
   if (rc) return rc;
   if (!out_dev) return GM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  launch_pdl(stage_noise_kernel, cdiv(batch * ((g->Z + 8) / 8), 256), 256, 0, s, static_cast<const float*>(nullptr), g->Zb, batch, g->Z, g->ZP,
-                                                   (unsigned long long)seed, (unsigned long long)(2 * step + (g_step ? 1 : 0)));
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(batch * ((g->Z + 8) / 8), 256), 256, 0, s, static_cast<const float*>(nullptr), g->Zb, batch, g->Z, g->ZP,
+                                                   (unsigned long long)seed, (unsigned long long)(2 * step + (g_step ? 1 : 0)), g->lo);
   const long long tot = (long long)batch * g->Z;
-  launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->Zb, g->ZP, out_dev, batch, g->Z);
+  launch_pdl("bf16_rows_to_f32_kernel", bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->Zb, g->ZP, out_dev, batch, g->Z, g->lo);
   g->ctx->launches += 2;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;

@@ -1,5 +1,5 @@
 // Peer exchange for the fused all-reduce + Adam kernel (kernels.cuh: adam_allreduce_kernel).
-// One cudaMalloc'ed region per rank = [2][nfloats] exchange buffer + flag array, exported with
+// One cudaMalloc'ed region per rank = [2][16 source ranks][nfloats] exchange slots + flag array, exported with
 // cudaIpcGetMemHandle; the host (gm_b200/parallel.py) gathers the 64-byte handles of all ranks
 // through torch.distributed and gm_comm_open maps them (NVLink peer access on the B200 box).
 
@@ -9,7 +9,7 @@ extern "C" int gm_comm_create(gm_ctx* c, int nfloats, gm_comm** out) {
   m->ctx = c;
   m->nfloats = (long long)rup(nfloats, kCommChunk);
   m->nblocks = int(m->nfloats / kCommChunk);
-  m->flag_off = size_t(2) * m->nfloats * sizeof(float);
+  m->flag_off = size_t(2) * kCommMaxWorld * m->nfloats * sizeof(float);   // [parity][source rank][nfloats]: peers push their chunks here
   m->stat_off = m->flag_off + size_t(2) * kCommMaxWorld * m->nblocks * sizeof(unsigned long long);
   m->sflag_off = m->stat_off + size_t(2) * kCommMaxWorld * kCommStatVals * sizeof(double);
   const size_t bytes = m->sflag_off + size_t(2) * kCommMaxWorld * sizeof(unsigned long long);
@@ -80,7 +80,7 @@ extern "C" int gm_gan_apply_allreduce(gm_gan* g, int net, const gm_adam_hp* hp, 
   }
   cm.rank = m->rank; cm.world = m->world; cm.nblocks = m->nblocks; cm.nfloats = m->nfloats;
   cm.seq = ++m->seq;
-  launch_pdl(adam_allreduce_kernel, cdiv(a.total, kCommChunk), 256, 0, static_cast<cudaStream_t>(stream), a, cm);
+  launch_pdl("adam_allreduce_kernel", adam_allreduce_kernel, cdiv(a.total, kCommChunk), 256, 0, static_cast<cudaStream_t>(stream), a, cm);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;

@@ -28,23 +28,21 @@ __global__ void __launch_bounds__(1024) custom_ds_kernel(const float* __restrict
 }
 
 // Generator side: the saved fake rows (bf16) become da2 = dfake * fake * (1 - fake), in place.
-__global__ void custom_da2_kernel(const float* __restrict__ dfake, __nv_bfloat16* __restrict__ fk, int rows, int x, int ld) {
+__global__ void custom_da2_kernel(const float* __restrict__ dfake, __nv_bfloat16* __restrict__ fk, int rows, int x, int ld, long long lo_off) {
   griddep_sync();
   const int groups = ld / 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)rows * groups) return;
   const int r = int(i / groups), c0 = int(i % groups) * 8;
-  uint4* cell = reinterpret_cast<uint4*>(fk + (long long)r * ld + c0);
-  const uint4 raw = *cell;
-  const __nv_bfloat16* f = reinterpret_cast<const __nv_bfloat16*>(&raw);
-  float v[8];
+  __nv_bfloat16* cell = fk + (long long)r * ld + c0;
+  float f[8], v[8];
+  load_bf16x8(cell, f, lo_off);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
-    const float a = __bfloat162float(f[j]);
-    v[j] = c < x ? dfake[(long long)r * x + c] * a * (1.f - a) : 0.f;
+    v[j] = c < x ? dfake[(long long)r * x + c] * f[j] * (1.f - f[j]) : 0.f;
   }
-  *cell = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  store_bf16x8(cell, v, lo_off);
 }
 }  // namespace gm
 
@@ -52,6 +50,7 @@ static int build_custom_plans(gm_gan* g, int B, CustomPlans** out) {
   auto it = g->cplans.find(B);
   if (it != g->cplans.end()) { *out = &it->second; return GM_OK; }
   gm_ctx* c = g->ctx;
+  PlanLoScope lo_scope(c, g->lo);
   CustomPlans cp;
   const int X = g->X, H = g->H, XP = g->XP, HP = g->HP;
   const float* pD = g->par[GM_NET_D];
@@ -107,11 +106,11 @@ extern "C" int gm_gan_d_forward(gm_gan* g, int slot, const float* x, int batch, 
   CustomPlans* cp;
   if ((rc = build_custom_plans(g, batch, &cp))) return rc;
   gm_ctx* c = g->ctx;
-  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, static_cast<const void*>(x), int(GM_IMG_F32), static_cast<const int*>(nullptr),
-             g->Xall + size_t(slot) * g->Bmax * g->XP, batch, g->X, g->XP, kNoSampler);
+  launch_pdl("stage_images_kernel", stage_images_kernel, c->num_sms * 8, 256, 0, s, static_cast<const void*>(x), int(GM_IMG_F32), static_cast<const int*>(nullptr),
+             g->Xall + size_t(slot) * g->Bmax * g->XP, batch, g->X, g->XP, kNoSampler, g->lo);
   c->launches++;
   if ((rc = launch_plan(c, cp->d1[slot], s))) return rc;
-  launch_pdl(scores_kernel, cdiv(batch, 256), 256, 0, s, g->slots + size_t(slot) * g->Bmax, 2 * cdiv(g->H, 208), g->nreg * g->Bmax,
+  launch_pdl("scores_kernel", scores_kernel, cdiv(batch, 256), 256, 0, s, g->slots + size_t(slot) * g->Bmax, 2 * cdiv(g->H, 208), g->nreg * g->Bmax,
              g->par[GM_NET_D] + g->D.off_b2, g->d.d_out_act, scores, batch);
   c->launches++;
   CU_OK(c, cudaGetLastError());
@@ -130,12 +129,12 @@ extern "C" int gm_gan_d_backward(gm_gan* g, int slot, int batch, const float* ds
   const int B = batch, H = g->H, HP = g->HP;
   const float* w2 = g->par[GM_NET_D] + g->D.off_w2;
   float* ds = g->ds + size_t(slot) * g->Bmax;
-  launch_pdl(custom_ds_kernel, 1, 1024, 0, s, g->slots + size_t(slot) * g->Bmax, 2 * cdiv(H, 208), g->nreg * g->Bmax,
+  launch_pdl("custom_ds_kernel", custom_ds_kernel, 1, 1024, 0, s, g->slots + size_t(slot) * g->Bmax, 2 * cdiv(H, 208), g->nreg * g->Bmax,
              g->par[GM_NET_D] + g->D.off_b2, g->d.d_out_act, dscore, ds, g->lossbuf + 1, B);
-  launch_pdl(dh_kernel, g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * HP * sizeof(float), s,
+  launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * HP * sizeof(float), s,
              g->Aall + size_t(slot) * g->Bmax * HP, static_cast<const float*>(ds), w2, g->DHall + size_t(slot) * g->Bmax * HP, g->dw2p, B, H, HP,
-             g->dh_rows_per_iter);
-  launch_pdl(colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
+             g->dh_rows_per_iter, g->lo);
+  launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
   c->launches += 3;
   if ((rc = launch_plan(c, cp->dw1[slot], s))) return rc;
   GradSegs gs;
@@ -147,7 +146,7 @@ extern "C" int gm_gan_d_backward(gm_gan* g, int slot, int batch, const float* ds
   gs.s[1] = {g->D.off_b1, g->H, 2, 0, pw.ldp, g->X, pw.splits, pw.part_stride, g->PD};
   gs.s[2] = {g->D.off_w2, g->H, 3, 0, 0, 0, 1, (long long)HP, g->dw2sum};
   gs.s[3] = {g->D.off_b2, 1, 3, 0, 0, 0, 1, 2, g->lossbuf + 1};
-  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_D]);
+  launch_pdl("finalize_grads_kernel", finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd[GM_NET_D]);
   c->launches++;
   if (dx) {
     GemmPlan pl = cp->dx[slot];
@@ -168,12 +167,12 @@ extern "C" int gm_gan_g_forward(gm_gan* g, const float* noise, int batch, float*
   if ((rc = build_plans(g, batch, &sp))) return rc;
   if ((rc = build_custom_plans(g, batch, &cp))) return rc;
   gm_ctx* c = g->ctx;
-  launch_pdl(stage_noise_kernel, cdiv(batch * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, batch, g->Z, g->ZP, uint64_t(0), uint64_t(0));
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(batch * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, batch, g->Z, g->ZP, uint64_t(0), uint64_t(0), g->lo);
   c->launches++;
   if ((rc = launch_plan(c, sp->g1, s))) return rc;
   if ((rc = launch_plan(c, cp->g2, s))) return rc;
   const long long tot = (long long)batch * g->X;
-  launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, static_cast<const __nv_bfloat16*>(g->DA2), g->XP, images, batch, g->X);
+  launch_pdl("bf16_rows_to_f32_kernel", bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, static_cast<const __nv_bfloat16*>(g->DA2), g->XP, images, batch, g->X, g->lo);
   c->launches++;
   CU_OK(c, cudaGetLastError());
   return GM_OK;
@@ -188,7 +187,7 @@ extern "C" int gm_gan_g_backward(gm_gan* g, int batch, const float* dimages, gm_
   if ((rc = build_plans(g, batch, &sp))) return rc;
   gm_ctx* c = g->ctx;
   const long long cells = (long long)batch * (g->XP / 8);
-  launch_pdl(custom_da2_kernel, unsigned((cells + 255) / 256), 256, 0, s, dimages, g->DA2, batch, g->X, g->XP);
+  launch_pdl("custom_da2_kernel", custom_da2_kernel, unsigned((cells + 255) / 256), 256, 0, s, dimages, g->DA2, batch, g->X, g->XP, g->lo);
   c->launches++;
   if ((rc = launch_plan(c, sp->dw2g, s))) return rc;
   if ((rc = launch_plan(c, sp->dhg, s))) return rc;

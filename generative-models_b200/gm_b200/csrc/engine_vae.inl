@@ -24,7 +24,14 @@ struct gm_vae {
   uint64_t pool_seed = 0;
   std::map<int, VaePlans> plans;
   std::vector<void*> allocs;
+  BfArena arena;
+  long long lo = 0;
 };
+
+static int vae_alloc(gm_vae* g, __nv_bfloat16** p, size_t count) {   // bf16 buffers come from the arena
+  g->arena.request(p, count);
+  return GM_OK;
+}
 
 template <typename T>
 static int vae_alloc(gm_vae* g, T** p, size_t count) {
@@ -52,7 +59,7 @@ extern "C" int gm_vae_create(gm_ctx* c, const gm_vae_desc* d, gm_vae** out) {
     return fail(c, GM_ERR_ARG, "image_size and hidden_dim must be positive multiples of 16");
   if (d->hidden_dim + 1 > 448 || 2 * d->z_dim > 64)
     return fail(c, GM_ERR_UNSUPPORTED, "hidden_dim <= 447 and z_dim <= 32 in this build (got %d, %d)", d->hidden_dim, d->z_dim);
-  if (d->dtype_mode != GM_PREC_BF16) return fail(c, GM_ERR_UNSUPPORTED, "dtype_mode %d is not built", d->dtype_mode);
+  if (d->dtype_mode != GM_PREC_BF16 && d->dtype_mode != GM_PREC_SPLIT) return fail(c, GM_ERR_ARG, "unknown dtype_mode %d", d->dtype_mode);
   gm_vae* g = new gm_vae();
   g->ctx = c; g->d = *d;
   const int X = g->X = d->image_size, H = g->H = d->hidden_dim, Z = g->Z = d->z_dim;
@@ -91,6 +98,12 @@ extern "C" int gm_vae_create(gm_ctx* c, const gm_vae_desc* d, gm_vae** out) {
   TRYV(vae_alloc(g, &g->Pmv, size_t(ns) * 64 * 448));
   TRYV(vae_alloc(g, &g->P3, size_t(ns / cdiv(H, BM) > 0 ? ns / cdiv(H, BM) : 1) * H * 64));
   TRYV(vae_alloc(g, &g->P4, size_t(ns / cdiv(X, BM) > 0 ? ns / cdiv(X, BM) : 1) * X * 448));
+  {
+    cudaError_t e = g->arena.finalize(d->dtype_mode == GM_PREC_SPLIT);
+    if (e != cudaSuccess) { rc = fail(c, GM_ERR_CUDA, "bf16 arena allocation failed: %s", cudaGetErrorString(e)); gm_vae_destroy(g); return rc; }
+    g->allocs.push_back(g->arena.base);
+    g->lo = g->arena.lo_off;
+  }
 #undef TRYV
   *out = g;
   return GM_OK;
@@ -115,6 +128,7 @@ extern "C" int gm_vae_bind(gm_vae* g, float* p, float* gr, float* m, float* v) {
 }
 
 static void vae_adam_segs(gm_vae* g, AdamParams& a) {
+  a.lo_off = g->lo;
   a.total = g->total;
   a.nseg = 4;
   a.seg[0] = {g->off_w1, g->H * g->X, g->X, g->W1_s, g->X, nullptr, 0};
@@ -130,7 +144,7 @@ extern "C" int gm_vae_sync_shadows(gm_vae* g, gm_stream stream) {
   memset(&a, 0, sizeof a);
   a.p = g->par; a.update = 0;
   vae_adam_segs(g, a);
-  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
+  launch_pdl("adam_kernel", adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -151,7 +165,7 @@ extern "C" int gm_vae_apply(gm_vae* g, const gm_adam_hp* hp, int step, gm_stream
   a.p = g->par; a.g = g->grd; a.m = g->am; a.v = g->av;
   fill_adam(a, hp, step);
   vae_adam_segs(g, a);
-  launch_pdl(adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
+  launch_pdl("adam_kernel", adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
@@ -165,6 +179,7 @@ static int vae_plans(gm_vae* g, int B, VaePlans** out) {
   auto it = g->plans.find(B);
   if (it != g->plans.end()) { *out = &it->second; return GM_OK; }
   gm_ctx* c = g->ctx;
+  PlanLoScope lo_scope(c, g->lo);
   VaePlans sp;
   const int X = g->X, H = g->H, Z = g->Z, XP = g->XP, HP = g->HP, ZP = g->ZP;
   const float* P = g->par;
@@ -229,11 +244,11 @@ static int vae_forward_core(gm_vae* g, VaePlans* sp, const void* images, int fmt
     const uint64_t bpe = g->pool_bpe > 0 ? uint64_t(g->pool_bpe) : 1;
     smp = make_sampler(g->pool_n, g->pool_seed, step / bpe, (step % bpe) * uint64_t(B));
   }
-  launch_pdl(stage_images_kernel, c->num_sms * 8, 256, 0, s, images, fmt, idx, g->Xin, B, g->X, g->XP, smp);
+  launch_pdl("stage_images_kernel", stage_images_kernel, c->num_sms * 8, 256, 0, s, images, fmt, idx, g->Xin, B, g->X, g->XP, smp, g->lo);
   c->launches++;
   if ((rc = launch_plan(c, sp->e1, s))) return rc;
   if ((rc = launch_plan(c, sp->e2, s))) return rc;
-  launch_pdl(vae_reparam_kernel, cdiv(B, 256), 256, 0, s, g->MULV, 64, eps, g->EPS, g->Zb, g->ZP, B, g->Z, seed, step, g->part_k);
+  launch_pdl("vae_reparam_kernel", vae_reparam_kernel, cdiv(B, 256), 256, 0, s, g->MULV, 64, eps, g->EPS, g->Zb, g->ZP, B, g->Z, seed, step, g->part_k, g->lo);
   c->launches++;
   if ((rc = launch_plan(c, sp->d1, s))) return rc;
   if ((rc = launch_plan(c, train ? sp->d2 : sp->d2_fwd, s))) return rc;
@@ -242,8 +257,8 @@ static int vae_forward_core(gm_vae* g, VaePlans* sp, const void* images, int fmt
 
 static void vae_losses(gm_vae* g, int B, cudaStream_t s) {
   const int nb = g->ctx->num_sms * 2;
-  launch_pdl(vae_rowsum_kernel, nb, 256, 0, s, g->slots_r, 2 * cdiv(g->X, 208), g->Bmax, B, g->part_r);
-  launch_pdl(vae_losses_final_kernel, 1, 256, 0, s, g->part_r, nb, g->part_k, cdiv(B, 256), g->losses);
+  launch_pdl("vae_rowsum_kernel", vae_rowsum_kernel, nb, 256, 0, s, g->slots_r, 2 * cdiv(g->X, 208), g->Bmax, B, g->part_r);
+  launch_pdl("vae_losses_final_kernel", vae_losses_final_kernel, 1, 256, 0, s, g->part_r, nb, g->part_k, cdiv(B, 256), g->losses);
   g->ctx->launches += 2;
 }
 
@@ -267,7 +282,7 @@ extern "C" int gm_vae_grad(gm_vae* g, const void* images, int img_fmt, const int
   if ((rc = launch_plan(c, sp->da3, s))) return rc;
   if ((rc = launch_plan(c, sp->gw3, s))) return rc;
   if ((rc = launch_plan(c, sp->dz, s))) return rc;
-  launch_pdl(vae_dlatent_kernel, cdiv(B * 64, 256), 256, 0, s, g->MULV, 64, g->DZ, 32, g->EPS, g->DML, 64, B, g->Z, 1.f);
+  launch_pdl("vae_dlatent_kernel", vae_dlatent_kernel, cdiv(B * 64, 256), 256, 0, s, g->MULV, 64, g->DZ, 32, g->EPS, g->DML, 64, B, g->Z, 1.f, g->lo);
   c->launches++;
   if ((rc = launch_plan(c, sp->gwmv, s))) return rc;
   if ((rc = launch_plan(c, sp->da1, s))) return rc;
@@ -285,7 +300,7 @@ extern "C" int gm_vae_grad(gm_vae* g, const void* images, int img_fmt, const int
   gs.s[5] = {g->off_b3, g->H, 2, 0, p3.ldp, g->Z, p3.splits, p3.part_stride, g->P3};
   gs.s[6] = {g->off_w4, g->X * g->H, 0, g->H, p4.ldp, 0, p4.splits, p4.part_stride, g->P4};
   gs.s[7] = {g->off_b4, g->X, 2, 0, p4.ldp, g->H, p4.splits, p4.part_stride, g->P4};
-  launch_pdl(finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd);
+  launch_pdl("finalize_grads_kernel", finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd);
   c->launches++;
   if (losses_dev) CU_OK(c, cudaMemcpyAsync(losses_dev, g->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   CU_OK(c, cudaGetLastError());
@@ -313,7 +328,7 @@ extern "C" int gm_vae_forward(gm_vae* g, const void* images, int img_fmt, int n,
   }
   if (out_images_dev) {
     const long long tot = (long long)n * g->X;
-    launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->DA4, g->XP, out_images_dev, n, g->X);
+    launch_pdl("bf16_rows_to_f32_kernel", bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->DA4, g->XP, out_images_dev, n, g->X, g->lo);
     g->ctx->launches++;
   }
   if (mu_logvar_dev)
@@ -332,12 +347,12 @@ extern "C" int gm_vae_decode(gm_vae* g, const float* z_dev, int n, float* out_im
   VaePlans* sp;
   int rc;
   if ((rc = vae_plans(g, n, &sp))) return rc;
-  launch_pdl(stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, z_dev, g->Zb, n, g->Z, g->ZP, 0, 0);
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, z_dev, g->Zb, n, g->Z, g->ZP, 0, 0, g->lo);
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->d1, s))) return rc;
   if ((rc = launch_plan(g->ctx, sp->d2_fwd, s))) return rc;
   const long long tot = (long long)n * g->X;
-  launch_pdl(bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->DA4, g->XP, out_images_dev, n, g->X);
+  launch_pdl("bf16_rows_to_f32_kernel", bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->DA4, g->XP, out_images_dev, n, g->X, g->lo);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;

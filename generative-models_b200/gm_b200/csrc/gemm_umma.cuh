@@ -72,6 +72,12 @@ struct GemmParams {
   int transpose;
   // optional phase timing (tools/time_phases.py): CTA 0 writes SM-clock stamps, see the kernel
   long long* dbg;
+  // ---- split-bf16 operands (SPLIT kernels, gm_prec GM_PREC_SPLIT): A = A_hi + A_lo, B = B_hi + B_lo as bf16 planes
+  // lo_off elements apart; the contraction runs over nparts = 3 operand pairs (hi,hi), (hi,lo), (lo,hi) of kb_part
+  // k-blocks each into the same accumulator (kblocks = 3 kb_part; the dropped lo*lo term is below fp32 resolution).
+  // bf16 outputs and aux inputs carry their residual plane at the same offset.
+  int nparts, kb_part;
+  long long lo_off;
 };
 
 // per-epilogue-warp staging tile for one 32-column block: 32 rows x (64 B data + 16 B pad):
@@ -127,10 +133,13 @@ struct GemmCfg {
 //    completions of both CTAs are signalled on the leader's full barrier, slots / accumulators
 //    are released with multicast commits, peer epilogue warps release the accumulator remotely.
 //  * MN-major kernels: each CTA TMA-multicasts half of the shared B tile to both CTAs.
-template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1, int CS = 1, int EW = 8>
+template <int BN1, int BN2, bool A_MN, bool B_MN, int ACT_T = -1, int AUX_T = -1, int BIAS_T = -1, int DOT_T = -1, int CS = 1, int EW = 8,
+          bool SPLIT = false>
 __global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
+  static_assert(!SPLIT || ACT_T < 0, "split operands: universal epilogue only");
   constexpr bool PAIR = (CS == 2) && !A_MN;
   using Cfg = GemmCfg<BN1, BN2, !A_MN, PAIR, EW>;
   constexpr int BN = Cfg::BN;
@@ -165,6 +174,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (SPLIT) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), PAIR ? 2 : 1);          // pair: both producers arrive on the leader's barrier
@@ -210,42 +220,46 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (leader) {
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-          const int k0 = kb * BK;
+          int kk = kb, opart = 0;
+          if constexpr (SPLIT) { opart = kb / p.kb_part; kk = kb - opart * p.kb_part; }
+          const CUtensorMap* const ta = (SPLIT && opart == 2) ? &tmA2 : &tmA;   // (hi,hi), (hi,lo), (lo,hi)
+          const CUtensorMap* const tb = (SPLIT && opart == 1) ? &tmB2 : &tmB;
+          const int k0 = kk * BK;
           if constexpr (PAIR) {
             // own A rows + own half of B into own smem; bytes of BOTH CTAs are counted on the
             // leader's full barrier (leader expects 2 x stage bytes, the peer just arrives)
             const uint32_t fb = mapa_cluster(full_bar(stage), 0);
             if (crank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
             else mbar_arrive_cluster(fb);
-            tma_load_2d_pair(a_dst, &tmA, fb, k0, m0);
-            tma_load_2d_pair(b_dst, &tmB, fb, k0, n0 + crank * (BN / 2));
+            tma_load_2d_pair(a_dst, ta, fb, k0, m0);
+            tma_load_2d_pair(b_dst, tb, fb, k0, n0 + crank * (BN / 2));
           } else {
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           if constexpr (!A_MN) {
-            tma_load_2d(a_dst, &tmA, full_bar(stage), k0, m0);
+            tma_load_2d(a_dst, ta, full_bar(stage), k0, m0);
           } else {
 #pragma unroll
             for (int a = 0; a < BM / 64; ++a)
-              tma_load_2d(a_dst + a * (BK * 128), &tmA, full_bar(stage), m0 + a * 64, k0);
+              tma_load_2d(a_dst + a * (BK * 128), ta, full_bar(stage), m0 + a * 64, k0);
           }
           if constexpr (CS == 1) {
             if constexpr (!B_MN) {
 #pragma unroll
               for (int b = 0; b < BN / Cfg::BOXN; ++b)
-                tma_load_2d(b_dst + b * (Cfg::BOXN * 128), &tmB, full_bar(stage), k0, n0 + b * Cfg::BOXN);
+                tma_load_2d(b_dst + b * (Cfg::BOXN * 128), tb, full_bar(stage), k0, n0 + b * Cfg::BOXN);
             } else {
 #pragma unroll
               for (int b = 0; b < BN / 64; ++b)
-                tma_load_2d(b_dst + b * (BK * 128), &tmB, full_bar(stage), n0 + b * 64, k0);
+                tma_load_2d(b_dst + b * (BK * 128), tb, full_bar(stage), n0 + b * 64, k0);
             }
           } else {
             // this CTA's share of the B tile, multicast to the whole cluster
             if constexpr (!B_MN) {
               constexpr int SL = BN / CS;   // rows per CTA (tensor-map box = SL rows)
-              tma_load_2d_mc(b_dst + crank * (SL * 128), &tmB, full_bar(stage), k0, n0 + crank * SL, kMcMask);
+              tma_load_2d_mc(b_dst + crank * (SL * 128), tb, full_bar(stage), k0, n0 + crank * SL, kMcMask);
             } else {
               for (int b = crank; b < BN / 64; b += CS)
-                tma_load_2d_mc(b_dst + b * (BK * 128), &tmB, full_bar(stage), n0 + b * 64, k0, kMcMask);
+                tma_load_2d_mc(b_dst + b * (BK * 128), tb, full_bar(stage), n0 + b * 64, k0, kMcMask);
             }
           }
           }
@@ -290,7 +304,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         full_wait += phase_clock() - tw0;
         const uint32_t a_src = smem_base + stage * Cfg::STAGE_BYTES;
         const uint32_t b_src = a_src + Cfg::A_BYTES;
-        const int krem = p.K - kb * BK;
+        int kk = kb;
+        if constexpr (SPLIT) kk = kb % p.kb_part;
+        const int krem = p.K - kk * BK;
         const int nk = krem >= BK ? BK / kUmmaK : (krem + kUmmaK - 1) / kUmmaK;
         if (leader) {
           uint32_t a_lo = ((a_src >> 4) & 0x3FFFu) | ((A_LBO >> 4) << 16);
@@ -480,6 +496,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (!last_block) aux_fetch(n0 + cb_next);   // overlaps with this block's math + stores
           }
+          uint4 axl[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if constexpr (SPLIT) {   // residual plane of the aux values of this lane's row (plain loads: the split kernels are not tuned)
+            if (p.lo_off != 0 && aux_mode != AUX_NONE && aux_mode != AUX_RELU_MASK && row_ok) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col0 + q * 8 < p.out_cols)
+                  axl[q] = __ldg(reinterpret_cast<const uint4*>(p.aux + p.lo_off + size_t(row) * p.ld_aux + col0 + q * 8));
+            }
+          }
           // accumulator columns -> registers: both chunks in flight, one wait
           uint32_t raw[2][16];
           const long long tl0 = phase_clock();
@@ -526,14 +551,20 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 } else if (act == ACT_SIGMOID) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = has_bias ? fast_sigmoid_half(v[j]) : fast_sigmoid(v[j]);
+                  for (int j = 0; j < 16; ++j) {
+                    if constexpr (SPLIT) v[j] = 1.f / (1.f + __expf(has_bias ? -2.f * v[j] : -v[j]));   // fp32-grade (tanh.approx is 2^-11)
+                    else v[j] = has_bias ? fast_sigmoid_half(v[j]) : fast_sigmoid(v[j]);
+                  }
                 }
                 if (aux_mode != AUX_NONE) {
                   const uint32_t w[8] = {ax[2 * q].x, ax[2 * q].y, ax[2 * q].z, ax[2 * q].w,
                                          ax[2 * q + 1].x, ax[2 * q + 1].y, ax[2 * q + 1].z, ax[2 * q + 1].w};
+                  const uint32_t wl[8] = {axl[2 * q].x, axl[2 * q].y, axl[2 * q].z, axl[2 * q].w,
+                                          axl[2 * q + 1].x, axl[2 * q + 1].y, axl[2 * q + 1].z, axl[2 * q + 1].w};
 #pragma unroll
                   for (int k2 = 0; k2 < 8; ++k2) {
-                    const float a_lo = bf16_lo(w[k2]), a_hi = bf16_hi(w[k2]);
+                    float a_lo = bf16_lo(w[k2]), a_hi = bf16_hi(w[k2]);
+                    if constexpr (SPLIT) { a_lo += bf16_lo(wl[k2]); a_hi += bf16_hi(wl[k2]); }
                     if (aux_mode == AUX_SIGMOID_GRAD) {
                       v[2 * k2] *= (l1_scale * a_lo) * (1.f - a_lo);
                       v[2 * k2 + 1] *= (l1_scale * a_hi) * (1.f - a_hi);
@@ -583,6 +614,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               {
                 const uint4 lo = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                 const uint4 hi = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                if constexpr (SPLIT) {   // residual plane of the output: v - bf16(v), straight from registers
+                  if (p.lo_off != 0 && p.out != nullptr && row_ok && c0 < p.out_cols) {
+                    uint4* ol = reinterpret_cast<uint4*>(p.out + p.lo_off + size_t(row) * p.ldo + c0);
+                    ol[0] = make_uint4(pack_bf16x2_residual(v[0], v[1], lo.x), pack_bf16x2_residual(v[2], v[3], lo.y),
+                                       pack_bf16x2_residual(v[4], v[5], lo.z), pack_bf16x2_residual(v[6], v[7], lo.w));
+                    ol[1] = make_uint4(pack_bf16x2_residual(v[8], v[9], hi.x), pack_bf16x2_residual(v[10], v[11], hi.y),
+                                       pack_bf16x2_residual(v[12], v[13], hi.z), pack_bf16x2_residual(v[14], v[15], hi.w));
+                  }
+                }
                 if (blk_tma) {
                   const uint32_t sw = (lane >> 1) & 3, rowb = stage_s + lane * 64;
                   sts128(rowb + (((2 * q) ^ sw) << 4), lo);

@@ -55,10 +55,15 @@ __host__ __device__ __forceinline__ unsigned int sampler_index(const Sampler& sp
 }
 
 __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const int* __restrict__ idx,
-                                    __nv_bfloat16* __restrict__ dst, int rows, int x, int ld, const Sampler smp) {
+                                    __nv_bfloat16* __restrict__ dst, int rows, int x, int ld, const Sampler smp, long long lo_off) {
   griddep_sync();
   const int groups = ld / 8;
   const long long total = (long long)rows * groups;
+  if (lo_off) {   // split mode: {0,1} pixels are exact in bf16 -> the rows' residual plane is zero (it may hold a previous tenant's values)
+    uint4* lo = reinterpret_cast<uint4*>(dst + lo_off);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+      lo[i] = make_uint4(0, 0, 0, 0);
+  }
   auto src_row = [&](int r) -> long long {
     if (idx) return (long long)idx[r];
     if (smp.n) return (long long)sampler_index(smp, smp.offset + (unsigned long long)r);
@@ -116,8 +121,7 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
       } else if (c == x) f = 1.f;
       v[j] = f;
     }
-    reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    store_bf16x8(dst + i * 8, v, lo_off);     // grey-level fp32 inputs keep their residuals in split mode
   }
 }
 
@@ -132,7 +136,7 @@ __global__ void sample_indices_kernel(const Sampler smp, int rows, int* __restri
 // One thread per (row, 8-column group); the Philox subsequence is the group index, the
 // offset the step stream, so every step / rank / group draws disjoint numbers.
 __global__ void stage_noise_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
-                                   int z, int ld, unsigned long long seed, unsigned long long stream_id) {
+                                   int z, int ld, unsigned long long seed, unsigned long long stream_id, long long lo_off) {
   griddep_sync();
   // One thread per (row, 8-column group that holds noise): every lane runs the Philox /
   // Box-Muller path (a thread per group of the padded row left 5 of 8 lanes idle in it).
@@ -160,8 +164,11 @@ __global__ void stage_noise_kernel(const float* __restrict__ src, __nv_bfloat16*
     if (c >= z) v[j] = (c == z) ? 1.f : 0.f;
   }
   uint4* row = reinterpret_cast<uint4*>(dst) + (long long)r * groups;
-  row[g] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  for (int pg = gz + g; pg < groups; pg += gz) row[pg] = make_uint4(0, 0, 0, 0);
+  store_bf16x8(dst + ((long long)r * groups + g) * 8, v, lo_off);
+  for (int pg = gz + g; pg < groups; pg += gz) {
+    row[pg] = make_uint4(0, 0, 0, 0);
+    if (lo_off) reinterpret_cast<uint4*>(dst + lo_off)[(long long)r * groups + pg] = make_uint4(0, 0, 0, 0);
+  }
 }
 
 // ---------------------------------------------------------------- block reduction (deterministic)
@@ -382,7 +389,7 @@ __global__ void colsum_kernel(const float* __restrict__ part, int nparts, int ld
 // blockDim = (ld/8) * rows_per_iter so a thread always owns the same 8 columns.
 __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ ds,
                           const float* __restrict__ w2, __nv_bfloat16* __restrict__ dh, float* __restrict__ dw2p,
-                          int rows, int h, int ld, int rows_per_iter) {
+                          int rows, int h, int ld, int rows_per_iter, long long lo_off) {
   griddep_sync();
   extern __shared__ float sh_acc[];  // [rows_per_iter][ld]
   const int groups = ld / 8;
@@ -397,15 +404,17 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
   // 4 independent rows in flight per thread (memory-level parallelism: this kernel is HBM-bound)
   const long long stride = (long long)gridDim.x * rows_per_iter;
   for (long long r0 = (long long)blockIdx.x * rows_per_iter + rl; r0 < rows; r0 += 4 * stride) {
-    uint4 av[4];
+    uint4 av[4], al[4];
     float dv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long r = r0 + u * stride;
       av[u] = make_uint4(0, 0, 0, 0);
+      al[u] = make_uint4(0, 0, 0, 0);
       dv[u] = 0.f;
       if (r < rows) {
         av[u] = __ldg(reinterpret_cast<const uint4*>(a + r * ld) + g);
+        if (lo_off) al[u] = __ldg(reinterpret_cast<const uint4*>(a + lo_off + r * ld) + g);
         dv[u] = ds ? ds[r] : 1.f;
       }
     }
@@ -415,17 +424,17 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
       if (r >= rows) break;
       const float d = dv[u];
       const uint32_t w4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+      const uint32_t l4[4] = {al[u].x, al[u].y, al[u].z, al[u].w};
       float o[8];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float lo = bf16_lo(w4[q]), hi = bf16_hi(w4[q]);
+        const float lo = bf16_lo(w4[q]), hi = bf16_hi(w4[q]);   // the sign of the hi part is the sign of the value
         o[2 * q] = lo > 0.f ? d * w[2 * q] : 0.f;
         o[2 * q + 1] = hi > 0.f ? d * w[2 * q + 1] : 0.f;
-        acc[2 * q] = fmaf(d, lo, acc[2 * q]);
-        acc[2 * q + 1] = fmaf(d, hi, acc[2 * q + 1]);
+        acc[2 * q] = fmaf(d, lo + bf16_lo(l4[q]), acc[2 * q]);
+        acc[2 * q + 1] = fmaf(d, hi + bf16_hi(l4[q]), acc[2 * q + 1]);
       }
-      reinterpret_cast<uint4*>(dh + r * ld)[g] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                             pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      store_bf16x8(dh + r * ld + g * 8, o, lo_off);
     }
   }
   if (dw2p == nullptr) return;
@@ -448,7 +457,7 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
 __global__ void xhat_kernel(const __nv_bfloat16* __restrict__ xr, const __nv_bfloat16* __restrict__ xf,
                             __nv_bfloat16* __restrict__ out, int rows, int x, int ld, int mode,
                             const float* __restrict__ rnd, const float* __restrict__ stats,
-                            unsigned long long seed, unsigned long long stream_id) {
+                            unsigned long long seed, unsigned long long stream_id, float dra_c, long long lo_off) {
   griddep_sync();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
@@ -460,33 +469,26 @@ __global__ void xhat_kernel(const __nv_bfloat16* __restrict__ xr, const __nv_bfl
     const double n = stats[2], s1 = stats[0], s2 = stats[1];
     sd = float(sqrt(fmax((s2 - s1 * s1 / n) / (n - 1.0), 0.0)));   // images.std(): unbiased, global
   }
+  sd *= dra_c;                                          // C of src/dra_gan.py:174,205
   for (int c0 = 0; c0 < ld; c0 += 8) {
-    const uint4 a = *reinterpret_cast<const uint4*>(xr + (long long)r * ld + c0);
-    uint4 b = make_uint4(0, 0, 0, 0);
-    if (mode == 0) b = *reinterpret_cast<const uint4*>(xf + (long long)r * ld + c0);
-    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
-    float v[8];
+    float va[8], vb[8], v[8];
+    load_bf16x8(xr + (long long)r * ld + c0, va, lo_off);
+    if (mode == 0) load_bf16x8(xf + (long long)r * ld + c0, vb, lo_off);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        const int c = c0 + 2 * q + hlf;
-        const float xa = hlf ? bf16_hi(ua[q]) : bf16_lo(ua[q]);
-        float o = (c == x && mode == 1) ? 1.f : 0.f;   // DRAGAN xhat rows carry a true backward path -> ones column
-        if (c < x) {
-          if (mode == 0) {
-            const float xb = hlf ? bf16_hi(ub[q]) : bf16_lo(ub[q]);
-            o = e * xa + (1.f - e) * xb;
-          } else {
-            const float u = rnd ? rnd[rows + (long long)r * x + c] : curand_uniform(&st);
-            o = e * xa + (1.f - e) * (xa + sd * u);
-          }
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float o = (c == x && mode == 1) ? 1.f : 0.f;   // DRAGAN xhat rows carry a true backward path -> ones column
+      if (c < x) {
+        if (mode == 0) {
+          o = e * va[j] + (1.f - e) * vb[j];
+        } else {
+          const float u = rnd ? rnd[rows + (long long)r * x + c] : curand_uniform(&st);
+          o = e * va[j] + (1.f - e) * (va[j] + sd * u);
         }
-        v[2 * q + hlf] = o;
       }
+      v[j] = o;
     }
-    *reinterpret_cast<uint4*>(out + (long long)r * ld + c0) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    store_bf16x8(out + (long long)r * ld + c0, v, lo_off);
   }
 }
 
@@ -570,17 +572,17 @@ __global__ void __launch_bounds__(kLossThreads) gp_final_kernel(const GpParams p
 }
 
 // rows[r, :] *= coef[r]  (bf16, in place)
-__global__ void scale_rows_kernel(__nv_bfloat16* __restrict__ a, const float* __restrict__ coef, int rows, int ld) {
+__global__ void scale_rows_kernel(__nv_bfloat16* __restrict__ a, const float* __restrict__ coef, int rows, int ld, long long lo_off) {
   griddep_sync();
   const int groups = ld / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)rows * groups;
        i += (long long)gridDim.x * blockDim.x) {
     const float c = coef[i / groups];
-    uint4 v = reinterpret_cast<uint4*>(a)[i];
-    uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    float v[8];
+    load_bf16x8(a + i * 8, v, lo_off);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) u[q] = pack_bf16x2(bf16_lo(u[q]) * c, bf16_hi(u[q]) * c);
-    reinterpret_cast<uint4*>(a)[i] = make_uint4(u[0], u[1], u[2], u[3]);
+    for (int j = 0; j < 8; ++j) v[j] *= c;
+    store_bf16x8(a + i * 8, v, lo_off);
   }
 }
 
@@ -591,7 +593,7 @@ __global__ void scale_rows_kernel(__nv_bfloat16* __restrict__ a, const float* __
 __global__ void vae_reparam_kernel(const float* __restrict__ mulv, int ldm, const float* __restrict__ eps_in,
                                    float* __restrict__ eps_out, __nv_bfloat16* __restrict__ zb, int ldz, int rows,
                                    int z, unsigned long long seed, unsigned long long stream_id,
-                                   double* __restrict__ part) {
+                                   double* __restrict__ part, long long lo_off) {
   griddep_sync();
   __shared__ double sh[256 / 32];
   double kl = 0.0;
@@ -614,8 +616,7 @@ __global__ void vae_reparam_kernel(const float* __restrict__ mulv, int ldm, cons
         }
         v[j] = o;
       }
-      *reinterpret_cast<uint4*>(zb + (long long)r * ldz + c0) =
-          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      store_bf16x8(zb + (long long)r * ldz + c0, v, lo_off);
     }
   }
   kl = block_sum<256>(kl, sh);
@@ -625,7 +626,7 @@ __global__ void vae_reparam_kernel(const float* __restrict__ mulv, int ldm, cons
 // dmu = mu + dz ; dlv = 0.5(e^lv - 1) + dz * eps * e^{lv/2} * 0.5  -> bf16 [rows, ld]: [dmu | dlv | 0]
 __global__ void vae_dlatent_kernel(const float* __restrict__ mulv, int ldm, const float* __restrict__ dz, int lddz,
                                    const float* __restrict__ eps, __nv_bfloat16* __restrict__ out, int ld, int rows,
-                                   int z, float scale) {
+                                   int z, float scale, long long lo_off) {
   griddep_sync();
   const long long i = blockIdx.x * 256ll + threadIdx.x;
   if (i >= (long long)rows * ld) return;
@@ -638,7 +639,9 @@ __global__ void vae_dlatent_kernel(const float* __restrict__ mulv, int ldm, cons
     const float lv = mulv[(long long)r * ldm + z + k];
     o = scale * (0.5f * (expf(lv) - 1.f) + dz[(long long)r * lddz + k] * eps[(long long)r * z + k] * expf(0.5f * lv) * 0.5f);
   }
-  out[i] = __float2bfloat16_rn(o);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+  out[i] = hi;
+  if (lo_off) out[i + lo_off] = __float2bfloat16_rn(o - __bfloat162float(hi));
 }
 
 // recon = sum over rows of the per-row slots (sum (x-out)^2); losses[0] = recon, [1] = kl
@@ -673,7 +676,7 @@ __global__ void __launch_bounds__(kLossThreads) info_loss_kernel(const float* __
                                                                   const float* __restrict__ noise, int ldn, int zd, int nd,
                                                                   int nc, int rows, float inv_b,
                                                                   __nv_bfloat16* __restrict__ dinf, int ldo,
-                                                                  double* __restrict__ part) {
+                                                                  double* __restrict__ part, long long lo_off) {
   griddep_sync();
   __shared__ double sh[kLossThreads / 32];
   double ce = 0, mse = 0;
@@ -690,13 +693,18 @@ __global__ void __launch_bounds__(kLossThreads) info_loss_kernel(const float* __
     const float lse = m + logf(se);
     ce += lse - v[tgt];
     __nv_bfloat16* o = dinf + (long long)r * ldo;
-    for (int c = 0; c < nd; ++c) o[c] = __float2bfloat16_rn((expf(v[c] - lse) - (c == tgt ? 1.f : 0.f)) * inv_b);
+    auto put = [&](int c, float val) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+      o[c] = hi;
+      if (lo_off) o[c + lo_off] = __float2bfloat16_rn(val - __bfloat162float(hi));
+    };
+    for (int c = 0; c < nd; ++c) put(c, (expf(v[c] - lse) - (c == tgt ? 1.f : 0.f)) * inv_b);
     for (int c = 0; c < nc; ++c) {
       const float d = v[nd + c] - t[zd + nd + c];
       mse += (double)d * d;
-      o[nd + c] = __float2bfloat16_rn(2.f * d * inv_b / nc);
+      put(nd + c, 2.f * d * inv_b / nc);
     }
-    for (int c = nd + nc; c < ldo; ++c) o[c] = __float2bfloat16_rn(0.f);
+    for (int c = nd + nc; c < ldo; ++c) put(c, 0.f);
   }
   ce = block_sum<kLossThreads>(ce, sh);
   mse = block_sum<kLossThreads>(mse, sh);
@@ -747,26 +755,19 @@ __global__ void began_control_kernel(float* __restrict__ state, float gamma, flo
 // reaches G(z) through D (T) and directly (-DRg)   (src/be_gan.py:256)
 __global__ void began_da2_kernel(const __nv_bfloat16* __restrict__ T, const __nv_bfloat16* __restrict__ DRg,
                                  const __nv_bfloat16* __restrict__ fake, __nv_bfloat16* __restrict__ out, int rows, int x,
-                                 int ld) {
+                                 int ld, long long lo_off) {
   griddep_sync();
   const int groups = ld / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)rows * groups;
        i += (long long)gridDim.x * blockDim.x) {
     const int c0 = int(i % groups) * 8;
-    const uint4 t = reinterpret_cast<const uint4*>(T)[i], d = reinterpret_cast<const uint4*>(DRg)[i],
-                f = reinterpret_cast<const uint4*>(fake)[i];
-    const uint32_t tt[4] = {t.x, t.y, t.z, t.w}, dd[4] = {d.x, d.y, d.z, d.w}, ff[4] = {f.x, f.y, f.z, f.w};
-    uint32_t o[4];
+    float t[8], d[8], f[8], o[8];
+    load_bf16x8(T + i * 8, t, lo_off);
+    load_bf16x8(DRg + i * 8, d, lo_off);
+    load_bf16x8(fake + i * 8, f, lo_off);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float f0 = bf16_lo(ff[q]), f1 = bf16_hi(ff[q]);
-      float v0 = (bf16_lo(tt[q]) - bf16_lo(dd[q])) * f0 * (1.f - f0);
-      float v1 = (bf16_hi(tt[q]) - bf16_hi(dd[q])) * f1 * (1.f - f1);
-      if (c0 + 2 * q >= x) v0 = 0.f;
-      if (c0 + 2 * q + 1 >= x) v1 = 0.f;
-      o[q] = pack_bf16x2(v0, v1);
-    }
-    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int j = 0; j < 8; ++j) o[j] = (c0 + j < x) ? (t[j] - d[j]) * f[j] * (1.f - f[j]) : 0.f;
+    store_bf16x8(out + i * 8, o, lo_off);
   }
 }
 
@@ -835,6 +836,7 @@ struct AdamParams {
   int update;                                        // 0: only refresh shadows
   const float* lr_scale;                             // nullable device scalar multiplying lr (BEGAN's plateau scheduler)
   AdamSeg seg[6]; int nseg;
+  long long lo_off;                                  // split mode: operand copies also get their residual plane
   // lazy gradients (gm_gan_set_lazy_grads): the flat gradient has not been formed yet; the
   // update gathers each element from the split-K partials itself and stores it to gout
   int gather; float* gout; GradSegs gsegs;
@@ -865,6 +867,11 @@ __device__ __forceinline__ void adam_element(const AdamParams& a, int i, float g
       const __nv_bfloat16 b = __float2bfloat16_rn(p);
       if (s.shadow) s.shadow[(long long)r * s.ld_s + c] = b;
       if (s.shadow_t) s.shadow_t[(long long)c * s.ld_t + r] = b;
+      if (a.lo_off) {
+        const __nv_bfloat16 bl = __float2bfloat16_rn(p - __bfloat162float(b));
+        if (s.shadow) s.shadow[(long long)r * s.ld_s + c + a.lo_off] = bl;
+        if (s.shadow_t) s.shadow_t[(long long)c * s.ld_t + r + a.lo_off] = bl;
+      }
     }
     return;
   }
@@ -898,7 +905,7 @@ constexpr int kCommMaxWorld = 16;
 constexpr int kCommChunk = 1024;
 constexpr int kCommStatVals = 4;
 struct CommDev {
-  float* x[kCommMaxWorld];                    // exchange buffers [2][nfloats] of every rank (own = local pointer)
+  float* x[kCommMaxWorld];                    // exchange regions [2][kCommMaxWorld][nfloats] of every rank (own = local pointer)
   unsigned long long* f[kCommMaxWorld];       // flag arrays [2][kCommMaxWorld][nblocks] of every rank
   int rank, world, nblocks;
   long long nfloats;
@@ -972,22 +979,39 @@ __global__ void __launch_bounds__(256) stats_exchange_kernel(double* __restrict_
     for (int v = 0; v < nvals; ++v) part[(long long)i * stride + v] = (i == 0) ? tot[v] : 0.0;
 }
 
+// PUSH protocol, 128-bit accesses: every thread owns 4 consecutive gradient elements (one float4).  It forms them
+// (split-K gather or the flat buffer), keeps them in registers and WRITES them into slot [parity][own rank] of every
+// peer's exchange region (posted NVLink stores, no round trip); after a system fence the block raises "chunk b of
+// step seq" in every peer's flag array; it then waits for its peers' flags on LOCAL memory and reads their chunks from
+// its OWN region (local HBM / L2, not over the link), sums in rank order - bitwise identical on every rank - and
+// applies Adam.  Exchange region of a rank: [2 parities][kCommMaxWorld source ranks][nfloats].
+__device__ __forceinline__ void st_relaxed_sys_v4(float* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(const AdamParams a, const CommDev cm) {
   griddep_sync();
   const int b = blockIdx.x, tid = threadIdx.x;
   const int par = int(cm.seq & 1ull);
-  const int base = b * kCommChunk;
-  float* mine = cm.x[cm.rank] + (long long)par * cm.nfloats;
+  const int i0 = b * kCommChunk + tid * 4;            // this thread's 4 elements (nfloats is a multiple of the chunk)
+  float g[4];
 #pragma unroll
-  for (int k = 0; k < kCommChunk / 256; ++k) {
-    const int i = base + k * 256 + tid;
-    if (i < a.total) mine[i] = a.gather ? gather_grad(a.gsegs, i) : a.g[i];
+  for (int j = 0; j < 4; ++j) {
+    const int i = i0 + j;
+    g[j] = i < a.total ? (a.gather ? gather_grad(a.gsegs, i) : a.g[i]) : 0.f;
   }
+  const long long slot = ((long long)par * kCommMaxWorld + cm.rank) * cm.nfloats + i0;
+  const float4 mine = make_float4(g[0], g[1], g[2], g[3]);
+  for (int r = 0; r < cm.world; ++r)
+    if (r != cm.rank) st_relaxed_sys_v4(cm.x[r] + slot, mine);
   __threadfence_system();
   __syncthreads();
-  if (tid < cm.world && tid != cm.rank)
-    st_release_sys(cm.f[tid] + ((long long)par * kCommMaxWorld + cm.rank) * cm.nblocks + b, cm.seq);
   if (tid < cm.world && tid != cm.rank) {
+    st_release_sys(cm.f[tid] + ((long long)par * kCommMaxWorld + cm.rank) * cm.nblocks + b, cm.seq);
     const unsigned long long* flag = cm.f[cm.rank] + ((long long)par * kCommMaxWorld + tid) * cm.nblocks + b;
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < cm.seq) {
@@ -995,17 +1019,19 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const AdamParams a,
     }
   }
   __syncthreads();
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < cm.world; ++r) {
+    const float4 v = (r == cm.rank) ? mine
+                                    : ld_relaxed_sys_v4(cm.x[cm.rank] + ((long long)par * kCommMaxWorld + r) * cm.nfloats + i0);
+    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+  }
+  const float out[4] = {sum.x, sum.y, sum.z, sum.w};
 #pragma unroll
-  for (int k = 0; k < kCommChunk / 256; ++k) {
-    const int i = base + k * 256 + tid;
-    if (i >= a.total) continue;
-    float g = 0.f;
-    for (int r = 0; r < cm.world; ++r) {
-      const float* src = cm.x[r] + (long long)par * cm.nfloats + i;
-      g += (r == cm.rank) ? mine[i] : ld_relaxed_sys(src);
-    }
-    a.gout[i] = g;
-    adam_element(a, i, g);
+  for (int j = 0; j < 4; ++j) {
+    const int i = i0 + j;
+    if (i >= a.total) break;
+    a.gout[i] = out[j];
+    adam_element(a, i, out[j]);
   }
 }
 

@@ -280,4 +280,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// ---- split-bf16 operands (gm_prec GM_PREC_SPLIT): a value v is carried as hi = bf16(v) and lo = bf16(v - hi)
+// (16 mantissa bits together); every bf16 buffer of an engine lives in one arena whose second half holds the
+// lo planes, so the lo twin of any bf16 pointer p is p + lo_off (elements).  lo_off == 0: plain bf16 mode.
+__device__ __forceinline__ uint32_t pack_bf16x2_residual(float a, float b, uint32_t hi_pair) {
+  return pack_bf16x2(a - bf16_lo(hi_pair), b - bf16_hi(hi_pair));
+}
+// 8 consecutive values -> 16 bytes of bf16 at dst (+ their residuals at dst + lo_off)
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float (&v)[8], long long lo_off) {
+  const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]), h2 = pack_bf16x2(v[4], v[5]), h3 = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(h0, h1, h2, h3);
+  if (lo_off)
+    *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(pack_bf16x2_residual(v[0], v[1], h0), pack_bf16x2_residual(v[2], v[3], h1),
+                                                         pack_bf16x2_residual(v[4], v[5], h2), pack_bf16x2_residual(v[6], v[7], h3));
+}
+// 16 bytes of bf16 at src (+ residuals at src + lo_off) -> 8 floats
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* src, float (&v)[8], long long lo_off) {
+  const uint4 a = *reinterpret_cast<const uint4*>(src);
+  const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { v[2 * q] = bf16_lo(u[q]); v[2 * q + 1] = bf16_hi(u[q]); }
+  if (lo_off) {
+    const uint4 b = *reinterpret_cast<const uint4*>(src + lo_off);
+    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { v[2 * q] += bf16_lo(w[q]); v[2 * q + 1] += bf16_hi(w[q]); }
+  }
+}
+
 }  // namespace gm

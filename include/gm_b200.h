@@ -269,7 +269,9 @@ long long gm_launch_count(gm_ctx* ctx, int reset);
 /* measurement aid (bench.py roofline): record CUDA events around every tensor-core
  * GEMM launch on its launch stream; gm_prof_collect synchronises and returns, per
  * kernel instantiation (4 slots), total ms, algorithmic FLOPs and launch count. */
-int gm_prof_enable(gm_ctx* ctx, int on);
+int gm_prof_enable(gm_ctx* ctx, int on);   /* 0 off, 1 GEMM launches by kind (gm_prof_collect), 2 every launch by name (gm_prof_report) */
+/* level-2 report: synchronises and writes "name,launches,total_ms" lines (in first-launch order) into buf; returns bytes needed */
+int gm_prof_report(gm_ctx* ctx, char* buf, int buflen);
 /* debug aid: CTA 0 of following gm_gemm_bf16 launches writes per-tile phase durations
  * (SM clocks) into dbg_dev (128 int64); pass NULL to stop. */
 int gm_debug_phase_buffer(gm_ctx* ctx, long long* dbg_dev);
