@@ -25,9 +25,7 @@ class DRAGANTrainer(GANTrainerBase):
 
     @builtin_step
     def train_D(self, images, LAMBDA=10, K=1, C=1):
-        if (LAMBDA, K, C) != (10, 1, 1):
-            raise ValueError("the fused penalty is built for the reference defaults LAMBDA=10, K=1, C=1")
-        return super().train_D(images)
+        return super().train_D(images, gp_lambda=float(LAMBDA), gp_k=float(K), dra_c=float(C))
 
     def _draw_aux(self, images):
         gen = getattr(self, "_noise_gen", None)

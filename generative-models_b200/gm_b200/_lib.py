@@ -39,6 +39,11 @@ class GemmDesc(C.Structure):
                 ("transpose", C.c_int)]
 
 
+class LossConsts(C.Structure):
+    _fields_ = [("gp_lambda", C.c_float), ("gp_k", C.c_float), ("dra_c", C.c_float), ("ls_a", C.c_float), ("ls_b", C.c_float),
+                ("ls_c", C.c_float)]
+
+
 class VaeDesc(C.Structure):
     _fields_ = [("image_size", C.c_int), ("hidden_dim", C.c_int), ("z_dim", C.c_int), ("max_batch", C.c_int),
                 ("dtype_mode", C.c_int)]
@@ -118,6 +123,7 @@ def lib():
     L.gm_vae_apply.argtypes = [vp, C.POINTER(AdamHP), i, vp]
     L.gm_vae_forward.argtypes = [vp, vp, i, i, vp, u64, u64, vp, vp, vp, vp]
     L.gm_vae_decode.argtypes = [vp, vp, i, vp, vp]
+    L.gm_gan_set_loss_consts.argtypes = [vp, C.POINTER(LossConsts)]
     L.gm_gan_set_sampler.argtypes = [vp, C.c_longlong, u64]
     L.gm_sampler_indices_host.argtypes = [C.c_longlong, u64, u64, u64, i, vp]
     L.gm_gan_sample_indices.argtypes = [vp, i, u64, vp, vp]

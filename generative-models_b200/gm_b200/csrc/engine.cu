@@ -126,6 +126,9 @@ static cudaError_t launch_pdl(const char* name, void (*kern)(KArgs...), dim3 gri
     }
     ~Scope() { if (on) { cudaEventRecord(r.e1, s); g_prof_all_recs.push_back(r); } }
   } scope(name, s);
+  // GM_PDL_SKIP=name1,name2: launch those kernels WITHOUT the programmatic-serialization attribute (tuning / bisecting)
+  static const char* skip = getenv("GM_PDL_SKIP");
+  const bool pdl = g_pdl && !(skip && strstr(skip, name) != nullptr);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid;
@@ -136,7 +139,7 @@ static cudaError_t launch_pdl(const char* name, void (*kern)(KArgs...), dim3 gri
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
@@ -168,7 +171,8 @@ static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
     at[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (g_pdl) {
+  static const char* skip_gemm = getenv("GM_PDL_SKIP");
+  if (g_pdl && !(skip_gemm && strstr(skip_gemm, "gemm") != nullptr)) {
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -655,6 +659,7 @@ struct gm_gan {
   int last_rows = 0;
   int region_rows = 0;   // rows per region of Xall/Aall/DHall (3 regions)
   gm_comm* comm = nullptr;   // attached communicator: batch statistics run over the global batch
+  gm_loss_consts lc = {10.f, 1.f, 1.f, 0.f, 1.f, 1.f};   // reference defaults: src/w_gp_gan.py:177, src/dra_gan.py:174, src/ls_gan.py:173,197
   long long pool_n = 0;      // on-device batch sampling over a resident pool of pool_n images (gm_gan_set_sampler)
   uint64_t pool_seed = 0;
   // lazy gradients: *_grad leaves the split-K partials, gm_gan_apply gathers + updates in one kernel
@@ -793,9 +798,9 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
     g->lo = g->arena.lo_off;
   }
 #undef TRY
-  if (g->H + 1 > 448 || g->Z + 1 > 64) {
+  if (g->H + 1 > 448 || g->Z + 1 > 448) {
     gm_gan_destroy(g);
-    return fail(c, GM_ERR_UNSUPPORTED, "hidden_dim <= 447 and z_dim <= 63 in this build (got %d, %d)", d->hidden_dim, d->z_dim);
+    return fail(c, GM_ERR_UNSUPPORTED, "hidden_dim <= 447 and generator input width <= 447 in this build (got %d, %d)", d->hidden_dim, d->z_dim);
   }
   *out = g;
   return GM_OK;
@@ -961,7 +966,7 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   if ((rc = plan_gemm(c, &sp.dw1g, 1, H, Z + 1, B, g->DHg, HP, g->Zb, ZP, Z + 1, g->max_splits))) return rc;
   {
     GemmParams& p = sp.dw1g.p;
-    p.epi = EPI_F32; p.part = g->PG1; p.ldp = 64; p.part_stride = (long long)H * 64; p.transpose = 0;
+    p.epi = EPI_F32; p.part = g->PG1; p.ldp = rup(Z + 1, 64); p.part_stride = (long long)H * p.ldp; p.transpose = 0;
     sp.dw1g.flops = 2.0 * H * Z * B;
   }
   if (g->d.variant == GM_BEGAN) {
@@ -1067,6 +1072,7 @@ static void launch_loss(gm_gan* g, int B, int g_step, float inv_b, cudaStream_t 
   lp.d_out = g->scores + (g_step ? B : 0);
   lp.loss = g->lossbuf;
   lp.fisher = g->fisher;
+  lp.ls_a = g->lc.ls_a; lp.ls_b = g->lc.ls_b; lp.ls_c = g->lc.ls_c;
   const int rows = g_step ? B : 2 * B;
   lp.nblk = cdiv(rows, kLossThreads) < g->loss_blocks ? cdiv(rows, kLossThreads) : g->loss_blocks;
   lp.partA = g->loss_part;
@@ -1233,7 +1239,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
       c->launches += 2;
     }
     launch_pdl("xhat_kernel", xhat_kernel, cdiv(B, 128), 128, 0, s, g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
-                                           mode, aux, g->stats, seed, 2 * step, 1.f, g->lo);
+                                           mode, aux, g->stats, seed, 2 * step, g->lc.dra_c, g->lo);
     c->launches++;
   }
   if ((rc = launch_plan(c, sp->d1_d, s))) return rc;
@@ -1253,7 +1259,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     gpp.slots_v = g->slots_v; gpp.nslots_v = 2 * cdiv(X, 208); gpp.slotv_ld = g->Bmax;
     gpp.b2 = g->par[GM_NET_D] + g->D.off_b2;
     gpp.rows = B; gpp.out_act = g->d.d_out_act;
-    gpp.lam = 10.f; gpp.K = 1.f; gpp.inv_b = inv_global_batch;
+    gpp.lam = g->lc.gp_lambda; gpp.K = g->lc.gp_k; gpp.inv_b = inv_global_batch;
     gpp.coef = g->coef; gpp.ds_gp = g->ds + 2 * B;
     gpp.part = g->gp_part; gpp.nblk = cdiv(B, kLossThreads) < c->num_sms * 2 ? cdiv(B, kLossThreads) : c->num_sms * 2;
     gpp.loss = g->lossbuf;
@@ -1517,6 +1523,14 @@ extern "C" int gm_gan_discriminate(gm_gan* g, const void* images, int img_fmt, i
 // On-device batch sampling: with a pool set (and gather_idx == NULL) gm_gan_d_grad reads row
 // perm_{seed,step}(r) of images_dev for batch row r - the first `batch` entries of a fresh pseudo-random
 // permutation of the pool per step, i.e. next(iter(DataLoader(shuffle=True))) (src/ns_gan.py:222-226).
+// Loss constants the reference passes as train_D / train_G keyword arguments: LAMBDA of the gradient penalty
+// (src/w_gp_gan.py:177; DRAGAN also K and C, src/dra_gan.py:174), LSGAN's targets a, b, c (src/ls_gan.py:173,197).
+extern "C" int gm_gan_set_loss_consts(gm_gan* g, const gm_loss_consts* lc) {
+  if (!g || !lc) return GM_ERR_ARG;
+  g->lc = *lc;
+  return GM_OK;
+}
+
 extern "C" int gm_gan_set_sampler(gm_gan* g, long long n_pool, uint64_t seed) {
   if (!g || n_pool < 0 || n_pool > 0x7FFFFFFFll) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_set_sampler: bad pool size") : GM_ERR_ARG;
   g->pool_n = n_pool; g->pool_seed = seed;

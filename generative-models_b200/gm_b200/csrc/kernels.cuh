@@ -202,6 +202,7 @@ struct LossParams {
   float* d_out;          // out (nullable): D output per row
   float* loss;           // out: [0] loss  [1] sum(ds) (= db2 grad)  [2..] variant scratch
   float* fisher;         // [0] LAMBDA  [1] RHO  (device state, V_FISHER only)
+  float ls_a, ls_b, ls_c;   // LSGAN targets: fake (a), real (b) in train_D, c in train_G (src/ls_gan.py:173,197)
   double* partA; double* partB; double* partR;   // per-block partials [nblk][4]
   int nblk;
   unsigned int* done;    // block-completion counter of PASS 2 (self-resetting): the last block finalises
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass_kernel(const LossParam
         case V_NS: case V_DRA: case V_RA: case V_INFO: l = -logf(d + kEps); g = -1.f / (d + kEps); break;
         case V_MM: l = logf((1.f - d) + kEps); g = -1.f / ((1.f - d) + kEps); break;
         case V_W: case V_WGP: case V_FISHER: l = -d; g = -1.f; break;
-        case V_LS: l = 0.5f * (d - 1.f) * (d - 1.f); g = d - 1.f; break;
+        case V_LS: l = 0.5f * (d - p.ls_c) * (d - p.ls_c); g = d - p.ls_c; break;
         case V_F_TV: { const float t = tanhf(d); l = -0.5f * t; g = -0.5f * (1.f - t * t); } break;
         case V_F_FKL: { const float e = expf(d - 1.f); l = -e; g = -e; } break;
         case V_F_RKL: l = 1.f + d; g = 1.f; break;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass_kernel(const LossParam
       switch (p.variant) {
         case V_NS: case V_MM: case V_DRA: case V_INFO: l = -logf(d + kEps); g = -1.f / (d + kEps); break;
         case V_W: case V_WGP: l = -d; g = -1.f; break;
-        case V_LS: l = 0.5f * (d - 1.f) * (d - 1.f); g = d - 1.f; break;
+        case V_LS: l = 0.5f * (d - p.ls_b) * (d - p.ls_b); g = d - p.ls_b; break;
         case V_RA: { const float q = 1.f / (1.f + expf(-(d - mg)));
                      l = -0.5f * logf(q + kEps); g = -0.5f * q * (1.f - q) / (q + kEps); } break;
         case V_FISHER: l = -d; g = -(1.f - c_f * d); break;   // lambda/rho terms added once in loss_final
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_pass_kernel(const LossParam
       switch (p.variant) {
         case V_NS: case V_MM: case V_DRA: case V_INFO: l = -logf((1.f - d) + kEps); g = 1.f / ((1.f - d) + kEps); break;
         case V_W: case V_WGP: l = d; g = 1.f; break;
-        case V_LS: l = 0.5f * d * d; g = d; break;
+        case V_LS: l = 0.5f * (d - p.ls_a) * (d - p.ls_a); g = d - p.ls_a; break;
         case V_RA: { const float q = 1.f / (1.f + expf(-(1.f - d)));
                      l = -0.5f * logf(q + kEps); g = 0.5f * (gq_mean + q * (1.f - q) / (q + kEps)); } break;
         case V_FISHER: l = d; g = 1.f + c_f * d; break;

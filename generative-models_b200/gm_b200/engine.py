@@ -128,6 +128,12 @@ class GanEngine:
         check(self.h, lib().gm_gan_g_grad_staged(self.g, batch, inv, C.c_void_p(self.loss_buf.data_ptr() + 4), _stream()))
         return self.loss_buf[1]
 
+    def set_loss_consts(self, gp_lambda=10.0, gp_k=1.0, dra_c=1.0, ls_a=0.0, ls_b=1.0, ls_c=1.0):
+        """LAMBDA / K / C of the gradient penalties, a / b / c of LSGAN (the reference's train_D / train_G kwargs)."""
+        lc = _lib.LossConsts(gp_lambda, gp_k, dra_c, ls_a, ls_b, ls_c)
+        check(self.h, lib().gm_gan_set_loss_consts(self.g, C.byref(lc)))
+        self.loss_consts = dict(gp_lambda=gp_lambda, gp_k=gp_k, dra_c=dra_c, ls_a=ls_a, ls_b=ls_b, ls_c=ls_c)
+
     def set_sampler(self, n_pool, seed=0):
         """On-device batch sampling: d_grad(images=pool, gather_idx=None, batch=B, step=s) then reads the first B
         rows of a fresh pseudo-random permutation of the pool per step (src/ns_gan.py:222-226)."""

@@ -330,6 +330,16 @@ class GANTrainerBase:
     def _after_engine_created(self, eng):
         pass
 
+    # loss constants the reference passes as train_D / train_G kwargs (LAMBDA, K, C; a, b, c): set the class / instance
+    # attribute `loss_consts` (e.g. dict(gp_lambda=5.0)) for the fused train() loop, or pass them to train_D / train_G
+    loss_consts = {}
+
+    def _set_consts(self, eng, **kw):
+        want = dict(self.loss_consts)
+        want.update(kw)
+        if getattr(eng, "loss_consts", None) != dict(dict(gp_lambda=10.0, gp_k=1.0, dra_c=1.0, ls_a=0.0, ls_b=1.0, ls_c=1.0), **want):
+            eng.set_loss_consts(**dict(dict(gp_lambda=10.0, gp_k=1.0, dra_c=1.0, ls_a=0.0, ls_b=1.0, ls_c=1.0), **want))
+
     def _draw_aux(self, images):
         """Extra random tensors train_D draws after the noise (WGAN-GP eps, DRAGAN delta/u)."""
         return None
@@ -503,6 +513,7 @@ class GANTrainerBase:
             batch = images.shape[0] if gather_idx is None else gather_idx.shape[0]
         eng = self._ensure_engine(batch)
         self._sync_once(eng)
+        self._set_consts(eng)
         world = getattr(self, "_world", 1)
         eng.set_lazy_grads(getattr(self, "_lazy", False))
         if getattr(self, "_comm", None) is not None and getattr(eng, "_comm_attached", None) is not self._comm:
@@ -529,6 +540,7 @@ class GANTrainerBase:
     def _fused_G(self, batch, hp, loss_out=None):
         eng = self._ensure_engine(batch)
         self._sync_once(eng)
+        self._set_consts(eng)
         noise = None if self._use_device_noise() else self.compute_noise(batch, self.model.z_dim)
         world = getattr(self, "_world", 1)
         loss = eng.g_grad(batch, noise=noise, inv_global_batch=par.inv_global_batch(batch, world), seed=self._philox_seed(),
@@ -551,12 +563,13 @@ class GANTrainerBase:
         eng.apply(net, hp)
 
     @builtin_step
-    def train_D(self, images):
+    def train_D(self, images, **consts):
         """Run 1 step of training for the discriminator (src/ns_gan.py:172-194): returns
         the loss; `.backward()` delivers the D gradients to model.D's parameters."""
         images = to_cuda(images)
         eng = self._ensure_engine(images.shape[0])
         eng.sync_if_stale()
+        self._set_consts(eng, **consts)
         eng.set_lazy_grads(False)       # .backward() reads the flat gradient: it must be formed by d_grad itself
         eng.set_sampler(0)
         noise = self.compute_noise(images.shape[0], self.model.z_dim)
@@ -565,11 +578,12 @@ class GANTrainerBase:
         return self._loss_tensor(D_NET, loss)
 
     @builtin_step
-    def train_G(self, images):
+    def train_G(self, images, **consts):
         """Run 1 step of training for the generator (src/ns_gan.py:196-216)."""
         batch = images.shape[0]
         eng = self._ensure_engine(batch)
         eng.sync_if_stale()
+        self._set_consts(eng, **consts)
         eng.set_lazy_grads(False)
         noise = self.compute_noise(batch, self.model.z_dim)
         loss = eng.g_grad(batch, noise=noise.float().contiguous(), seed=self._seed, step=self._step)

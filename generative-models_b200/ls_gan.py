@@ -23,15 +23,11 @@ class LSGANTrainer(GANTrainerBase):
 
     @builtin_step
     def train_D(self, images, a=0, b=1):
-        if (a, b) != (0, 1):
-            raise ValueError("the fused LSGAN loss is built for the reference defaults a=0, b=1")
-        return super().train_D(images)
+        return super().train_D(images, ls_a=float(a), ls_b=float(b))
 
     @builtin_step
     def train_G(self, images, c=1):
-        if c != 1:
-            raise ValueError("the fused LSGAN loss is built for the reference default c=1")
-        return super().train_G(images)
+        return super().train_G(images, ls_c=float(c))
 
 
 if __name__ == "__main__":

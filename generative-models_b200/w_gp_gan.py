@@ -26,9 +26,7 @@ class WGPGANTrainer(GANTrainerBase):
 
     @builtin_step
     def train_D(self, images, LAMBDA=10):
-        if LAMBDA != 10:
-            raise ValueError("the fused penalty is built for the reference default LAMBDA=10")
-        return super().train_D(images)
+        return super().train_D(images, gp_lambda=float(LAMBDA))
 
     def _draw_aux(self, images):
         return to_cuda(torch.rand(images.shape[0], 1, generator=getattr(self, "_noise_gen", None))).reshape(-1).contiguous()     # src/w_gp_gan.py:197

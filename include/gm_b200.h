@@ -171,6 +171,11 @@ int gm_gan_apply_allreduce(gm_gan* gan, int net, const gm_adam_hp* hp, int step,
  * comm == NULL detaches (per-rank statistics). */
 int gm_gan_attach_comm(gm_gan* gan, gm_comm* comm);
 
+/* Loss constants the reference passes as train_D / train_G keyword arguments (defaults = the reference's):
+ * gradient-penalty LAMBDA (src/w_gp_gan.py:177), DRAGAN's K and C (src/dra_gan.py:174), LSGAN's a, b, c
+ * (src/ls_gan.py:173,197).  Takes effect from the next gm_gan_d_grad / gm_gan_g_grad. */
+typedef struct { float gp_lambda, gp_k, dra_c, ls_a, ls_b, ls_c; } gm_loss_consts;
+int gm_gan_set_loss_consts(gm_gan* gan, const gm_loss_consts* consts);
 /* On-device batch sampling — replaces `next(iter(DataLoader(shuffle=True)))` (src/ns_gan.py:222-226): with a
  * resident pool of n_pool images (images_dev of gm_gan_d_grad) and gather_idx_dev == NULL, batch row r of step
  * `step` reads pool row perm_{seed,step}(r), perm a pseudo-random permutation of [0, n_pool) drawn per step
