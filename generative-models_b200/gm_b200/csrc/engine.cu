@@ -127,8 +127,10 @@ static cudaError_t launch_pdl(const char* name, void (*kern)(KArgs...), dim3 gri
     ~Scope() { if (on) { cudaEventRecord(r.e1, s); g_prof_all_recs.push_back(r); } }
   } scope(name, s);
   // GM_PDL_SKIP=name1,name2: launch those kernels WITHOUT the programmatic-serialization attribute (tuning / bisecting)
+  // xhat_kernel never takes the attribute: launched early behind the generator's output GEMM its CTAs pile up on the
+  // first SMs that GEMM frees and the 40 us kernel turns into 700 us (profiles/r2_pdl_bisect.md)
   static const char* skip = getenv("GM_PDL_SKIP");
-  const bool pdl = g_pdl && !(skip && strstr(skip, name) != nullptr);
+  const bool pdl = g_pdl && !(skip && strstr(skip, name) != nullptr) && strcmp(name, "xhat_kernel") != 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid;
@@ -1238,7 +1240,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
       launch_pdl("moments_final_kernel", moments_final_kernel, 1, 256, 0, s, g->mom_part, c->num_sms * 2, float(double(B) * X * stat_world(g)), g->stats);
       c->launches += 2;
     }
-    launch_pdl("xhat_kernel", xhat_kernel, cdiv(B, 128), 128, 0, s, g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
+    launch_pdl("xhat_kernel", xhat_kernel, c->num_sms * 8, 256, 0, s, g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
                                            mode, aux, g->stats, seed, 2 * step, g->lc.dra_c, g->lo);
     c->launches++;
   }
@@ -1565,6 +1567,22 @@ extern "C" int gm_gan_debug_noise(gm_gan* g, int batch, uint64_t seed, uint64_t 
   const long long tot = (long long)batch * g->Z;
   launch_pdl("bf16_rows_to_f32_kernel", bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->Zb, g->ZP, out_dev, batch, g->Z, g->lo);
   g->ctx->launches += 2;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+// debug / test aid: an internal bf16 activation buffer as fp32 (hi + lo in split mode), out_dev [rows, cols];
+// which: 0 Zb, 1 Hg, 2 Xall, 3 Aall, 4 DHall, 5 DA2, 6 DHg; row0 = first row
+extern "C" int gm_gan_debug_read(gm_gan* g, int which, int row0, int rows, int cols, float* out_dev, gm_stream stream) {
+  if (!g || !out_dev || rows <= 0 || cols <= 0 || row0 < 0) return GM_ERR_ARG;
+  const int plane = which / 16;   // 0: hi + lo, 1: hi plane only, 2: lo plane only
+  which %= 16;
+  const __nv_bfloat16* src[7] = {g->Zb, g->Hg, g->Xall, g->Aall, g->DHall, g->DA2, g->DHg};
+  const int ld[7] = {g->ZP, g->HP, g->XP, g->HP, g->HP, g->XP, g->HP};
+  if (which < 0 || which > 6 || cols > ld[which]) return fail(g->ctx, GM_ERR_ARG, "gm_gan_debug_read: bad buffer / extent");
+  const long long tot = (long long)rows * cols;
+  launch_pdl("bf16_rows_to_f32_kernel", bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream),
+             src[which] + size_t(row0) * ld[which] + (plane == 2 ? g->lo : 0), ld[which], out_dev, rows, cols, plane == 0 ? g->lo : 0ll);
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
 }

@@ -144,6 +144,14 @@ class GanEngine:
         check(self.h, lib().gm_gan_sample_indices(self.g, batch, int(step), _ptr(out), _stream()))
         return out
 
+    BUFFERS = {"Zb": 0, "Hg": 1, "Xall": 2, "Aall": 3, "DHall": 4, "DA2": 5, "DHg": 6}
+
+    def debug_read(self, which, row0, rows, cols, plane=0):
+        """An internal bf16 activation buffer as fp32 [rows, cols] (plane 0: hi + lo in split mode, 1: hi, 2: lo); tests only."""
+        out = torch.empty(rows, cols, device=self.device, dtype=torch.float32)
+        check(self.h, lib().gm_gan_debug_read(self.g, self.BUFFERS[which] + 16 * plane, row0, rows, cols, _ptr(out), _stream()))
+        return out
+
     def debug_noise(self, batch, seed, step, g_step=False):
         """The on-device Philox noise of (seed, step) as the bf16 operand values, [batch, z] fp32."""
         out = torch.empty(batch, self.z_dim, device=self.device, dtype=torch.float32)

@@ -190,6 +190,10 @@ int gm_gan_sample_indices(gm_gan* gan, int batch, uint64_t step, int* idx_dev, g
  * as the bf16-rounded operand values, out_dev [batch, z] fp32 (tests). */
 int gm_gan_debug_noise(gm_gan* gan, int batch, uint64_t seed, uint64_t step, int g_step, float* out_dev, gm_stream stream);
 
+/* test aid: an internal bf16 activation buffer as fp32 (hi + lo planes summed in split mode) -> out_dev [rows, cols];
+ * which: 0 noise operand, 1 G hidden, 2 image rows [real|fake|...], 3 D hidden, 4 D hidden gradient, 5 dL/dG-pre-sigmoid, 6 G hidden gradient */
+int gm_gan_debug_read(gm_gan* gan, int which, int row0, int rows, int cols, float* out_dev, gm_stream stream);
+
 /* D outputs of the last *_grad call (D step: batch real then batch fake; G step:
  * batch fake) -> dst_dev; what the reference names DX_score / DG_score. */
 int gm_gan_scores(gm_gan* gan, float* dst_dev, int n, gm_stream stream);

@@ -54,6 +54,59 @@ def _engine(variant, batch=B):
     return eng
 
 
+# ReLU boundaries.  dReLU/da is discontinuous at a = 0: a hidden unit whose pre-activation is ~1e-6 (fp32 rounding
+# level of a 784-term dot product) lands on either side depending on the summation order - the reference itself flips
+# such units between BLAS thread counts (8 vs 1 thread differ at 3e-7) - and one flipped unit moves a
+# batch-64 gradient by ~1e-2.  For units with |a| < TOL_A the oracle therefore takes the side the device took (read
+# back from the engine's activation buffers); every other unit must agree by itself.  The number of such units is
+# reported (0 or 1 per step at these sizes).
+TOL_A = 2e-5
+
+
+class DeviceReluSides:
+    """Context manager: patches oracle.ref_math's forward functions so that near-boundary ReLU units take the
+    device's side.  d_regions: row offsets (in units of B) of the D-hidden rows for successive d_forward calls."""
+
+    def __init__(self, eng, d_regions, g_hidden=True):
+        self.eng, self.d_regions, self.g_hidden, self.count = eng, list(d_regions), g_hidden, 0
+
+    def __enter__(self):
+        self._d, self._g, self._calls = R.d_forward, R.g_forward, 0
+
+        def d_forward(P, x, *a, **k):
+            fw = self._d(P, x, *a, **k)
+            reg = self.d_regions[min(self._calls, len(self.d_regions) - 1)]
+            self._calls += 1
+            near = np.abs(fw["a1"]) < TOL_A
+            if near.any():
+                n = fw["a1"].shape[0]
+                act = self.eng.debug_read("Aall", reg * n, n, fw["a1"].shape[1]).cpu().numpy() != 0
+                for key in ("h", "hq"):
+                    v = fw[key].copy()
+                    v[near] = np.where(act[near], 1e-30, 0.0)
+                    fw[key] = v
+                self.count += int(near.sum())
+            return fw
+
+        def g_forward(P, z, *a, **k):
+            fw = self._g(P, z, *a, **k)
+            near = np.abs(fw["a1"]) < TOL_A
+            if self.g_hidden and near.any():
+                n = fw["a1"].shape[0]
+                act = self.eng.debug_read("Hg", 0, n, fw["a1"].shape[1]).cpu().numpy() > 0
+                v = fw["h"].copy()
+                v[near] = np.where(act[near], 1e-30, 0.0)
+                fw["h"] = v
+                self.count += int(near.sum())
+            return fw
+        R.d_forward, R.g_forward = d_forward, g_forward
+        return self
+
+    def __exit__(self, *exc):
+        R.d_forward, R.g_forward = self._d, self._g
+        return False
+
+
 def _aux_from(draws_iter, case):
     if case == "wgp":
         eps = next(draws_iter)
@@ -77,24 +130,29 @@ def test_step1_every_output_within_1e3(case):
     st = dict(LAMBDA=0.0, RHO=1e-6) if case == "fisher" else None
     if case == "fisher":
         eng.fisher_state(0.0, 1e-6)
-    Lo, go, _ = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), aux_o, st)
     Ld = eng.d_grad(torch.from_numpy(x).cuda(), noise=torch.from_numpy(z1).cuda(), aux=aux_d).item()
     sc = eng.scores(2 * B).cpu().numpy()
     gD = [v.cpu().numpy() for v in eng.views(1, eng.grads[1])]
+    with DeviceReluSides(eng, d_regions=[0, 1, 2], g_hidden=False) as sides_d:   # D hidden rows: real, fake, xhat
+        Lo, go, _ = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), aux_o, st)
     rep = {"D_loss_vs_golden": abs(Ld - float(fx["step1_D_loss"])) / max(abs(float(fx["step1_D_loss"])), 1e-3),
            "D_loss_vs_oracle": abs(Ld - Lo) / max(abs(Lo), 1e-3),
            "DX_score": _nrel(sc[:B], fx["step1_score_0"]), "DG_score": _nrel(sc[B:], fx["step1_score_1"])}
     for nme, g in zip(D_NAMES, gD):
         rep["grad_" + nme] = _nrel(g, go[nme])
-    Lgo, ggo, _ = R.gan_g_step(P, case, z2.astype(np.float64))
     Lg = eng.g_grad(B, noise=torch.from_numpy(z2).cuda()).item()
+    with DeviceReluSides(eng, d_regions=[1]) as sides_g:                         # the G step's D rows are the fake region
+        Lgo, ggo, _ = R.gan_g_step(P, case, z2.astype(np.float64))
     rep["G_loss_vs_golden"] = abs(Lg - float(fx["step1_G_loss"])) / max(abs(float(fx["step1_G_loss"])), 1e-3)
     for nme, g in zip(G_NAMES, [v.cpu().numpy() for v in eng.views(0, eng.grads[0])]):
         rep["grad_" + nme] = _nrel(g, ggo[nme])
+    rep["relu_units_at_boundary"] = sides_d.count + sides_g.count
     _REPORT["step1_" + case] = rep
     _dump()
+    assert rep["relu_units_at_boundary"] <= 8, rep
     for k, v in rep.items():
-        assert v < TOL, (k, v, rep)
+        if k != "relu_units_at_boundary":
+            assert v < TOL, (k, v, rep)
 
 
 @pytest.mark.parametrize("case", ROW_VARIANTS + GP_VARIANTS)
