@@ -309,10 +309,49 @@ def make_vae_case():
     print("vae recon %s kl %s" % (np.round(out["recon_loss"], 4), np.round(out["kl_loss"], 5)))
 
 
+# --------------------------------------------------------------------------
+# reference-made checkpoints (src/ns_gan.py:283-290, src/vae.py save_model): written by the reference's own
+# save_model, loaded by the drop-in load_model in tests/test_dropin_gpu.py.  Small models (hidden 32, z 8) keep
+# the files at ~200 KB; the reference's outputs on fixed inputs are stored beside them.
+# --------------------------------------------------------------------------
+def make_checkpoints():
+    rng = np.random.default_rng(99)
+    x = gm_images(16, seed=5)
+    ns = import_ref("ns_gan")
+    torch.manual_seed(77)
+    model = ns.NSGAN(784, 32, 8)
+    it = [(torch.from_numpy(x).view(16, 1, 28, 28), torch.zeros(16, dtype=torch.long))]
+    tr = ns.NSGANTrainer(model, it, it, it, viz=False)
+    tr.train(num_epochs=2, G_lr=2e-4, D_lr=2e-4, D_steps=1)          # two real training steps before saving
+    path = os.path.join(HERE, "ref_nsgan_h32_z8.ckpt")
+    tr.save_model(path)
+    z = rng.standard_normal((16, 8)).astype(np.float32)
+    with torch.no_grad():
+        gz = model.G(torch.from_numpy(z)).numpy()
+        dx = model.D(torch.from_numpy(x)).numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_nsgan_h32_z8_outputs.npz"), z=z, x_bits=np.packbits(x.astype(np.uint8)), G_z=gz, D_x=dx,
+                        keys=np.array(list(model.state_dict().keys())))
+    vae = import_ref("vae")
+    torch.manual_seed(78)
+    vmodel = vae.VAE(784, 32, 8)
+    vtr = vae.VAETrainer(vmodel, it, it, it, viz=False)
+    vtr.train(num_epochs=2, lr=1e-3, weight_decay=1e-5)
+    vpath = os.path.join(HERE, "ref_vae_h32_z8.ckpt")
+    vtr.save_model(vpath)
+    with torch.no_grad():
+        mu, lv = vmodel.encoder(torch.from_numpy(x))
+        dec = vmodel.decoder(torch.from_numpy(z)).numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_vae_h32_z8_outputs.npz"), z=z, x_bits=np.packbits(x.astype(np.uint8)), mu=mu.numpy(),
+                        log_var=lv.numpy(), decoded=dec, keys=np.array(list(vmodel.state_dict().keys())))
+    print("checkpoints:", os.path.getsize(path), os.path.getsize(vpath), "bytes")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or (list(GAN_CASES) + ["vae"])
+    which = sys.argv[1:] or (list(GAN_CASES) + ["vae", "checkpoints"])
     for c in which:
         if c == "vae":
             make_vae_case()
+        elif c == "checkpoints":
+            make_checkpoints()
         else:
             make_gan_case(c)

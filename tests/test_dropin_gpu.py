@@ -1,6 +1,8 @@
 """The reference-facing class surface (generative-models_b200/*.py) on the GPU: same
 names / signatures / attributes as src/*.py, the reference's own training loop runs
 unchanged against it, and losses match the golden fixtures of the unmodified reference."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -236,3 +238,39 @@ def test_custom_path_gradients_match_oracle():
     s1 = model.D(images); model.D(images); model.D(images)
     with pytest.raises(RuntimeError, match="overwritten"):
         s1.sum().backward()
+
+
+def test_reference_made_checkpoints_reproduce_the_reference_outputs():
+    """A checkpoint written by the reference's save_model (src/ns_gan.py:283-285; fixture made by
+    tests/golden/make_golden.py) goes through the drop-in load_model and the CUDA forward kernels reproduce
+    the reference's G(z), D(x) / VAE encoder and decoder outputs stored beside it."""
+    import ns_gan
+    import vae as V
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ref = np.load(os.path.join(here, "ref_nsgan_h32_z8_outputs.npz"))
+    x = np.unpackbits(ref["x_bits"])[: 16 * 784].reshape(16, 784).astype(np.float32)
+    it = [(torch.from_numpy(x).view(16, 1, 28, 28), torch.zeros(16, dtype=torch.long))]
+    model = ns_gan.NSGAN(784, 32, 8)
+    tr = ns_gan.NSGANTrainer(model, it, it, it)
+    tr.load_model(os.path.join(here, "ref_nsgan_h32_z8.ckpt"))
+    with torch.no_grad():
+        gz = model.G(torch.from_numpy(ref["z"])).cpu().numpy()
+        dx = model.D(torch.from_numpy(x)).cpu().numpy()
+    assert np.linalg.norm(gz - ref["G_z"]) / np.linalg.norm(ref["G_z"]) < 5e-3          # bf16 operands
+    assert np.linalg.norm(dx.ravel() - ref["D_x"].ravel()) / np.linalg.norm(ref["D_x"]) < 5e-3
+    vref = np.load(os.path.join(here, "ref_vae_h32_z8_outputs.npz"))
+    vmodel = V.VAE(784, 32, 8)
+    vtr = V.VAETrainer(vmodel, it, it, it)
+    vtr.load_model(os.path.join(here, "ref_vae_h32_z8.ckpt"))
+    vtr._ensure_engine(16)
+    with torch.no_grad():
+        mu, lv = vmodel.encoder(torch.from_numpy(x))
+        dec = vmodel.decoder(torch.from_numpy(vref["z"]))
+    assert np.linalg.norm(mu.cpu().numpy() - vref["mu"]) / np.linalg.norm(vref["mu"]) < 1e-2
+    assert np.linalg.norm(lv.cpu().numpy() - vref["log_var"]) / np.linalg.norm(vref["log_var"]) < 1e-2
+    assert np.linalg.norm(dec.cpu().numpy() - vref["decoded"]) / np.linalg.norm(vref["decoded"]) < 5e-3
+    # and the round trip: save_model of the drop-in is readable by torch.load with the same keys
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        tr.save_model(os.path.join(d, "m.ckpt"))
+        assert list(torch.load(os.path.join(d, "m.ckpt")).keys()) == list(ref["keys"])

@@ -65,3 +65,25 @@ def test_every_header_function_has_ctypes_argtypes():
     no_args = {"gm_version"}
     missing = [n for n in names if n not in no_args and ("L.%s.argtypes" % n) not in src]
     assert not missing, missing
+
+
+def test_reference_made_checkpoints_load_into_the_dropin_modules():
+    """tests/golden/ref_*.ckpt were written by the REFERENCE's own save_model (tests/golden/make_golden.py
+    make_checkpoints): same state_dict keys, shapes and values load into the drop-in modules (src/ns_gan.py:283-290)."""
+    import numpy as np
+    import ns_gan
+    import vae as V
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sd = torch.load(os.path.join(here, "ref_nsgan_h32_z8.ckpt"))
+    model = ns_gan.NSGAN(784, 32, 8)
+    assert list(sd.keys()) == list(model.state_dict().keys())
+    model.load_state_dict(sd)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    assert list(np.load(os.path.join(here, "ref_nsgan_h32_z8_outputs.npz"))["keys"]) == list(sd.keys())
+    vsd = torch.load(os.path.join(here, "ref_vae_h32_z8.ckpt"))
+    vmodel = V.VAE(784, 32, 8)
+    assert list(vsd.keys()) == list(vmodel.state_dict().keys())
+    vmodel.load_state_dict(vsd)
+    for k, v in vmodel.state_dict().items():
+        assert torch.equal(v, vsd[k]), k
