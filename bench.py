@@ -140,6 +140,7 @@ class Workload:
             init_vae_weights(self.eng)
             self.hp = gm_b200.AdamHP.make(1e-3, weight_decay=1e-5)          # src/vae.py:127,139-142
             self.eng.set_sampler(pool_n, max(pool_n // B, 1), 3435 + rank)
+            self.eng.set_lazy_grads(world == 1)                               # gradient gather fused into the Adam kernel
             self.loss_buf = self.eng.loss_buf
         else:
             self.eng = gm_b200.GanEngine(X, H, Z, max_batch=B, variant=name, d_out_act="relu" if name == "wgp" else "sigmoid",

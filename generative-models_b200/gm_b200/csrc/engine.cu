@@ -212,7 +212,8 @@ static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
   if (p.dot_sq && (bias || dot || aux != AUX_NONE || p.act != ACT_NONE)) return launch_inst<208, 0, false, false>(pl, s);
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 0>(pl, s);
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_NONE, 1, 0>(pl, s);
-  if (bias && dot && p.dot_mask && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 3>(pl, s);
+  if (bias && dot && p.dot_mask == 1 && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 3>(pl, s);
+  if (bias && dot && p.dot_mask == 2 && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 4>(pl, s);
   if (p.dot_mask) return launch_inst<208, 0, false, false>(pl, s);
   if (bias && dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 1>(pl, s);
   if (!bias && !dot && aux == AUX_SIGMOID_GRAD && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_SIGMOID_GRAD, 0, 0>(pl, s);
@@ -892,6 +893,7 @@ extern "C" int gm_gan_materialize_grads(gm_gan* g, gm_stream stream) {
 static void set_bf16_epi(GemmParams& p, __nv_bfloat16* out, int ldo, int out_cols, int pad_one, const float* bias, int act) {
   p.epi = EPI_BF16; p.out = out; p.ldo = ldo; p.out_cols = out_cols; p.pad_one = pad_one; p.bias = bias; p.act = act;
   p.aux = nullptr; p.aux_mode = AUX_NONE; p.dot_w = nullptr; p.dot_out = nullptr; p.dot_sq = 0; p.row_scale = nullptr; p.row_split = 0; p.dot_mask = 0; p.row_vec = nullptr;
+  p.mask_row0 = 0; p.out_alt = nullptr;
 }
 
 static int build_plans(gm_gan* g, int B, StepPlans** out) {
@@ -920,6 +922,11 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   if ((rc = plan_gemm(c, &sp.d1_d, 0, nfwd * B, H, X, g->Xall, XP, g->W1d_s, X, H, 1))) return rc;
   set_bf16_epi(sp.d1_d.p, g->Aall, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
   sp.d1_d.p.dot_w = pD + g->D.off_w2; sp.d1_d.p.dot_out = g->slots; sp.d1_d.p.dot_ld = slot_ld;
+  if (g->nreg == 3) {
+    // WGAN-GP: the x_hat rows leave D's first layer directly as U = w2 * relu'(a_hat) (the penalty's first-gradient
+    // operand) in the U region of DHall - no separate pass over their activations
+    sp.d1_d.p.dot_mask = 2; sp.d1_d.p.mask_row0 = 2 * B; sp.d1_d.p.out_alt = g->DHall + size_t(2) * B * HP;
+  }
   if ((rc = plan_gemm(c, &sp.d1_g, 0, B, H, X, Xfake, XP, g->W1d_s, X, H, 1))) return rc;
   set_bf16_epi(sp.d1_g.p, Afake, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
   sp.d1_g.p.dot_w = pD + g->D.off_w2; sp.d1_g.p.dot_out = g->slots + B; sp.d1_g.p.dot_ld = slot_ld;
@@ -946,7 +953,10 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
     sp.gp_v.p.dot_sq = 1; sp.gp_v.p.dot_out = g->slots_v; sp.gp_v.p.dot_ld = g->Bmax;
     if ((rc = plan_gemm(c, &sp.gp_t, 0, B, H, X, Rrows, XP, g->W1d_s, X, H, 1))) return rc;
     set_bf16_epi(sp.gp_t.p, g->DHg, HP, H, 0, nullptr, ACT_NONE);
-    sp.gp_t.p.aux = g->Aall + size_t(2) * B * HP; sp.gp_t.p.ld_aux = HP; sp.gp_t.p.aux_mode = AUX_RELU_MASK;
+    // T = coef * (V W1^T) * relu'(a_hat): the per-row factor of R = coef V is applied in the epilogue (R itself is never
+    // formed; dGP/dW1 = (coef U)^T V uses the scaled U rows instead), the mask comes from the U rows (nonzero <=> active)
+    sp.gp_t.p.aux = g->DHall + rreg * HP; sp.gp_t.p.ld_aux = HP; sp.gp_t.p.aux_mode = AUX_RELU_MASK;
+    sp.gp_t.p.row_vec = g->coef;
   }
   // dX of D w.r.t. fake, times sigmoid'(fake): DA2 = (DHfake W1d) * fake(1-fake)
   if ((rc = plan_gemm(c, &sp.dx, 0, B, X, H, Afake, HP, g->W1d_t, H, X, 1))) return rc;
@@ -1251,10 +1261,11 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   c->launches += 2;
   if (gp) {
     const size_t rreg = size_t(g->nreg - 1) * B;
-    // U = 1[a_hat > 0] * w2  -> DHall rows of the R region
-    launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, nullptr, w2, g->DHall + rreg * HP, nullptr,
-                                                          B, H, HP, g->dh_rows_per_iter, g->lo);
-    c->launches++;
+    if (g->nreg != 3) {   // DRAGAN keeps a_hat (its penalty back-propagates through s(x_hat) too): U = 1[a_hat > 0] * w2 by a pass
+      launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, nullptr, w2, g->DHall + rreg * HP, nullptr,
+                                                            B, H, HP, g->dh_rows_per_iter, g->lo);
+      c->launches++;
+    }
     if ((rc = launch_plan(c, sp->gp_v, s))) return rc;          // V = U W1 -> R region of Xall, ||V||^2 -> slots_v
     GpParams gpp;
     gpp.slots_s = g->slots + 2 * B; gpp.nslots_s = 2 * cdiv(H, 208); gpp.slot_ld = g->nreg * g->Bmax;
@@ -1267,10 +1278,11 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     gpp.loss = g->lossbuf;
     launch_pdl("gp_rows_kernel", gp_rows_kernel, gpp.nblk, kLossThreads, 0, s, gpp);
     launch_pdl("gp_final_kernel", gp_final_kernel, 1, kLossThreads, 0, s, gpp);
-    launch_pdl("scale_rows_kernel", scale_rows_kernel, c->num_sms * 4, 256, 0, s, g->Xall + rreg * XP, g->coef, B, XP, g->lo);   // R = coef * V
+    launch_pdl("scale_rows_kernel", scale_rows_kernel, c->num_sms * 4, 256, 0, s, g->DHall + rreg * HP, g->coef, B, HP, g->lo);   // U <- coef * U
     c->launches += 3;
-    if ((rc = launch_plan(c, sp->gp_t, s))) return rc;          // T = (R W1^T) * mask -> DHg
-    launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->DHg, nullptr, w2, g->DA2, g->dw2p2, B, H, HP, g->dh_rows_per_iter, g->lo);
+    if ((rc = launch_plan(c, sp->gp_t, s))) return rc;          // T = coef (V W1^T) * mask -> DHg
+    // dGP/dw2 = column sums of T (block partials; no output rows)
+    launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->DHg, nullptr, w2, static_cast<__nv_bfloat16*>(nullptr), g->dw2p2, B, H, HP, g->dh_rows_per_iter, g->lo);
     launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p2, g->dh_blocks, HP, HP, g->dw2sum + HP);
     c->launches += 2;
     if (g->nreg == 4) {   // DRAGAN: the penalty also back-propagates through s(xhat)

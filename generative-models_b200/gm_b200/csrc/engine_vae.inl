@@ -20,6 +20,8 @@ struct gm_vae {
   float *MULV = nullptr, *DZ = nullptr, *EPS = nullptr, *slots_r = nullptr, *losses = nullptr;
   float *P1 = nullptr, *Pmv = nullptr, *P3 = nullptr, *P4 = nullptr;
   double *part_r = nullptr, *part_k = nullptr;
+  bool lazy = false, pend = false;      // lazy gradients: gm_vae_apply gathers the split-K partials itself
+  GradSegs pend_segs;
   long long pool_n = 0, pool_bpe = 0;   // on-device epoch sampler (gm_vae_set_sampler)
   uint64_t pool_seed = 0;
   std::map<int, VaePlans> plans;
@@ -92,7 +94,7 @@ extern "C" int gm_vae_create(gm_ctx* c, const gm_vae_desc* d, gm_vae** out) {
   TRYV(vae_alloc(g, &g->slots_r, size_t(2 * cdiv(X, 208)) * B));
   TRYV(vae_alloc(g, &g->losses, 4));
   TRYV(vae_alloc(g, &g->part_r, size_t(c->num_sms) * 2));
-  TRYV(vae_alloc(g, &g->part_k, size_t(cdiv(int(B), 256))));
+  TRYV(vae_alloc(g, &g->part_k, size_t(cdiv(int(B) * ((Z + 8) / 8), 256))));
   const int ns = c->num_sms;
   TRYV(vae_alloc(g, &g->P1, size_t(ns / cdiv(H, BM) > 0 ? ns / cdiv(H, BM) : 1) * H * 896 * cdiv(X + 1, 896)));
   TRYV(vae_alloc(g, &g->Pmv, size_t(ns) * 64 * 448));
@@ -165,8 +167,30 @@ extern "C" int gm_vae_apply(gm_vae* g, const gm_adam_hp* hp, int step, gm_stream
   a.p = g->par; a.g = g->grd; a.m = g->am; a.v = g->av;
   fill_adam(a, hp, step);
   vae_adam_segs(g, a);
+  if (g->pend) { a.gather = 1; a.gout = g->grd; a.gsegs = g->pend_segs; g->pend = false; }
   launch_pdl("adam_kernel", adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
+static void vae_flush_pending(gm_vae* g, cudaStream_t s) {
+  if (!g->pend) return;
+  launch_pdl("finalize_grads_kernel", finalize_grads_kernel, cdiv(g->pend_segs.total, 256), 256, 0, s, g->pend_segs, g->grd);
+  g->ctx->launches++;
+  g->pend = false;
+}
+// Lazy gradients (single-GPU fast path, like gm_gan_set_lazy_grads): gm_vae_grad leaves the split-K partials and the
+// following gm_vae_apply gathers, stores the flat gradient and applies Adam in one kernel.
+extern "C" int gm_vae_set_lazy_grads(gm_vae* g, int on, gm_stream stream) {
+  if (!g) return GM_ERR_ARG;
+  if (!on) vae_flush_pending(g, static_cast<cudaStream_t>(stream));
+  g->lazy = on != 0;
+  return GM_OK;
+}
+extern "C" int gm_vae_materialize_grads(gm_vae* g, gm_stream stream) {
+  if (!g) return GM_ERR_ARG;
+  vae_flush_pending(g, static_cast<cudaStream_t>(stream));
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
 }
@@ -248,7 +272,7 @@ static int vae_forward_core(gm_vae* g, VaePlans* sp, const void* images, int fmt
   c->launches++;
   if ((rc = launch_plan(c, sp->e1, s))) return rc;
   if ((rc = launch_plan(c, sp->e2, s))) return rc;
-  launch_pdl("vae_reparam_kernel", vae_reparam_kernel, cdiv(B, 256), 256, 0, s, g->MULV, 64, eps, g->EPS, g->Zb, g->ZP, B, g->Z, seed, step, g->part_k, g->lo);
+  launch_pdl("vae_reparam_kernel", vae_reparam_kernel, cdiv(B * ((g->Z + 8) / 8), 256), 256, 0, s, g->MULV, 64, eps, g->EPS, g->Zb, g->ZP, B, g->Z, seed, step, g->part_k, g->lo);
   c->launches++;
   if ((rc = launch_plan(c, sp->d1, s))) return rc;
   if ((rc = launch_plan(c, train ? sp->d2 : sp->d2_fwd, s))) return rc;
@@ -258,7 +282,7 @@ static int vae_forward_core(gm_vae* g, VaePlans* sp, const void* images, int fmt
 static void vae_losses(gm_vae* g, int B, cudaStream_t s) {
   const int nb = g->ctx->num_sms * 2;
   launch_pdl("vae_rowsum_kernel", vae_rowsum_kernel, nb, 256, 0, s, g->slots_r, 2 * cdiv(g->X, 208), g->Bmax, B, g->part_r);
-  launch_pdl("vae_losses_final_kernel", vae_losses_final_kernel, 1, 256, 0, s, g->part_r, nb, g->part_k, cdiv(B, 256), g->losses);
+  launch_pdl("vae_losses_final_kernel", vae_losses_final_kernel, 1, 256, 0, s, g->part_r, nb, g->part_k, cdiv(B * ((g->Z + 8) / 8), 256), g->losses);
   g->ctx->launches += 2;
 }
 
@@ -275,6 +299,7 @@ extern "C" int gm_vae_grad(gm_vae* g, const void* images, int img_fmt, const int
   int rc;
   if ((rc = vae_plans(g, batch, &sp))) return rc;
   const int B = batch;
+  vae_flush_pending(g, s);      // a pending gradient lives in the partial buffers this call overwrites
   if ((rc = vae_forward_core(g, sp, images, img_fmt, gather_idx, B, eps_dev, seed, step, true, s))) return rc;
   vae_losses(g, B, s);
   (void)grad_scale;   // the reference's VAE losses are sums: data-parallel ranks SUM unscaled gradients
@@ -282,7 +307,7 @@ extern "C" int gm_vae_grad(gm_vae* g, const void* images, int img_fmt, const int
   if ((rc = launch_plan(c, sp->da3, s))) return rc;
   if ((rc = launch_plan(c, sp->gw3, s))) return rc;
   if ((rc = launch_plan(c, sp->dz, s))) return rc;
-  launch_pdl("vae_dlatent_kernel", vae_dlatent_kernel, cdiv(B * 64, 256), 256, 0, s, g->MULV, 64, g->DZ, 32, g->EPS, g->DML, 64, B, g->Z, 1.f, g->lo);
+  launch_pdl("vae_dlatent_kernel", vae_dlatent_kernel, cdiv(B * 8, 256), 256, 0, s, g->MULV, 64, g->DZ, 32, g->EPS, g->DML, 64, B, g->Z, 1.f, g->lo);
   c->launches++;
   if ((rc = launch_plan(c, sp->gwmv, s))) return rc;
   if ((rc = launch_plan(c, sp->da1, s))) return rc;
@@ -300,8 +325,11 @@ extern "C" int gm_vae_grad(gm_vae* g, const void* images, int img_fmt, const int
   gs.s[5] = {g->off_b3, g->H, 2, 0, p3.ldp, g->Z, p3.splits, p3.part_stride, g->P3};
   gs.s[6] = {g->off_w4, g->X * g->H, 0, g->H, p4.ldp, 0, p4.splits, p4.part_stride, g->P4};
   gs.s[7] = {g->off_b4, g->X, 2, 0, p4.ldp, g->H, p4.splits, p4.part_stride, g->P4};
-  launch_pdl("finalize_grads_kernel", finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd);
-  c->launches++;
+  if (g->lazy) { g->pend_segs = gs; g->pend = true; }
+  else {
+    launch_pdl("finalize_grads_kernel", finalize_grads_kernel, cdiv(gs.total, 256), 256, 0, s, gs, g->grd);
+    c->launches++;
+  }
   if (losses_dev) CU_OK(c, cudaMemcpyAsync(losses_dev, g->losses, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   CU_OK(c, cudaGetLastError());
   return GM_OK;

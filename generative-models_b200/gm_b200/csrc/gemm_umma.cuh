@@ -58,6 +58,11 @@ struct GemmParams {
   // dot_mask: with the row-dot, store dot_w[n] * 1[v > 0] instead of v (the G step needs only
   // M = w2 * relu'(a1) of D's hidden layer: dL/dx = ds * (M W1), src/ns_gan.py:57-60 backward)
   int dot_mask;
+  // dot_mask == 2 (DOT_T 4; WGAN-GP's D forward over [real; fake; x_hat] rows): rows >= mask_row0 store the mask form
+  // U = w2 * relu'(a1) (what the penalty's first gradient needs) at out_alt + (row - mask_row0) * ldo,
+  // the rows below keep the activations at out + row * ldo
+  int mask_row0;
+  __nv_bfloat16* out_alt;
   // tma_store: full 32-column blocks of the bf16 output leave through the output tensor map
   // (cp.async.bulk.tensor store of the warp's swizzled staging tile) instead of LDS + STG
   int tma_store;
@@ -358,8 +363,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int act = ACT_T >= 0 ? ACT_T : p.act;
     const int aux_mode = AUX_T >= 0 ? AUX_T : p.aux_mode;
     const bool has_bias = BIAS_T >= 0 ? (BIAS_T != 0) : (p.bias != nullptr);
-    const bool has_dot = DOT_T >= 0 ? (DOT_T == 1 || DOT_T == 3) : (p.dot_w != nullptr);
-    const bool mask_out = DOT_T >= 0 ? (DOT_T == 3) : (p.dot_mask != 0);
+    const bool has_dot = DOT_T >= 0 ? (DOT_T == 1 || DOT_T == 3 || DOT_T == 4) : (p.dot_w != nullptr);
+    constexpr bool kRowMask = DOT_T == 4 || DOT_T < 0;   // per-row choice between activation and mask output
+    const bool mask_all = DOT_T >= 0 ? (DOT_T == 3) : (p.dot_mask == 1);
+    const bool mask_rows = DOT_T >= 0 ? (DOT_T == 4) : (p.dot_mask == 2);
     const bool has_sq = DOT_T >= 0 ? (DOT_T == 2) : (p.dot_sq != 0);
     const bool tma_st = !A_MN && p.tma_store != 0;
     bool st_pending = false;   // a bulk store may still be reading this warp's staging tile
@@ -385,6 +392,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = wrow0 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
+      const bool mask_out = mask_all || (kRowMask && mask_rows && row >= p.mask_row0);
       constexpr bool kUniversal = ACT_T < 0;
       if (!A_MN && !(kUniversal && p.epi == EPI_F32)) {
        if constexpr (!A_MN) {
@@ -469,7 +477,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bool released = false;
         float l1_scale = 0.f;
         if (aux_mode == AUX_L1) l1_scale = __ldg(p.row_scale + (row < p.row_split ? 0 : 1));
-        if (aux_mode == AUX_SIGMOID_GRAD) l1_scale = (p.row_vec != nullptr && row_ok) ? __ldg(p.row_vec + row) : 1.f;
+        if (aux_mode == AUX_SIGMOID_GRAD || aux_mode == AUX_RELU_MASK) l1_scale = (p.row_vec != nullptr && row_ok) ? __ldg(p.row_vec + row) : 1.f;
 #pragma unroll 1
         for (int bi = 0; part + bi * kParts < kBlocks; ++bi) {
           const int cb = (part + bi * kParts) * kEpiCols;
@@ -583,8 +591,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                       v[2 * k2] = -2.f * d0 * v[2 * k2] * (1.f - v[2 * k2]);
                       v[2 * k2 + 1] = -2.f * d1 * v[2 * k2 + 1] * (1.f - v[2 * k2 + 1]);
                     } else {
-                      v[2 * k2] = a_lo > 0.f ? v[2 * k2] : 0.f;
-                      v[2 * k2 + 1] = a_hi > 0.f ? v[2 * k2 + 1] : 0.f;
+                      // aux is a post-ReLU activation (>= 0) or the mask form w2 * relu'(a): nonzero <=> the unit is active
+                      v[2 * k2] = a_lo != 0.f ? v[2 * k2] * l1_scale : 0.f;
+                      v[2 * k2 + 1] = a_hi != 0.f ? v[2 * k2 + 1] * l1_scale : 0.f;
                     }
                   }
                 }
@@ -616,7 +625,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint4 hi = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
                 if constexpr (SPLIT) {   // residual plane of the output: v - bf16(v), straight from registers
                   if (p.lo_off != 0 && p.out != nullptr && row_ok && c0 < p.out_cols) {
-                    uint4* ol = reinterpret_cast<uint4*>(p.out + p.lo_off + size_t(row) * p.ldo + c0);
+                    __nv_bfloat16* ob = (mask_rows && row >= p.mask_row0) ? p.out_alt + size_t(row - p.mask_row0) * p.ldo : p.out + size_t(row) * p.ldo;
+                    uint4* ol = reinterpret_cast<uint4*>(ob + p.lo_off + c0);
                     ol[0] = make_uint4(pack_bf16x2_residual(v[0], v[1], lo.x), pack_bf16x2_residual(v[2], v[3], lo.y),
                                        pack_bf16x2_residual(v[4], v[5], lo.z), pack_bf16x2_residual(v[6], v[7], lo.w));
                     ol[1] = make_uint4(pack_bf16x2_residual(v[8], v[9], hi.x), pack_bf16x2_residual(v[10], v[11], hi.y),
@@ -650,9 +660,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __nv_bfloat16* o = p.out + size_t(wrow0 + lr) * p.ldo + col0 + lc * 8;
             const uint32_t sa = stage_s + lr * kEpiPitch + lc * 16;
 #pragma unroll
-            for (int it = 0; it < 4; ++it)
-              if (wrow0 + it * 8 + lr < p.M)
-                *reinterpret_cast<uint4*>(o + size_t(it * 8) * p.ldo) = lds128(sa + it * 8 * kEpiPitch);
+            for (int it = 0; it < 4; ++it) {
+              const int rr = wrow0 + it * 8 + lr;
+              if (rr < p.M) {
+                __nv_bfloat16* dst = o + size_t(it * 8) * p.ldo;
+                if constexpr (kRowMask) {
+                  if (mask_rows && rr >= p.mask_row0) dst = p.out_alt + size_t(rr - p.mask_row0) * p.ldo + col0 + lc * 8;
+                }
+                *reinterpret_cast<uint4*>(dst) = lds128(sa + it * 8 * kEpiPitch);
+              }
+            }
           }
           __syncwarp();
         }

@@ -435,7 +435,7 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
         acc[2 * q] = fmaf(d, lo + bf16_lo(l4[q]), acc[2 * q]);
         acc[2 * q + 1] = fmaf(d, hi + bf16_hi(l4[q]), acc[2 * q + 1]);
       }
-      store_bf16x8(dh + r * ld + g * 8, o, lo_off);
+      if (dh != nullptr) store_bf16x8(dh + r * ld + g * 8, o, lo_off);
     }
   }
   if (dw2p == nullptr) return;
@@ -611,28 +611,38 @@ __global__ void vae_reparam_kernel(const float* __restrict__ mulv, int ldm, cons
                                    int z, unsigned long long seed, unsigned long long stream_id,
                                    double* __restrict__ part, long long lo_off) {
   griddep_sync();
+  // One thread per (row, 8-column group of the latent row): 32-byte reads of mu / log_var / eps, one 16-byte store of z
+  // (the thread-per-row version read 256-byte-strided rows: 47 us at B = 131072 for 60 MB).  Philox subsequence = cell.
   __shared__ double sh[256 / 32];
+  const int groups = ldz / 8, gz = (z + 8) / 8;
+  const long long t = blockIdx.x * 256ll + threadIdx.x;
   double kl = 0.0;
-  const int r = blockIdx.x * 256 + threadIdx.x;
-  if (r < rows) {
-    curandStatePhilox4_32_10_t st;
-    if (eps_in == nullptr) curand_init(seed ^ 0x5851F42D4C957F2Dull, (unsigned long long)r, stream_id * 64ull, &st);
-    for (int c0 = 0; c0 < ldz; c0 += 8) {
-      float v[8];
+  if (t < (long long)rows * gz) {
+    const int r = int(t / gz), g = int(t % gz), c0 = g * 8;
+    float v[8], e[8];
+    if (eps_in == nullptr && c0 < z) {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seed ^ 0x5851F42D4C957F2Dull, (unsigned long long)r * groups + g, stream_id * 64ull, &st);
+      const float4 a = curand_normal4(&st), b = curand_normal4(&st);
+      e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        float o = (c == z) ? 1.f : 0.f;
-        if (c < z) {
-          const float mu = mulv[(long long)r * ldm + c], lv = mulv[(long long)r * ldm + z + c];
-          const float e = eps_in ? eps_in[(long long)r * z + c] : curand_normal(&st);
-          eps_out[(long long)r * z + c] = e;
-          o = mu + e * expf(0.5f * lv);
-          kl += 0.5 * ((double)mu * mu + exp((double)lv) - lv - 1.0);
-        }
-        v[j] = o;
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float o = (c == z) ? 1.f : 0.f;
+      if (c < z) {
+        const float mu = mulv[(long long)r * ldm + c], lv = mulv[(long long)r * ldm + z + c];
+        const float ee = eps_in ? eps_in[(long long)r * z + c] : e[j];
+        eps_out[(long long)r * z + c] = ee;
+        o = mu + ee * expf(0.5f * lv);
+        kl += 0.5 * ((double)mu * mu + exp((double)lv) - lv - 1.0);
       }
-      store_bf16x8(zb + (long long)r * ldz + c0, v, lo_off);
+      v[j] = o;
+    }
+    store_bf16x8(zb + (long long)r * ldz + c0, v, lo_off);
+    for (int pg = gz + g; pg < groups; pg += gz) {      // this thread's share of the row's zero padding
+      reinterpret_cast<uint4*>(zb)[(long long)r * groups + pg] = make_uint4(0, 0, 0, 0);
+      if (lo_off) reinterpret_cast<uint4*>(zb + lo_off)[(long long)r * groups + pg] = make_uint4(0, 0, 0, 0);
     }
   }
   kl = block_sum<256>(kl, sh);
@@ -640,24 +650,31 @@ __global__ void vae_reparam_kernel(const float* __restrict__ mulv, int ldm, cons
 }
 
 // dmu = mu + dz ; dlv = 0.5(e^lv - 1) + dz * eps * e^{lv/2} * 0.5  -> bf16 [rows, ld]: [dmu | dlv | 0]
+// One thread per (row, 8 output columns): a group never straddles the mu / log_var boundary when z % 8 == 0;
+// otherwise the per-element branch below handles it.
 __global__ void vae_dlatent_kernel(const float* __restrict__ mulv, int ldm, const float* __restrict__ dz, int lddz,
                                    const float* __restrict__ eps, __nv_bfloat16* __restrict__ out, int ld, int rows,
                                    int z, float scale, long long lo_off) {
   griddep_sync();
-  const long long i = blockIdx.x * 256ll + threadIdx.x;
-  if (i >= (long long)rows * ld) return;
-  const int r = int(i / ld), c = int(i % ld);
-  float o = 0.f;
-  if (c < z) {
-    o = scale * (mulv[(long long)r * ldm + c] + dz[(long long)r * lddz + c]);
-  } else if (c < 2 * z) {
-    const int k = c - z;
-    const float lv = mulv[(long long)r * ldm + z + k];
-    o = scale * (0.5f * (expf(lv) - 1.f) + dz[(long long)r * lddz + k] * eps[(long long)r * z + k] * expf(0.5f * lv) * 0.5f);
+  const int groups = ld / 8;
+  const long long t = blockIdx.x * 256ll + threadIdx.x;
+  if (t >= (long long)rows * groups) return;
+  const int r = int(t / groups), c0 = int(t % groups) * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float o = 0.f;
+    if (c < z) {
+      o = scale * (mulv[(long long)r * ldm + c] + dz[(long long)r * lddz + c]);
+    } else if (c < 2 * z) {
+      const int k = c - z;
+      const float lv = mulv[(long long)r * ldm + z + k];
+      o = scale * (0.5f * (expf(lv) - 1.f) + dz[(long long)r * lddz + k] * eps[(long long)r * z + k] * expf(0.5f * lv) * 0.5f);
+    }
+    v[j] = o;
   }
-  const __nv_bfloat16 hi = __float2bfloat16_rn(o);
-  out[i] = hi;
-  if (lo_off) out[i + lo_off] = __float2bfloat16_rn(o - __bfloat162float(hi));
+  store_bf16x8(out + (long long)r * ld + c0, v, lo_off);
 }
 
 // recon = sum over rows of the per-row slots (sum (x-out)^2); losses[0] = recon, [1] = kl

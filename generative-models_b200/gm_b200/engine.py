@@ -403,6 +403,14 @@ class VaeEngine:
         s % batches_per_epoch of the permutation of epoch s // batches_per_epoch (src/vae.py:150)."""
         check(self.h, lib().gm_vae_set_sampler(self.g, int(n_pool), int(batches_per_epoch), int(seed) & 0xFFFFFFFFFFFFFFFF))
 
+    def set_lazy_grads(self, on=True):
+        """Single-GPU fast path: grad() leaves split-K partials, apply() gathers + updates in one kernel; self.grads is
+        then valid only after apply() (or materialize_grads())."""
+        check(self.h, lib().gm_vae_set_lazy_grads(self.g, 1 if on else 0, _stream()))
+
+    def materialize_grads(self):
+        check(self.h, lib().gm_vae_materialize_grads(self.g, _stream()))
+
     def last_eps(self, batch):
         out = torch.empty(batch, self.z_dim, device=self.device, dtype=torch.float32)
         check(self.h, lib().gm_vae_last_eps(self.g, _ptr(out), batch, _stream()))

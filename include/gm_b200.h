@@ -262,6 +262,10 @@ int gm_vae_grad(gm_vae* vae, const void* images_dev, int img_fmt, const int* gat
  * batches_per_epoch) of the permutation of epoch (s / batches_per_epoch) over the resident pool — the
  * `for batch in self.train_iter` of src/vae.py:150 without host work.  n_pool == 0: off. */
 int gm_vae_set_sampler(gm_vae* vae, long long n_pool, long long batches_per_epoch, uint64_t seed);
+/* lazy gradients, as gm_gan_set_lazy_grads: gm_vae_apply gathers the split-K partials, stores the flat gradient and
+ * applies Adam in one kernel; gm_vae_materialize_grads forms the flat gradient earlier (e.g. before an all-reduce). */
+int gm_vae_set_lazy_grads(gm_vae* vae, int on, gm_stream stream);
+int gm_vae_materialize_grads(gm_vae* vae, gm_stream stream);
 /* eps of the last gm_vae_grad / gm_vae_forward call (src/vae.py:104; the Philox draw when eps_dev was NULL) -> out_dev [batch, z] */
 int gm_vae_last_eps(gm_vae* vae, float* out_dev, int batch, gm_stream stream);
 /* optimizer.step() with coupled weight decay (src/vae.py:139-142,162). */

@@ -239,10 +239,13 @@ def gradient_penalty(P, xhat, out_act, lam=10.0, K=1.0, pre="D.", q=_exact):
     gp = lam * np.mean((n - K) ** 2)
     r = (2 * lam / B) * (n - K)                      # dGP/dn  [B,1]
     safe = np.where(nv > 0, nv, 1)
-    R = q("R", np.where(nv > 0, r * qq / safe, 0) * V)   # dGP/dV  [B,X]
+    coef = np.where(nv > 0, r * qq / safe, 0)            # dGP/dV = coef * V  [B,1]
+    # the CUDA path never forms R = coef * V: it scales the smaller U rows (dGP/dW1 = (coef U)^T V) and applies coef
+    # as a per-row factor in the epilogue of T's GEMM; with q = identity this is the same arithmetic
+    Us = q("dh", coef * U)
     g = {}
-    g[pre + "linear.weight"] = U.T @ R
-    T = q("T", (R @ q("W", W1).T) * M)
+    g[pre + "linear.weight"] = Us.T @ V
+    T = q("T", coef * (V @ q("W", W1).T) * M)
     g[pre + "discriminate.weight"] = np.sum(T, axis=0, keepdims=True)
     g[pre + "linear.bias"] = np.zeros_like(b1)
     g[pre + "discriminate.bias"] = np.zeros(1, dtype=xhat.dtype)

@@ -124,3 +124,29 @@ def test_forward_at_batch_512_pair_mode_fp32_head():
     lv_r = h1 @ v["encoder.log_var.weight"].t() + v["encoder.log_var.bias"]
     assert _nrel(mu.cpu().numpy(), mu_r.cpu().numpy()) < 5e-3
     assert _nrel(lv.cpu().numpy(), lv_r.cpu().numpy()) < 5e-3
+
+
+def test_lazy_gradients_are_bit_identical():
+    """gm_vae_set_lazy_grads: gathering the split-K partials inside the Adam kernel gives exactly the parameters,
+    moments and flat gradient of the finalize-then-Adam path."""
+    import gm_b200
+    fx = load_case("vae")
+    x = torch.from_numpy(images_from_bits(fx)).cuda()
+    g = torch.Generator().manual_seed(3)
+    eps = [torch.randn(B, 20, generator=g).cuda() for _ in range(3)]
+    hp = gm_b200.AdamHP.make(1e-3, weight_decay=1e-5)
+
+    def run(lazy):
+        eng = _engine()
+        eng.set_lazy_grads(lazy)
+        grads = []
+        for t in range(3):
+            eng.grad(x, eps=eps[t])
+            eng.apply(hp)
+            grads.append(eng.grads.clone())
+        return eng.params.clone(), eng.exp_avg_sq.clone(), grads
+    p0, v0, g0 = run(False)
+    p1, v1, g1 = run(True)
+    assert torch.equal(p0, p1) and torch.equal(v0, v1)
+    for a, b in zip(g0, g1):
+        assert torch.equal(a, b)
