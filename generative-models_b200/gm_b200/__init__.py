@@ -8,3 +8,4 @@ from ._lib import (GmError, lib, lib_path, ctx, gemm_bf16, adam_step, launch_cou
 from .engine import GanEngine, InfoGanEngine, VaeEngine  # noqa: F401
 
 HAS_SPLIT_PRECISION = True       # fp32-grade split-bf16 operand mode (gm_prec GM_PREC_SPLIT)
+from .graph import GraphedGanStep, graphed_gan_step  # noqa: E402,F401

@@ -123,6 +123,9 @@ def lib():
     L.gm_vae_apply.argtypes = [vp, C.POINTER(AdamHP), i, vp]
     L.gm_vae_forward.argtypes = [vp, vp, i, i, vp, u64, u64, vp, vp, vp, vp]
     L.gm_vae_decode.argtypes = [vp, vp, i, vp, vp]
+    L.gm_gan_use_device_step.argtypes = [vp, i, vp, vp]
+    L.gm_gan_device_steps.argtypes = [vp, vp, vp]
+    L.gm_ctx_set_pdl.argtypes = [vp, i]
     L.gm_gan_set_loss_consts.argtypes = [vp, C.POINTER(LossConsts)]
     L.gm_gan_set_sampler.argtypes = [vp, C.c_longlong, u64]
     L.gm_sampler_indices_host.argtypes = [C.c_longlong, u64, u64, u64, i, vp]

@@ -58,18 +58,20 @@ static inline uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-static Sampler make_sampler(long long n, uint64_t seed, uint64_t round, uint64_t offset) {
+static Sampler make_sampler(long long n, uint64_t seed, uint64_t round, uint64_t offset, const unsigned long long* step_ptr = nullptr) {
   Sampler sp;
   sp.n = n > 0 ? unsigned(n) : 0u;
   int bits = 2;
   while (bits < 32 && (1ull << bits) < (unsigned long long)(n > 0 ? n : 1)) ++bits;
   if (bits & 1) ++bits;
   sp.half_bits = unsigned(bits / 2);
-  sp.key = splitmix64(splitmix64(seed) ^ (round * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull));
+  sp.seed_mix = splitmix64(seed);
+  sp.key = sampler_key(sp.seed_mix, round);
   sp.offset = offset;
+  sp.step_ptr = step_ptr;      // device-step mode: the kernel derives the key from *step_ptr instead of `round`
   return sp;
 }
-static const Sampler kNoSampler = {0u, 1u, 0ull, 0ull};
+static const Sampler kNoSampler = {0u, 1u, 0ull, 0ull, nullptr, 0ull};
 
 // ------------------------------------------------------------------ tensor maps
 // 2-D bf16 row-major matrix: `inner` contiguous elements per row (logical extent, may
@@ -218,6 +220,7 @@ static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
   if (bias && dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 1>(pl, s);
   if (!bias && !dot && aux == AUX_SIGMOID_GRAD && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_SIGMOID_GRAD, 0, 0>(pl, s);
   if (!bias && !dot && aux == AUX_RELU_MASK && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_RELU_MASK, 0, 0>(pl, s);
+  if (!bias && !dot && aux == AUX_NONZERO_MASK && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONZERO_MASK, 0, 0>(pl, s);
   if (bias && !dot && aux == AUX_L1 && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_L1, 1, 0>(pl, s);
   if (bias && !dot && aux == AUX_VAE_OUT && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_VAE_OUT, 1, 0>(pl, s);
   if (!bias && !dot && aux == AUX_NONE && p.act == ACT_NONE && p.dot_sq) return launch_inst<208, 0, false, false, ACT_NONE, AUX_NONE, 0, 2>(pl, s);
@@ -662,6 +665,9 @@ struct gm_gan {
   int last_rows = 0;
   int region_rows = 0;   // rows per region of Xall/Aall/DHall (3 regions)
   gm_comm* comm = nullptr;   // attached communicator: batch statistics run over the global batch
+  // device-step mode (CUDA-graph replay of the step): [0] Adam steps of G, [1] Adam steps of D, [2] train_G calls, [3] train_D calls
+  unsigned long long* dstep = nullptr;
+  bool dev_step = false;
   gm_loss_consts lc = {10.f, 1.f, 1.f, 0.f, 1.f, 1.f};   // reference defaults: src/w_gp_gan.py:177, src/dra_gan.py:174, src/ls_gan.py:173,197
   long long pool_n = 0;      // on-device batch sampling over a resident pool of pool_n images (gm_gan_set_sampler)
   uint64_t pool_seed = 0;
@@ -858,6 +864,12 @@ extern "C" int gm_gan_sync_shadows(gm_gan* g, int net, gm_stream stream) {
 }
 
 static void flush_pending(gm_gan* g, cudaStream_t s);
+static void bump_step(gm_gan* g, int which, cudaStream_t s) {
+  if (!g->dev_step) return;
+  launch_pdl("bump_step_kernel", bump_step_kernel, 1, 32, 0, s, g->dstep + which);
+  g->ctx->launches++;
+}
+
 
 extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, gm_stream stream) {
   if (!g || net < 0 || net > 1 || !hp || step <= 0) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_apply: bad argument") : GM_ERR_ARG;
@@ -871,8 +883,10 @@ extern "C" int gm_gan_apply(gm_gan* g, int net, const gm_adam_hp* hp, int step, 
     a.gather = 1; a.gout = g->grd[net]; a.gsegs = g->pend_segs[net];
     g->pend[net] = false;
   }
+  if (g->dev_step) a.step_ptr = g->dstep + net;   // bias corrections from the device counter (`step` is ignored)
   launch_pdl("adam_kernel", adam_kernel, cdiv(a.total, 256), 256, 0, static_cast<cudaStream_t>(stream), a);
   g->ctx->launches++;
+  bump_step(g, net, static_cast<cudaStream_t>(stream));
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;
 }
@@ -955,7 +969,7 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
     set_bf16_epi(sp.gp_t.p, g->DHg, HP, H, 0, nullptr, ACT_NONE);
     // T = coef * (V W1^T) * relu'(a_hat): the per-row factor of R = coef V is applied in the epilogue (R itself is never
     // formed; dGP/dW1 = (coef U)^T V uses the scaled U rows instead), the mask comes from the U rows (nonzero <=> active)
-    sp.gp_t.p.aux = g->DHall + rreg * HP; sp.gp_t.p.ld_aux = HP; sp.gp_t.p.aux_mode = AUX_RELU_MASK;
+    sp.gp_t.p.aux = g->DHall + rreg * HP; sp.gp_t.p.ld_aux = HP; sp.gp_t.p.aux_mode = AUX_NONZERO_MASK;
     sp.gp_t.p.row_vec = g->coef;
   }
   // dX of D w.r.t. fake, times sigmoid'(fake): DA2 = (DHfake W1d) * fake(1-fake)
@@ -1046,8 +1060,9 @@ static int check_step_args(gm_gan* g, int batch) {
   return GM_OK;
 }
 
-static int run_generator(gm_gan* g, StepPlans* sp, int B, const float* noise, uint64_t seed, uint64_t stream_id, cudaStream_t s) {
-  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(B * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, B, g->Z, g->ZP, seed, stream_id, g->lo);
+static int run_generator(gm_gan* g, StepPlans* sp, int B, const float* noise, uint64_t seed, uint64_t stream_id, cudaStream_t s,
+                         const unsigned long long* step_ptr = nullptr) {
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(B * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, B, g->Z, g->ZP, seed, stream_id, g->lo, step_ptr);
   g->ctx->launches++;
   int rc;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
@@ -1231,12 +1246,13 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   Sampler smp = kNoSampler;
   if (!gather_idx && g->pool_n > 0) {
     if (B > g->pool_n) return fail(c, GM_ERR_ARG, "batch (%d) exceeds the sampler's pool (%lld)", B, g->pool_n);
-    smp = make_sampler(g->pool_n, g->pool_seed, step, 0);     // a fresh permutation every step (src/ns_gan.py:224)
+    smp = make_sampler(g->pool_n, g->pool_seed, step, 0, g->dev_step ? g->dstep + 3 : nullptr);     // a fresh permutation every step (src/ns_gan.py:224)
   }
   launch_pdl("stage_images_kernel", stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP, smp, g->lo);
   c->launches++;
-  if ((rc = run_generator(g, sp, B, noise, seed, 2 * step, s))) return rc;
-  if (g->d.variant == GM_BEGAN) return began_d_grad(g, sp, B, loss_dev, s);
+  const unsigned long long* dptr = g->dev_step ? g->dstep + 3 : nullptr;   // device-step mode: the train_D call counter
+  if ((rc = run_generator(g, sp, B, noise, seed, g->dev_step ? 0 : 2 * step, s, dptr))) return rc;
+  if (g->d.variant == GM_BEGAN) { rc = began_d_grad(g, sp, B, loss_dev, s); bump_step(g, 3, s); return rc; }
   const bool gp = g->nreg > 2;
   const int H = g->H, HP = g->HP, X = g->X, XP = g->XP;
   const float* w2 = g->par[GM_NET_D] + g->D.off_w2;
@@ -1251,7 +1267,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
       c->launches += 2;
     }
     launch_pdl("xhat_kernel", xhat_kernel, c->num_sms * 8, 256, 0, s, g->Xall, g->Xall + size_t(B) * XP, g->Xall + size_t(2) * B * XP, B, X, XP,
-                                           mode, aux, g->stats, seed, 2 * step, g->lc.dra_c, g->lo);
+                                           mode, aux, g->stats, seed, g->dev_step ? 0 : 2 * step, g->lc.dra_c, g->lo, dptr);
     c->launches++;
   }
   if ((rc = launch_plan(c, sp->d1_d, s))) return rc;
@@ -1305,6 +1321,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   emit_grads(g, GM_NET_D, gs, s);
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   g->last_rows = 2 * B;
+  bump_step(g, 3, s);
   CU_OK(c, cudaGetLastError());
   return GM_OK;
 }
@@ -1322,8 +1339,8 @@ static int g_grad_impl(gm_gan* g, int batch, const float* noise, float inv_globa
   const int B = batch;
   gm_ctx* c = g->ctx;
   flush_pending(g, s);
-  if (!staged && (rc = run_generator(g, sp, B, noise, seed, 2 * step + 1, s))) return rc;
-  if (g->d.variant == GM_BEGAN) return began_g_grad(g, sp, B, loss_dev, s);
+  if (!staged && (rc = run_generator(g, sp, B, noise, seed, g->dev_step ? 1 : 2 * step + 1, s, g->dev_step ? g->dstep + 2 : nullptr))) return rc;
+  if (g->d.variant == GM_BEGAN) { rc = began_g_grad(g, sp, B, loss_dev, s); bump_step(g, 2, s); return rc; }
   if ((rc = launch_plan(c, sp->d1_g, s))) return rc;
   launch_loss(g, B, 1, inv_global_batch, s);
   if ((rc = launch_plan(c, sp->dx, s))) return rc;
@@ -1343,6 +1360,7 @@ static int g_grad_impl(gm_gan* g, int batch, const float* noise, float inv_globa
   emit_grads(g, GM_NET_G, gs, s);
   if (loss_dev) CU_OK(c, cudaMemcpyAsync(loss_dev, g->lossbuf, sizeof(float), cudaMemcpyDeviceToDevice, s));
   g->last_rows = B;
+  bump_step(g, 2, s);
   CU_OK(c, cudaGetLastError());
   return GM_OK;
 }
@@ -1505,7 +1523,7 @@ extern "C" int gm_gan_generate(gm_gan* g, const float* noise, int n, float* imag
   int rc;
   if ((rc = build_plans(g, B, &sp))) return rc;
   // stage n noise rows (rows n..B-1 keep whatever they held; their outputs are not read)
-  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, n, g->Z, g->ZP, 0, 0, g->lo);
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, n, g->Z, g->ZP, 0, 0, g->lo, static_cast<const unsigned long long*>(nullptr));
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->g1, s))) return rc;
   if ((rc = launch_plan(g->ctx, sp->g2, s))) return rc;
@@ -1539,6 +1557,42 @@ extern "C" int gm_gan_discriminate(gm_gan* g, const void* images, int img_fmt, i
 // permutation of the pool per step, i.e. next(iter(DataLoader(shuffle=True))) (src/ns_gan.py:222-226).
 // Loss constants the reference passes as train_D / train_G keyword arguments: LAMBDA of the gradient penalty
 // (src/w_gp_gan.py:177; DRAGAN also K and C, src/dra_gan.py:174), LSGAN's targets a, b, c (src/ls_gan.py:173,197).
+// Device-step mode: the per-step scalars the host normally passes - Adam's step count (bias correction), the Philox
+// stream of train_D / train_G, the sampler's round - live in device counters that the step's own kernels advance, so one
+// captured CUDA graph of (gm_gan_d_grad, gm_gan_apply(D), gm_gan_g_grad, gm_gan_apply(G)) replays as successive train
+// steps (the launch-bound small-batch regime, BASELINE configs[0]).  counters4 = {Adam steps done on G, on D, train_G
+// calls, train_D calls}; the `step` arguments of those entry points are ignored while the mode is on.
+extern "C" int gm_gan_use_device_step(gm_gan* g, int on, const unsigned long long* counters4_host, gm_stream stream) {
+  if (!g) return GM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (on) {
+    if (!g->dstep) {
+      void* q = nullptr;
+      CU_OK(g->ctx, cudaMalloc(&q, 4 * sizeof(unsigned long long)));
+      g->allocs.push_back(q);
+      g->dstep = static_cast<unsigned long long*>(q);
+    }
+    unsigned long long zero[4] = {0, 0, 0, 0};
+    CU_OK(g->ctx, cudaMemcpyAsync(g->dstep, counters4_host ? counters4_host : zero, sizeof zero, cudaMemcpyHostToDevice, s));
+    CU_OK(g->ctx, cudaStreamSynchronize(s));
+  }
+  g->dev_step = on != 0;
+  return GM_OK;
+}
+extern "C" int gm_gan_device_steps(gm_gan* g, unsigned long long* counters4_host, gm_stream stream) {
+  if (!g || !counters4_host || !g->dstep) return g ? fail(g->ctx, GM_ERR_STATE, "device-step mode was never enabled") : GM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CU_OK(g->ctx, cudaMemcpyAsync(counters4_host, g->dstep, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CU_OK(g->ctx, cudaStreamSynchronize(s));
+  return GM_OK;
+}
+// programmatic dependent launch on / off at run time (stream capture on drivers that reject programmatic edges)
+extern "C" int gm_ctx_set_pdl(gm_ctx* c, int on) {
+  if (!c) return GM_ERR_ARG;
+  g_pdl = on != 0;
+  return GM_OK;
+}
+
 extern "C" int gm_gan_set_loss_consts(gm_gan* g, const gm_loss_consts* lc) {
   if (!g || !lc) return GM_ERR_ARG;
   g->lc = *lc;
@@ -1575,7 +1629,7 @@ extern "C" int gm_gan_debug_noise(gm_gan* g, int batch, uint64_t seed, uint64_t 
   if (!out_dev) return GM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(batch * ((g->Z + 8) / 8), 256), 256, 0, s, static_cast<const float*>(nullptr), g->Zb, batch, g->Z, g->ZP,
-                                                   (unsigned long long)seed, (unsigned long long)(2 * step + (g_step ? 1 : 0)), g->lo);
+                                                   (unsigned long long)seed, (unsigned long long)(2 * step + (g_step ? 1 : 0)), g->lo, static_cast<const unsigned long long*>(nullptr));
   const long long tot = (long long)batch * g->Z;
   launch_pdl("bf16_rows_to_f32_kernel", bf16_rows_to_f32_kernel, unsigned((tot + 255) / 256), 256, 0, s, g->Zb, g->ZP, out_dev, batch, g->Z, g->lo);
   g->ctx->launches += 2;

@@ -167,7 +167,7 @@ extern "C" int gm_gan_g_forward(gm_gan* g, const float* noise, int batch, float*
   if ((rc = build_plans(g, batch, &sp))) return rc;
   if ((rc = build_custom_plans(g, batch, &cp))) return rc;
   gm_ctx* c = g->ctx;
-  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(batch * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, batch, g->Z, g->ZP, uint64_t(0), uint64_t(0), g->lo);
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(batch * ((g->Z + 8) / 8), 256), 256, 0, s, noise, g->Zb, batch, g->Z, g->ZP, uint64_t(0), uint64_t(0), g->lo, static_cast<const unsigned long long*>(nullptr));
   c->launches++;
   if ((rc = launch_plan(c, sp->g1, s))) return rc;
   if ((rc = launch_plan(c, cp->g2, s))) return rc;

@@ -375,7 +375,7 @@ extern "C" int gm_vae_decode(gm_vae* g, const float* z_dev, int n, float* out_im
   VaePlans* sp;
   int rc;
   if ((rc = vae_plans(g, n, &sp))) return rc;
-  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, z_dev, g->Zb, n, g->Z, g->ZP, 0, 0, g->lo);
+  launch_pdl("stage_noise_kernel", stage_noise_kernel, cdiv(n * ((g->Z + 8) / 8), 256), 256, 0, s, z_dev, g->Zb, n, g->Z, g->ZP, 0, 0, g->lo, static_cast<const unsigned long long*>(nullptr));
   g->ctx->launches++;
   if ((rc = launch_plan(g->ctx, sp->d1, s))) return rc;
   if ((rc = launch_plan(g->ctx, sp->d2_fwd, s))) return rc;

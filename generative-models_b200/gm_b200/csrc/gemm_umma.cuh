@@ -32,7 +32,8 @@ constexpr int kSmemBudget = 225 * 1024;
 
 enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
-enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2, AUX_VAE_OUT = 3, AUX_L1 = 4 };
+// AUX_NONZERO_MASK: like AUX_RELU_MASK for an aux that holds the SIGNED mask form w2 * relu'(a) (nonzero <=> active unit)
+enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2, AUX_VAE_OUT = 3, AUX_L1 = 4, AUX_NONZERO_MASK = 5 };
 
 struct GemmParams {
   int M, N, K;          // logical extents; K counts contraction elements
@@ -477,7 +478,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bool released = false;
         float l1_scale = 0.f;
         if (aux_mode == AUX_L1) l1_scale = __ldg(p.row_scale + (row < p.row_split ? 0 : 1));
-        if (aux_mode == AUX_SIGMOID_GRAD || aux_mode == AUX_RELU_MASK) l1_scale = (p.row_vec != nullptr && row_ok) ? __ldg(p.row_vec + row) : 1.f;
+        if (aux_mode == AUX_SIGMOID_GRAD || aux_mode == AUX_RELU_MASK || aux_mode == AUX_NONZERO_MASK) l1_scale = (p.row_vec != nullptr && row_ok) ? __ldg(p.row_vec + row) : 1.f;
 #pragma unroll 1
         for (int bi = 0; part + bi * kParts < kBlocks; ++bi) {
           const int cb = (part + bi * kParts) * kEpiCols;
@@ -506,7 +507,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           uint4 axl[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
           if constexpr (SPLIT) {   // residual plane of the aux values of this lane's row (plain loads: the split kernels are not tuned)
-            if (p.lo_off != 0 && aux_mode != AUX_NONE && aux_mode != AUX_RELU_MASK && row_ok) {
+            if (p.lo_off != 0 && aux_mode != AUX_NONE && aux_mode != AUX_RELU_MASK && aux_mode != AUX_NONZERO_MASK && row_ok) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 if (col0 + q * 8 < p.out_cols)
@@ -591,9 +592,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                       v[2 * k2] = -2.f * d0 * v[2 * k2] * (1.f - v[2 * k2]);
                       v[2 * k2 + 1] = -2.f * d1 * v[2 * k2 + 1] * (1.f - v[2 * k2 + 1]);
                     } else {
-                      // aux is a post-ReLU activation (>= 0) or the mask form w2 * relu'(a): nonzero <=> the unit is active
-                      v[2 * k2] = a_lo != 0.f ? v[2 * k2] * l1_scale : 0.f;
-                      v[2 * k2 + 1] = a_hi != 0.f ? v[2 * k2 + 1] * l1_scale : 0.f;
+                      // aux > 0 (post-ReLU activation), or aux != 0 for the signed mask form w2 * relu'(a)
+                      const bool on0 = aux_mode == AUX_NONZERO_MASK ? a_lo != 0.f : a_lo > 0.f;
+                      const bool on1 = aux_mode == AUX_NONZERO_MASK ? a_hi != 0.f : a_hi > 0.f;
+                      v[2 * k2] = on0 ? v[2 * k2] * l1_scale : 0.f;
+                      v[2 * k2 + 1] = on1 ? v[2 * k2 + 1] * l1_scale : 0.f;
                     }
                   }
                 }

@@ -32,7 +32,17 @@ enum : int { IMG_F32 = 0, IMG_U8 = 1, IMG_BITS = 2, IMG_BF16PAD = 3 };
 struct Sampler {
   unsigned int n, half_bits;
   unsigned long long key, offset;
+  // device-step mode (CUDA-graph replay): the permutation's round comes from a device counter, key = f(seed_mix, *step_ptr)
+  const unsigned long long* step_ptr;
+  unsigned long long seed_mix;
 };
+__host__ __device__ __forceinline__ unsigned long long splitmix64_hd(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ unsigned long long sampler_key(unsigned long long seed_mix, unsigned long long round) {
+  return splitmix64_hd(seed_mix ^ (round * 0xD1342543DE82EF95ull + 0x2545F4914F6CDD1Dull));
+}
 __host__ __device__ __forceinline__ unsigned int sampler_mix(unsigned int x, unsigned int k) {
   x ^= k; x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
   return x;
@@ -55,10 +65,12 @@ __host__ __device__ __forceinline__ unsigned int sampler_index(const Sampler& sp
 }
 
 __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const int* __restrict__ idx,
-                                    __nv_bfloat16* __restrict__ dst, int rows, int x, int ld, const Sampler smp, long long lo_off) {
+                                    __nv_bfloat16* __restrict__ dst, int rows, int x, int ld, const Sampler smp_in, long long lo_off) {
   griddep_sync();
   const int groups = ld / 8;
   const long long total = (long long)rows * groups;
+  Sampler smp = smp_in;
+  if (smp.step_ptr) smp.key = sampler_key(smp.seed_mix, *smp.step_ptr);
   if (lo_off) {   // split mode: {0,1} pixels are exact in bf16 -> the rows' residual plane is zero (it may hold a previous tenant's values)
     uint4* lo = reinterpret_cast<uint4*>(dst + lo_off);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -126,8 +138,10 @@ __global__ void stage_images_kernel(const void* __restrict__ src, int fmt, const
 }
 
 // the batch's source-row indices as the staging kernel draws them (tests, gm_sample_indices)
-__global__ void sample_indices_kernel(const Sampler smp, int rows, int* __restrict__ out) {
+__global__ void sample_indices_kernel(const Sampler smp_in, int rows, int* __restrict__ out) {
   griddep_sync();
+  Sampler smp = smp_in;
+  if (smp.step_ptr) smp.key = sampler_key(smp.seed_mix, *smp.step_ptr);
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) out[r] = smp.n ? int(sampler_index(smp, smp.offset + (unsigned long long)r)) : r;
 }
@@ -136,8 +150,10 @@ __global__ void sample_indices_kernel(const Sampler smp, int rows, int* __restri
 // One thread per (row, 8-column group); the Philox subsequence is the group index, the
 // offset the step stream, so every step / rank / group draws disjoint numbers.
 __global__ void stage_noise_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
-                                   int z, int ld, unsigned long long seed, unsigned long long stream_id, long long lo_off) {
+                                   int z, int ld, unsigned long long seed, unsigned long long stream_id, long long lo_off,
+                                   const unsigned long long* __restrict__ step_ptr) {
   griddep_sync();
+  if (step_ptr) stream_id += 2ull * (*step_ptr);      // device-step mode: stream = 2 * step (+ 1 for train_G)
   // One thread per (row, 8-column group that holds noise): every lane runs the Philox /
   // Box-Muller path (a thread per group of the padded row left 5 of 8 lanes idle in it).
   // The thread also writes its share of the row's zero padding groups.
@@ -458,8 +474,10 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
 __global__ void xhat_kernel(const __nv_bfloat16* __restrict__ xr, const __nv_bfloat16* __restrict__ xf,
                             __nv_bfloat16* __restrict__ out, int rows, int x, int ld, int mode,
                             const float* __restrict__ rnd, const float* __restrict__ stats,
-                            unsigned long long seed, unsigned long long stream_id, float dra_c, long long lo_off) {
+                            unsigned long long seed, unsigned long long stream_id, float dra_c, long long lo_off,
+                            const unsigned long long* __restrict__ step_ptr) {
   griddep_sync();
+  if (step_ptr) stream_id += 2ull * (*step_ptr);
   // One warp per row, lanes walk the row's 16-byte groups (coalesced; the previous thread-per-row version moved the
   // same bytes in 108 us instead of ~40).  Philox: the row's eps / delta comes from subsequence r (lane-uniform),
   // DRAGAN's per-element u from subsequence rows + r * groups + g.
@@ -870,6 +888,7 @@ struct AdamParams {
   const float* lr_scale;                             // nullable device scalar multiplying lr (BEGAN's plateau scheduler)
   AdamSeg seg[6]; int nseg;
   long long lo_off;                                  // split mode: operand copies also get their residual plane
+  const unsigned long long* step_ptr;                // device-step mode: bias corrections from the device step counter (+1)
   // lazy gradients (gm_gan_set_lazy_grads): the flat gradient has not been formed yet; the
   // update gathers each element from the split-K partials itself and stores it to gout
   int gather; float* gout; GradSegs gsegs;
@@ -879,14 +898,20 @@ struct AdamParams {
 __device__ __forceinline__ void adam_element(const AdamParams& a, int i, float g) {
   float p = a.p[i];
   if (a.update) {
+    float bc1 = a.bc1, bc2_sqrt = a.bc2_sqrt;
+    if (a.step_ptr) {   // the host's formulas (fill_adam) on the device counter
+      const double t = double(*a.step_ptr + 1ull);
+      bc1 = float(1.0 - pow(double(a.b1), t));
+      bc2_sqrt = float(sqrt(1.0 - pow(double(a.b2), t)));
+    }
     if (a.wd != 0.f) g = fmaf(a.wd, p, g);
     const float m = a.b1 * a.m[i] + (1.f - a.b1) * g;
     const float v = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
     a.m[i] = m;
     a.v[i] = v;
-    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
     const float lr = a.lr_scale ? a.lr * a.lr_scale[0] : a.lr;
-    p = p - (lr / a.bc1) * (m / denom);
+    p = p - (lr / bc1) * (m / denom);
     if (a.clamp > 0.f) p = fminf(fmaxf(p, -a.clamp), a.clamp);
     a.p[i] = p;
   }
@@ -908,6 +933,12 @@ __device__ __forceinline__ void adam_element(const AdamParams& a, int i, float g
     }
     return;
   }
+}
+
+// device-step mode: counter += 1 after the kernels that read it (stream order)
+__global__ void bump_step_kernel(unsigned long long* __restrict__ ctr) {
+  griddep_sync();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += 1ull;
 }
 
 __global__ void adam_kernel(const AdamParams a) {

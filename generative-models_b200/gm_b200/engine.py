@@ -128,6 +128,29 @@ class GanEngine:
         check(self.h, lib().gm_gan_g_grad_staged(self.g, batch, inv, C.c_void_p(self.loss_buf.data_ptr() + 4), _stream()))
         return self.loss_buf[1]
 
+    def use_device_step(self, on=True):
+        """Device-step mode (include/gm_b200.h: gm_gan_use_device_step): Adam step counts, Philox streams and the
+        sampler round come from device counters, so a captured CUDA graph of one train step replays as successive
+        steps.  Turning it on seeds the counters from this engine's host-side step counts; turning it off reads
+        them back."""
+        buf = (C.c_ulonglong * 4)()
+        if on:
+            buf[0], buf[1] = self.steps[0], self.steps[1]
+            buf[2], buf[3] = getattr(self, "_g_calls", 0), getattr(self, "_d_calls", 0)
+            check(self.h, lib().gm_gan_use_device_step(self.g, 1, buf, _stream()))
+            self._device_step = True
+        elif getattr(self, "_device_step", False):
+            check(self.h, lib().gm_gan_device_steps(self.g, buf, _stream()))
+            self.steps = [int(buf[0]), int(buf[1])]
+            self._g_calls, self._d_calls = int(buf[2]), int(buf[3])
+            check(self.h, lib().gm_gan_use_device_step(self.g, 0, None, _stream()))
+            self._device_step = False
+
+    def device_steps(self):
+        buf = (C.c_ulonglong * 4)()
+        check(self.h, lib().gm_gan_device_steps(self.g, buf, _stream()))
+        return [int(v) for v in buf]
+
     def set_loss_consts(self, gp_lambda=10.0, gp_k=1.0, dra_c=1.0, ls_a=0.0, ls_b=1.0, ls_c=1.0):
         """LAMBDA / K / C of the gradient penalties, a / b / c of LSGAN (the reference's train_D / train_G kwargs)."""
         lc = _lib.LossConsts(gp_lambda, gp_k, dra_c, ls_a, ls_b, ls_c)

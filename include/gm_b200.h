@@ -171,6 +171,15 @@ int gm_gan_apply_allreduce(gm_gan* gan, int net, const gm_adam_hp* hp, int step,
  * comm == NULL detaches (per-rank statistics). */
 int gm_gan_attach_comm(gm_gan* gan, gm_comm* comm);
 
+/* Device-step mode (CUDA-graph replay of the train step; the launch-bound small-batch regime of BASELINE configs[0]):
+ * Adam's step count, the Philox streams of train_D / train_G and the sampler's round live in device counters advanced by
+ * the step's own kernels, so ONE captured graph of gm_gan_d_grad, gm_gan_apply(D), gm_gan_g_grad, gm_gan_apply(G) replays
+ * as successive steps of src/ns_gan.py:126-156.  counters4 = {Adam steps done on G, on D, train_G calls, train_D calls}
+ * (NULL = zeros).  While on, the `step` arguments of those entry points are ignored. */
+int gm_gan_use_device_step(gm_gan* gan, int on, const unsigned long long* counters4_host, gm_stream stream);
+int gm_gan_device_steps(gm_gan* gan, unsigned long long* counters4_host, gm_stream stream);
+/* programmatic dependent launch on / off at run time (default on; GM_NO_PDL=1 starts with it off) */
+int gm_ctx_set_pdl(gm_ctx* ctx, int on);
 /* Loss constants the reference passes as train_D / train_G keyword arguments (defaults = the reference's):
  * gradient-penalty LAMBDA (src/w_gp_gan.py:177), DRAGAN's K and C (src/dra_gan.py:174), LSGAN's a, b, c
  * (src/ls_gan.py:173,197).  Takes effect from the next gm_gan_d_grad / gm_gan_g_grad. */

@@ -226,3 +226,37 @@ def test_vae_step_at_bench_settings_matches_fp32_autograd(prec):
     for k, v in rep.items():
         if k not in ("recon", "kl"):
             assert v < (TOL[prec] if prec == "split" else 3e-2), (k, v, rep)
+
+
+def test_graph_replay_matches_host_driven_steps():
+    """Device-step mode + CUDA-graph replay (the small-batch regime): N replays == N host-driven steps, bit for bit
+    (same sampler rounds, Philox streams and Adam bias corrections from the device counters)."""
+    import gm_b200
+    B, N, seed = 64, 50000, 4242
+    bits = _pool(N)
+    hp = gm_b200.AdamHP.make(2e-4)
+
+    def host_driven(steps):
+        eng = _gan_engine("ns", B, "bf16")
+        eng.set_lazy_grads(True)
+        eng.set_sampler(N, seed)
+        for s in range(steps):
+            eng.d_grad(bits, fmt="bits", batch=B, seed=seed, step=s)
+            eng.apply(1, hp)
+            eng.g_grad(B, seed=seed, step=s)
+            eng.apply(0, hp)
+        return eng
+    ref = host_driven(3 + 5)
+    eng = _gan_engine("ns", B, "bf16")
+    step = gm_b200.GraphedGanStep(eng, bits, N, B, hp, hp, seed=seed, warmup=3)     # 3 eager warm-up steps + capture
+    for _ in range(5 - 1):                                                           # the capture itself does not execute
+        step()
+    step()
+    torch.cuda.synchronize()
+    assert eng.device_steps() == [8, 8, 8, 8]
+    step.close()
+    assert eng.steps == [8, 8]
+    for net in (0, 1):
+        assert torch.equal(eng.params[net], ref.params[net]), net
+        assert torch.equal(eng.exp_avg_sq[net], ref.exp_avg_sq[net])
+    assert torch.equal(eng.loss_buf, ref.loss_buf)
