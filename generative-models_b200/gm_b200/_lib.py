@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
                 ("bias", C.c_void_p), ("act", C.c_int),
                 ("aux", C.c_void_p), ("ld_aux", C.c_int), ("aux_mode", C.c_int),
                 ("dot_w", C.c_void_p), ("dot_out", C.c_void_p), ("dot_ld", C.c_int),
-                ("transpose", C.c_int)]
+                ("transpose", C.c_int), ("act_slope", C.c_float)]
 
 
 class LossConsts(C.Structure):
@@ -123,6 +123,15 @@ def lib():
     L.gm_vae_apply.argtypes = [vp, C.POINTER(AdamHP), i, vp]
     L.gm_vae_forward.argtypes = [vp, vp, i, i, vp, u64, u64, vp, vp, vp, vp]
     L.gm_vae_decode.argtypes = [vp, vp, i, vp, vp]
+    ll = C.c_longlong
+    L.gm_im2col_k4s2.argtypes = [vp, vp, i, i, i, i, i, vp, i, vp]
+    L.gm_col2im_k4s2.argtypes = [vp, vp, i, i, i, i, i, vp, i, i, vp, i, f, vp]
+    L.gm_bn_forward.argtypes = [vp, vp, ll, i, i, vp, vp, f, i, f, vp, i, vp, vp, f, vp]
+    L.gm_bn_backward.argtypes = [vp, vp, vp, ll, i, i, vp, vp, vp, i, f, vp, i, vp, vp]
+    L.gm_cast_bf16.argtypes = [vp, vp, i, i, vp, i, vp, i, vp]
+    L.gm_pack_col0.argtypes = [vp, vp, i, vp, i, vp]
+    L.gm_noise_rows.argtypes = [vp, vp, vp, i, i, i, u64, u64, vp]
+    L.gm_loss_rows.argtypes = [vp, i, i, vp, i, i, f, vp, vp, vp, vp]
     L.gm_gan_use_device_step.argtypes = [vp, i, vp, vp]
     L.gm_gan_device_steps.argtypes = [vp, vp, vp]
     L.gm_ctx_set_pdl.argtypes = [vp, i]
@@ -209,7 +218,7 @@ def prof_collect():
 
 
 def gemm_bf16(A, B, out, mode="nt", N=None, K=None, M=None, bias=None, act=0, aux=None, aux_mode=0, pad_one=False,
-              out_cols=None, dot_w=None, dot_out=None, transpose=False):
+              out_cols=None, dot_w=None, dot_out=None, transpose=False, act_slope=0.2):
     """Thin wrapper over gm_gemm_bf16 for torch CUDA tensors (unit tests, level-(ii)
     use).  mode 'nt': A [M, lda] / B [N, ldb] bf16 with K contiguous;  mode 'tn':
     A [K, lda] / B [K, ldb] bf16 (contraction over rows).  `out` bf16 [M, ldc] or fp32."""
@@ -238,6 +247,7 @@ def gemm_bf16(A, B, out, mode="nt", N=None, K=None, M=None, bias=None, act=0, au
     d.dot_out = dot_out.data_ptr() if dot_out is not None else None
     d.dot_ld = dot_out.stride(0) if dot_out is not None else 0
     d.transpose = int(transpose)
+    d.act_slope = act_slope
     h = ctx()
     check(h, lib().gm_gemm_bf16(h, C.byref(d), _stream()))
 

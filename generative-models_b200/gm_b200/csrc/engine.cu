@@ -10,6 +10,7 @@
 #include "gm_b200.h"
 #include "gemm_umma.cuh"
 #include "kernels.cuh"
+#include "conv_ops.cuh"
 
 using namespace gm;
 
@@ -29,6 +30,9 @@ struct gm_ctx {
   bool prof = false;
   long long* dbg = nullptr;   // phase-timing buffer handed to the next generic GEMM (tools/time_phases.py)
   bool use_clusters = true;   // GM_NO_CLUSTERS=1 disables the CTA-pair multicast path (debug)
+  void* red = nullptr;        // scratch of the conv building blocks' two-stage reductions (engine_conv.inl)
+  size_t red_bytes = 0;
+  void* loss_zero = nullptr;  // 64 zero bytes: bias / Fisher state / completion counter for gm_loss_rows
   long long plan_lo = 0;      // > 0 while an engine in split-operand mode builds its plans: element offset of the lo planes
   struct ProfRec { cudaEvent_t e0, e1; int kind; double flops; };
   std::vector<ProfRec> prof_recs;
@@ -416,6 +420,8 @@ extern "C" int gm_ctx_create(int device, gm_ctx** out) {
 extern "C" int gm_ctx_destroy(gm_ctx* c) {
   if (!c) return GM_OK;
   if (c->scratch) cudaFree(c->scratch);
+  if (c->red) cudaFree(c->red);
+  if (c->loss_zero) cudaFree(c->loss_zero);
   delete c;
   return GM_OK;
 }
@@ -505,6 +511,7 @@ extern "C" int gm_gemm_bf16(gm_ctx* c, const gm_gemm_desc* d, gm_stream stream) 
     p.pad_one = d->pad_one;
     p.bias = d->bias_dev;
     p.act = d->act;
+    p.act_slope = d->act_slope;
     p.aux = static_cast<const __nv_bfloat16*>(d->aux_dev);
     p.ld_aux = d->ld_aux;
     p.aux_mode = d->aux_dev ? d->aux_mode : AUX_NONE;
@@ -1667,3 +1674,4 @@ extern "C" int gm_gan_fisher_state(gm_gan* g, float* lambda_rho_host, int set, g
 #include "engine_custom.inl"
 #include "engine_comm.inl"
 #include "engine_vae.inl"
+#include "engine_conv.inl"

@@ -31,7 +31,7 @@ constexpr int gemm_threads(int epi_warps) { return 64 + epi_warps * 32; }
 constexpr int kSmemBudget = 225 * 1024;
 
 enum : int { EPI_BF16 = 0, EPI_F32 = 1 };
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_LRELU = 3 };   // LeakyReLU(act_slope): universal epilogue only
 // AUX_NONZERO_MASK: like AUX_RELU_MASK for an aux that holds the SIGNED mask form w2 * relu'(a) (nonzero <=> active unit)
 enum : int { AUX_NONE = 0, AUX_SIGMOID_GRAD = 1, AUX_RELU_MASK = 2, AUX_VAE_OUT = 3, AUX_L1 = 4, AUX_NONZERO_MASK = 5 };
 
@@ -84,6 +84,7 @@ struct GemmParams {
   // bf16 outputs and aux inputs carry their residual plane at the same offset.
   int nparts, kb_part;
   long long lo_off;
+  float act_slope;      // ACT_LRELU
 };
 
 // per-epilogue-warp staging tile for one 32-column block: 32 rows x (64 B data + 16 B pad):
@@ -558,6 +559,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (act == ACT_RELU) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                } else if (ACT_T < 0 && act == ACT_LRELU) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : p.act_slope * v[j];
                 } else if (act == ACT_SIGMOID) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {

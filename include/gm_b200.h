@@ -94,6 +94,7 @@ typedef struct {
   const void* aux_dev; int ld_aux, aux_mode;
   const float* dot_w_dev; float* dot_out_dev; int dot_ld;
   int transpose;
+  float act_slope;   /* act 3 = LeakyReLU(act_slope) */
 } gm_gemm_desc;
 int gm_gemm_bf16(gm_ctx* ctx, const gm_gemm_desc* d, gm_stream stream);
 
@@ -285,6 +286,33 @@ int gm_vae_forward(gm_vae* vae, const void* images_dev, int img_fmt, int n, cons
                    uint64_t step, float* out_images_dev, float* mu_logvar_dev, float* losses_dev, gm_stream stream);
 /* Decoder.forward (src/vae.py:74-77) for sampling. */
 int gm_vae_decode(gm_vae* vae, const float* z_dev, int n, float* out_images_dev, gm_stream stream);
+
+/* ---- conv building blocks (DCGAN path, BASELINE configs[4]; README.md:68,96 recommends DCGAN, the reference has no
+ * implementation).  NHWC bf16 activations as row-major matrices [B*H*W, C]; a 4x4 stride-2 pad-1 convolution is
+ * gm_im2col_k4s2 + gm_gemm_bf16, a transposed convolution gm_gemm_bf16 + gm_col2im_k4s2; their gradients are the same
+ * two data movements with the roles swapped.  The DCGAN engine that sequences them is gm_b200/dcgan.py. */
+int gm_im2col_k4s2(gm_ctx* ctx, const void* x_dev, int B, int H, int W, int C, int ldx, void* col_dev, int ldc, gm_stream stream);
+/* mode 0: sum of taps, 1: sigmoid(sum), 2: sum * LeakyReLU'(aux), 3: sum * aux (1 - aux) */
+int gm_col2im_k4s2(gm_ctx* ctx, const void* col_dev, int ldc, int B, int Hi, int Wi, int C, void* y_dev, int ldy, int mode,
+                   const void* aux_dev, int ld_aux, float slope, gm_stream stream);
+/* nn.BatchNorm2d in training mode over NHWC rows, fused with the following activation (act 0 none, 1 ReLU, 2 LeakyReLU) */
+int gm_bn_forward(gm_ctx* ctx, const void* x_dev, long long rows, int C, int ld, const float* gamma_dev, const float* beta_dev, float eps,
+                  int act, float slope, void* y_dev, int ldy, float* stats_dev /* [2][C]: mean, invstd */,
+                  float* running_dev /* [2][C] or NULL */, float momentum, gm_stream stream);
+int gm_bn_backward(gm_ctx* ctx, const void* dy_dev, const void* x_dev, long long rows, int C, int ld, const float* stats_dev,
+                   const float* gamma_dev, const float* beta_dev, int act, float slope, void* dx_dev, int lddx,
+                   float* dgb_dev /* [2][C]: dbeta, dgamma */, gm_stream stream);
+/* fp32 [R, C] -> bf16 [R, ld] and / or its transpose [C, ld_t] (the two GEMM operand forms of a weight matrix) */
+int gm_cast_bf16(gm_ctx* ctx, const float* src_dev, int R, int C, void* dst_dev, int ld, void* dst_t_dev, int ld_t, gm_stream stream);
+/* out [rows, ld] bf16 with column 0 = v[r], the rest 0 */
+int gm_pack_col0(gm_ctx* ctx, const float* v_dev, int rows, void* out_dev, int ld, gm_stream stream);
+/* generator noise rows as a bf16 GEMM operand: Philox N(0,1) (noise_dev NULL) or a caller tensor [rows, z] fp32 */
+int gm_noise_rows(gm_ctx* ctx, const float* noise_dev, void* out_dev, int rows, int z, int ld, uint64_t seed, uint64_t stream_id,
+                  gm_stream stream);
+/* the adversarial loss + dL/dlogit on a logit vector (train_D: batch real then batch fake rows; train_G: batch fake rows);
+ * row-wise variants only (NS, MM, W, LS, f-GAN) */
+int gm_loss_rows(gm_ctx* ctx, int variant, int out_act, const float* logits_dev, int batch, int g_step, float inv_global_batch,
+                 float* ds_dev, float* d_out_dev, float* loss_dev, gm_stream stream);
 
 /* number of this library's kernels launched since the last call with reset != 0 */
 long long gm_launch_count(gm_ctx* ctx, int reset);

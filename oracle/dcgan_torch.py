@@ -1,0 +1,70 @@
+"""DCGAN oracle — TEST INFRASTRUCTURE, not product code.
+
+The reference has no convolutional model (README.md:68 recommends DCGAN, README.md:96 lists it as To-Do), so parity for
+BASELINE configs[4] is "doubly unpinned" (SURVEY.md 8f): this file is OUR plain-PyTorch fp32 statement of the
+architecture (torch.nn Conv2d / ConvTranspose2d / BatchNorm2d on the CPU) driven by the reference's own NSGAN
+formulas — train_D: -mean(log(D(x)+1e-8) + log(1-D(G(z))+1e-8)) (src/ns_gan.py:191-192), train_G:
+-mean(log(D(G(z))+1e-8)) (src/ns_gan.py:214), D(images) and D(G(z)) as separate forward calls (BatchNorm statistics per
+call), autograd backward, torch.optim.Adam.  tests/test_dcgan_gpu.py compares the CUDA conv path with it."""
+import torch
+import torch.nn as nn
+
+
+class Generator(nn.Module):
+    def __init__(self, hd=64, z=100, ch=3):
+        super().__init__()
+        c = [8 * hd, 4 * hd, 2 * hd, hd, ch]
+        self.l1 = nn.ConvTranspose2d(z, c[0], 4, 1, 0, bias=False)
+        self.l2 = nn.ConvTranspose2d(c[0], c[1], 4, 2, 1, bias=False)
+        self.l3 = nn.ConvTranspose2d(c[1], c[2], 4, 2, 1, bias=False)
+        self.l4 = nn.ConvTranspose2d(c[2], c[3], 4, 2, 1, bias=False)
+        self.l5 = nn.ConvTranspose2d(c[3], c[4], 4, 2, 1, bias=False)
+        self.bn1, self.bn2, self.bn3, self.bn4 = (nn.BatchNorm2d(k) for k in c[:4])
+
+    def forward(self, z):
+        x = z.view(z.shape[0], -1, 1, 1)
+        x = torch.relu(self.bn1(self.l1(x)))
+        x = torch.relu(self.bn2(self.l2(x)))
+        x = torch.relu(self.bn3(self.l3(x)))
+        x = torch.relu(self.bn4(self.l4(x)))
+        return torch.sigmoid(self.l5(x)).reshape(z.shape[0], -1)          # flat [B, ch*64*64] like src/ns_gan.py:46
+
+
+class Discriminator(nn.Module):
+    def __init__(self, hd=64, ch=3):
+        super().__init__()
+        c = [hd, 2 * hd, 4 * hd, 8 * hd]
+        self.ch = ch
+        self.l1 = nn.Conv2d(ch, c[0], 4, 2, 1, bias=False)
+        self.l2 = nn.Conv2d(c[0], c[1], 4, 2, 1, bias=False)
+        self.l3 = nn.Conv2d(c[1], c[2], 4, 2, 1, bias=False)
+        self.l4 = nn.Conv2d(c[2], c[3], 4, 2, 1, bias=False)
+        self.l5 = nn.Conv2d(c[3], 1, 4, 1, 0, bias=False)
+        self.bn2, self.bn3, self.bn4 = (nn.BatchNorm2d(k) for k in c[1:])
+
+    def logits(self, x):
+        x = x.view(x.shape[0], self.ch, 64, 64)                            # un-flatten (src/ns_gan.py:225 flattens)
+        x = nn.functional.leaky_relu(self.l1(x), 0.2)
+        x = nn.functional.leaky_relu(self.bn2(self.l2(x)), 0.2)
+        x = nn.functional.leaky_relu(self.bn3(self.l3(x)), 0.2)
+        x = nn.functional.leaky_relu(self.bn4(self.l4(x)), 0.2)
+        return self.l5(x).view(-1, 1)
+
+    def forward(self, x):
+        return torch.sigmoid(self.logits(x))
+
+
+def load_from_engine_weights(G, D, sd):
+    """sd: DcganEngine.torch_weights()."""
+    with torch.no_grad():
+        for tag, net in (("G", G), ("D", D)):
+            for name, p in net.named_parameters():
+                p.copy_(sd["%s.%s" % (tag, name)].to(p.dtype))
+
+
+def d_loss(G, D, images, z):
+    return -torch.mean(torch.log(D(images) + 1e-8) + torch.log(1 - D(G(z)) + 1e-8))      # src/ns_gan.py:191-192
+
+
+def g_loss(G, D, z):
+    return -torch.mean(torch.log(D(G(z)) + 1e-8))                                          # src/ns_gan.py:214

@@ -1,0 +1,154 @@
+"""DCGAN conv path (BASELINE configs[4]) on the GPU: the conv building blocks against torch's own conv / batch-norm
+ops, and the whole NSGAN train step (forward, losses, every gradient tensor, Adam) against the plain-PyTorch oracle
+(oracle/dcgan_torch.py).  bf16 tensor-core operands: tolerances are norm-relative and stated per check."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+_REPORT = {}
+
+
+def _nrel(a, b):
+    a, b = a.double().reshape(-1).cpu(), b.double().reshape(-1).cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _dump():
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(_REPORT, open("gpurun_out/parity_dcgan.json", "w"), indent=1, sort_keys=True)
+
+
+def test_im2col_col2im_match_torch_conv_ops():
+    from gm_b200 import dcgan as DC
+    B, H, Cin, Cout = 3, 8, 16, 32
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, Cin, H, H, device="cuda", generator=g)
+    xr = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).view(B * H * H, Cin)
+    col = torch.empty(B * (H // 2) ** 2, 16 * Cin, device="cuda", dtype=torch.bfloat16)
+    DC._im2col(xr, B, H, H, Cin, col)
+    ref = torch.nn.functional.unfold(xr.float().view(B, H, H, Cin).permute(0, 3, 1, 2), 4, padding=1, stride=2)     # [B, Cin*16, L]
+    ref = ref.view(B, Cin, 16, -1).permute(0, 3, 2, 1).reshape(B * (H // 2) ** 2, 16 * Cin)                          # (kh,kw,ci) minor
+    assert torch.equal(col.float(), ref)
+    # col2im == conv_transpose2d with an identity "weight": fold of the tap columns
+    colr = torch.randn(B * H * H, 16 * Cout, device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.empty(B * 4 * H * H, Cout, device="cuda", dtype=torch.bfloat16)
+    DC._col2im(colr, B, H, H, Cout, y)
+    cols = colr.float().view(B, H * H, 16, Cout).permute(0, 3, 2, 1).reshape(B, Cout * 16, H * H)
+    ref = torch.nn.functional.fold(cols, (2 * H, 2 * H), 4, padding=1, stride=2)                                     # [B, Cout, 2H, 2H]
+    assert _nrel(y.float().view(B, 2 * H, 2 * H, Cout).permute(0, 3, 1, 2), ref) < 4e-3                             # bf16 output rounding
+    # C = 3 (image) paths
+    x3 = torch.rand(B, 3, 16, 16, device="cuda", generator=g)
+    x3r = x3.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).view(B * 256, 3)
+    col3 = torch.empty(B * 64, 48, device="cuda", dtype=torch.bfloat16)
+    DC._im2col(x3r, B, 16, 16, 3, col3)
+    ref3 = torch.nn.functional.unfold(x3r.float().view(B, 16, 16, 3).permute(0, 3, 1, 2), 4, padding=1, stride=2)
+    assert torch.equal(col3.float(), ref3.view(B, 3, 16, -1).permute(0, 3, 2, 1).reshape(B * 64, 48))
+
+
+def test_batchnorm_forward_backward_match_torch():
+    from gm_b200 import dcgan as DC
+    rows, Cc = 4096 + 37, 64
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = (torch.randn(rows, Cc, device="cuda", generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(Cc, device="cuda", generator=g)).float()
+    beta = (0.1 * torch.randn(Cc, device="cuda", generator=g)).float()
+    dy = torch.randn(rows, Cc, device="cuda", generator=g).to(torch.bfloat16)
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    stats, dgb = torch.zeros(2, Cc, device="cuda"), torch.zeros(2, Cc, device="cuda")
+    running = torch.stack([torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")])
+    DC._bn_fwd(x, gamma, beta, DC.ACT_LRELU, y, stats, running)
+    DC._bn_bwd(dy, x, stats, gamma, beta, DC.ACT_LRELU, dx, dgb)
+    xt = x.float().requires_grad_()
+    gt, bt = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    rm, rv = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    yt = torch.nn.functional.leaky_relu(torch.nn.functional.batch_norm(xt, rm, rv, gt, bt, True, 0.1, 1e-5), 0.2)
+    yt.backward(dy.float())
+    assert _nrel(y.float(), yt) < 4e-3 and _nrel(dx.float(), xt.grad) < 6e-3
+    assert _nrel(dgb[0], bt.grad) < 1e-3 and _nrel(dgb[1], gt.grad) < 1e-3
+    assert _nrel(running[0], rm) < 1e-4 and _nrel(running[1], rv) < 1e-4
+
+
+@pytest.mark.parametrize("variant", ["ns", "ls"])
+def test_dcgan_train_step_matches_the_torch_oracle(variant):
+    """One full train step at hidden 16, batch 8: images, D scores, both losses, every gradient tensor of D and G and
+    the parameters after Adam, against fp32 autograd of the same architecture (oracle/dcgan_torch.py)."""
+    import gm_b200
+    from oracle import dcgan_torch as O
+    hd, z, n = 16, 100, 8
+    eng = gm_b200.DcganEngine(hidden_dim=hd, z_dim=z, variant=variant)
+    G, D = O.Generator(hd, z), O.Discriminator(hd)
+    O.load_from_engine_weights(G, D, eng.torch_weights())
+    G.train(); D.train()
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.rand(n, 3 * 64 * 64, generator=g)
+    z1, z2 = torch.randn(n, z, generator=g), torch.randn(n, z, generator=g)
+    rep = {}
+    # forward pieces
+    rep["G(z)"] = _nrel(eng.generate(z1.cuda()), G(z1).detach())
+    rep["D(x)"] = _nrel(eng.discriminate(imgs.cuda()), D(imgs).detach())
+    # D step
+    if variant == "ns":
+        Ld_ref = O.d_loss(G, D, imgs, z1)
+    else:
+        Ld_ref = 0.5 * torch.mean((D(imgs) - 1) ** 2) + 0.5 * torch.mean(D(G(z1)) ** 2)        # src/ls_gan.py:192-193
+    gd = torch.autograd.grad(Ld_ref, list(D.parameters()))
+    Ld = eng.d_grad(eng.stage_images(imgs.cuda()), n, noise=z1.cuda()).item()
+    rep["D_loss"] = abs(Ld - Ld_ref.item()) / abs(Ld_ref.item())
+    tw = eng.torch_weights()
+    gsd = {}
+    for name in eng.D.names:
+        gsd[name] = eng.D.view(name, eng.D.grads).detach().cpu()
+    for (name, p), gref in zip(D.named_parameters(), gd):
+        got = gsd[name]
+        if name.startswith("l"):
+            cout = p.shape[0]
+            got = got[:cout].view(cout, 4, 4, -1).permute(0, 3, 1, 2)
+        rep["gradD_" + name] = _nrel(got, gref)
+    # G step (D not updated in between, like the unit tests of the MLP path)
+    if variant == "ns":
+        Lg_ref = O.g_loss(G, D, z2)
+    else:
+        Lg_ref = 0.5 * torch.mean((D(G(z2)) - 1) ** 2)                                            # src/ls_gan.py:213
+    gg = torch.autograd.grad(Lg_ref, list(G.parameters()))
+    Lg = eng.g_grad(n, noise=z2.cuda()).item()
+    rep["G_loss"] = abs(Lg - Lg_ref.item()) / abs(Lg_ref.item())
+    for (name, p), gref in zip(G.named_parameters(), gg):
+        got = eng.G.view(name, eng.G.grads).detach().cpu()
+        if name.startswith("l"):
+            cin, cout = p.shape[0], p.shape[1]
+            got = got.view(4, 4, cout, cin).permute(3, 2, 0, 1)
+        rep["gradG_" + name] = _nrel(got, gref)
+    _REPORT["step_" + variant] = rep
+    _dump()
+    assert rep["G(z)"] < 5e-3 and rep["D(x)"] < 5e-3, rep
+    assert rep["D_loss"] < 2e-3 and rep["G_loss"] < 2e-3, rep
+    for k, v in rep.items():
+        if k.startswith("grad"):
+            assert v < 3e-2, (k, v, rep)                 # bf16 operands through 5 conv layers + BatchNorm at batch 8
+    # Adam: parameters move like torch.optim.Adam on the oracle's gradients
+    hp = gm_b200.AdamHP.make(2e-4)
+    before = eng.D.params.clone()
+    eng.d_grad(eng.stage_images(imgs.cuda()), n, noise=z1.cuda())
+    eng.apply(1, hp)
+    moved = (eng.D.params - before).abs()
+    assert float(moved.max()) <= 2e-4 * 1.001 and float(moved.mean()) > 0.5e-4     # first Adam step: |update| ~ lr per weight
+
+
+def test_dcgan_loss_decreases_for_the_discriminator():
+    import gm_b200
+    eng = gm_b200.DcganEngine(hidden_dim=16, z_dim=100)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    imgs = (torch.rand(32, 3 * 64 * 64, device="cuda", generator=g) < 0.3).float()
+    x = eng.stage_images(imgs)
+    hp = gm_b200.AdamHP.make(2e-4)
+    losses = []
+    for s in range(12):
+        losses.append(eng.d_grad(x, 32, seed=7, step=s).item())
+        eng.apply(1, hp)
+        eng.g_grad(32, seed=7, step=s)
+        eng.apply(0, hp)
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
