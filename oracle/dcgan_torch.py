@@ -8,9 +8,23 @@ formulas — train_D: -mean(log(D(x)+1e-8) + log(1-D(G(z))+1e-8)) (src/ns_gan.py
 call), autograd backward, torch.optim.Adam.  tests/test_dcgan_gpu.py compares the CUDA conv path with it."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _id(t):
+    return t
+
+
+def bf16_points(t):
+    """Rounding model of the CUDA path: every tensor it stores as a bf16 GEMM operand / activation (weights' operand
+    copies, z, conv outputs before BatchNorm, activations, the generated image) is rounded to bf16 in the forward pass;
+    autograd treats the rounding as identity (the CUDA path applies the bf16-weight gradient to the fp32 master too)."""
+    return t + (t.to(torch.bfloat16).float() - t).detach()
 
 
 class Generator(nn.Module):
+    q = staticmethod(_id)          # set to bf16_points to model the CUDA path's storage rounding
+
     def __init__(self, hd=64, z=100, ch=3):
         super().__init__()
         c = [8 * hd, 4 * hd, 2 * hd, hd, ch]
@@ -22,15 +36,19 @@ class Generator(nn.Module):
         self.bn1, self.bn2, self.bn3, self.bn4 = (nn.BatchNorm2d(k) for k in c[:4])
 
     def forward(self, z):
-        x = z.view(z.shape[0], -1, 1, 1)
-        x = torch.relu(self.bn1(self.l1(x)))
-        x = torch.relu(self.bn2(self.l2(x)))
-        x = torch.relu(self.bn3(self.l3(x)))
-        x = torch.relu(self.bn4(self.l4(x)))
-        return torch.sigmoid(self.l5(x)).reshape(z.shape[0], -1)          # flat [B, ch*64*64] like src/ns_gan.py:46
+        q = self.q
+        x = q(z).view(z.shape[0], -1, 1, 1)
+        x = q(torch.relu(self.bn1(q(F.conv_transpose2d(x, q(self.l1.weight), None, 1, 0)))))
+        x = q(torch.relu(self.bn2(q(F.conv_transpose2d(x, q(self.l2.weight), None, 2, 1)))))
+        x = q(torch.relu(self.bn3(q(F.conv_transpose2d(x, q(self.l3.weight), None, 2, 1)))))
+        x = q(torch.relu(self.bn4(q(F.conv_transpose2d(x, q(self.l4.weight), None, 2, 1)))))
+        x = q(torch.sigmoid(F.conv_transpose2d(x, q(self.l5.weight), None, 2, 1)))
+        return x.reshape(z.shape[0], -1)                                    # flat [B, ch*64*64] like src/ns_gan.py:46
 
 
 class Discriminator(nn.Module):
+    q = staticmethod(_id)
+
     def __init__(self, hd=64, ch=3):
         super().__init__()
         c = [hd, 2 * hd, 4 * hd, 8 * hd]
@@ -43,12 +61,13 @@ class Discriminator(nn.Module):
         self.bn2, self.bn3, self.bn4 = (nn.BatchNorm2d(k) for k in c[1:])
 
     def logits(self, x):
-        x = x.view(x.shape[0], self.ch, 64, 64)                            # un-flatten (src/ns_gan.py:225 flattens)
-        x = nn.functional.leaky_relu(self.l1(x), 0.2)
-        x = nn.functional.leaky_relu(self.bn2(self.l2(x)), 0.2)
-        x = nn.functional.leaky_relu(self.bn3(self.l3(x)), 0.2)
-        x = nn.functional.leaky_relu(self.bn4(self.l4(x)), 0.2)
-        return self.l5(x).view(-1, 1)
+        q = self.q
+        x = q(x).view(x.shape[0], self.ch, 64, 64)                         # un-flatten (src/ns_gan.py:225 flattens)
+        x = q(F.leaky_relu(F.conv2d(x, q(self.l1.weight), None, 2, 1), 0.2))
+        x = q(F.leaky_relu(self.bn2(q(F.conv2d(x, q(self.l2.weight), None, 2, 1))), 0.2))
+        x = q(F.leaky_relu(self.bn3(q(F.conv2d(x, q(self.l3.weight), None, 2, 1))), 0.2))
+        x = q(F.leaky_relu(self.bn4(q(F.conv2d(x, q(self.l4.weight), None, 2, 1))), 0.2))
+        return F.conv2d(x, q(self.l5.weight), None, 1, 0).view(-1, 1)
 
     def forward(self, x):
         return torch.sigmoid(self.logits(x))
