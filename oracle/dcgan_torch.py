@@ -22,6 +22,19 @@ def bf16_points(t):
     return t + (t.to(torch.bfloat16).float() - t).detach()
 
 
+def conv_transpose_k4s2(x, w, q=_id):
+    """ConvTranspose2d(k=4, s=2, p=1) written the way the CUDA path computes it: one matrix product per input pixel
+    (col = x Wm^T, [(kh, kw, co)] columns) followed by the fold of the tap columns (col2im).  With q = identity this is
+    F.conv_transpose2d; with q = bf16_points the tap columns are rounded to bf16 before they are summed, as on the device."""
+    B, Cin, H, W = x.shape
+    Cout = w.shape[1]
+    xr = x.permute(0, 2, 3, 1).reshape(B * H * W, Cin)
+    Wm = w.permute(2, 3, 1, 0).reshape(16 * Cout, Cin)
+    col = q(xr @ Wm.t())
+    cols = col.view(B, H * W, 16, Cout).permute(0, 3, 2, 1).reshape(B, Cout * 16, H * W)
+    return F.fold(cols, (2 * H, 2 * W), 4, padding=1, stride=2)
+
+
 class Generator(nn.Module):
     q = staticmethod(_id)          # set to bf16_points to model the CUDA path's storage rounding
 
@@ -39,10 +52,10 @@ class Generator(nn.Module):
         q = self.q
         x = q(z).view(z.shape[0], -1, 1, 1)
         x = q(torch.relu(self.bn1(q(F.conv_transpose2d(x, q(self.l1.weight), None, 1, 0)))))
-        x = q(torch.relu(self.bn2(q(F.conv_transpose2d(x, q(self.l2.weight), None, 2, 1)))))
-        x = q(torch.relu(self.bn3(q(F.conv_transpose2d(x, q(self.l3.weight), None, 2, 1)))))
-        x = q(torch.relu(self.bn4(q(F.conv_transpose2d(x, q(self.l4.weight), None, 2, 1)))))
-        x = q(torch.sigmoid(F.conv_transpose2d(x, q(self.l5.weight), None, 2, 1)))
+        x = q(torch.relu(self.bn2(q(conv_transpose_k4s2(x, q(self.l2.weight), q)))))
+        x = q(torch.relu(self.bn3(q(conv_transpose_k4s2(x, q(self.l3.weight), q)))))
+        x = q(torch.relu(self.bn4(q(conv_transpose_k4s2(x, q(self.l4.weight), q)))))
+        x = q(torch.sigmoid(conv_transpose_k4s2(x, q(self.l5.weight), q)))
         return x.reshape(z.shape[0], -1)                                    # flat [B, ch*64*64] like src/ns_gan.py:46
 
 
