@@ -29,11 +29,27 @@ for p in (ROOT, os.path.join(ROOT, "generative-models_b200")):
 
 X, H, Z = 784, 400, 20
 # algorithmic FLOPs of one train step per image
-FLOP_PER_IMG = {"ns": 6326400.0, "wgp": 8836800.0, "vae": 3280000.0}
-DEFAULT_BATCH = {"ns": 65536, "wgp": 65536, "vae": 131072}
+def _dcgan_flop_per_img(hd=64, z=100, ch=3):
+    """algorithmic FLOPs of one NSGAN train step with the DCGAN conv nets (2 FLOP / MAC; needed work only, as SURVEY 8a
+    counts the MLP: D step = G fwd + 2 D fwd + 2 D bwd (weight grads + input grads above layer 1); G step = G fwd + D fwd +
+    D input-grad chain + G bwd)"""
+    gc, dc = [8 * hd, 4 * hd, 2 * hd, hd, ch], [hd, 2 * hd, 4 * hd, 8 * hd]
+    d_l = [1024 * dc[0] * 16 * ch, 256 * dc[1] * 16 * dc[0], 64 * dc[2] * 16 * dc[1], 16 * dc[3] * 16 * dc[2], 16 * dc[3]]
+    g_l = [z * 16 * gc[0], 16 * gc[0] * 16 * gc[1], 64 * gc[1] * 16 * gc[2], 256 * gc[2] * 16 * gc[3], 1024 * gc[3] * 16 * gc[4]]
+    Df, Gf = 2.0 * sum(d_l), 2.0 * sum(g_l)
+    d_bwd = 2.0 * (2 * sum(d_l) - d_l[0])            # wgrad everywhere + dgrad except into the image
+    d_dgrad = 2.0 * sum(d_l)                          # G step: input-gradient chain only, down to the image
+    g_bwd = 2.0 * (2 * sum(g_l) - g_l[0])            # wgrad everywhere + dgrad except into z
+    return (Gf + 2 * Df + 2 * d_bwd) + (Gf + Df + d_dgrad + g_bwd)
+
+
+FLOP_PER_IMG = {"ns": 6326400.0, "wgp": 8836800.0, "vae": 3280000.0, "dcgan": _dcgan_flop_per_img()}
+DEFAULT_BATCH = {"ns": 65536, "wgp": 65536, "vae": 131072, "dcgan": 1024}
 CONFIG_NAME = {"ns": "NSGAN MLP (D 784-400-1, G 20-400-784), BASELINE configs[1]",
                "wgp": "WGAN-GP MLP (ReLU critic, lambda 10 gradient penalty, closed-form double backward), BASELINE configs[2]",
-               "vae": "VAE MLP (784-400-(20,20), 20-400-784; SSE + KL as src/vae.py:203,212), BASELINE configs[3]"}
+               "vae": "VAE MLP (784-400-(20,20), 20-400-784; SSE + KL as src/vae.py:203,212), BASELINE configs[3]",
+               "dcgan": "NSGAN with DCGAN conv G / D (64x64x3, hidden 64, z 100; im2col + tcgen05 GEMM convolutions, BatchNorm), "
+                        "BASELINE configs[4]: global batch 8192 on 8 GPUs = 1024 per GPU, NCCL all-reduce of the G / D gradients"}
 METRIC = "train_step_images_per_sec"
 
 
@@ -135,7 +151,14 @@ class Workload:
         self.s = 0
         self.overlap = False
         self.inv = par.inv_global_batch(B, world)
-        if name == "vae":
+        if name == "dcgan":
+            self.eng = gm_b200.DcganEngine(hidden_dim=64, z_dim=100, channels=3, variant="ns")
+            self.hpG, self.hpD = gm_b200.AdamHP.make(2e-4), gm_b200.AdamHP.make(2e-4)
+            g = torch.Generator(device=pool_bits.device).manual_seed(77 + rank)
+            # device-resident synthetic images, NHWC bf16 rows, 4 batches (100 MB > the per-step reuse window)
+            self.pool = (torch.rand(4 * B * 4096, 3, device=pool_bits.device, generator=g) < 0.3).to(torch.bfloat16)
+            self.loss_buf = self.eng.loss_buf
+        elif name == "vae":
             self.eng = gm_b200.VaeEngine(X, H, Z, max_batch=B, precision=prec)
             init_vae_weights(self.eng)
             self.hp = gm_b200.AdamHP.make(1e-3, weight_decay=1e-5)          # src/vae.py:127,139-142
@@ -161,6 +184,18 @@ class Workload:
     def step(self, batch_bits=None):
         eng, B, s = self.eng, self.B, self.s
         self.s += 1
+        if self.name == "dcgan":
+            if batch_bits is None:
+                x = self.pool[(s % 4) * B * 4096:(s % 4 + 1) * B * 4096]
+            else:                                   # e2e leg: a uint8 NCHW-flattened host batch that just landed on the device
+                x = eng.stage_images(batch_bits)
+            eng.d_grad(x, B, inv_global_batch=self.inv, seed=self.seed, step=s)
+            self.par.sum_gradients(eng.D.grads)     # NCCL all-reduce (SUM) of the flat D gradient; no-op on one GPU
+            eng.apply(1, self.hpD)
+            eng.g_grad(B, inv_global_batch=self.inv, seed=self.seed, step=s)
+            self.par.sum_gradients(eng.G.grads)
+            eng.apply(0, self.hpG)
+            return
         if self.name == "vae":
             if batch_bits is None:
                 eng.set_sampler(self.N, max(self.N // B, 1), 3435)
@@ -230,7 +265,7 @@ def run_ours(args):
     B = args.batch or DEFAULT_BATCH[name]
     N = max(4 * 65536, 2 * B)                 # pool: 262144 images = 25.7 MB packed (412 MB as bf16 rows)
     bits = make_pool(N, dev, rank)
-    comm = par.make_peer_comm(330000) if name != "vae" else None
+    comm = par.make_peer_comm(330000) if name in ("ns", "wgp") else None
 
     def barrier():
         if world > 1:
@@ -300,10 +335,14 @@ def run_ours(args):
     # copy of each step's batch and the D2H read of its losses are inside the timed region
     e2e_steps = args.steps
     nb = 4
-    host = [torch.empty(B, X // 8, dtype=torch.uint8).pin_memory() for _ in range(nb)]
+    row_bytes = 3 * 64 * 64 if name == "dcgan" else X // 8          # dcgan: one byte per pixel value, NCHW flattened
+    host = [torch.empty(B, row_bytes, dtype=torch.uint8).pin_memory() for _ in range(nb)]
     for k, hb in enumerate(host):
-        hb.copy_(bits[(k * B) % (N - B + 1):(k * B) % (N - B + 1) + B].cpu())
-    stage = [torch.empty(B, X // 8, dtype=torch.uint8, device=dev) for _ in range(2)]
+        if name == "dcgan":
+            hb.copy_((torch.rand(B, row_bytes) < 0.3).to(torch.uint8))
+        else:
+            hb.copy_(bits[(k * B) % (N - B + 1):(k * B) % (N - B + 1) + B].cpu())
+    stage = [torch.empty(B, row_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
     host_loss = torch.zeros(e2e_steps + 8, 2).pin_memory()
     copy_stream = torch.cuda.Stream()
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -340,7 +379,7 @@ def run_ours(args):
     if world == 1 and not args.headline_only:
         # ---- the other BASELINE configs on the same box, shorter runs (same timing rules)
         others = {}
-        for other in [w for w in ("ns", "wgp", "vae") if w != name]:
+        for other in [w for w in ("ns", "wgp", "vae", "dcgan") if w != name]:
             Bo = DEFAULT_BATCH[other]
             wo = Workload(other, Bo, bits, N, rank, world, None)
             for _ in range(3):
@@ -375,6 +414,7 @@ def run_ours(args):
                                                            "1 D update + 1 G update per step, Adam"),
                       "global_batch": B * world, "parallelism": "dp%d" % world,
                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                            "NCCL all-reduce (SUM) of the flat G / D gradients" if name in ("dcgan", "vae") else
                                             "fused peer all-reduce + Adam kernel (push over CUDA-IPC NVLink mappings)%s" % (
                                                 ", D exchange overlapped with the G forward" if os.environ.get("GM_DP_OVERLAP") == "1" else "")
                                             if comm is not None
@@ -383,8 +423,9 @@ def run_ours(args):
                                 "by the in-kernel permutation sampler; per-step working set ~1.5 GB > L2, no L2 flush needed" % N,
                       "noise": "on-device Philox"},
            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "ms_per_step": round(ms_e2e / e2e_steps, 4),
-                   "h2d_bytes_per_step": B * X // 8, "d2h_bytes_per_step": 8,
-                   "input_format": "1 bit/pixel packed rows in pinned host memory, double-buffered H2D"},
+                   "h2d_bytes_per_step": B * row_bytes, "d2h_bytes_per_step": 8,
+                   "input_format": ("uint8 NCHW-flattened images in pinned host memory, double-buffered H2D" if name == "dcgan" else
+                                    "1 bit/pixel packed rows in pinned host memory, double-buffered H2D")},
            "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 4), "clocks": clocks, "roofline": roofline,
            "losses_last_step": losses}
     out.update(extra)
@@ -565,7 +606,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the workload's BASELINE batch)")
-    ap.add_argument("--workload", default="ns", choices=["ns", "wgp", "vae"])
+    ap.add_argument("--workload", default="ns", choices=["ns", "wgp", "vae", "dcgan"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--headline-only", action="store_true", help="skip the other workloads / trainer / small-batch legs")

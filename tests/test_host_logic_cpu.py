@@ -87,3 +87,23 @@ def test_reference_made_checkpoints_load_into_the_dropin_modules():
     vmodel.load_state_dict(vsd)
     for k, v in vmodel.state_dict().items():
         assert torch.equal(v, vsd[k]), k
+
+
+def test_dcgan_dropin_surface_without_a_gpu():
+    """dc_gan.py mirrors the NSGAN class surface for the conv model the README recommends (README.md:68,96): usual DCGAN
+    state_dict keys / shapes, the reference's attributes, and a loud failure instead of a CPU fallback."""
+    import dc_gan
+    from gm_b200 import GmError
+    model = dc_gan.DCGAN(image_size=64 * 64 * 3, hidden_dim=16, z_dim=100)
+    sd = model.state_dict()
+    assert sd["G.l1.weight"].shape == (100, 128, 4, 4) and sd["G.l5.weight"].shape == (16, 3, 4, 4)
+    assert sd["D.l1.weight"].shape == (16, 3, 4, 4) and sd["D.l5.weight"].shape == (1, 128, 4, 4)
+    assert "G.bn1.running_mean" in sd and "D.bn4.weight" in sd and "D.bn1.weight" not in sd
+    assert (model.z_dim, model.image_size, model.hidden_dim, model.shape) == (100, 12288, 16, 64)
+    it = [(torch.zeros(2, 3, 64, 64), torch.zeros(2))]
+    tr = dc_gan.DCGANTrainer(model, it, it, it)
+    assert tr.Glosses == [] and tr.num_epochs == 0 and tr.name == "DCGAN"
+    with pytest.raises(GmError):
+        model.G(torch.randn(2, 100))
+    with pytest.raises(GmError):
+        dc_gan.DCGAN(image_size=784)
