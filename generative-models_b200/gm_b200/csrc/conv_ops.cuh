@@ -150,14 +150,17 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const __nv_bfloa
     part[((long long)blockIdx.x * 2 + which) * C + ch] = t;
   }
 }
-// stats[0][C] = mean, stats[1][C] = invstd; running[0] mean, running[1] var (nullable)
+// stats[0][C] = mean, stats[1][C] = invstd; running[0] mean, running[1] var (nullable).  One WARP per channel: the lanes
+// stride over the per-block partials (a thread per channel walked all ~600 partials serially: 67 us for a 2 KB result).
 __global__ void bn_finalize_kernel(const double* __restrict__ part, int nblk, int C, double count, float eps,
                                    float* __restrict__ stats, float* __restrict__ running, float momentum) {
   griddep_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < nblk; ++i) { s1 += part[((long long)i * 2) * C + c]; s2 += part[((long long)i * 2 + 1) * C + c]; }
+  for (int i = lane; i < nblk; i += 32) { s1 += part[((long long)i * 2) * C + c]; s2 += part[((long long)i * 2 + 1) * C + c]; }
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if (lane != 0) return;
   const double mean = s1 / count;
   const double var = fmax(s2 / count - mean * mean, 0.0);       // biased, as torch normalises with
   stats[c] = float(mean);
@@ -245,15 +248,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const __nv_b
     part[((long long)blockIdx.x * 2 + which) * C + ch] = t;
   }
 }
-// dgb[0][C] = dbeta, dgb[1][C] = dgamma
+// dgb[0][C] = dbeta, dgb[1][C] = dgamma; one warp per output value
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk, int C, float* __restrict__ dgb) {
   griddep_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= 2 * C) return;
   const int which = c / C, ch = c % C;
   double t = 0.0;
-  for (int i = 0; i < nblk; ++i) t += part[((long long)i * 2 + which) * C + ch];
-  dgb[c] = float(t);
+  for (int i = lane; i < nblk; i += 32) t += part[((long long)i * 2 + which) * C + ch];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) dgb[c] = float(t);
 }
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, long long rows, int C, int ld,
                                     const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,

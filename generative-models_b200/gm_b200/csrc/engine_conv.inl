@@ -54,7 +54,7 @@ extern "C" int gm_bn_forward(gm_ctx* c, const void* x, long long rows, int C, in
   if (!cfg) { cudaFuncSetAttribute(bn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
               cudaFuncSetAttribute(bn_bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); cfg = true; }
   launch_pdl("bn_partial_kernel", bn_partial_kernel, nblk, kBnThreads, smem, s, static_cast<const __nv_bfloat16*>(x), rows, C, ld, part);
-  launch_pdl("bn_finalize_kernel", bn_finalize_kernel, cdiv(C, 128), 128, 0, s, static_cast<const double*>(part), nblk, C, double(rows), eps, stats_dev,
+  launch_pdl("bn_finalize_kernel", bn_finalize_kernel, cdiv(C * 32, 256), 256, 0, s, static_cast<const double*>(part), nblk, C, double(rows), eps, stats_dev,
              running_dev, momentum);
   launch_pdl("bn_apply_kernel", bn_apply_kernel, c->num_sms * 16, 256, 0, s, static_cast<const __nv_bfloat16*>(x), rows, C, ld,
              static_cast<const float*>(stats_dev), gamma, beta, act, slope, static_cast<__nv_bfloat16*>(y), ldy);
@@ -80,7 +80,7 @@ extern "C" int gm_bn_backward(gm_ctx* c, const void* dy, const void* x, long lon
   const size_t smem = size_t(rpi) * 2 * C * sizeof(double);
   launch_pdl("bn_bwd_partial_kernel", bn_bwd_partial_kernel, nblk, kBnThreads, smem, s, static_cast<const __nv_bfloat16*>(dy),
              static_cast<const __nv_bfloat16*>(x), rows, C, ld, stats_dev, gamma, beta, act, slope, part);
-  launch_pdl("bn_bwd_finalize_kernel", bn_bwd_finalize_kernel, cdiv(2 * C, 128), 128, 0, s, static_cast<const double*>(part), nblk, C, dgb_dev);
+  launch_pdl("bn_bwd_finalize_kernel", bn_bwd_finalize_kernel, cdiv(2 * C * 32, 256), 256, 0, s, static_cast<const double*>(part), nblk, C, dgb_dev);
   launch_pdl("bn_bwd_apply_kernel", bn_bwd_apply_kernel, c->num_sms * 16, 256, 0, s, static_cast<const __nv_bfloat16*>(dy),
              static_cast<const __nv_bfloat16*>(x), rows, C, ld, stats_dev, gamma, beta, act, slope, static_cast<const float*>(dgb_dev),
              float(1.0 / double(rows)), static_cast<__nv_bfloat16*>(dx), lddx);
