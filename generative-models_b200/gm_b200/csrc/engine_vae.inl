@@ -22,7 +22,7 @@ struct gm_vae {
   double *part_r = nullptr, *part_k = nullptr;
   bool lazy = false, pend = false;      // lazy gradients: gm_vae_apply gathers the split-K partials itself
   GradSegs pend_segs;
-  long long pool_n = 0, pool_bpe = 0;   // on-device epoch sampler (gm_vae_set_sampler)
+  long long pool_n = 0, pool_bpe = 0, pool_bs = 0;   // on-device epoch sampler (gm_vae_set_sampler)
   uint64_t pool_seed = 0;
   std::map<int, VaePlans> plans;
   std::vector<void*> allocs;
@@ -113,9 +113,9 @@ extern "C" int gm_vae_create(gm_ctx* c, const gm_vae_desc* d, gm_vae** out) {
 
 // On-device epoch shuffling: gm_vae_grad(step) with gather_idx == NULL reads batch (step % batches_per_epoch)
 // of the pseudo-random permutation of epoch (step / batches_per_epoch) over a resident pool (src/vae.py:150).
-extern "C" int gm_vae_set_sampler(gm_vae* g, long long n_pool, long long batches_per_epoch, uint64_t seed) {
-  if (!g || n_pool < 0 || n_pool > 0x7FFFFFFFll || batches_per_epoch < 0) return g ? fail(g->ctx, GM_ERR_ARG, "gm_vae_set_sampler: bad argument") : GM_ERR_ARG;
-  g->pool_n = n_pool; g->pool_bpe = batches_per_epoch; g->pool_seed = seed;
+extern "C" int gm_vae_set_sampler(gm_vae* g, long long n_pool, long long batches_per_epoch, long long batch_size, uint64_t seed) {
+  if (!g || n_pool < 0 || n_pool > 0x7FFFFFFFll || batches_per_epoch < 0 || batch_size < 0) return g ? fail(g->ctx, GM_ERR_ARG, "gm_vae_set_sampler: bad argument") : GM_ERR_ARG;
+  g->pool_n = n_pool; g->pool_bpe = batches_per_epoch; g->pool_bs = batch_size; g->pool_seed = seed;
   return GM_OK;
 }
 
@@ -266,7 +266,7 @@ static int vae_forward_core(gm_vae* g, VaePlans* sp, const void* images, int fmt
   if (!idx && g->pool_n > 0) {
     // batch (step mod batches_per_epoch) of this epoch's permutation: a true epoch like `for batch in train_iter` (src/vae.py:150)
     const uint64_t bpe = g->pool_bpe > 0 ? uint64_t(g->pool_bpe) : 1;
-    smp = make_sampler(g->pool_n, g->pool_seed, step / bpe, (step % bpe) * uint64_t(B));
+    smp = make_sampler(g->pool_n, g->pool_seed, step / bpe, (step % bpe) * uint64_t(g->pool_bs > 0 ? g->pool_bs : B));
   }
   launch_pdl("stage_images_kernel", stage_images_kernel, c->num_sms * 8, 256, 0, s, images, fmt, idx, g->Xin, B, g->X, g->XP, smp, g->lo);
   c->launches++;

@@ -421,10 +421,12 @@ class VaeEngine:
                                         _ptr(self.loss_buf), _stream()))
         return self.loss_buf
 
-    def set_sampler(self, n_pool, batches_per_epoch, seed=0):
+    def set_sampler(self, n_pool, batches_per_epoch, seed=0, batch_size=0):
         """On-device epoch shuffling: grad(images=pool, gather_idx=None, batch=B, step=s) reads batch
-        s % batches_per_epoch of the permutation of epoch s // batches_per_epoch (src/vae.py:150)."""
-        check(self.h, lib().gm_vae_set_sampler(self.g, int(n_pool), int(batches_per_epoch), int(seed) & 0xFFFFFFFFFFFFFFFF))
+        s % batches_per_epoch of the permutation of epoch s // batches_per_epoch (src/vae.py:150); batch_size = the
+        loader's nominal batch when the last batch of an epoch is shorter."""
+        check(self.h, lib().gm_vae_set_sampler(self.g, int(n_pool), int(batches_per_epoch), int(batch_size),
+                                               int(seed) & 0xFFFFFFFFFFFFFFFF))
 
     def set_lazy_grads(self, on=True):
         """Single-GPU fast path: grad() leaves split-K partials, apply() gathers + updates in one kernel; self.grads is

@@ -17,6 +17,15 @@ from gm_b200 import AdamHP, GmError, VaeEngine
 from gm_b200.gan_api import to_cuda
 
 
+def _engine_of(module, what, batch):
+    """The engine behind an Encoder / Decoder: the Trainer's (grown on demand), or - for a detached copy such as
+    VAETrainer.best_model - a private inference engine built lazily from the copy's own parameters."""
+    parent = module._parent() if getattr(module, "_parent", None) is not None else None
+    if parent is None:
+        raise GmError(what + " is not part of a VAE: construct it through VAE(...)")
+    return parent._engine_for(batch, what)
+
+
 class Encoder(nn.Module):
     """ MLP encoder for VAE (src/vae.py:47-61). Input is an image, outputs are mu, log_var """
 
@@ -27,11 +36,9 @@ class Encoder(nn.Module):
         self.log_var = nn.Linear(hidden_dim, z_dim)
 
     def forward(self, x):
-        eng = getattr(self, "_engine", None)
-        if eng is None:
-            raise GmError("Encoder is not attached to a CUDA engine yet: construct the VAETrainer first")
-        eng.sync_all()
-        _, mu, lv, _ = eng.forward(to_cuda(x).float(), want_images=False)
+        x = to_cuda(x).float()
+        eng = _engine_of(self, "Encoder", x.shape[0])
+        _, mu, lv, _ = eng.forward(x, want_images=False)
         return mu, lv
 
 
@@ -44,11 +51,10 @@ class Decoder(nn.Module):
         self.recon = nn.Linear(hidden_dim, image_size)
 
     def forward(self, z):
-        eng = getattr(self, "_engine", None)
-        if eng is None:
-            raise GmError("Decoder is not attached to a CUDA engine yet: construct the VAETrainer first")
-        eng.sync_all()
-        return eng.decode(to_cuda(z))
+        z = to_cuda(z)
+        if z.dim() == 1:                       # the reference decodes single latent vectors too (src/vae.py:289-290)
+            z = z.view(1, -1)
+        return _engine_of(self, "Decoder", z.shape[0]).decode(z)
 
 
 class VAE(nn.Module):
@@ -60,13 +66,41 @@ class VAE(nn.Module):
         self.encoder = Encoder(image_size=image_size, hidden_dim=hidden_dim, z_dim=z_dim)
         self.decoder = Decoder(z_dim=z_dim, hidden_dim=hidden_dim, image_size=image_size)
         self.shape = int(image_size ** 0.5)
+        import weakref
+        for mod in (self.encoder, self.decoder):
+            object.__setattr__(mod, "_parent", weakref.ref(self))
+        object.__setattr__(self, "_owner", None)        # weakref to the VAETrainer that trains this model
+        object.__setattr__(self, "_own_engine", None)   # private inference engine of a detached copy
+
+    def _engine_for(self, batch, what="VAE"):
+        owner = self._owner() if self._owner is not None else None
+        if owner is not None:
+            eng = owner._ensure_engine(batch)
+            eng.sync_all()
+            return eng
+        if not torch.cuda.is_available():
+            raise GmError(what + " is not attached to a CUDA engine yet: construct the VAETrainer first "
+                          "(there is no eager/CPU path)")
+        eng = self._own_engine
+        if eng is None or batch > eng.max_batch:
+            eng = VaeEngine(self.image_size, self.hidden_dim, self.z_dim, max_batch=max(batch, 64))
+            object.__setattr__(self, "_own_engine", eng)
+        eng.load({k: v.data for k, v in self.named_parameters()})
+        return eng
+
+    def __deepcopy__(self, memo):
+        """A detached copy (the reference keeps `best_model = deepcopy(model)`, src/vae.py:178-180): same class, cloned
+        parameter values, no link to the Trainer's engine - its encoder / decoder run on a private engine built on use."""
+        new = VAE(self.image_size, self.hidden_dim, self.z_dim)
+        with torch.no_grad():
+            for (_, a), (_, b) in zip(new.named_parameters(), self.named_parameters()):
+                a.copy_(b.detach().cpu())
+        new.train(self.training)
+        return new
 
     def forward(self, x):
-        eng = getattr(self.encoder, "_engine", None)
-        if eng is None:
-            raise GmError("VAE is not attached to a CUDA engine yet: construct the VAETrainer first")
-        eng.sync_all()
         x = to_cuda(x).float()
+        eng = self._engine_for(x.shape[0])
         eps = to_cuda(torch.randn(x.shape[0], self.z_dim))          # src/vae.py:104
         out, mu, lv, _ = eng.forward(x, eps=eps)
         return out, mu, lv
@@ -94,6 +128,8 @@ class _VaeLoss(torch.autograd.Function):
 
 
 class VAETrainer:
+    device_noise = True        # in-kernel Philox eps + resident dataset in train(); False: the reference's host draws
+
     def __init__(self, model, train_iter, val_iter, test_iter, viz=False):
         """ Object to hold data iterators, train the model (src/vae.py:109-125) """
         self.model = model
@@ -106,6 +142,8 @@ class VAETrainer:
         self.num_epochs = 0
         self._engine, self._max_batch, self._step = None, 0, 0
         self._seed = int(torch.initial_seed() & 0x7FFFFFFF)
+        import weakref
+        object.__setattr__(model, "_owner", weakref.ref(self))
 
     def _ensure_engine(self, batch):
         if self._engine is not None and batch <= self._max_batch:
@@ -122,8 +160,6 @@ class VAETrainer:
             eng.exp_avg.copy_(old.exp_avg)
             eng.exp_avg_sq.copy_(old.exp_avg_sq)
             eng.steps = old.steps
-        for mod in (m.encoder, m.decoder):
-            object.__setattr__(mod, "_engine", eng)
         self._engine, self._max_batch = eng, batch
         return eng
 
@@ -134,17 +170,41 @@ class VAETrainer:
         if self._engine is not None:
             self._engine.reset_optimizer()
             self._engine.sync_all()
+        # fast path (default): the train split packed to 1 bit/pixel in HBM once, batches drawn by the in-kernel epoch
+        # sampler, eps by in-kernel Philox, gradient gather fused into Adam - no host work per step.  `device_noise =
+        # False` (or a non-binary / non-TensorDataset loader) keeps the reference's host draws (torch.manual_seed replay).
+        from gm_b200.gan_api import DeviceDataset
+        resident = DeviceDataset.from_loader(self.train_iter, getattr(self, "_resident", None)) if self.device_noise else None
+        self._resident = resident
         for epoch in range(1, num_epochs + 1):
             self.model.train()
             per_step = []
-            for batch in self.train_iter:
-                images = self._images(batch)
-                eng = self._ensure_engine(images.shape[0])
-                eps = to_cuda(torch.randn(images.shape[0], self.model.z_dim))      # src/vae.py:104
-                per_step.append(eng.grad(images, eps=eps, seed=self._seed, step=self._step).clone())
-                eng.apply(hp)
-                self._step += 1
-            vals = torch.stack(per_step).tolist()
+            if resident is not None:
+                bs = min(resident.batch_size, resident.n)
+                nb = len(resident)
+                eng = self._ensure_engine(bs)
+                eng.set_lazy_grads(True)
+                eng.set_sampler(resident.n, nb, self._seed + 7919 * epoch, batch_size=bs)
+                ring = torch.zeros(nb, 2, device="cuda")
+                try:
+                    for k in range(nb):
+                        rows = min(bs, resident.n - k * bs)                        # the last batch of an epoch may be short
+                        ring[k].copy_(eng.grad(resident.bits, fmt="bits", batch=rows, seed=self._seed, step=k))
+                        eng.apply(hp)
+                        self._step += 1
+                finally:
+                    eng.set_lazy_grads(False)
+                    eng.set_sampler(0, 0, 0)
+                vals = ring.tolist()
+            else:
+                for batch in self.train_iter:
+                    images = self._images(batch)
+                    eng = self._ensure_engine(images.shape[0])
+                    eps = to_cuda(torch.randn(images.shape[0], self.model.z_dim))      # src/vae.py:104
+                    per_step.append(eng.grad(images, eps=eps, seed=self._seed, step=self._step).clone())
+                    eng.apply(hp)
+                    self._step += 1
+                vals = torch.stack(per_step).tolist()
             epoch_recon, epoch_kl = [v[0] for v in vals], [v[1] for v in vals]
             epoch_loss = [a + b for a, b in zip(epoch_recon, epoch_kl)]
             self.kl_loss.extend(epoch_kl)
@@ -152,7 +212,7 @@ class VAETrainer:
             self.model.eval()
             val_loss = self.evaluate(self.val_iter)
             if val_loss < self.best_val_loss:
-                self.best_model = deepcopy(self.model.state_dict())     # the reference deep-copies the module
+                self.best_model = deepcopy(self.model)                  # a detached module copy, like src/vae.py:178-180
                 self.best_val_loss = val_loss
             print("Epoch[%d/%d], Total Loss: %.4f, Reconst Loss: %.4f, KL Div: %.7f, Val Loss: %.4f"
                   % (epoch, num_epochs, np.mean(epoch_loss), np.mean(epoch_recon), np.mean(epoch_kl), val_loss))
@@ -205,6 +265,44 @@ class VAETrainer:
         z = to_cuda(torch.randn(num_images, self.model.z_dim))
         sample = self.model.decoder(z)
         return sample.view(num_images, self.model.shape, self.model.shape)
+
+    def sample_interpolated_images(self):
+        """ Viz method 2 (src/vae.py:278-293): decode the interpolation between two random latent vectors; returns the
+        list of decoded images instead of displaying them """
+        z1 = torch.normal(torch.zeros(self.model.z_dim), 1)
+        z2 = torch.normal(torch.zeros(self.model.z_dim), 1)
+        out = []
+        for alpha in np.linspace(0, 1, self.model.z_dim):
+            z = to_cuda(float(alpha) * z1 + (1 - float(alpha)) * z2)
+            out.append(self.model.decoder(z).view(-1, self.model.shape, self.model.shape))
+        return out
+
+    def explore_latent_space(self, num_epochs=3):
+        """ Viz method 3 (src/vae.py:295-338): train a VAE with a 2-d latent space, collect the variational means of the
+        train split and decode a 10 x 10 grid of latent points; returns the trained (best) model, and keeps the means /
+        grid samples in self.latent_means / self.latent_grid instead of plotting them """
+        train_iter, val_iter, test_iter = get_data()                                   # noqa: F405
+        latent_model = VAE(image_size=784, hidden_dim=400, z_dim=2)
+        latent_space = VAETrainer(latent_model, train_iter, val_iter, test_iter)
+        latent_space.train(num_epochs)
+        latent_model = latent_space.best_model
+        data = []
+        for images, labels in train_iter:
+            mu, _ = latent_model.encoder(to_cuda(images.view(images.shape[0], -1)))
+            data.append(torch.cat([labels.view(-1, 1).float(), mu.cpu()], dim=1))
+        self.latent_means = torch.cat(data)
+        mu = torch.stack([torch.FloatTensor([m1, m2]) for m1 in np.linspace(-2, 2, 10) for m2 in np.linspace(-2, 2, 10)])
+        self.latent_grid = latent_model.decoder(to_cuda(mu)).view(mu.shape[0], -1, latent_model.shape, latent_model.shape)
+        return latent_model
+
+    def make_all(self):
+        """ Execute all latent space viz methods outlined in this class (src/vae.py:340-350) """
+        print('Sampled images from latent space:')
+        self.sample_images(save=False)
+        print('Interpolating between two randomly sampled')
+        self.sample_interpolated_images()
+        print('Exploring latent representations')
+        _ = self.explore_latent_space()
 
     def viz_loss(self):
         try:

@@ -268,10 +268,11 @@ int gm_vae_sync_shadows(gm_vae* vae, gm_stream stream);
 int gm_vae_grad(gm_vae* vae, const void* images_dev, int img_fmt, const int* gather_idx_dev, int batch,
                 const float* eps_dev, float grad_scale, uint64_t seed, uint64_t step, float* losses_dev,
                 gm_stream stream);
-/* On-device epoch shuffling for gm_vae_grad (gather_idx_dev == NULL): step s reads batch (s mod
- * batches_per_epoch) of the permutation of epoch (s / batches_per_epoch) over the resident pool — the
- * `for batch in self.train_iter` of src/vae.py:150 without host work.  n_pool == 0: off. */
-int gm_vae_set_sampler(gm_vae* vae, long long n_pool, long long batches_per_epoch, uint64_t seed);
+/* On-device epoch shuffling for gm_vae_grad (gather_idx_dev == NULL): step s reads batch k = s mod batches_per_epoch
+ * (rows [k * batch_size, k * batch_size + batch) of the permutation of epoch s / batches_per_epoch) of the resident
+ * pool — the `for batch in self.train_iter` of src/vae.py:150 without host work; batch_size is the loader's nominal
+ * batch (the last batch of an epoch may be shorter; 0 = the batch of the call).  n_pool == 0: off. */
+int gm_vae_set_sampler(gm_vae* vae, long long n_pool, long long batches_per_epoch, long long batch_size, uint64_t seed);
 /* lazy gradients, as gm_gan_set_lazy_grads: gm_vae_apply gathers the split-K partials, stores the flat gradient and
  * applies Adam in one kernel; gm_vae_materialize_grads forms the flat gradient earlier (e.g. before an all-reduce). */
 int gm_vae_set_lazy_grads(gm_vae* vae, int on, gm_stream stream);

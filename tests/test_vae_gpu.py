@@ -150,3 +150,32 @@ def test_lazy_gradients_are_bit_identical():
     assert torch.equal(p0, p1) and torch.equal(v0, v1)
     for a, b in zip(g0, g1):
         assert torch.equal(a, b)
+
+
+def test_trainer_fast_path_and_detached_best_model():
+    """VAETrainer.train over a DataLoader(TensorDataset): resident 1-bit dataset + in-kernel epoch sampler + Philox eps
+    (no host work per step), a short last batch, best_model as a detached MODULE whose encoder / decoder run
+    (src/vae.py:178-180,304), and the viz helpers' computations."""
+    import vae as V
+    g = torch.Generator().manual_seed(0)
+    imgs = (torch.rand(250, 1, 28, 28, generator=g) < 0.13).float()
+    ds = torch.utils.data.TensorDataset(imgs, torch.zeros(250, dtype=torch.long))
+    loader = torch.utils.data.DataLoader(ds, batch_size=64, shuffle=True)          # 4 batches, the last one has 58 rows
+    model = V.VAE(784, 400, 20)
+    tr = V.VAETrainer(model, loader, loader, loader)
+    tr.train(num_epochs=3, lr=1e-3, weight_decay=1e-5)
+    assert len(tr.recon_loss) == 12 and all(np.isfinite(tr.recon_loss)) and all(np.isfinite(tr.kl_loss))
+    full = [tr.recon_loss[i] / 64 for i in range(12) if i % 4 != 3]
+    assert np.mean(full[-3:]) < np.mean(full[:3])                                  # it learns (per-sample SSE falls)
+    assert tr._resident is not None                                                 # the fast path ran
+    best = tr.best_model
+    assert isinstance(best, V.VAE) and best is not model
+    mu, lv = best.encoder(imgs[:16].view(16, -1))                                  # private lazy engine of the copy
+    assert mu.shape == (16, 20) and torch.isfinite(mu).all()
+    dec = best.decoder(torch.randn(5, 20))
+    assert dec.shape == (5, 784)
+    p0 = best.decoder.recon.weight.clone()
+    tr.train(num_epochs=1)                                                          # training on does not move the detached copy
+    assert torch.equal(best.decoder.recon.weight, p0) or tr.best_model is not best
+    out = tr.sample_interpolated_images()
+    assert len(out) == 20 and out[0].shape == (1, 28, 28)
