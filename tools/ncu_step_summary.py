@@ -37,7 +37,15 @@ if nt:
     print("\nK-major 128x208 launches: %d, mean DRAM bytes per launch %.1f MB" % (len(nt), avg / 1e6))
     if "--write-traffic" in sys.argv:
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        json.dump({"kernel": "gemm_umma<208,0,K-major> (%d launches per NSGAN step)" % len(nt),
+        wl = "ns"
+        for a in sys.argv[2:]:
+            if a.startswith("--workload="):
+                wl = a.split("=", 1)[1]
+        path = os.path.join(root, "profiles", "traffic.json")
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        if "dram_bytes_per_launch" in cur:      # round-1 flat format
+            cur = {}
+        cur[wl] = {"kernel": "gemm_umma<208,0,K-major> (%d launches captured)" % len(nt),
                    "dram_bytes_per_launch": int(avg), "launches_captured": len(nt),
-                   "source": "%s (ncu --set full --clock-control none, bench.py --steps 2 --warmup 3)" % os.path.relpath(rep, root)},
-                  open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)
+                   "source": "%s (ncu --set full --clock-control none, bench.py --workload %s --steps 2)" % (os.path.basename(rep), wl)}
+        json.dump(cur, open(path, "w"), indent=1)
