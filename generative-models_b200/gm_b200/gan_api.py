@@ -15,6 +15,7 @@ import weakref
 import numpy as np
 import torch
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from . import parallel as par
@@ -202,6 +203,7 @@ class _GForward(torch.autograd.Function):
         return engine.g_forward(noise)
 
     @staticmethod
+    @once_differentiable        # the backward is a CUDA kernel chain: a create_graph=True caller gets an error, not a silently missing term
     def backward(ctx, dimages):
         eng = ctx.engine
         if eng.g_generation != ctx.generation:
@@ -225,6 +227,7 @@ class _DForward(torch.autograd.Function):
         return engine.d_forward(ctx.slot, x).view(-1, 1)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dscore):
         eng = ctx.engine
         if eng.d_generation[ctx.slot] != ctx.generation:
