@@ -130,6 +130,7 @@ def lib():
     L.gm_bn_backward.argtypes = [vp, vp, vp, ll, i, i, vp, vp, vp, i, f, vp, i, vp, vp]
     L.gm_cast_bf16.argtypes = [vp, vp, i, i, vp, i, vp, i, vp]
     L.gm_pack_col0.argtypes = [vp, vp, i, vp, i, vp]
+    L.gm_stage_images.argtypes = [vp, vp, i, vp, vp, i, i, i, vp]
     L.gm_noise_rows.argtypes = [vp, vp, vp, i, i, i, u64, u64, vp]
     L.gm_loss_rows.argtypes = [vp, i, i, vp, i, i, f, vp, vp, vp, vp]
     L.gm_gan_use_device_step.argtypes = [vp, i, vp, vp]

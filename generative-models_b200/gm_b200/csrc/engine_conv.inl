@@ -156,3 +156,15 @@ extern "C" int gm_noise_rows(gm_ctx* c, const float* noise_dev, void* out, int r
   CU_OK(c, cudaGetLastError());
   return GM_OK;
 }
+
+// images (gm_img_fmt: fp32 | u8 | 1-bit packed) -> bf16 rows [rows, ld] with a ones column at x (the bias-gradient trick of
+// the MLP engines) - process_batch's flatten + to_cuda (src/ns_gan.py:222-226, src/ae.py:150-151) as a standalone step
+extern "C" int gm_stage_images(gm_ctx* c, const void* images, int img_fmt, const int* gather_idx, void* out, int rows, int x, int ld,
+                               gm_stream stream) {
+  if (!c || !images || !out || rows <= 0 || x <= 0 || ld < x + 1 || ld % 8) return c ? fail(c, GM_ERR_ARG, "gm_stage_images: bad argument") : GM_ERR_ARG;
+  launch_pdl("stage_images_kernel", stage_images_kernel, c->num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream), images, img_fmt, gather_idx,
+             static_cast<__nv_bfloat16*>(out), rows, x, ld, kNoSampler, 0ll);
+  c->launches++;
+  CU_OK(c, cudaGetLastError());
+  return GM_OK;
+}

@@ -307,6 +307,9 @@ int gm_bn_backward(gm_ctx* ctx, const void* dy_dev, const void* x_dev, long long
 int gm_cast_bf16(gm_ctx* ctx, const float* src_dev, int R, int C, void* dst_dev, int ld, void* dst_t_dev, int ld_t, gm_stream stream);
 /* out [rows, ld] bf16 with column 0 = v[r], the rest 0 */
 int gm_pack_col0(gm_ctx* ctx, const float* v_dev, int rows, void* out_dev, int ld, gm_stream stream);
+/* process_batch (src/ns_gan.py:222-226, src/ae.py:150-151) as a standalone step: images -> bf16 rows [rows, ld], ones column at x */
+int gm_stage_images(gm_ctx* ctx, const void* images_dev, int img_fmt, const int* gather_idx_dev, void* out_dev, int rows, int x, int ld,
+                    gm_stream stream);
 /* generator noise rows as a bf16 GEMM operand: Philox N(0,1) (noise_dev NULL) or a caller tensor [rows, z] fp32 */
 int gm_noise_rows(gm_ctx* ctx, const float* noise_dev, void* out_dev, int rows, int z, int ld, uint64_t seed, uint64_t stream_id,
                   gm_stream stream);

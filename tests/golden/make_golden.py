@@ -346,12 +346,45 @@ def make_checkpoints():
     print("checkpoints:", os.path.getsize(path), os.path.getsize(vpath), "bytes")
 
 
+def make_ae_case():
+    """src/ae.py: 3 train steps of the reference's AutoencoderTrainer on one fixed batch (no randomness in the model)."""
+    mod = import_ref("ae")
+    rng = np.random.default_rng(4321)
+    Hh = 32
+    W = {"encoder.linear": (rng.uniform(-1 / 28, 1 / 28, (Hh, X)).astype(np.float32), rng.uniform(-1 / 28, 1 / 28, (Hh,)).astype(np.float32)),
+         "decoder.linear": (rng.uniform(-Hh ** -0.5, Hh ** -0.5, (X, Hh)).astype(np.float32), rng.uniform(-Hh ** -0.5, Hh ** -0.5, (X,)).astype(np.float32))}
+    x = gm_images(B, seed=3435)
+    it = [(torch.from_numpy(x).view(B, 1, 28, 28), torch.zeros(B, dtype=torch.long))] * STEPS
+    out = {"images_bits": np.packbits(x.astype(np.uint8))}
+    for k, (w, b) in W.items():
+        out["init_" + k + ".weight"], out["init_" + k + ".bias"] = w, b
+    model = mod.Autoencoder(X, Hh)
+    load_weights(model, W)
+    tr = mod.AutoencoderTrainer(model, it, it[:1], it[:1], viz=False)
+    tr.train(num_epochs=1, lr=1e-3, weight_decay=1e-5)
+    out["recon_loss"] = np.asarray(tr.recon_loss, np.float64)
+    for name, p in model.state_dict().items():
+        summarise("final_" + name, p.numpy(), out)
+    model2 = mod.Autoencoder(X, Hh)
+    load_weights(model2, W)
+    tr2 = mod.AutoencoderTrainer(model2, it, it[:1], it[:1], viz=False)
+    loss = tr2.compute_batch(it[0])
+    loss.backward()
+    out["step1_loss"] = np.float64(loss.item())
+    for name, p in model2.named_parameters():
+        summarise("step1_grad_" + name, p.grad.numpy(), out)
+    np.savez_compressed(os.path.join(HERE, "ae.npz"), **out)
+    print("ae recon", np.round(out["recon_loss"], 3))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or (list(GAN_CASES) + ["vae", "checkpoints"])
+    which = sys.argv[1:] or (list(GAN_CASES) + ["vae", "checkpoints", "ae"])
     for c in which:
         if c == "vae":
             make_vae_case()
         elif c == "checkpoints":
             make_checkpoints()
+        elif c == "ae":
+            make_ae_case()
         else:
             make_gan_case(c)

@@ -1,0 +1,76 @@
+"""Standard autoencoder (src/ae.py) through gm_b200.AeEngine and the ae.py drop-in, against the golden fixture made by the
+UNMODIFIED reference (tests/golden/make_golden.py make_ae_case): step-1 loss and every gradient tensor, the 3-step loss
+trajectory and the final weights.  bf16 tensor-core operands, fp32 loss / gradients / Adam."""
+import numpy as np
+import pytest
+import torch
+
+from inputs import load_case, images_from_bits, B, STEPS
+
+pytestmark = pytest.mark.gpu
+
+
+def _err(fx, key, arr):
+    a = np.asarray(arr, np.float64).reshape(-1)
+    if key in fx:
+        ref, got = fx[key].astype(np.float64).reshape(-1), a
+    else:
+        ref, got = fx[key + "__samp"].astype(np.float64), a[fx[key + "__idx"]]
+    return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def _init(fx):
+    return {k[5:]: fx[k] for k in fx if k.startswith("init_")}
+
+
+def test_engine_step_and_trajectory_against_the_reference():
+    import gm_b200
+    fx = load_case("ae")
+    eng = gm_b200.AeEngine(784, 32, max_batch=B)
+    eng.load(_init(fx))
+    x = torch.from_numpy(images_from_bits(fx)).cuda()
+    loss = eng.grad(x).item()
+    assert abs(loss - float(fx["step1_loss"])) < 1e-3 * float(fx["step1_loss"])
+    g = eng.views(eng.grads)
+    for name in g:
+        assert _err(fx, "step1_grad_" + name, g[name].cpu().numpy()) < 2e-2, name          # bf16 operands at batch 64
+    hp = gm_b200.AdamHP.make(1e-3, weight_decay=1e-5)
+    eng.reset_optimizer()
+    losses = []
+    for _ in range(STEPS):
+        losses.append(eng.grad(x).item())
+        eng.apply(hp)
+    np.testing.assert_allclose(losses, fx["recon_loss"], rtol=1e-3)
+    for name, w in eng.views().items():
+        assert _err(fx, "final_" + name, w.cpu().numpy()) < 2e-3, name
+    out, l2 = eng.forward(x, want_loss=True)
+    assert out.shape == (B, 784) and float(out.min()) >= 0 and float(out.max()) <= 1 and l2.item() < losses[-1]
+
+
+def test_dropin_module_runs_the_reference_driver_code():
+    import ae
+    fx = load_case("ae")
+    model = ae.Autoencoder(image_size=784, hidden_dim=32)
+    sd = model.state_dict()
+    for k, v in _init(fx).items():
+        sd[k] = torch.from_numpy(v.copy())
+    model.load_state_dict(sd)
+    assert list(sd.keys()) == ["encoder.linear.weight", "encoder.linear.bias", "decoder.linear.weight", "decoder.linear.bias"]
+    x = torch.from_numpy(images_from_bits(fx)).view(B, 1, 28, 28)
+    it = [(x, torch.zeros(B, dtype=torch.long))] * STEPS
+    tr = ae.AutoencoderTrainer(model, it, it[:1], it[:1], viz=False)
+    tr.train(num_epochs=1, lr=1e-3, weight_decay=1e-5)
+    np.testing.assert_allclose(tr.recon_loss, fx["recon_loss"], rtol=1e-3)
+    assert tr.num_epochs == 1 and tr.best_val_loss < 1e10
+    rec = tr.reconstruct_images(x[:16], 0, save=False)
+    assert rec.shape == (16, 28, 28)
+    codes = model.encoder(x[:4].view(4, -1))
+    assert codes.shape == (4, 32) and float(codes.min()) >= 0
+    assert model.decoder(codes).shape == (4, 784)
+    # the reference's loop body: loss.backward() + a torch optimizer on the module parameters
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt.zero_grad()
+    loss = tr.compute_batch(it[0])
+    loss.backward()
+    assert model.decoder.linear.weight.grad is not None and float(model.decoder.linear.weight.grad.abs().sum()) > 0
+    opt.step()

@@ -310,3 +310,90 @@ def test_split_and_bf16_engines_agree_on_bf16_scale():
     ls, lb = eng_s.d_grad(x, noise=z).item(), eng_b.d_grad(x, noise=z).item()
     assert abs(ls - lb) < 1e-3 * abs(ls)
     assert 1e-5 < _nrel(eng_b.grads[1].cpu().numpy(), eng_s.grads[1].cpu().numpy()) < 6e-2
+
+
+def _torch_step_grads(eng, x, zd, zg, variant, consts, aux=None):
+    """fp32 autograd (TF32 off) of the reference's formulas with explicit loss constants -> (Ld, gD flat, Lg, gG flat)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Wg1, bg1, Wg2, bg2 = [t.clone().requires_grad_() for t in eng.views(0)]
+    Wd1, bd1, Wd2, bd2 = [t.clone().requires_grad_() for t in eng.views(1)]
+    relu_out = variant == "wgp"
+
+    def Gf(zz):
+        return torch.sigmoid(torch.relu(zz @ Wg1.t() + bg1) @ Wg2.t() + bg2)
+
+    def Df(xx):
+        s = torch.relu(xx @ Wd1.t() + bd1) @ Wd2.t() + bd2
+        return torch.relu(s) if relu_out else torch.sigmoid(s)
+    n = x.shape[0]
+    fake = Gf(zd)
+    DX, DG = Df(x), Df(fake)
+    if variant == "ls":                                                          # src/ls_gan.py:192-193,213
+        Ld = 0.5 * torch.mean((DX - consts["b"]) ** 2) + 0.5 * torch.mean((DG - consts["a"]) ** 2)
+    elif variant == "ns":
+        Ld = -torch.mean(torch.log(DX + 1e-8) + torch.log(1 - DG + 1e-8))
+    else:
+        if variant == "wgp":                                                     # src/w_gp_gan.py:197-218
+            eps = aux.view(-1, 1)
+            xh = (eps * x + (1 - eps) * fake.detach()).requires_grad_()
+            base = torch.mean(DG) - torch.mean(DX)
+        else:                                                                    # src/dra_gan.py:195-220
+            delta, u = aux[:n].view(-1, 1), aux[n:].view(n, -1)
+            xh = (delta * x + (1 - delta) * (x + consts["C"] * x.std() * u)).requires_grad_()
+            base = -torch.mean(torch.log(DX + 1e-8) + torch.log(1 - DG + 1e-8))
+        gr = torch.autograd.grad(Df(xh), xh, torch.ones(n, 1, device="cuda"), create_graph=True, retain_graph=True)[0]
+        Ld = base + consts["LAMBDA"] * torch.mean((gr.norm(2, dim=1) - consts.get("K", 1.0)) ** 2)
+    gD = torch.cat([t.reshape(-1) for t in torch.autograd.grad(Ld, [Wd1, bd1, Wd2, bd2])])
+    DGg = Df(Gf(zg))
+    if variant == "ls":
+        Lg = 0.5 * torch.mean((DGg - consts["c"]) ** 2)
+    elif variant == "wgp":
+        Lg = -torch.mean(DGg)
+    else:
+        Lg = -torch.mean(torch.log(DGg + 1e-8))
+    gG = torch.cat([t.reshape(-1) for t in torch.autograd.grad(Lg, [Wg1, bg1, Wg2, bg2])])
+    return Ld.item(), gD, Lg.item(), gG
+
+
+@pytest.mark.parametrize("case", ["ls_abc", "wgp_lambda5", "dra_lkc", "ns_h256_z128"])
+def test_loss_constants_and_notebook_shapes(case):
+    """The loss constants the reference passes as train_D / train_G kwargs (a, b, c of src/ls_gan.py:173,197; LAMBDA of
+    src/w_gp_gan.py:177; LAMBDA, K, C of src/dra_gan.py:174) at non-default values, and the shapes of notebooks 11 / 13 / 14
+    (hidden 256, z 128): losses and flat D / G gradients within 1e-3 of fp32 autograd (split operand mode, batch 128)."""
+    import gm_b200
+    import torch.nn as nn
+    variant = case.split("_")[0]
+    Hh, Zz = (256, 128) if case == "ns_h256_z128" else (400, 20)
+    n = 128
+    eng = gm_b200.GanEngine(784, Hh, Zz, max_batch=n, variant=variant, d_out_act="relu" if variant == "wgp" else "sigmoid",
+                            precision="split")
+    torch.manual_seed(4321)
+    g1, g2, d1, d2 = nn.Linear(Zz, Hh), nn.Linear(Hh, 784), nn.Linear(784, Hh), nn.Linear(Hh, 1)
+    eng.load(0, [g1.weight.data, g1.bias.data, g2.weight.data, g2.bias.data])
+    eng.load(1, [d1.weight.data, d1.bias.data, d2.weight.data, d2.bias.data])
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = (torch.rand(n, 784, device="cuda", generator=g) < 0.1307).float()
+    zd, zg = torch.randn(n, Zz, device="cuda", generator=g), torch.randn(n, Zz, device="cuda", generator=g)
+    consts, aux = {}, None
+    if case == "ls_abc":
+        consts = dict(a=0.1, b=0.9, c=0.8)
+        eng.set_loss_consts(ls_a=0.1, ls_b=0.9, ls_c=0.8)
+    elif case == "wgp_lambda5":
+        consts = dict(LAMBDA=5.0)
+        eng.set_loss_consts(gp_lambda=5.0)
+        aux = torch.rand(n, device="cuda", generator=g)
+    elif case == "dra_lkc":
+        consts = dict(LAMBDA=5.0, K=0.7, C=0.5)
+        eng.set_loss_consts(gp_lambda=5.0, gp_k=0.7, dra_c=0.5)
+        aux = torch.cat([torch.rand(n, device="cuda", generator=g), torch.rand(n * 784, device="cuda", generator=g)])
+    Ld_ref, gD, Lg_ref, gG = _torch_step_grads(eng, x, zd, zg, variant, consts, aux)
+    Ld = eng.d_grad(x, noise=zd, aux=aux).item()
+    flatD = eng.grads[1].clone()
+    Lg = eng.g_grad(n, noise=zg).item()
+    flatG = eng.grads[0].clone()
+    rep = {"D_loss": abs(Ld - Ld_ref) / max(abs(Ld_ref), 0.5), "G_loss": abs(Lg - Lg_ref) / max(abs(Lg_ref), 0.5),
+           "gD": _nrel(flatD.cpu().numpy(), gD.cpu().numpy()), "gG": _nrel(flatG.cpu().numpy(), gG.cpu().numpy())}
+    _REPORT["consts_" + case] = rep
+    _dump()
+    for k, v in rep.items():
+        assert v < TOL, (k, v, rep)
