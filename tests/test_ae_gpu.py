@@ -33,7 +33,7 @@ def test_engine_step_and_trajectory_against_the_reference():
     assert abs(loss - float(fx["step1_loss"])) < 1e-3 * float(fx["step1_loss"])
     g = eng.views(eng.grads)
     for name in g:
-        assert _err(fx, "step1_grad_" + name, g[name].cpu().numpy()) < 2e-2, name          # bf16 operands at batch 64
+        assert _err(fx, "step1_grad_" + name, g[name].cpu().numpy()) < 3e-2, name          # bf16 operands at batch 64 (as the VAE test)
     hp = gm_b200.AdamHP.make(1e-3, weight_decay=1e-5)
     eng.reset_optimizer()
     losses = []
