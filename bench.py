@@ -506,8 +506,40 @@ def bench_small_batch(dev):
                 rec["cuda_graph"] = {"error": str(exc)[:200]}
         out["b%d" % Bs] = rec
         del wl
+    out["trainer_b64_epoch"] = bench_trainer_small()
     out["unit"] = "images/s"
     return out
+
+
+def bench_trainer_small():
+    """BASELINE configs[0] through the reference's own API on the GPU: NSGANTrainer.train(1 epoch) over a shuffling
+    DataLoader(TensorDataset) of N = 50000 images at B = 64 (782 steps) - what the cpu_baseline leg runs on the host."""
+    import torch
+    import ns_gan
+    g = torch.Generator().manual_seed(3435)
+    imgs = (torch.rand(50000, 1, 28, 28, generator=g) < 0.1307).float()
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(imgs, torch.zeros(50000, dtype=torch.long)), batch_size=64, shuffle=True)
+    res = {}
+    for mode in ("cuda_graph", "eager_launch"):
+        torch.manual_seed(1234)
+        model = ns_gan.NSGAN(784, 400, 20)
+        tr = ns_gan.NSGANTrainer(model, loader, loader, loader, viz=False)
+        tr.cuda_graph = mode == "cuda_graph"
+        so, sink = sys.stdout, open(os.devnull, "w")
+        try:
+            sys.stdout = sink
+            tr.train(num_epochs=1)                                   # packing + engine + capture
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tr.train(num_epochs=1, G_lr=2e-4, D_lr=2e-4, D_steps=1)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        finally:
+            sys.stdout = so
+            sink.close()
+        res[mode] = {"value": round(782 * 64 / dt, 1), "ms_per_step": round(dt / 782 * 1e3, 4)}
+    res["api"] = "ns_gan.NSGANTrainer(...).train(num_epochs=1): 782 steps of B=64 over N=50000, wall clock around the call"
+    return res
 
 
 def bench_parity_mode(args, bits, N, rank, timed):

@@ -280,6 +280,59 @@ class _FusedLoss(torch.autograd.Function):
         return None, None, None, None
 
 
+class _StepGraph:
+    """One captured outer train step of a GANTrainerBase (see GANTrainerBase.cuda_graph)."""
+
+    def __init__(self, trainer, eng):
+        self.tr, self.eng, self.ready, self.graph = trainer, eng, False, None
+        self.scratch = None
+
+    @staticmethod
+    def begin(tr):
+        res = getattr(tr, "_resident", None)
+        if not (tr.cuda_graph and res is not None and getattr(tr, "_world", 1) == 1 and tr._use_device_noise()):
+            return None
+        batch = min(res.batch_size, res.n)
+        if batch > tr.cuda_graph_max_batch or type(tr)._fused_D is not GANTrainerBase._fused_D or type(tr)._fused_G is not GANTrainerBase._fused_G:
+            return None
+        eng = tr._ensure_engine(batch)
+        eng._g_calls, eng._d_calls = tr._step, tr._dcount
+        eng.use_device_step(True)              # Adam steps / Philox streams / sampler rounds now come from device counters
+        return _StepGraph(tr, eng)
+
+    def capture(self, D_steps, batch, hpD, hpG):
+        tr, eng = self.tr, self.eng
+        if tr._engine is not eng:              # the engine was re-created (grown) under us: stay eager
+            return
+        self.scratch = torch.zeros(D_steps + 1, device="cuda")
+        torch.cuda.synchronize()
+        try:
+            g = torch.cuda.CUDAGraph()
+            d0, s0 = tr._dcount, tr._step
+            with torch.cuda.graph(g):
+                for k in range(D_steps):
+                    tr._fused_D(tr._resident.bits, hpD, batch=batch, loss_out=self.scratch[k])
+                tr._fused_G(batch, hpG, loss_out=self.scratch[D_steps])
+            tr._dcount, tr._step = d0, s0      # capturing executes nothing
+            self.graph, self.ready, self.D_steps = g, True, D_steps
+        except RuntimeError as exc:            # pragma: no cover  (capture not possible here: keep launching eagerly)
+            print("[gm_b200] CUDA-graph capture of the train step failed (%s); continuing with eager launches" % str(exc)[:120])
+            self.graph, self.ready = None, False
+
+    def replay(self, ring_col):
+        self.graph.replay()
+        ring_col.copy_(self.scratch)
+        self.tr._dcount += self.D_steps
+        self.tr._step += 1
+
+    def end(self):
+        try:
+            torch.cuda.synchronize()
+            self.eng.use_device_step(False)
+        except GmError:                        # pragma: no cover
+            pass
+
+
 class GANTrainerBase:
     """Object to hold data iterators, train a GAN variant (src/ns_gan.py:77-290)."""
     variant = "ns"
@@ -366,8 +419,10 @@ class GANTrainerBase:
         epoch_steps = int(np.ceil(len(self.train_iter) / D_steps))
         self._resident = DeviceDataset.from_loader(self.train_iter, getattr(self, "_resident", None)) if self.device_dataset else None
         self._dp_begin()
+        graph = None
         try:
             self._pre_train(num_epochs, hpG, hpD, D_steps, extra)
+            graph = _StepGraph.begin(self)
             for epoch in range(1, num_epochs + 1):
                 self.model.train()
                 # the kernels write each step's loss straight into this epoch's device log
@@ -375,6 +430,10 @@ class GANTrainerBase:
                 done = 0
                 try:
                     for i in range(epoch_steps):
+                        if graph is not None and graph.ready:
+                            graph.replay(ring[:, i])                # one launch from the host: the whole outer step
+                            done = i + 1
+                            continue
                         for k in range(D_steps):
                             if self._resident is not None:          # on-device shuffle + gather, no host work
                                 batch = min(self._resident.batch_size, self._resident.n)
@@ -385,6 +444,8 @@ class GANTrainerBase:
                                 self._fused_D(images, hpD, loss_out=ring[k, i])
                         self._fused_G(batch, hpG, loss_out=ring[D_steps, i])
                         done = i + 1
+                        if graph is not None and not graph.ready:
+                            graph.capture(D_steps, batch, hpD, hpG)   # the first outer step ran eagerly (plans, attributes)
                 finally:
                     # an interrupted epoch (KeyboardInterrupt in a notebook) still logs the steps it ran;
                     # one device->host read per epoch
@@ -397,7 +458,16 @@ class GANTrainerBase:
                 if self.viz:
                     self.generate_images(epoch)
         finally:
+            if graph is not None:
+                graph.end()
             self._dp_end()
+
+    # CUDA-graph replay of the outer step (D_steps D updates + 1 G update) for launch-bound batch sizes - the reference's own
+    # regime, batch 64 / 100 (src/ns_gan.py:311-314, src/utils.py:16): with the resident dataset and in-kernel noise nothing
+    # in a step depends on host data, the engine keeps its step counters on the device (gm_gan_use_device_step) and every
+    # step after the first is ONE graph launch.  Set `trainer.cuda_graph = False` to launch every kernel from the host.
+    cuda_graph = True
+    cuda_graph_max_batch = 8192
 
     # ------------------------------------------------------------------ data-parallel / fast-path state of one train() call
     def _dp_begin(self):

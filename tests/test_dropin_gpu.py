@@ -274,3 +274,30 @@ def test_reference_made_checkpoints_reproduce_the_reference_outputs():
     with tempfile.TemporaryDirectory() as d:
         tr.save_model(os.path.join(d, "m.ckpt"))
         assert list(torch.load(os.path.join(d, "m.ckpt")).keys()) == list(ref["keys"])
+
+
+@pytest.mark.parametrize("mod_name,cls,kw", [("ns_gan", "NSGAN", {}), ("w_gp_gan", "WGPGAN", dict(D_steps=2)), ("fisher_gan", "FisherGAN", {})])
+def test_trainer_cuda_graph_replay_equals_eager_launches(mod_name, cls, kw):
+    """Trainer.train at the reference's batch size replays one captured CUDA graph per outer step (GANTrainerBase.cuda_graph);
+    losses and parameters are bit-identical to launching every kernel from the host."""
+    import importlib
+    mod = importlib.import_module(mod_name)
+    g = torch.Generator().manual_seed(0)
+    imgs = (torch.rand(1000, 1, 28, 28, generator=g) < 0.13).float()
+    ds = torch.utils.data.TensorDataset(imgs, torch.zeros(1000, dtype=torch.long))
+
+    def run(use_graph):
+        torch.manual_seed(21)
+        loader = torch.utils.data.DataLoader(ds, batch_size=100, shuffle=True)
+        model = getattr(mod, cls)(784, 400, 20)
+        tr = getattr(mod, cls + "Trainer")(model, loader, loader, loader)
+        tr.cuda_graph = use_graph
+        tr.train(num_epochs=2, **kw)
+        tr.train(num_epochs=1, **kw)                     # a second call: fresh optimizers, counters carried over
+        return tr, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+    t0, p0 = run(False)
+    t1, p1 = run(True)
+    assert len(t1.Dlosses) == len(t0.Dlosses) == 3 * int(np.ceil(10 / kw.get("D_steps", 1)))
+    assert t0.Dlosses == t1.Dlosses and t0.Glosses == t1.Glosses
+    assert torch.equal(p0, p1)
+    assert (t0._step, t0._dcount) == (t1._step, t1._dcount)
