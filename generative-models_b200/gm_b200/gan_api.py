@@ -465,8 +465,12 @@ class GANTrainerBase:
     # CUDA-graph replay of the outer step (D_steps D updates + 1 G update) for launch-bound batch sizes - the reference's own
     # regime, batch 64 / 100 (src/ns_gan.py:311-314, src/utils.py:16): with the resident dataset and in-kernel noise nothing
     # in a step depends on host data, the engine keeps its step counters on the device (gm_gan_use_device_step) and every
-    # step after the first is ONE graph launch.  Set `trainer.cuda_graph = False` to launch every kernel from the host.
-    cuda_graph = True
+    # step after the first is ONE graph launch.  Bit-identical to eager launches (tests/test_dropin_gpu.py) but MEASURED
+    # SLOWER on the B200 (B = 64: 0.216 ms/step replayed vs 0.142 ms/step eager through this loop; 0.149 vs 0.143 at engine
+    # level): the step is a chain of ~22 dependent kernels of ~6.5 us whose prologues already overlap through programmatic
+    # dependent launch, the host needs only 0.07-0.09 ms to enqueue it, and every graph launch adds its own start / drain
+    # gap.  Hence off by default; `trainer.cuda_graph = True` turns it on (a host-bound caller, e.g. a slow CPU, gains).
+    cuda_graph = False
     cuda_graph_max_batch = 8192
 
     # ------------------------------------------------------------------ data-parallel / fast-path state of one train() call

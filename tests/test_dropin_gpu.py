@@ -278,8 +278,8 @@ def test_reference_made_checkpoints_reproduce_the_reference_outputs():
 
 @pytest.mark.parametrize("mod_name,cls,kw", [("ns_gan", "NSGAN", {}), ("w_gp_gan", "WGPGAN", dict(D_steps=2)), ("fisher_gan", "FisherGAN", {})])
 def test_trainer_cuda_graph_replay_equals_eager_launches(mod_name, cls, kw):
-    """Trainer.train at the reference's batch size replays one captured CUDA graph per outer step (GANTrainerBase.cuda_graph);
-    losses and parameters are bit-identical to launching every kernel from the host."""
+    """Trainer.train at the reference's batch size can replay one captured CUDA graph per outer step (GANTrainerBase.cuda_graph,
+    opt-in); losses and parameters are bit-identical to launching every kernel from the host."""
     import importlib
     mod = importlib.import_module(mod_name)
     g = torch.Generator().manual_seed(0)
