@@ -150,6 +150,7 @@ class Workload:
         self.seed = par.rank_seed(1000, rank)
         self.s = 0
         self.overlap = False
+        self.split_exchange = False
         self.inv = par.inv_global_batch(B, world)
         if name == "dcgan":
             self.eng = gm_b200.DcganEngine(hidden_dim=64, z_dim=100, channels=3, variant="ns")
@@ -177,6 +178,7 @@ class Workload:
             # GM_DP_OVERLAP=1: the D-gradient exchange + Adam runs on a side stream under the G step's generator
             # forward, which does not depend on the D update (gm_gan_g_forward_stage / gm_gan_g_grad_staged)
             self.overlap = comm is not None and os.environ.get("GM_DP_OVERLAP", "0") == "1"
+            self.split_exchange = os.environ.get("GM_DP_SPLIT", "1") == "1"
             if self.overlap:
                 self.side = torch.cuda.Stream()
                 self.ev_d, self.ev_a = torch.cuda.Event(), torch.cuda.Event()
@@ -213,6 +215,18 @@ class Workload:
         else:
             eng.set_sampler(0, 0)
             eng.d_grad(batch_bits, fmt="bits", batch=B, inv_global_batch=self.inv, seed=self.seed, step=s)
+        if self.comm is not None and self.split_exchange and not self.overlap:
+            # two-phase exchange on ONE stream: publish the D gradient, run the G step's generator forward (independent of
+            # the D update), then wait + sum + Adam; publish the G gradient, stage the next step's real rows, then finish
+            eng.exchange_begin(1, self.comm)
+            eng.g_forward_stage(B, seed=self.seed, step=s)
+            eng.apply_allreduce(1, self.hpD, self.comm)
+            eng.g_grad_staged(B, inv_global_batch=self.inv)
+            eng.exchange_begin(0, self.comm)
+            if batch_bits is None:
+                eng.d_stage(self.bits, fmt="bits", batch=B, step=s + 1)
+            eng.apply_allreduce(0, self.hpG, self.comm)
+            return
         if self.overlap:
             torch = self.torch
             self.ev_d.record()

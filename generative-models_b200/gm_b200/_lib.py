@@ -87,6 +87,7 @@ def lib():
     L.gm_gan_bind.argtypes = [vp, i, vp, vp, vp, vp]
     L.gm_gan_sync_shadows.argtypes = [vp, i, vp]
     L.gm_gan_d_grad.argtypes = [vp, vp, i, vp, i, vp, vp, f, u64, u64, vp, vp]
+    L.gm_gan_d_stage.argtypes = [vp, vp, i, vp, i, u64, vp]
     L.gm_gan_g_grad.argtypes = [vp, i, vp, f, u64, u64, vp, vp]
     L.gm_gan_g_forward_stage.argtypes = [vp, i, vp, u64, u64, vp]
     L.gm_gan_g_grad_staged.argtypes = [vp, i, f, vp, vp]
@@ -107,6 +108,7 @@ def lib():
     L.gm_comm_open.argtypes = [vp, i, i, vp]
     L.gm_comm_destroy.argtypes = [vp]
     L.gm_gan_attach_comm.argtypes = [vp, vp]
+    L.gm_gan_exchange_begin.argtypes = [vp, i, vp, vp]
     L.gm_gan_apply_allreduce.argtypes = [vp, i, C.POINTER(AdamHP), i, vp, vp]
     L.gm_gan_set_lazy_grads.argtypes = [vp, i, vp]
     L.gm_gan_materialize_grads.argtypes = [vp, vp]

@@ -626,6 +626,7 @@ struct gm_comm {
   void* peer[kCommMaxWorld] = {};
   bool opened = false;
   unsigned long long seq = 0, seq_stats = 0;
+  unsigned long long begun[2] = {0, 0};   // seq of a gm_gan_exchange_begin(net) whose finish half has not run yet (0: none)
 };
 
 
@@ -675,6 +676,7 @@ struct gm_gan {
   // device-step mode (CUDA-graph replay of the step): [0] Adam steps of G, [1] Adam steps of D, [2] train_G calls, [3] train_D calls
   unsigned long long* dstep = nullptr;
   bool dev_step = false;
+  int staged_batch = 0;      // > 0: gm_gan_d_stage already staged this many real rows for the next gm_gan_d_grad
   gm_loss_consts lc = {10.f, 1.f, 1.f, 0.f, 1.f, 1.f};   // reference defaults: src/w_gp_gan.py:177, src/dra_gan.py:174, src/ls_gan.py:173,197
   long long pool_n = 0;      // on-device batch sampling over a resident pool of pool_n images (gm_gan_set_sampler)
   uint64_t pool_seed = 0;
@@ -1237,6 +1239,33 @@ extern "C" int gm_gan_began_control(gm_gan* g, float gamma, float lambda, float 
   return GM_OK;
 }
 
+// real rows -> Xall[0:B] (bf16, ones column); with a sampler pool and no gather_idx the kernel draws the batch rows itself
+static int stage_real_rows(gm_gan* g, const void* images, int img_fmt, const int* gather_idx, int B, uint64_t step, cudaStream_t s) {
+  gm_ctx* c = g->ctx;
+  Sampler smp = kNoSampler;
+  if (!gather_idx && g->pool_n > 0) {
+    if (B > g->pool_n) return fail(c, GM_ERR_ARG, "batch (%d) exceeds the sampler's pool (%lld)", B, g->pool_n);
+    smp = make_sampler(g->pool_n, g->pool_seed, step, 0, g->dev_step ? g->dstep + 3 : nullptr);     // a fresh permutation every step (src/ns_gan.py:224)
+  }
+  launch_pdl("stage_images_kernel", stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP, smp, g->lo);
+  c->launches++;
+  return GM_OK;
+}
+
+// process_batch of the NEXT train_D (src/ns_gan.py:222-226) ahead of time: stages the real rows now; the following gm_gan_d_grad
+// with the same batch skips its own staging.  Nothing of a G step reads those rows, so a data-parallel host enqueues this
+// between gm_gan_exchange_begin(G) and gm_gan_apply_allreduce(G).  `step` = the step argument the later gm_gan_d_grad gets.
+extern "C" int gm_gan_d_stage(gm_gan* g, const void* images, int img_fmt, const int* gather_idx, int batch, uint64_t step, gm_stream stream) {
+  int rc = check_step_args(g, batch);
+  if (rc) return rc;
+  if (!images) return fail(g->ctx, GM_ERR_ARG, "images is null");
+  if (g->dev_step) return fail(g->ctx, GM_ERR_STATE, "gm_gan_d_stage is not available in device-step mode");
+  if ((rc = stage_real_rows(g, images, img_fmt, gather_idx, batch, step, static_cast<cudaStream_t>(stream)))) return rc;
+  g->staged_batch = batch;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
 extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const int* gather_idx, int batch,
                              const float* noise, const float* aux, float inv_global_batch, uint64_t seed,
                              uint64_t step, float* loss_dev, gm_stream stream) {
@@ -1250,13 +1279,11 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   gm_ctx* c = g->ctx;
   flush_pending(g, s);
   // real rows -> Xall[0:B] (bf16, ones column)
-  Sampler smp = kNoSampler;
-  if (!gather_idx && g->pool_n > 0) {
-    if (B > g->pool_n) return fail(c, GM_ERR_ARG, "batch (%d) exceeds the sampler's pool (%lld)", B, g->pool_n);
-    smp = make_sampler(g->pool_n, g->pool_seed, step, 0, g->dev_step ? g->dstep + 3 : nullptr);     // a fresh permutation every step (src/ns_gan.py:224)
+  if (g->staged_batch == B) {
+    g->staged_batch = 0;       // the real rows are already in place (gm_gan_d_stage)
+  } else {
+    if ((rc = stage_real_rows(g, images, img_fmt, gather_idx, B, step, s))) return rc;
   }
-  launch_pdl("stage_images_kernel", stage_images_kernel, c->num_sms * 8, 256, 0, s, images, img_fmt, gather_idx, g->Xall, B, g->X, g->XP, smp, g->lo);
-  c->launches++;
   const unsigned long long* dptr = g->dev_step ? g->dstep + 3 : nullptr;   // device-step mode: the train_D call counter
   if ((rc = run_generator(g, sp, B, noise, seed, g->dev_step ? 0 : 2 * step, s, dptr))) return rc;
   if (g->d.variant == GM_BEGAN) { rc = began_d_grad(g, sp, B, loss_dev, s); bump_step(g, 3, s); return rc; }

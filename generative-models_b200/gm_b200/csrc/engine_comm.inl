@@ -60,6 +60,41 @@ extern "C" int gm_comm_destroy(gm_comm* m) {
 // optimizer.step() of one net on every rank at once: SUM all-reduce of the flat gradient over the
 // peer mappings fused with Adam (replaces dist.all_reduce + gm_gan_apply).  Every rank must call it
 // with the same net / step, in the same order.
+static int comm_dev(gm_gan* g, gm_comm* m, int total, CommDev& cm) {
+  if (total > m->nfloats) return fail(g->ctx, GM_ERR_ARG, "exchange buffer too small (%lld < %d)", m->nfloats, total);
+  memset(&cm, 0, sizeof cm);
+  for (int r = 0; r < m->world; ++r) {
+    cm.x[r] = static_cast<float*>(m->peer[r]);
+    cm.f[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(m->peer[r]) + m->flag_off);
+  }
+  cm.rank = m->rank; cm.world = m->world; cm.nblocks = m->nblocks; cm.nfloats = m->nfloats;
+  return GM_OK;
+}
+
+// First half of gm_gan_apply_allreduce: publish this rank's gradient of `net` to every peer and return - no waiting.  Work that
+// does not depend on the update may be enqueued before the matching gm_gan_apply_allreduce (which then only waits, sums and
+// applies Adam): the G step's generator forward under the D exchange, the next step's image staging under the G exchange.
+extern "C" int gm_gan_exchange_begin(gm_gan* g, int net, gm_comm* m, gm_stream stream) {
+  if (!g || net < 0 || net > 1 || !m) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_exchange_begin: bad argument") : GM_ERR_ARG;
+  if (!m->opened) return fail(g->ctx, GM_ERR_STATE, "gm_comm_open has not been called");
+  if (m->begun[net]) return fail(g->ctx, GM_ERR_STATE, "exchange of net %d already begun", net);
+  if (!g->grd[net]) return fail(g->ctx, GM_ERR_STATE, "net %d not bound", net);
+  AdamParams a;
+  memset(&a, 0, sizeof a);
+  a.g = g->grd[net];
+  a.total = net == GM_NET_G ? g->G.total : g->D.total;
+  if (g->pend[net]) { a.gather = 1; a.gsegs = g->pend_segs[net]; g->pend[net] = false; }
+  CommDev cm;
+  int rc = comm_dev(g, m, a.total, cm);
+  if (rc) return rc;
+  cm.seq = ++m->seq;
+  m->begun[net] = cm.seq;
+  launch_pdl("adam_exchange_push_kernel", adam_exchange_push_kernel, cdiv(a.total, kCommChunk), 256, 0, static_cast<cudaStream_t>(stream), a, cm);
+  g->ctx->launches++;
+  CU_OK(g->ctx, cudaGetLastError());
+  return GM_OK;
+}
+
 extern "C" int gm_gan_apply_allreduce(gm_gan* g, int net, const gm_adam_hp* hp, int step, gm_comm* m, gm_stream stream) {
   if (!g || net < 0 || net > 1 || !hp || step <= 0 || !m) return g ? fail(g->ctx, GM_ERR_ARG, "gm_gan_apply_allreduce: bad argument") : GM_ERR_ARG;
   if (!m->opened) return fail(g->ctx, GM_ERR_STATE, "gm_comm_open has not been called");
@@ -69,18 +104,19 @@ extern "C" int gm_gan_apply_allreduce(gm_gan* g, int net, const gm_adam_hp* hp, 
   a.p = g->par[net]; a.g = g->grd[net]; a.m = g->am[net]; a.v = g->av[net];
   fill_adam(a, hp, step);
   adam_segs(g, net, a);
-  if (a.total > m->nfloats) return fail(g->ctx, GM_ERR_ARG, "exchange buffer too small (%lld < %d)", m->nfloats, a.total);
   a.gout = g->grd[net];
-  if (g->pend[net]) { a.gather = 1; a.gsegs = g->pend_segs[net]; g->pend[net] = false; }
   CommDev cm;
-  memset(&cm, 0, sizeof cm);
-  for (int r = 0; r < m->world; ++r) {
-    cm.x[r] = static_cast<float*>(m->peer[r]);
-    cm.f[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(m->peer[r]) + m->flag_off);
+  int rc = comm_dev(g, m, a.total, cm);
+  if (rc) return rc;
+  if (m->begun[net]) {          // second half of a begun exchange: wait for the peers, sum, update
+    cm.seq = m->begun[net];
+    m->begun[net] = 0;
+    launch_pdl("adam_exchange_finish_kernel", adam_exchange_finish_kernel, cdiv(a.total, kCommChunk), 256, 0, static_cast<cudaStream_t>(stream), a, cm);
+  } else {
+    if (g->pend[net]) { a.gather = 1; a.gsegs = g->pend_segs[net]; g->pend[net] = false; }
+    cm.seq = ++m->seq;
+    launch_pdl("adam_allreduce_kernel", adam_allreduce_kernel, cdiv(a.total, kCommChunk), 256, 0, static_cast<cudaStream_t>(stream), a, cm);
   }
-  cm.rank = m->rank; cm.world = m->world; cm.nblocks = m->nblocks; cm.nfloats = m->nfloats;
-  cm.seq = ++m->seq;
-  launch_pdl("adam_allreduce_kernel", adam_allreduce_kernel, cdiv(a.total, kCommChunk), 256, 0, static_cast<cudaStream_t>(stream), a, cm);
   g->ctx->launches++;
   CU_OK(g->ctx, cudaGetLastError());
   return GM_OK;

@@ -1099,4 +1099,56 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const AdamParams a,
   }
 }
 
+
+// The same exchange in two kernels, so that work which does not depend on the update can run between them (the G step's
+// generator forward under the D exchange; the next step's image staging under the G exchange): `push` forms the gradient
+// chunk, stores it in its OWN slot and in every peer's, fences and raises the flags - it never waits; `finish` waits for
+// the peers' flags, sums all slots of its own region in rank order and applies Adam.
+__global__ void __launch_bounds__(256) adam_exchange_push_kernel(const AdamParams a, const CommDev cm) {
+  griddep_sync();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int par = int(cm.seq & 1ull);
+  const int i0 = b * kCommChunk + tid * 4;
+  float g[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = i0 + j;
+    g[j] = i < a.total ? (a.gather ? gather_grad(a.gsegs, i) : a.g[i]) : 0.f;
+  }
+  const long long slot = ((long long)par * kCommMaxWorld + cm.rank) * cm.nfloats + i0;
+  const float4 mine = make_float4(g[0], g[1], g[2], g[3]);
+  for (int r = 0; r < cm.world; ++r) st_relaxed_sys_v4(cm.x[r] + slot, mine);      // own region included
+  __threadfence_system();
+  __syncthreads();
+  if (tid < cm.world && tid != cm.rank)
+    st_release_sys(cm.f[tid] + ((long long)par * kCommMaxWorld + cm.rank) * cm.nblocks + b, cm.seq);
+}
+__global__ void __launch_bounds__(256) adam_exchange_finish_kernel(const AdamParams a, const CommDev cm) {
+  griddep_sync();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int par = int(cm.seq & 1ull);
+  const int i0 = b * kCommChunk + tid * 4;
+  if (tid < cm.world && tid != cm.rank) {
+    const unsigned long long* flag = cm.f[cm.rank] + ((long long)par * kCommMaxWorld + tid) * cm.nblocks + b;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < cm.seq) {
+      if (clock64() - t0 > 40000000000ll) __trap();   // ~20 s: a peer died
+    }
+  }
+  __syncthreads();
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < cm.world; ++r) {
+    const float4 v = ld_relaxed_sys_v4(cm.x[cm.rank] + ((long long)par * kCommMaxWorld + r) * cm.nfloats + i0);
+    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+  }
+  const float out[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = i0 + j;
+    if (i >= a.total) break;
+    a.gout[i] = out[j];
+    adam_element(a, i, out[j]);
+  }
+}
+
 }  // namespace gm

@@ -110,6 +110,11 @@ class GanEngine:
                                           _ptr(aux), inv, seed, step, _ptr(dst), _stream()))
         return dst
 
+    def d_stage(self, images, fmt="f32", gather_idx=None, batch=None, step=0):
+        """process_batch of the next d_grad ahead of time (the following d_grad with the same batch skips its staging)."""
+        B = batch if batch is not None else (gather_idx.numel() if gather_idx is not None else images.shape[0])
+        check(self.h, lib().gm_gan_d_stage(self.g, _ptr(images), IMG_FMTS[fmt], _ptr(gather_idx), B, step, _stream()))
+
     def g_grad(self, batch, noise=None, inv_global_batch=None, seed=0, step=0, loss_out=None):
         """train_G + backward (src/ns_gan.py:196-216,155)."""
         inv = 1.0 / batch if inv_global_batch is None else inv_global_batch
@@ -122,11 +127,12 @@ class GanEngine:
         host overlap it with the D-gradient exchange running on another stream)."""
         check(self.h, lib().gm_gan_g_forward_stage(self.g, batch, _ptr(noise), seed, step, _stream()))
 
-    def g_grad_staged(self, batch, inv_global_batch=None):
+    def g_grad_staged(self, batch, inv_global_batch=None, loss_out=None):
         """Second half of g_grad after g_forward_stage: D on the fake rows, loss, backward through D and G."""
         inv = 1.0 / batch if inv_global_batch is None else inv_global_batch
-        check(self.h, lib().gm_gan_g_grad_staged(self.g, batch, inv, C.c_void_p(self.loss_buf.data_ptr() + 4), _stream()))
-        return self.loss_buf[1]
+        dst = self.loss_buf[1] if loss_out is None else loss_out
+        check(self.h, lib().gm_gan_g_grad_staged(self.g, batch, inv, _ptr(dst), _stream()))
+        return dst
 
     def use_device_step(self, on=True):
         """Device-step mode (include/gm_b200.h: gm_gan_use_device_step): Adam step counts, Philox streams and the
@@ -202,6 +208,11 @@ class GanEngine:
         `comm` (parallel.PeerComm) fused with Adam, one kernel per rank."""
         self.steps[net] += 1
         check(self.h, lib().gm_gan_apply_allreduce(self.g, net, C.byref(hp), self.steps[net], comm.c, _stream()))
+
+    def exchange_begin(self, net, comm):
+        """First half of apply_allreduce: publish the gradient to the peers without waiting (work that does not depend on
+        the update can be enqueued before the matching apply_allreduce)."""
+        check(self.h, lib().gm_gan_exchange_begin(self.g, net, comm.c, _stream()))
 
     def attach_comm(self, comm):
         """Batch statistics (RaNS / Fisher / DRAGAN / BEGAN) over the global batch of all ranks of `comm`

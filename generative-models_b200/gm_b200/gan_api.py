@@ -501,6 +501,11 @@ class GANTrainerBase:
 
     def _dp_end(self):
         """Always runs (try/finally): leave the engine with materialised gradients and no dangling communicator."""
+        try:
+            if self._engine is not None and getattr(self, "_d_begun", None) is not None and self._comm is not None:
+                self._finish_d_exchange(self._engine)
+        except GmError:          # pragma: no cover
+            self._d_begun = None
         self._lazy = False
         self._noise_gen = None
         eng = self._engine
@@ -589,6 +594,7 @@ class GANTrainerBase:
         if batch is None:
             batch = images.shape[0] if gather_idx is None else gather_idx.shape[0]
         eng = self._ensure_engine(batch)
+        self._finish_d_exchange(eng)             # a D exchange begun by the previous D sub-step (D_steps > 1)
         self._sync_once(eng)
         self._set_consts(eng)
         world = getattr(self, "_world", 1)
@@ -611,7 +617,14 @@ class GANTrainerBase:
         if loss_out is None:
             loss = loss.clone()
         self._dcount += 1
-        self._dp_apply(eng, D_NET, hp)
+        comm = getattr(self, "_comm", None)
+        if comm is not None and self.split_exchange:
+            # publish the D gradient now; the wait + sum + Adam half runs after the G step's generator forward (_fused_G),
+            # which does not depend on the D update and absorbs the NVLink latency and the ranks' arrival skew
+            eng.exchange_begin(D_NET, comm)
+            self._d_begun = hp
+        else:
+            self._dp_apply(eng, D_NET, hp)
         return loss
 
     def _fused_G(self, batch, hp, loss_out=None):
@@ -620,13 +633,26 @@ class GANTrainerBase:
         self._set_consts(eng)
         noise = None if self._use_device_noise() else self.compute_noise(batch, self.model.z_dim)
         world = getattr(self, "_world", 1)
-        loss = eng.g_grad(batch, noise=noise, inv_global_batch=par.inv_global_batch(batch, world), seed=self._philox_seed(),
-                          step=self._step, loss_out=loss_out)
+        if getattr(self, "_d_begun", None) is not None:
+            eng.g_forward_stage(batch, noise=noise, seed=self._philox_seed(), step=self._step)     # independent of the D update
+            self._finish_d_exchange(eng)
+            loss = eng.g_grad_staged(batch, inv_global_batch=par.inv_global_batch(batch, world), loss_out=loss_out)
+        else:
+            loss = eng.g_grad(batch, noise=noise, inv_global_batch=par.inv_global_batch(batch, world), seed=self._philox_seed(),
+                              step=self._step, loss_out=loss_out)
         if loss_out is None:
             loss = loss.clone()
         self._dp_apply(eng, G_NET, hp)
         self._step += 1
         return loss
+
+    split_exchange = True     # two-phase gradient exchange (gm_gan_exchange_begin / gm_gan_apply_allreduce) under data parallelism
+
+    def _finish_d_exchange(self, eng):
+        hp = getattr(self, "_d_begun", None)
+        if hp is not None:
+            self._d_begun = None
+            eng.apply_allreduce(D_NET, hp, self._comm)
 
     def _dp_apply(self, eng, net, hp):
         """optimizer.step(); under data parallelism preceded by the SUM of the flat gradient - fused into

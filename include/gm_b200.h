@@ -133,6 +133,9 @@ int gm_gan_sync_shadows(gm_gan* gan, int net, gm_stream stream);
 int gm_gan_d_grad(gm_gan* gan, const void* images_dev, int img_fmt, const int* gather_idx_dev, int batch,
                   const float* noise_dev, const float* aux_dev, float inv_global_batch, uint64_t seed,
                   uint64_t step, float* loss_dev, gm_stream stream);
+/* process_batch of the next train_D ahead of time (stages the real rows; the following gm_gan_d_grad with the same batch
+ * skips its staging).  `step` = the step the later gm_gan_d_grad is called with. */
+int gm_gan_d_stage(gm_gan* gan, const void* images_dev, int img_fmt, const int* gather_idx_dev, int batch, uint64_t step, gm_stream stream);
 /* train_G + G_loss.backward() (src/ns_gan.py:196-216,155), G gradients only. */
 int gm_gan_g_grad(gm_gan* gan, int batch, const float* noise_dev, float inv_global_batch, uint64_t seed,
                   uint64_t step, float* loss_dev, gm_stream stream);
@@ -165,6 +168,12 @@ int gm_comm_handle(gm_comm* comm, void* out64);
 int gm_comm_open(gm_comm* comm, int rank, int world, const void* handles /* world x 64 bytes, rank order */);
 int gm_comm_destroy(gm_comm* comm);
 int gm_gan_apply_allreduce(gm_gan* gan, int net, const gm_adam_hp* hp, int step, gm_comm* comm, gm_stream stream);
+/* The exchange in two halves: gm_gan_exchange_begin publishes this rank's gradient to every peer and never waits; the next
+ * gm_gan_apply_allreduce(net) then only waits for the peers, sums and applies Adam.  Work that does not depend on the update
+ * goes between them on the same stream - the generator forward of train_G (gm_gan_g_forward_stage) under the D exchange, the
+ * image staging of the next train_D (gm_gan_d_stage) under the G exchange - and absorbs the NVLink latency and the ranks'
+ * arrival skew. */
+int gm_gan_exchange_begin(gm_gan* gan, int net, gm_comm* comm, gm_stream stream);
 /* Batch statistics over the GLOBAL batch under data parallelism (RaNS mean(DG) src/ra_gan.py:204, Fisher
  * moments src/fisher_gan.py:214-218, DRAGAN images.std() src/dra_gan.py:204, BEGAN DX / DG of the K
  * controller src/be_gan.py:189-190): with a communicator attached, gm_gan_d_grad exchanges the partial

@@ -384,6 +384,7 @@ def test_fused_peer_allreduce_adam_two_ranks():
            "--master-port", "29533", os.path.join(root, "tools", "peer_allreduce_check.py")]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "PEER_ALLREDUCE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "SPLIT_EXCHANGE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]          # begin / finish halves == fused
     # RaNS / Fisher / DRAGAN batch statistics are exchanged on the device: 2 ranks x B rows reproduce the
     # gradients (and Fisher's lambda update) of one process with 2B rows
     assert "GLOBAL_BATCH_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

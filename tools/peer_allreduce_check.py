@@ -81,9 +81,28 @@ for net in (0, 1):
     dist.all_gather(allp, mine)
     assert all(torch.equal(allp[0], t) for t in allp), "replicas diverged"
 assert worst < 1e-5, worst
+# the exchange in two halves (gm_gan_exchange_begin ... gm_gan_apply_allreduce) with independent work in between - the G step's
+# generator forward under the D exchange, the next step's image staging under the G exchange - gives bitwise the same replicas
+eng2 = engine()
+eng2.set_lazy_grads(True)
+eng2.d_stage(xs[0], step=0)
+for s in range(STEPS):
+    eng2.d_grad(xs[s], noise=zs[2 * s], inv_global_batch=inv, step=s)
+    eng2.exchange_begin(1, comm)
+    eng2.g_forward_stage(B, noise=zs[2 * s + 1], step=s)
+    eng2.apply_allreduce(1, hp, comm)
+    eng2.g_grad_staged(B, inv_global_batch=inv)
+    eng2.exchange_begin(0, comm)
+    if s + 1 < STEPS:
+        eng2.d_stage(xs[s + 1], step=s + 1)
+    eng2.apply_allreduce(0, hp, comm)
+torch.cuda.synchronize()
+for net in (0, 1):
+    assert torch.equal(eng2.params[net], eng.params[net]), "two-phase exchange differs from the fused one"
 comm.close()
 if rank == 0:
     print("PEER_ALLREDUCE_OK world=%d worst_rel=%.3g" % (world, worst))
+    print("SPLIT_EXCHANGE_OK")
 
 
 # ---- global-batch equivalence: `world` ranks x Bl rows == one engine with world*Bl rows ----------
