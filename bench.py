@@ -178,7 +178,9 @@ class Workload:
             # GM_DP_OVERLAP=1: the D-gradient exchange + Adam runs on a side stream under the G step's generator
             # forward, which does not depend on the D update (gm_gan_g_forward_stage / gm_gan_g_grad_staged)
             self.overlap = comm is not None and os.environ.get("GM_DP_OVERLAP", "0") == "1"
-            self.split_exchange = os.environ.get("GM_DP_SPLIT", "1") == "1"
+            # GM_DP_SPLIT=1: two-phase exchange with independent work in between - measured SLOWER than the fused kernel
+            # (2 GPUs 0.7235 vs 0.690 ms/step, 8 GPUs 0.7424 vs 0.7125; profiles/r2_exchange.md), so off by default
+            self.split_exchange = os.environ.get("GM_DP_SPLIT", "0") == "1"
             if self.overlap:
                 self.side = torch.cuda.Stream()
                 self.ev_d, self.ev_a = torch.cuda.Event(), torch.cuda.Event()

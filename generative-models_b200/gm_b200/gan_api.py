@@ -646,7 +646,9 @@ class GANTrainerBase:
         self._step += 1
         return loss
 
-    split_exchange = True     # two-phase gradient exchange (gm_gan_exchange_begin / gm_gan_apply_allreduce) under data parallelism
+    # two-phase gradient exchange (gm_gan_exchange_begin ... gm_gan_apply_allreduce with the G forward in between) under data
+    # parallelism: bitwise the same replicas, but measured slower than the fused kernel on 2 and 8 B200s (profiles/r2_exchange.md)
+    split_exchange = False
 
     def _finish_d_exchange(self, eng):
         hp = getattr(self, "_d_begun", None)
