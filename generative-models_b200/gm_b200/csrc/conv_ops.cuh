@@ -12,31 +12,76 @@
 namespace gm {
 
 // ---------------------------------------------------------------- im2col / col2im (kernel 4, stride 2, pad 1)
+// Both are pure HBM-bound data movements (the column matrix is 4x the activation it comes from, up to 537 MB at B = 1024),
+// so the kernels are written for memory-level parallelism and cheap index arithmetic (the first versions ran at ~40 % of
+// the HBM rate: one 16-byte access in flight per thread behind a chain of 64-bit divisions, profiles/r2i_timeline_dcgan.md):
+// 32-bit indices (the host checks the extents), divisions by the grid extents as shifts when they are powers of two, kUnroll
+// independent items per thread with all loads issued before the first store.
+struct FastDiv {            // x / d and x % d for 32-bit x; shift >= 0 when d is a power of two
+  uint32_t d;
+  int shift;
+};
+__host__ __device__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.shift = -1;
+  for (int s = 0; s < 32; ++s)
+    if ((1u << s) == d) f.shift = s;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv f) { return f.shift >= 0 ? (x >> f.shift) : (x / f.d); }
+__device__ __forceinline__ void fdivmod(uint32_t x, const FastDiv f, uint32_t& q, uint32_t& r) {
+  q = fdiv(x, f);
+  r = x - q * f.d;
+}
+constexpr int kConvUnroll = 4;
+
 // x [B, H, W, C] (row pitch ldx elements per pixel) -> col [(b, ho, wo), (kh, kw, c)] with Ho = H/2, Wo = W/2.
-// One thread per (output pixel, tap, 8-channel group) when C % 8 == 0, else per (output pixel, tap) with a scalar loop.
-__global__ void im2col_k4s2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int ldx,
-                                   __nv_bfloat16* __restrict__ col, int ldc) {
+// VEC: C % 8 == 0, one item = (output pixel, tap, 8-channel group) = one 16-byte copy (consecutive items are consecutive
+// 16-byte chunks of the column matrix: the dominant stream, the writes, is perfectly linear); else one item = (output pixel,
+// tap) with a scalar channel loop (the 3-channel image layer).
+template <bool VEC>
+__global__ void __launch_bounds__(256) im2col_k4s2_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int C, int ldx,
+                                                          __nv_bfloat16* __restrict__ col, int ldc, uint32_t total, FastDiv dcg,
+                                                          FastDiv dwo, FastDiv dho) {
   griddep_sync();
-  const int Ho = H >> 1, Wo = W >> 1;
-  const int cg = (C % 8 == 0) ? C / 8 : 1;
-  const long long total = (long long)B * Ho * Wo * 16 * cg;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = int(t % cg);
-    long long r = t / cg;
-    const int tap = int(r % 16);
-    r /= 16;                                        // output pixel index (b, ho, wo)
-    const int wo = int(r % Wo), ho = int((r / Wo) % Ho), b = int(r / ((long long)Wo * Ho));
-    const int kh = tap >> 2, kw = tap & 3;
-    const int iy = 2 * ho - 1 + kh, ix = 2 * wo - 1 + kw;
-    const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
-    __nv_bfloat16* dst = col + r * ldc + tap * C;
-    const __nv_bfloat16* src = x + (((long long)b * H + iy) * W + ix) * ldx;
-    if (C % 8 == 0) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (ok) v = __ldg(reinterpret_cast<const uint4*>(src) + g);
-      reinterpret_cast<uint4*>(dst)[g] = v;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += stride * kConvUnroll) {
+    const __nv_bfloat16* src[kConvUnroll];
+    __nv_bfloat16* dst[kConvUnroll];
+    bool ok[kConvUnroll], live[kConvUnroll];
+#pragma unroll
+    for (int u = 0; u < kConvUnroll; ++u) {
+      const uint32_t t = t0 + u * stride;
+      live[u] = t < total && t >= t0;                 // t >= t0: no wrap-around past 2^32
+      uint32_t r, g = 0;
+      if (VEC) fdivmod(t, dcg, r, g); else r = t;
+      const uint32_t tap = r & 15u;
+      r >>= 4;                                        // output pixel index (b, ho, wo)
+      uint32_t q, wo, b, ho;
+      fdivmod(r, dwo, q, wo);
+      fdivmod(q, dho, b, ho);
+      const int kh = int(tap >> 2), kw = int(tap & 3u);
+      const int iy = 2 * int(ho) - 1 + kh, ix = 2 * int(wo) - 1 + kw;
+      ok[u] = live[u] && iy >= 0 && iy < H && ix >= 0 && ix < W;
+      dst[u] = col + size_t(r) * ldc + tap * C + g * 8;
+      src[u] = x + ((size_t(b) * H + iy) * W + ix) * ldx + g * 8;
+    }
+    if (VEC) {
+      uint4 v[kConvUnroll];
+#pragma unroll
+      for (int u = 0; u < kConvUnroll; ++u) {
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (ok[u]) v[u] = __ldg(reinterpret_cast<const uint4*>(src[u]));
+      }
+#pragma unroll
+      for (int u = 0; u < kConvUnroll; ++u)
+        if (live[u]) *reinterpret_cast<uint4*>(dst[u]) = v[u];
     } else {
-      for (int c = 0; c < C; ++c) dst[c] = ok ? src[c] : __float2bfloat16_rn(0.f);
+#pragma unroll
+      for (int u = 0; u < kConvUnroll; ++u)
+        if (live[u])
+          for (int c = 0; c < C; ++c) dst[u][c] = ok[u] ? src[u][c] : __float2bfloat16_rn(0.f);
     }
   }
 }
@@ -45,102 +90,167 @@ __global__ void im2col_k4s2_kernel(const __nv_bfloat16* __restrict__ x, int B, i
 // <= 4 taps that reach it; deterministic, no atomics).  Fused tail, by `mode`:
 //   0: y = sum                       1: y = sigmoid(sum)                  (generator output, src/ns_gan.py:45-46)
 //   2: y = sum * lrelu'(aux)         3: y = sum * aux (1 - aux)           (gradients through a LeakyReLU / sigmoid output)
+// VEC: one item = (output pixel, 8-channel group): four predicated 16-byte loads (+ one of aux) in flight, 2 items per thread.
 enum : int { C2I_NONE = 0, C2I_SIGMOID = 1, C2I_LRELU_GRAD = 2, C2I_SIGMOID_GRAD = 3 };
-__global__ void col2im_k4s2_kernel(const __nv_bfloat16* __restrict__ col, int ldc, int B, int Hi, int Wi, int C,
-                                   __nv_bfloat16* __restrict__ y, int ldy, int mode, const __nv_bfloat16* __restrict__ aux,
-                                   int ld_aux, float slope) {
+template <bool VEC>
+__global__ void __launch_bounds__(256) col2im_k4s2_kernel(const __nv_bfloat16* __restrict__ col, int ldc, int Hi, int Wi, int C,
+                                                          __nv_bfloat16* __restrict__ y, int ldy, int mode,
+                                                          const __nv_bfloat16* __restrict__ aux, int ld_aux, float slope, uint32_t total,
+                                                          FastDiv dcg, FastDiv dwo, FastDiv dho) {
   griddep_sync();
-  const int Ho = 2 * Hi, Wo = 2 * Wi;
-  const int cg = (C % 8 == 0) ? C / 8 : 1, cw = (C % 8 == 0) ? 8 : C;
-  const long long total = (long long)B * Ho * Wo * cg;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = int(t % cg);
-    const long long pix = t / cg;
-    const int ox = int(pix % Wo), oy = int((pix / Wo) % Ho), b = int(pix / ((long long)Wo * Ho));
-    float acc[8];
+  constexpr int U = 2;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  if constexpr (VEC) {
+    for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += stride * U) {
+      uint4 v[U][4], av[U];
+      uint32_t pix[U], g[U];
+      bool live[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // taps with (oy + 1 - kh) even and in range: kh in {(oy + 1) & 1, ((oy + 1) & 1) + 2}
+      for (int u = 0; u < U; ++u) {
+        const uint32_t t = t0 + u * stride;
+        live[u] = t < total && t >= t0;
+        fdivmod(t, dcg, pix[u], g[u]);
+        uint32_t q, ox, b, oy;
+        fdivmod(pix[u], dwo, q, ox);
+        fdivmod(q, dho, b, oy);
+        // taps with (oy + 1 - kh) even and in range: kh in {(oy + 1) & 1, ((oy + 1) & 1) + 2}
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int kh = ((oy + 1) & 1) + 2 * a, iy = (oy + 1 - kh) >> 1;
-      if (iy < 0 || iy >= Hi) continue;
+        for (int a = 0; a < 2; ++a) {
+          const int kh = int((oy + 1) & 1u) + 2 * a, iy = (int(oy) + 1 - kh) >> 1;
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        const int kw = ((ox + 1) & 1) + 2 * bb, ix = (ox + 1 - kw) >> 1;
-        if (ix < 0 || ix >= Wi) continue;
-        const __nv_bfloat16* src = col + (((long long)b * Hi + iy) * Wi + ix) * ldc + (kh * 4 + kw) * C + g * 8;
-        if (cw == 8) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+          for (int bb = 0; bb < 2; ++bb) {
+            const int kw = int((ox + 1) & 1u) + 2 * bb, ix = (int(ox) + 1 - kw) >> 1;
+            const bool ok = live[u] && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (ok) w = __ldg(reinterpret_cast<const uint4*>(col + ((size_t(b) * Hi + iy) * Wi + ix) * ldc + (kh * 4 + kw) * C + g[u] * 8));
+            v[u][a * 2 + bb] = w;
+          }
+        }
+        av[u] = make_uint4(0, 0, 0, 0);
+        if (mode >= C2I_LRELU_GRAD && live[u]) av[u] = __ldg(reinterpret_cast<const uint4*>(aux + size_t(pix[u]) * ld_aux + g[u] * 8));
+      }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { acc[2 * q] += bf16_lo(u[q]); acc[2 * q + 1] += bf16_hi(u[q]); }
-        } else {
-          for (int c = 0; c < cw; ++c) acc[c] += __bfloat162float(src[c]);
+      for (int u = 0; u < U; ++u) {
+        if (!live[u]) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                    // summation order: (kh, kw) ascending
+          const uint32_t w[4] = {v[u][k].x, v[u][k].y, v[u][k].z, v[u][k].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { acc[2 * q] += bf16_lo(w[q]); acc[2 * q + 1] += bf16_hi(w[q]); }
+        }
+        const uint32_t aw[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float val = acc[c];
+          const float a = (c & 1) ? bf16_hi(aw[c >> 1]) : bf16_lo(aw[c >> 1]);
+          if (mode == C2I_SIGMOID) val = 1.f / (1.f + __expf(-val));
+          else if (mode == C2I_LRELU_GRAD) val = a > 0.f ? val : slope * val;
+          else if (mode == C2I_SIGMOID_GRAD) val = val * a * (1.f - a);
+          o[c] = val;
+        }
+        store_bf16x8(y + size_t(pix[u]) * ldy + g[u] * 8, o, 0);
+      }
+    }
+  } else {
+    // C < 8 (the 3-channel image layer): one thread per output pixel, scalar channels
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += stride) {
+      uint32_t q, ox, b, oy;
+      fdivmod(pix, dwo, q, ox);
+      fdivmod(q, dho, b, oy);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int kh = int((oy + 1) & 1u) + 2 * a, iy = (int(oy) + 1 - kh) >> 1;
+        if (iy < 0 || iy >= Hi) continue;
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const int kw = int((ox + 1) & 1u) + 2 * bb, ix = (int(ox) + 1 - kw) >> 1;
+          if (ix < 0 || ix >= Wi) continue;
+          const __nv_bfloat16* src = col + ((size_t(b) * Hi + iy) * Wi + ix) * ldc + (kh * 4 + kw) * C;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < C) acc[c] += __bfloat162float(src[c]);
+        }
+      }
+      const __nv_bfloat16* ap = aux + size_t(pix) * ld_aux;
+      __nv_bfloat16* dst = y + size_t(pix) * ldy;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < C) {
+          float val = acc[c];
+          if (mode == C2I_SIGMOID) val = 1.f / (1.f + __expf(-val));
+          else if (mode >= C2I_LRELU_GRAD) {
+            const float a = __bfloat162float(ap[c]);
+            val = mode == C2I_LRELU_GRAD ? (a > 0.f ? val : slope * val) : val * a * (1.f - a);
+          }
+          dst[c] = __float2bfloat16_rn(val);
         }
       }
     }
-    float av[8];
-    if (mode >= C2I_LRELU_GRAD) {
-      const __nv_bfloat16* ap = aux + pix * ld_aux + g * 8;
-      for (int c = 0; c < cw; ++c) av[c] = __bfloat162float(ap[c]);
-    }
-    __nv_bfloat16* dst = y + pix * ldy + g * 8;
-    float o[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float v = acc[c];
-      if (c < cw) {
-        if (mode == C2I_SIGMOID) v = 1.f / (1.f + __expf(-v));
-        else if (mode == C2I_LRELU_GRAD) v = av[c] > 0.f ? v : slope * v;
-        else if (mode == C2I_SIGMOID_GRAD) v = v * av[c] * (1.f - av[c]);
-      }
-      o[c] = v;
-    }
-    if (cw == 8) store_bf16x8(dst, o, 0);
-    else for (int c = 0; c < cw; ++c) dst[c] = __float2bfloat16_rn(o[c]);
   }
 }
 
 // ---------------------------------------------------------------- BatchNorm2d, training mode (batch statistics)
 // x [rows, C] bf16 (rows = B*H*W).  Pass 1: per-block partial column sums (sum, sum of squares; fp32 per thread over a
-// slab of rows, double across the block) -> part [nblk][2][C].  Pass 2 (one block per 32 channels... one thread per
-// channel): mean, invstd (+ running statistics, momentum 0.1, unbiased variance like torch).  Pass 3: y = act(gamma *
-// (x - mean) * invstd + beta).  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
+// slab of rows, double across the block) -> part [nblk][2][C].  Pass 2 (a warp per channel): mean, invstd (+ running
+// statistics, momentum 0.1, unbiased variance like torch).  Pass 3: y = act(gamma * (x - mean) * invstd + beta).
+// act: 0 none, 1 ReLU, 2 LeakyReLU(slope).  Thread mapping of every pass: thread = (8-channel group g, row lane rl), the
+// block walks rpi = 256 / groups rows per iteration - no division in the loops, per-channel constants in registers, and
+// kBnUnroll rows per thread in flight (HBM-bound: the first versions had one 16-byte load in flight per thread and re-read
+// gamma / beta / mean / invstd from global memory for every element, 25-45 % of the HBM rate).
 constexpr int kBnThreads = 256;
+constexpr int kBnUnroll = 4;
+constexpr int kBnStatUnroll = 8;
+// The double-precision running sums of a thread live in ITS slots of the block's shared array (the same array the final
+// cross-row reduction reads), not in registers: 32 fewer registers per thread = more resident warps with loads in flight.
 __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, int ld,
                                                                  double* __restrict__ part) {
   griddep_sync();
-  extern __shared__ double bn_sh[];                  // [rows_per_iter][2 * C]
+  extern __shared__ double bn_sh[];                  // [rows_per_iter][2][C]
   const int groups = C / 8;
   const int g = threadIdx.x % groups, rl = threadIdx.x / groups, rpi = kBnThreads / groups;
-  float s1[8], s2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  double d1[8], d2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { d1[j] = 0.0; d2[j] = 0.0; }
-  int since = 0;
   if (rl < rpi) {
-    for (long long r = (long long)blockIdx.x * rpi + rl; r < rows; r += (long long)gridDim.x * rpi) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * ld) + g);
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    double* const my1 = bn_sh + (rl * 2 + 0) * C + g * 8;
+    double* const my2 = bn_sh + (rl * 2 + 1) * C + g * 8;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float a = bf16_lo(u[q]), b = bf16_hi(u[q]);
-        s1[2 * q] += a; s2[2 * q] = fmaf(a, a, s2[2 * q]);
-        s1[2 * q + 1] += b; s2[2 * q + 1] = fmaf(b, b, s2[2 * q + 1]);
+    for (int j = 0; j < 8; ++j) { my1[j] = 0.0; my2[j] = 0.0; }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    int since = 0;
+    const long long rstep = (long long)gridDim.x * rpi;
+    for (long long r0 = (long long)blockIdx.x * rpi + rl; r0 < rows; r0 += rstep * kBnStatUnroll) {
+      uint4 v[kBnStatUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnStatUnroll; ++u) {
+        const long long r = r0 + u * rstep;
+        v[u] = make_uint4(0, 0, 0, 0);                // zero rows add nothing to either sum
+        if (r < rows) v[u] = __ldg(reinterpret_cast<const uint4*>(x + r * ld) + g);
       }
-      if (++since == 64) {     // flush the fp32 running sums into doubles (long columns: B*H*W up to 8 M rows)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+      for (int u = 0; u < kBnStatUnroll; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = bf16_lo(w[q]), b = bf16_hi(w[q]);
+          s1[2 * q] += a; s2[2 * q] = fmaf(a, a, s2[2 * q]);
+          s1[2 * q + 1] += b; s2[2 * q + 1] = fmaf(b, b, s2[2 * q + 1]);
+        }
+      }
+      if (++since == 64 / kBnStatUnroll) {   // flush the fp32 running sums into doubles every 64 rows (B*H*W up to 8 M rows)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { my1[j] += s1[j]; my2[j] += s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
         since = 0;
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { bn_sh[(rl * 2 + 0) * C + g * 8 + j] = d1[j]; bn_sh[(rl * 2 + 1) * C + g * 8 + j] = d2[j]; }
+    for (int j = 0; j < 8; ++j) { my1[j] += s1[j]; my2[j] += s2[j]; }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += kBnThreads) {
@@ -158,7 +268,17 @@ __global__ void bn_finalize_kernel(const double* __restrict__ part, int nblk, in
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int i = lane; i < nblk; i += 32) { s1 += part[((long long)i * 2) * C + c]; s2 += part[((long long)i * 2 + 1) * C + c]; }
+  for (int i0 = lane; i0 < nblk; i0 += 32 * 8) {          // 16 loads in flight per lane (was a serial chain of ~19 round trips)
+    double a1[8], a2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + 32 * u;
+      a1[u] = i < nblk ? part[((long long)i * 2) * C + c] : 0.0;
+      a2[u] = i < nblk ? part[((long long)i * 2 + 1) * C + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s1 += a1[u]; s2 += a2[u]; }
+  }
   for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
   if (lane != 0) return;
   const double mean = s1 / count;
@@ -170,75 +290,108 @@ __global__ void bn_finalize_kernel(const double* __restrict__ part, int nblk, in
     running[C + c] = (1.f - momentum) * running[C + c] + momentum * float(var * count / fmax(count - 1.0, 1.0));
   }
 }
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, int ld, const float* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int act, float slope,
-                                __nv_bfloat16* __restrict__ y, int ldy) {
+// y = act(x * sc + sh) with sc = gamma invstd, sh = beta - mean sc (two registers per channel)
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, int ld,
+                                                               const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int act, float slope,
+                                                               __nv_bfloat16* __restrict__ y, int ldy) {
   griddep_sync();
   const int groups = C / 8;
-  const long long total = rows * groups;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = int(t % groups);
-    const long long r = t / groups;
-    float v[8];
-    load_bf16x8(x + r * ld + g * 8, v, 0);
+  const int g = threadIdx.x % groups, rl = threadIdx.x / groups, rpi = kBnThreads / groups;
+  if (rl >= rpi) return;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      float o = gamma[c] * (v[j] - stats[c]) * stats[C + c] + beta[c];
-      if (act == 1) o = fmaxf(o, 0.f);
-      else if (act == 2) o = o > 0.f ? o : slope * o;
-      v[j] = o;
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    sc[j] = gamma[c] * stats[C + c];
+    sh[j] = fmaf(-stats[c], sc[j], beta[c]);
+  }
+  const long long rstep = (long long)gridDim.x * rpi;
+  for (long long r0 = (long long)blockIdx.x * rpi + rl; r0 < rows; r0 += rstep * kBnUnroll) {
+    uint4 v[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long long r = r0 + u * rstep;
+      if (r < rows) v[u] = __ldg(reinterpret_cast<const uint4*>(x + r * ld) + g);
     }
-    store_bf16x8(y + r * ldy + g * 8, v, 0);
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long long r = r0 + u * rstep;
+      if (r >= rows) break;
+      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xv = (j & 1) ? bf16_hi(w[j >> 1]) : bf16_lo(w[j >> 1]);
+        float t = fmaf(xv, sc[j], sh[j]);
+        if (act == 1) t = fmaxf(t, 0.f);
+        else if (act == 2) t = t > 0.f ? t : slope * t;
+        o[j] = t;
+      }
+      store_bf16x8(y + r * ldy + g * 8, o, 0);
+    }
   }
 }
 
 // backward: g = dy * act'(gamma xhat + beta); dbeta = sum g; dgamma = sum g xhat;
 //           dx = gamma invstd / N * (N g - dbeta - xhat dgamma)            (torch.nn.functional.batch_norm backward)
 // Pass 1: partial sums (dbeta, dgamma) with the bn_partial layout; pass 2: finalise into dgb [2][C] fp32; pass 3: dx.
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                                                                     long long rows, int C, int ld, const float* __restrict__ stats,
-                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                     int act, float slope, double* __restrict__ part) {
+constexpr int kBnBwdUnroll = 4;                       // two operands per row: 8 loads in flight
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                                        long long rows, int C, int ld, const float* __restrict__ stats,
+                                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                        int act, float slope, double* __restrict__ part) {
   griddep_sync();
   extern __shared__ double bn_sh[];
   const int groups = C / 8;
   const int g = threadIdx.x % groups, rl = threadIdx.x / groups, rpi = kBnThreads / groups;
-  float mu[8], is[8], ga[8], be[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { const int c = g * 8 + j; mu[j] = stats[c]; is[j] = stats[C + c]; ga[j] = gamma[c]; be[j] = beta[c]; }
-  double d1[8], d2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { d1[j] = 0.0; d2[j] = 0.0; }
-  float s1[8], s2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  int since = 0;
   if (rl < rpi) {
-    for (long long r = (long long)blockIdx.x * rpi + rl; r < rows; r += (long long)gridDim.x * rpi) {
-      float xv[8], gv[8];
-      load_bf16x8(x + r * ld + g * 8, xv, 0);
-      load_bf16x8(dy + r * ld + g * 8, gv, 0);
+    float mu[8], is[8], ga[8], be[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (xv[j] - mu[j]) * is[j];
-        const float pre = ga[j] * xh + be[j];
-        float gg = gv[j];
-        if (act == 1) gg = pre > 0.f ? gg : 0.f;
-        else if (act == 2) gg = pre > 0.f ? gg : slope * gg;
-        s1[j] += gg;
-        s2[j] = fmaf(gg, xh, s2[j]);
+    for (int j = 0; j < 8; ++j) { const int c = g * 8 + j; mu[j] = stats[c]; is[j] = stats[C + c]; ga[j] = gamma[c]; be[j] = beta[c]; }
+    double* const my1 = bn_sh + (rl * 2 + 0) * C + g * 8;
+    double* const my2 = bn_sh + (rl * 2 + 1) * C + g * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { my1[j] = 0.0; my2[j] = 0.0; }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    int since = 0;
+    const long long rstep = (long long)gridDim.x * rpi;
+    for (long long r0 = (long long)blockIdx.x * rpi + rl; r0 < rows; r0 += rstep * kBnBwdUnroll) {
+      uint4 vx[kBnBwdUnroll], vg[kBnBwdUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnBwdUnroll; ++u) {
+        const long long r = r0 + u * rstep;
+        vx[u] = make_uint4(0, 0, 0, 0); vg[u] = make_uint4(0, 0, 0, 0);   // dy = 0 rows add nothing
+        if (r < rows) {
+          vx[u] = __ldg(reinterpret_cast<const uint4*>(x + r * ld) + g);
+          vg[u] = __ldg(reinterpret_cast<const uint4*>(dy + r * ld) + g);
+        }
       }
-      if (++since == 64) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
+      for (int u = 0; u < kBnBwdUnroll; ++u) {
+        const uint32_t wx[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w}, wg[4] = {vg[u].x, vg[u].y, vg[u].z, vg[u].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xv = (j & 1) ? bf16_hi(wx[j >> 1]) : bf16_lo(wx[j >> 1]);
+          float gg = (j & 1) ? bf16_hi(wg[j >> 1]) : bf16_lo(wg[j >> 1]);
+          const float xh = (xv - mu[j]) * is[j];
+          const float pre = ga[j] * xh + be[j];
+          if (act == 1) gg = pre > 0.f ? gg : 0.f;
+          else if (act == 2) gg = pre > 0.f ? gg : slope * gg;
+          s1[j] += gg;
+          s2[j] = fmaf(gg, xh, s2[j]);
+        }
+      }
+      if (++since == 64 / kBnBwdUnroll) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { my1[j] += s1[j]; my2[j] += s2[j]; s1[j] = 0.f; s2[j] = 0.f; }
         since = 0;
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { bn_sh[(rl * 2 + 0) * C + g * 8 + j] = d1[j]; bn_sh[(rl * 2 + 1) * C + g * 8 + j] = d2[j]; }
+    for (int j = 0; j < 8; ++j) { my1[j] += s1[j]; my2[j] += s2[j]; }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += kBnThreads) {
@@ -255,34 +408,63 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk
   if (c >= 2 * C) return;
   const int which = c / C, ch = c % C;
   double t = 0.0;
-  for (int i = lane; i < nblk; i += 32) t += part[((long long)i * 2 + which) * C + ch];
+  for (int i0 = lane; i0 < nblk; i0 += 32 * 8) {
+    double a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + 32 * u;
+      a[u] = i < nblk ? part[((long long)i * 2 + which) * C + ch] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t += a[u];
+  }
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   if (lane == 0) dgb[c] = float(t);
 }
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, long long rows, int C, int ld,
-                                    const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    int act, float slope, const float* __restrict__ dgb, float inv_count,
-                                    __nv_bfloat16* __restrict__ dx, int lddx) {
+__global__ void __launch_bounds__(kBnThreads, 2) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                                   long long rows, int C, int ld, const float* __restrict__ stats,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   int act, float slope, const float* __restrict__ dgb, float inv_count,
+                                                                   __nv_bfloat16* __restrict__ dx, int lddx) {
   griddep_sync();
   const int groups = C / 8;
-  const long long total = rows * groups;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = int(t % groups);
-    const long long r = t / groups;
-    float xv[8], gv[8];
-    load_bf16x8(x + r * ld + g * 8, xv, 0);
-    load_bf16x8(dy + r * ld + g * 8, gv, 0);
+  const int g = threadIdx.x % groups, rl = threadIdx.x / groups, rpi = kBnThreads / groups;
+  if (rl >= rpi) return;
+  float mu[8], is[8], ga[8], be[8], db[8], dg[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float xh = (xv[j] - stats[c]) * stats[C + c];
-      const float pre = gamma[c] * xh + beta[c];
-      float gg = gv[j];
-      if (act == 1) gg = pre > 0.f ? gg : 0.f;
-      else if (act == 2) gg = pre > 0.f ? gg : slope * gg;
-      gv[j] = gamma[c] * stats[C + c] * (gg - inv_count * (dgb[c] + xh * dgb[C + c]));
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    mu[j] = stats[c]; is[j] = stats[C + c]; ga[j] = gamma[c]; be[j] = beta[c]; db[j] = dgb[c]; dg[j] = dgb[C + c];
+  }
+  const long long rstep = (long long)gridDim.x * rpi;
+  for (long long r0 = (long long)blockIdx.x * rpi + rl; r0 < rows; r0 += rstep * kBnBwdUnroll) {
+    uint4 vx[kBnBwdUnroll], vg[kBnBwdUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnBwdUnroll; ++u) {
+      const long long r = r0 + u * rstep;
+      if (r < rows) {
+        vx[u] = __ldg(reinterpret_cast<const uint4*>(x + r * ld) + g);
+        vg[u] = __ldg(reinterpret_cast<const uint4*>(dy + r * ld) + g);
+      }
     }
-    store_bf16x8(dx + r * lddx + g * 8, gv, 0);
+#pragma unroll
+    for (int u = 0; u < kBnBwdUnroll; ++u) {
+      const long long r = r0 + u * rstep;
+      if (r >= rows) break;
+      const uint32_t wx[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w}, wg[4] = {vg[u].x, vg[u].y, vg[u].z, vg[u].w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xv = (j & 1) ? bf16_hi(wx[j >> 1]) : bf16_lo(wx[j >> 1]);
+        float gg = (j & 1) ? bf16_hi(wg[j >> 1]) : bf16_lo(wg[j >> 1]);
+        const float xh = (xv - mu[j]) * is[j];
+        const float pre = ga[j] * xh + be[j];
+        if (act == 1) gg = pre > 0.f ? gg : 0.f;
+        else if (act == 2) gg = pre > 0.f ? gg : slope * gg;
+        o[j] = ga[j] * is[j] * (gg - inv_count * (db[j] + xh * dg[j]));
+      }
+      store_bf16x8(dx + r * lddx + g * 8, o, 0);
+    }
   }
 }
 

@@ -153,7 +153,7 @@ static cudaError_t launch_pdl(const char* name, void (*kern)(KArgs...), dim3 gri
 
 template <int BN1, int BN2, bool AMN, bool BMN, int ACT_T, int AUX_T, int BIAS_T, int DOT_T, int CS, int EW, bool SPLIT = false>
 static cudaError_t launch_cs(const GemmPlan& pl, cudaStream_t s) {
-  using Cfg = GemmCfg<BN1, BN2, !AMN, (CS == 2) && !AMN, EW>;
+  using Cfg = GemmCfg<BN1, BN2, !AMN, (CS == 2) && !AMN, EW, EpiVecExtra<AUX_T, BIAS_T, DOT_T, EW>::value>;
   auto kern = gemm_umma_kernel<BN1, BN2, AMN, BMN, ACT_T, AUX_T, BIAS_T, DOT_T, CS, EW, SPLIT>;
   // the opt-in to > 48 KB dynamic shared memory is per (function, device)
   static bool configured[64] = {};
@@ -382,7 +382,13 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int nspli
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float t = 0.f;
-  for (int s = 0; s < nsplit; ++s) t += part[i + s * stride];
+  for (int s0 = 0; s0 < nsplit; s0 += 8) {     // eight partials in flight, summed in split order
+    float a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = (s0 + u < nsplit) ? part[i + (long long)(s0 + u) * stride] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t += a[u];
+  }
   out[i] = t;
 }
 

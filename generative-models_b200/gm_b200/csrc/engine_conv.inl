@@ -13,11 +13,29 @@ static int conv_scratch(gm_ctx* c, size_t bytes, double** out) {
   return GM_OK;
 }
 
+// grid of a grid-stride elementwise kernel: enough 256-thread blocks to fill the GPU (8 per SM), no more than the work needs
+static unsigned conv_grid(const gm_ctx* c, unsigned long long items, int per_thread) {
+  const unsigned long long want = (items + 256ull * per_thread - 1) / (256ull * per_thread);
+  const unsigned long long cap = (unsigned long long)c->num_sms * 8;
+  return unsigned(want < cap ? (want ? want : 1) : cap);
+}
+
 extern "C" int gm_im2col_k4s2(gm_ctx* c, const void* x, int B, int H, int W, int C, int ldx, void* col, int ldc, gm_stream stream) {
   if (!c || !x || !col || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (H & 1) || (W & 1)) return c ? fail(c, GM_ERR_ARG, "gm_im2col_k4s2: bad argument") : GM_ERR_ARG;
   if (ldc < 16 * C || ldx < C || (C % 8 == 0 && ((ldx % 8) || (ldc % 8)))) return fail(c, GM_ERR_ARG, "gm_im2col_k4s2: leading dimensions");
-  launch_pdl("im2col_k4s2_kernel", im2col_k4s2_kernel, c->num_sms * 16, 256, 0, static_cast<cudaStream_t>(stream),
-             static_cast<const __nv_bfloat16*>(x), B, H, W, C, ldx, static_cast<__nv_bfloat16*>(col), ldc);
+  const bool vec = C % 8 == 0;
+  const unsigned long long rows = (unsigned long long)B * (H / 2) * (W / 2);
+  const unsigned long long total = rows * 16 * (vec ? C / 8 : 1);
+  if (total >= (1ull << 31)) return fail(c, GM_ERR_UNSUPPORTED, "gm_im2col_k4s2: more than 2^31 16-byte items (%llu): split the batch", total);
+  const FastDiv dcg = make_fastdiv(vec ? C / 8 : 1), dwo = make_fastdiv(W / 2), dho = make_fastdiv(H / 2);
+  const unsigned grid = conv_grid(c, total, kConvUnroll);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (vec)
+    launch_pdl("im2col_k4s2_kernel", im2col_k4s2_kernel<true>, grid, 256, 0, s, static_cast<const __nv_bfloat16*>(x), H, W, C, ldx,
+               static_cast<__nv_bfloat16*>(col), ldc, uint32_t(total), dcg, dwo, dho);
+  else
+    launch_pdl("im2col_k4s2_kernel", im2col_k4s2_kernel<false>, grid, 256, 0, s, static_cast<const __nv_bfloat16*>(x), H, W, C, ldx,
+               static_cast<__nv_bfloat16*>(col), ldc, uint32_t(total), dcg, dwo, dho);
   c->launches++;
   CU_OK(c, cudaGetLastError());
   return GM_OK;
@@ -28,9 +46,20 @@ extern "C" int gm_col2im_k4s2(gm_ctx* c, const void* col, int ldc, int B, int Hi
   if (!c || !col || !y || B <= 0 || Hi <= 0 || Wi <= 0 || C <= 0 || mode < 0 || mode > 3) return c ? fail(c, GM_ERR_ARG, "gm_col2im_k4s2: bad argument") : GM_ERR_ARG;
   if (mode >= C2I_LRELU_GRAD && !aux) return fail(c, GM_ERR_ARG, "gm_col2im_k4s2: mode %d needs aux", mode);
   if (ldc < 16 * C || ldy < C) return fail(c, GM_ERR_ARG, "gm_col2im_k4s2: leading dimensions");
-  launch_pdl("col2im_k4s2_kernel", col2im_k4s2_kernel, c->num_sms * 16, 256, 0, static_cast<cudaStream_t>(stream),
-             static_cast<const __nv_bfloat16*>(col), ldc, B, Hi, Wi, C, static_cast<__nv_bfloat16*>(y), ldy, mode,
-             static_cast<const __nv_bfloat16*>(aux), ld_aux, slope);
+  const bool vec = C % 8 == 0;
+  if (!vec && C > 8) return fail(c, GM_ERR_UNSUPPORTED, "gm_col2im_k4s2: C must be a multiple of 8 or below 8 (got %d)", C);
+  if (vec && ((ldc % 8) || (ldy % 8) || (mode >= C2I_LRELU_GRAD && (ld_aux % 8)))) return fail(c, GM_ERR_ARG, "gm_col2im_k4s2: leading dimensions (multiples of 8)");
+  const unsigned long long total = (unsigned long long)B * (2 * Hi) * (2 * Wi) * (vec ? C / 8 : 1);
+  if (total >= (1ull << 31)) return fail(c, GM_ERR_UNSUPPORTED, "gm_col2im_k4s2: more than 2^31 items (%llu): split the batch", total);
+  const FastDiv dcg = make_fastdiv(vec ? C / 8 : 1), dwo = make_fastdiv(2 * Wi), dho = make_fastdiv(2 * Hi);
+  const unsigned grid = conv_grid(c, total, vec ? 2 : 1);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (vec)
+    launch_pdl("col2im_k4s2_kernel", col2im_k4s2_kernel<true>, grid, 256, 0, s, static_cast<const __nv_bfloat16*>(col), ldc, Hi, Wi, C,
+               static_cast<__nv_bfloat16*>(y), ldy, mode, static_cast<const __nv_bfloat16*>(aux), ld_aux, slope, uint32_t(total), dcg, dwo, dho);
+  else
+    launch_pdl("col2im_k4s2_kernel", col2im_k4s2_kernel<false>, grid, 256, 0, s, static_cast<const __nv_bfloat16*>(col), ldc, Hi, Wi, C,
+               static_cast<__nv_bfloat16*>(y), ldy, mode, static_cast<const __nv_bfloat16*>(aux), ld_aux, slope, uint32_t(total), dcg, dwo, dho);
   c->launches++;
   CU_OK(c, cudaGetLastError());
   return GM_OK;
@@ -56,7 +85,7 @@ extern "C" int gm_bn_forward(gm_ctx* c, const void* x, long long rows, int C, in
   launch_pdl("bn_partial_kernel", bn_partial_kernel, nblk, kBnThreads, smem, s, static_cast<const __nv_bfloat16*>(x), rows, C, ld, part);
   launch_pdl("bn_finalize_kernel", bn_finalize_kernel, cdiv(C * 32, 256), 256, 0, s, static_cast<const double*>(part), nblk, C, double(rows), eps, stats_dev,
              running_dev, momentum);
-  launch_pdl("bn_apply_kernel", bn_apply_kernel, c->num_sms * 16, 256, 0, s, static_cast<const __nv_bfloat16*>(x), rows, C, ld,
+  launch_pdl("bn_apply_kernel", bn_apply_kernel, conv_grid(c, (unsigned long long)rows * (C / 8), kBnUnroll), kBnThreads, 0, s, static_cast<const __nv_bfloat16*>(x), rows, C, ld,
              static_cast<const float*>(stats_dev), gamma, beta, act, slope, static_cast<__nv_bfloat16*>(y), ldy);
   c->launches += 3;
   CU_OK(c, cudaGetLastError());
@@ -71,7 +100,7 @@ extern "C" int gm_bn_backward(gm_ctx* c, const void* dy, const void* x, long lon
   if (!c || !dy || !x || !dx || !gamma || !beta || !stats_dev || !dgb_dev || rows <= 0 || C <= 0 || C % 8 || ld % 8 || lddx % 8)
     return c ? fail(c, GM_ERR_ARG, "gm_bn_backward: bad argument") : GM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int nblk = c->num_sms * 4;
+  const int nblk = c->num_sms * 2   /* 2 resident blocks per SM (register budget) */;
   double* part;
   int rc = conv_scratch(c, size_t(nblk) * 2 * C * sizeof(double), &part);
   if (rc) return rc;
@@ -81,7 +110,7 @@ extern "C" int gm_bn_backward(gm_ctx* c, const void* dy, const void* x, long lon
   launch_pdl("bn_bwd_partial_kernel", bn_bwd_partial_kernel, nblk, kBnThreads, smem, s, static_cast<const __nv_bfloat16*>(dy),
              static_cast<const __nv_bfloat16*>(x), rows, C, ld, stats_dev, gamma, beta, act, slope, part);
   launch_pdl("bn_bwd_finalize_kernel", bn_bwd_finalize_kernel, cdiv(2 * C * 32, 256), 256, 0, s, static_cast<const double*>(part), nblk, C, dgb_dev);
-  launch_pdl("bn_bwd_apply_kernel", bn_bwd_apply_kernel, c->num_sms * 16, 256, 0, s, static_cast<const __nv_bfloat16*>(dy),
+  launch_pdl("bn_bwd_apply_kernel", bn_bwd_apply_kernel, conv_grid(c, (unsigned long long)rows * (C / 8), kBnBwdUnroll), kBnThreads, 0, s, static_cast<const __nv_bfloat16*>(dy),
              static_cast<const __nv_bfloat16*>(x), rows, C, ld, stats_dev, gamma, beta, act, slope, static_cast<const float*>(dgb_dev),
              float(1.0 / double(rows)), static_cast<__nv_bfloat16*>(dx), lddx);
   c->launches += 3;

@@ -105,7 +105,11 @@ __device__ __forceinline__ long long phase_clock() { return 0; }
 constexpr bool kPhaseTiming = false;
 #endif
 
-template <int BN1, int BN2, bool STAGED_EPI = true, bool PAIR = false, int EW = 8>
+// VEC_EXTRA: additional per-warp bytes behind the bias / row-dot staging (EpiVecExtra: room for the cp.async aux tile of
+// the epilogues that have a bias AND an aux operand - VAE decoder output, BEGAN decoder)
+template <int AUX_T, int BIAS_T, int DOT_T, int EW>
+struct EpiVecExtra { static constexpr int value = (AUX_T > 0 && BIAS_T > 0 && DOT_T == 0 && EW == 16) ? 512 : 0; };
+template <int BN1, int BN2, bool STAGED_EPI = true, bool PAIR = false, int EW = 8, int VEC_EXTRA = 0>
 struct GemmCfg {
   static constexpr int BN = BN1 + BN2;
   static constexpr int NACC = (2 * BN <= 512) ? 2 : 1;
@@ -115,7 +119,8 @@ struct GemmCfg {
   // per-warp staging tile + per-warp copies of its blocks' bias / row-dot weight slices
   static constexpr int EPI_WARPS = EW;
   static_assert(EW == 8 || (EW == 16 && STAGED_EPI), "8 or 16 epilogue warps");
-  static constexpr int EPI_BYTES = STAGED_EPI ? EPI_WARPS * (kEpiStageBytes + kEpiVecBytes) : 0;
+  static constexpr int VEC_BYTES = kEpiVecBytes + VEC_EXTRA;
+  static constexpr int EPI_BYTES = STAGED_EPI ? EPI_WARPS * (kEpiStageBytes + VEC_BYTES) : 0;
   static_assert(!STAGED_EPI || (BN + kEpiCols - 1) / kEpiCols <= kEpiVecBlocks * (EPI_WARPS / 8), "bias/dot staging too small");
   static constexpr int STAGES_RAW = (kSmemBudget - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -148,7 +153,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   static_assert(!SPLIT || ACT_T < 0, "split operands: universal epilogue only");
   constexpr bool PAIR = (CS == 2) && !A_MN;
-  using Cfg = GemmCfg<BN1, BN2, !A_MN, PAIR, EW>;
+  using Cfg = GemmCfg<BN1, BN2, !A_MN, PAIR, EW, EpiVecExtra<AUX_T, BIAS_T, DOT_T, EW>::value>;
   constexpr int BN = Cfg::BN;
   constexpr int NACC = Cfg::NACC;
   constexpr int STAGES = Cfg::STAGES;
@@ -361,7 +366,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int my_stage = grp & 1;   // accumulator stage this warp serves when NACC == 2
     const int part = A_MN ? 0 : (grp >> 1);   // which interleaved set of 32-column blocks (K-major kernels)
     const uint32_t stage_s = bar_base + 512u + uint32_t(e) * kEpiStageBytes;  // staging tile (NT kernels)
-    const uint32_t vec_s = bar_base + 512u + kEpiWarps * kEpiStageBytes + uint32_t(e) * kEpiVecBytes;
+    const uint32_t vec_s = bar_base + 512u + kEpiWarps * kEpiStageBytes + uint32_t(e) * Cfg::VEC_BYTES;
     const int act = ACT_T >= 0 ? ACT_T : p.act;
     const int aux_mode = AUX_T >= 0 ? AUX_T : p.aux_mode;
     const bool has_bias = BIAS_T >= 0 ? (BIAS_T != 0) : (p.bias != nullptr);
@@ -410,7 +415,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         //    No registers held across the block, no STS (the 96-register budget of the
         //    16-warp epilogue was spilling / re-reading S2R and constants, profiles/r1e);
         //  * otherwise: coalesced LDG into registers, transposed through the staging tile.
-        constexpr bool kAuxAsync = (AUX_T > 0) && (BIAS_T == 0) && (DOT_T == 0);
+        //    With a bias (VAE decoder output, BEGAN decoder; 16 epilogue warps) the tile sits behind the warp's four bias
+        //    blocks in an enlarged staging area: the register path (16 registers held across the block) spilled there.
+        constexpr bool kAuxAsync = (AUX_T > 0) && (DOT_T == 0) && (BIAS_T == 0 || EpiVecExtra<AUX_T, BIAS_T, DOT_T, EW>::value > 0);
+        const uint32_t auxt_s = vec_s + (BIAS_T > 0 ? 512u : 0u);   // 32 rows x 64 B, chunks XOR-swizzled
         uint4 pre[kAuxAsync ? 1 : 4];
         auto aux_fetch = [&](int c_first) {
           const int c = c_first + lc * 8;
@@ -421,7 +429,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool ok = r < p.M && c < p.out_cols;
             if constexpr (kAuxAsync) {
               const __nv_bfloat16* src = ok ? p.aux + size_t(r) * p.ld_aux + c : p.aux;
-              cp_async16_zfill(vec_s + rl * 64 + ((lc ^ ((rl >> 1) & 3)) << 4), src, ok ? 16u : 0u);
+              cp_async16_zfill(auxt_s + rl * 64 + ((lc ^ ((rl >> 1) & 3)) << 4), src, ok ? 16u : 0u);
             } else {
               pre[it] = make_uint4(0, 0, 0, 0);
               if (ok) pre[it] = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(r) * p.ld_aux + c));
@@ -447,8 +455,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               if (has_dot) wz = __ldg(reinterpret_cast<const uint4*>(p.dot_w + c));
             }
-            if (has_bias) sts128(vec_s + (blk * kEpiCols + c4) * 4, bz);
-            if (has_dot) sts128(vec_s + kEpiVecBytes / 2 + (blk * kEpiCols + c4) * 4, wz);
+            if (blk < kEpiVecBlocks / kParts) {   // a warp of the 16-warp epilogue owns at most 4 blocks: the rest of the area may hold its aux tile
+              if (has_bias) sts128(vec_s + (blk * kEpiCols + c4) * 4, bz);
+              if (has_dot) sts128(vec_s + kEpiVecBytes / 2 + (blk * kEpiCols + c4) * 4, wz);
+            }
           }
           __syncwarp();
         }
@@ -494,7 +504,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               cp_async_wait_all();
               __syncwarp();
 #pragma unroll
-              for (int q = 0; q < 4; ++q) ax[q] = lds128(vec_s + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+              for (int q = 0; q < 4; ++q) ax[q] = lds128(auxt_s + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
             } else {
               stage_acquire();
 #pragma unroll

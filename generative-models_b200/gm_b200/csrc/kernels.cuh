@@ -847,17 +847,25 @@ __device__ __forceinline__ float gather_grad(const GradSegs& segs, int i) {
     if (s.kind <= 1) off = (long long)(j / s.cols) * s.ld + (j % s.cols);
     else if (s.kind == 2) off = (long long)j * s.ld + s.col;
     else off = j;
-    // four independent partial sums (loads in flight), combined in a fixed order -> deterministic
+    // four independent partial sums, combined in a fixed order -> deterministic; the partials are fetched eight at a
+    // time (all loads issued before the first add: the kernel is a chain of dependent memory round trips otherwise)
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
     const float* src = s.src + off;
     int q = 0;
-    for (; q + 4 <= s.nsplit; q += 4) {
-      t0 += src[(long long)q * s.split_stride];
-      t1 += src[(long long)(q + 1) * s.split_stride];
-      t2 += src[(long long)(q + 2) * s.split_stride];
-      t3 += src[(long long)(q + 3) * s.split_stride];
+    for (; q + 8 <= s.nsplit; q += 8) {
+      float a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = src[(long long)(q + u) * s.split_stride];
+      t0 += a[0]; t1 += a[1]; t2 += a[2]; t3 += a[3];
+      t0 += a[4]; t1 += a[5]; t2 += a[6]; t3 += a[7];
     }
-    for (; q < s.nsplit; ++q) t0 += src[(long long)q * s.split_stride];
+    {                                   // tail of up to 7 partials: predicated loads, same accumulator pattern
+      float a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = (q + u < s.nsplit) ? src[(long long)(q + u) * s.split_stride] : 0.f;
+      t0 += a[0]; t1 += a[1]; t2 += a[2]; t3 += a[3];
+      t0 += a[4]; t1 += a[5]; t2 += a[6]; t3 += a[7];
+    }
     return (t0 + t1) + (t2 + t3);
   }
   return 0.f;
