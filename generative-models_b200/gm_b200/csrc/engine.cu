@@ -220,6 +220,7 @@ static cudaError_t launch_nt208(const GemmPlan& pl, cudaStream_t s) {
   if (bias && !dot && aux == AUX_NONE && p.act == ACT_SIGMOID) return launch_inst<208, 0, false, false, ACT_SIGMOID, AUX_NONE, 1, 0>(pl, s);
   if (bias && dot && p.dot_mask == 1 && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 3>(pl, s);
   if (bias && dot && p.dot_mask == 2 && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 4>(pl, s);
+  if (bias && dot && p.dot_mask == 3 && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 5>(pl, s);
   if (p.dot_mask) return launch_inst<208, 0, false, false>(pl, s);
   if (bias && dot && aux == AUX_NONE && p.act == ACT_RELU) return launch_inst<208, 0, false, false, ACT_RELU, AUX_NONE, 1, 1>(pl, s);
   if (!bias && !dot && aux == AUX_SIGMOID_GRAD && p.act == ACT_NONE) return launch_inst<208, 0, false, false, ACT_NONE, AUX_SIGMOID_GRAD, 0, 0>(pl, s);
@@ -255,13 +256,13 @@ static int launch_plan(gm_ctx* c, const GemmPlan& pl, cudaStream_t s) {
     static const char* kKind[4] = {"gemm_nt208", "gemm_nt64", "gemm_tn448", "gemm_tn64"};
     static std::map<int, std::string> names;   // interned: kind + epilogue signature
     const GemmParams& q = pl.p;
-    const int key = pl.kind | (q.act << 4) | (q.aux_mode << 8) | ((q.dot_w != nullptr) << 12) | (q.dot_mask << 13) | (q.dot_sq << 14) |
-                    ((q.bias != nullptr) << 15) | ((q.epi == EPI_F32) << 16) | ((q.K >= 512) << 17) | ((q.nparts == 3) << 18);
+    const int key = pl.kind | (q.act << 4) | (q.aux_mode << 8) | ((q.dot_w != nullptr) << 12) | (q.dot_sq << 14) |
+                    ((q.bias != nullptr) << 15) | ((q.epi == EPI_F32) << 16) | ((q.K >= 512) << 17) | ((q.nparts == 3) << 18) | (q.dot_mask << 19);
     auto it = names.find(key);
     if (it == names.end()) {
       char buf[128];
       snprintf(buf, sizeof buf, "%s[act%d aux%d%s%s%s%s%s K%s%s]", kKind[pl.kind], q.act, q.aux_mode, q.bias ? " bias" : "", q.dot_w ? " dot" : "",
-               q.dot_mask ? " mask" : "", q.dot_sq ? " sq" : "", q.epi == EPI_F32 ? " f32" : "", q.K >= 512 ? "long" : "short", q.nparts == 3 ? " split" : "");
+               q.dot_mask == 3 ? " pre" : (q.dot_mask ? " mask" : ""), q.dot_sq ? " sq" : "", q.epi == EPI_F32 ? " f32" : "", q.K >= 512 ? "long" : "short", q.nparts == 3 ? " split" : "");
       it = names.emplace(key, buf).first;
     }
     pa.name = it->second.c_str();
@@ -658,6 +659,9 @@ struct gm_gan {
   float *dw2p2 = nullptr, *dw2p3 = nullptr, *slots_v = nullptr, *coef = nullptr, *stats = nullptr;
   double *gp_part = nullptr, *mom_part = nullptr;
   int nreg = 2;                  // row regions of Xall/Aall/DHall: real, fake (, xhat, R)
+  // WGAN-GP: D's first layer is linear, so the penalty's hidden pre-activation is eps a(x) + (1-eps) a(G(z)): the x_hat
+  // rows and their third of the D-layer GEMM are not formed (gp_hat_kernel).  GM_WGP_XHAT=1 keeps the materialised rows.
+  bool wgp_linear = false;
   // InfoGAN: auxiliary network Q (image -> hidden -> disc+cont codes), its own Adam state and a
   // SECOND Adam state for G (MI_optimizer spans G and Q, src/info_gan.py:146-148)
   NetLayout Qn;
@@ -741,6 +745,10 @@ extern "C" int gm_gan_create(gm_ctx* c, const gm_gan_desc* d, gm_gan** out) {
   g->D.init(g->X, g->H, d->variant == GM_BEGAN ? g->X : 1);
   g->region_rows = g->Bmax;
   g->nreg = d->variant == GM_WGP ? 3 : (d->variant == GM_DRA ? 4 : 2);
+  {
+    const char* e = getenv("GM_WGP_XHAT");
+    g->wgp_linear = d->variant == GM_WGP && !(e && atoi(e) != 0) && g->HP <= 64 * kGpHatGroups * 4;   // gp_hat_kernel: <= 2 column groups per lane
+  }
   const size_t B = g->Bmax;
   const size_t NR = g->nreg;
   int rc = GM_OK;
@@ -947,13 +955,17 @@ static int build_plans(gm_gan* g, int B, StepPlans** out) {
   if ((rc = plan_gemm(c, &sp.g2, 0, B, X, H, g->Hg, HP, g->W2g_s, H, XP, 1))) return rc;
   set_bf16_epi(sp.g2.p, Xfake, XP, XP, 1, pG + g->G.off_b2, ACT_SIGMOID);
   // D layer 1 (+ fused 400->1 row-dot) on [real; fake] (D step) and on fake only (G step)
-  const int nfwd = g->nreg > 2 ? 3 : 2;      // GP variants also score the interpolated rows
+  const int nfwd = (g->nreg > 2 && !g->wgp_linear) ? 3 : 2;      // GP variants also score the interpolated rows (when they exist)
   if ((rc = plan_gemm(c, &sp.d1_d, 0, nfwd * B, H, X, g->Xall, XP, g->W1d_s, X, H, 1))) return rc;
   set_bf16_epi(sp.d1_d.p, g->Aall, HP, H, 0, pD + g->D.off_b1, ACT_RELU);
   sp.d1_d.p.dot_w = pD + g->D.off_w2; sp.d1_d.p.dot_out = g->slots; sp.d1_d.p.dot_ld = slot_ld;
-  if (g->nreg == 3) {
-    // WGAN-GP: the x_hat rows leave D's first layer directly as U = w2 * relu'(a_hat) (the penalty's first-gradient
-    // operand) in the U region of DHall - no separate pass over their activations
+  if (g->wgp_linear) {
+    // WGAN-GP: the real / fake rows keep their PRE-activations (ReLU inside the row-dot and in dh_kernel): gp_hat_kernel
+    // forms a_hat = eps a(x) + (1-eps) a(G(z)) from them
+    sp.d1_d.p.dot_mask = 3;
+  } else if (g->nreg == 3) {
+    // WGAN-GP with materialised x_hat rows: they leave D's first layer directly as U = w2 * relu'(a_hat) (the penalty's
+    // first-gradient operand) in the U region of DHall - no separate pass over their activations
     sp.d1_d.p.dot_mask = 2; sp.d1_d.p.mask_row0 = 2 * B; sp.d1_d.p.out_alt = g->DHall + size_t(2) * B * HP;
   }
   if ((rc = plan_gemm(c, &sp.d1_g, 0, B, H, X, Xfake, XP, g->W1d_s, X, H, 1))) return rc;
@@ -1297,7 +1309,7 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
   const int H = g->H, HP = g->HP, X = g->X, XP = g->XP;
   const float* w2 = g->par[GM_NET_D] + g->D.off_w2;
   const size_t dh_smem = size_t(g->dh_rows_per_iter) * HP * sizeof(float);
-  if (gp) {
+  if (gp && !g->wgp_linear) {
     // interpolated rows (region 2): WGAN-GP between real and fake, DRAGAN around the real data
     const int mode = g->d.variant == GM_DRA ? 1 : 0;
     if (mode == 1) {
@@ -1311,15 +1323,22 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     c->launches++;
   }
   if ((rc = launch_plan(c, sp->d1_d, s))) return rc;
+  if (g->wgp_linear) {
+    // U = w2 * relu'(a_hat) and the logit part of s(x_hat) from the pre-activations of the real / fake rows
+    launch_pdl("gp_hat_kernel", gp_hat_kernel, c->num_sms * 8, 256, 0, s, g->Aall, g->Aall + size_t(B) * HP, w2, g->DHall + size_t(2) * B * HP,
+               g->slots + 2 * B, 2 * cdiv(H, 208), g->nreg * g->Bmax, B, H, HP, aux, seed, g->dev_step ? 0 : 2 * step, g->lo, dptr);
+    c->launches++;
+  }
   launch_loss(g, B, 0, inv_global_batch, s);
-  launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall, g->ds, w2, g->DHall, g->dw2p, 2 * B, H, HP, g->dh_rows_per_iter, g->lo);
+  launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall, g->ds, w2, g->DHall, g->dw2p, 2 * B, H, HP, g->dh_rows_per_iter, g->lo,
+             g->wgp_linear ? 1 : 0);
   launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
   c->launches += 2;
   if (gp) {
     const size_t rreg = size_t(g->nreg - 1) * B;
     if (g->nreg != 3) {   // DRAGAN keeps a_hat (its penalty back-propagates through s(x_hat) too): U = 1[a_hat > 0] * w2 by a pass
       launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, nullptr, w2, g->DHall + rreg * HP, nullptr,
-                                                            B, H, HP, g->dh_rows_per_iter, g->lo);
+                                                            B, H, HP, g->dh_rows_per_iter, g->lo, 0);
       c->launches++;
     }
     if ((rc = launch_plan(c, sp->gp_v, s))) return rc;          // V = U W1 -> R region of Xall, ||V||^2 -> slots_v
@@ -1338,12 +1357,12 @@ extern "C" int gm_gan_d_grad(gm_gan* g, const void* images, int img_fmt, const i
     c->launches += 3;
     if ((rc = launch_plan(c, sp->gp_t, s))) return rc;          // T = coef (V W1^T) * mask -> DHg
     // dGP/dw2 = column sums of T (block partials; no output rows)
-    launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->DHg, nullptr, w2, static_cast<__nv_bfloat16*>(nullptr), g->dw2p2, B, H, HP, g->dh_rows_per_iter, g->lo);
+    launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->DHg, nullptr, w2, static_cast<__nv_bfloat16*>(nullptr), g->dw2p2, B, H, HP, g->dh_rows_per_iter, g->lo, 0);
     launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p2, g->dh_blocks, HP, HP, g->dw2sum + HP);
     c->launches += 2;
     if (g->nreg == 4) {   // DRAGAN: the penalty also back-propagates through s(xhat)
       launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, dh_smem, s, g->Aall + size_t(2) * B * HP, g->ds + 2 * B, w2,
-                                                            g->DHall + size_t(2) * B * HP, g->dw2p3, B, H, HP, g->dh_rows_per_iter, g->lo);
+                                                            g->DHall + size_t(2) * B * HP, g->dw2p3, B, H, HP, g->dh_rows_per_iter, g->lo, 0);
       launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p3, g->dh_blocks, HP, HP, g->dw2sum + 2 * HP);
       c->launches += 2;
     }

@@ -133,7 +133,7 @@ extern "C" int gm_gan_d_backward(gm_gan* g, int slot, int batch, const float* ds
              g->par[GM_NET_D] + g->D.off_b2, g->d.d_out_act, dscore, ds, g->lossbuf + 1, B);
   launch_pdl("dh_kernel", dh_kernel, g->dh_blocks, g->dh_threads, size_t(g->dh_rows_per_iter) * HP * sizeof(float), s,
              g->Aall + size_t(slot) * g->Bmax * HP, static_cast<const float*>(ds), w2, g->DHall + size_t(slot) * g->Bmax * HP, g->dw2p, B, H, HP,
-             g->dh_rows_per_iter, g->lo);
+             g->dh_rows_per_iter, g->lo, 0);
   launch_pdl("colsum_kernel", colsum_kernel, cdiv(HP * 32, 256), 256, 0, s, g->dw2p, g->dh_blocks, HP, HP, g->dw2sum);
   c->launches += 3;
   if ((rc = launch_plan(c, cp->dw1[slot], s))) return rc;

@@ -62,6 +62,8 @@ struct GemmParams {
   // dot_mask == 2 (DOT_T 4; WGAN-GP's D forward over [real; fake; x_hat] rows): rows >= mask_row0 store the mask form
   // U = w2 * relu'(a1) (what the penalty's first gradient needs) at out_alt + (row - mask_row0) * ldo,
   // the rows below keep the activations at out + row * ldo
+  // dot_mask == 3 (DOT_T 5; WGAN-GP's D forward when the x_hat rows are never materialised): the row-dot runs on relu(v)
+  // but the PRE-activation v is stored (the penalty's mask is 1[eps pre_real + (1-eps) pre_fake > 0], gp_hat_kernel)
   int mask_row0;
   __nv_bfloat16* out_alt;
   // tma_store: full 32-column blocks of the bf16 output leave through the output tensor map
@@ -370,7 +372,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int act = ACT_T >= 0 ? ACT_T : p.act;
     const int aux_mode = AUX_T >= 0 ? AUX_T : p.aux_mode;
     const bool has_bias = BIAS_T >= 0 ? (BIAS_T != 0) : (p.bias != nullptr);
-    const bool has_dot = DOT_T >= 0 ? (DOT_T == 1 || DOT_T == 3 || DOT_T == 4) : (p.dot_w != nullptr);
+    const bool has_dot = DOT_T >= 0 ? (DOT_T == 1 || DOT_T == 3 || DOT_T == 4 || DOT_T == 5) : (p.dot_w != nullptr);
+    const bool store_pre = DOT_T >= 0 ? (DOT_T == 5) : (p.dot_mask == 3);   // ReLU only inside the row-dot
     constexpr bool kRowMask = DOT_T == 4 || DOT_T < 0;   // per-row choice between activation and mask output
     const bool mask_all = DOT_T >= 0 ? (DOT_T == 3) : (p.dot_mask == 1);
     const bool mask_rows = DOT_T >= 0 ? (DOT_T == 4) : (p.dot_mask == 2);
@@ -567,8 +570,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   }
                 }
                 if (act == ACT_RELU) {
+                  if (!store_pre) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                  }
                 } else if (ACT_T < 0 && act == ACT_LRELU) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : p.act_slope * v[j];
@@ -622,8 +627,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                   for (int k4 = 0; k4 < 4; ++k4) {
                     const uint4 w = lds128(vec_s + kEpiVecBytes / 2 + (bi * kEpiCols + q * 16 + k4 * 4) * 4);
-                    dot = fmaf(v[4 * k4 + 0], __uint_as_float(w.x), dot); dot = fmaf(v[4 * k4 + 1], __uint_as_float(w.y), dot);
-                    dot = fmaf(v[4 * k4 + 2], __uint_as_float(w.z), dot); dot = fmaf(v[4 * k4 + 3], __uint_as_float(w.w), dot);
+                    if (store_pre) {   // v holds pre-activations: the activation enters the dot product only
+                      dot = fmaf(fmaxf(v[4 * k4 + 0], 0.f), __uint_as_float(w.x), dot); dot = fmaf(fmaxf(v[4 * k4 + 1], 0.f), __uint_as_float(w.y), dot);
+                      dot = fmaf(fmaxf(v[4 * k4 + 2], 0.f), __uint_as_float(w.z), dot); dot = fmaf(fmaxf(v[4 * k4 + 3], 0.f), __uint_as_float(w.w), dot);
+                    } else {
+                      dot = fmaf(v[4 * k4 + 0], __uint_as_float(w.x), dot); dot = fmaf(v[4 * k4 + 1], __uint_as_float(w.y), dot);
+                      dot = fmaf(v[4 * k4 + 2], __uint_as_float(w.z), dot); dot = fmaf(v[4 * k4 + 3], __uint_as_float(w.w), dot);
+                    }
                     if (mask_out) {
                       v[4 * k4 + 0] = v[4 * k4 + 0] > 0.f ? __uint_as_float(w.x) : 0.f;
                       v[4 * k4 + 1] = v[4 * k4 + 1] > 0.f ? __uint_as_float(w.y) : 0.f;

@@ -406,7 +406,8 @@ __global__ void colsum_kernel(const float* __restrict__ part, int nparts, int ld
 // blockDim = (ld/8) * rows_per_iter so a thread always owns the same 8 columns.
 __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ ds,
                           const float* __restrict__ w2, __nv_bfloat16* __restrict__ dh, float* __restrict__ dw2p,
-                          int rows, int h, int ld, int rows_per_iter, long long lo_off) {
+                          int rows, int h, int ld, int rows_per_iter, long long lo_off, int pre) {
+  // pre != 0: `a` holds PRE-activations (WGAN-GP's D forward, GemmParams.dot_mask == 3): relu is applied here
   griddep_sync();
   extern __shared__ float sh_acc[];  // [rows_per_iter][ld]
   const int groups = ld / 8;
@@ -448,8 +449,10 @@ __global__ void dh_kernel(const __nv_bfloat16* __restrict__ a, const float* __re
         const float lo = bf16_lo(w4[q]), hi = bf16_hi(w4[q]);   // the sign of the hi part is the sign of the value
         o[2 * q] = lo > 0.f ? d * w[2 * q] : 0.f;
         o[2 * q + 1] = hi > 0.f ? d * w[2 * q + 1] : 0.f;
-        acc[2 * q] = fmaf(d, lo + bf16_lo(l4[q]), acc[2 * q]);
-        acc[2 * q + 1] = fmaf(d, hi + bf16_hi(l4[q]), acc[2 * q + 1]);
+        const float a0 = (pre && !(lo > 0.f)) ? 0.f : lo + bf16_lo(l4[q]);
+        const float a1 = (pre && !(hi > 0.f)) ? 0.f : hi + bf16_hi(l4[q]);
+        acc[2 * q] = fmaf(d, a0, acc[2 * q]);
+        acc[2 * q + 1] = fmaf(d, a1, acc[2 * q + 1]);
       }
       if (dh != nullptr) store_bf16x8(dh + r * ld + g * 8, o, lo_off);
     }
@@ -522,6 +525,93 @@ __global__ void xhat_kernel(const __nv_bfloat16* __restrict__ xr, const __nv_bfl
         v[j] = o;
       }
       store_bf16x8(out + (long long)r * ld + c0, v, lo_off);
+    }
+  }
+}
+
+// WGAN-GP without materialised x_hat rows.  D's first layer is linear, so for x_hat = eps x + (1 - eps) G(z)
+// (src/w_gp_gan.py:197-201) the hidden pre-activation is  a_hat = eps a(x) + (1 - eps) a(G(z))  - the interpolated rows and
+// their share of the D-layer GEMM are never formed.  From the stored pre-activations of the real and fake rows (bf16, or
+// hi + lo planes in split mode) one warp per row writes what the penalty needs: U = w2 * relu'(a_hat) (the first
+// gradient's operand, bf16 [+ residual plane]) and the logit part s = sum_n w2[n] relu(a_hat[n]) into slot 0 of the row's
+// logit slots (the other slots are zeroed; b2 is added by the reader).  eps: rnd[r] or the same Philox draw as xhat_kernel.
+constexpr int kGpHatGroups = 2;    // 16-byte column groups per lane: ld <= 512 columns
+__global__ void gp_hat_kernel(const __nv_bfloat16* __restrict__ pre_r, const __nv_bfloat16* __restrict__ pre_f, const float* __restrict__ w2,
+                              __nv_bfloat16* __restrict__ U, float* __restrict__ slots, int nslots, int slot_ld, int rows, int h, int ld,
+                              const float* __restrict__ rnd, unsigned long long seed, unsigned long long stream_id, long long lo_off,
+                              const unsigned long long* __restrict__ step_ptr) {
+  griddep_sync();
+  if (step_ptr) stream_id += 2ull * (*step_ptr);
+  const int groups = ld / 8;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  // this lane's columns (the same for every row): w2 stays in registers
+  float wv[kGpHatGroups][8];
+#pragma unroll
+  for (int k = 0; k < kGpHatGroups; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (lane + 32 * k) * 8 + j;
+      wv[k][j] = (lane + 32 * k < groups && c < h) ? w2[c] : 0.f;
+    }
+  // two rows per pass, raw 16-byte loads first (predicated, no branches between them): 8 (16 in split mode) loads in
+  // flight per lane - the kernel is HBM-bound
+  const uint4 z4 = make_uint4(0, 0, 0, 0);
+  for (int r0 = w; r0 < rows; r0 += 2 * nwarps) {
+    uint4 ra[2][kGpHatGroups], rb[2][kGpHatGroups], la[2][kGpHatGroups], lb[2][kGpHatGroups];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int r = r0 + t * nwarps;
+#pragma unroll
+      for (int k = 0; k < kGpHatGroups; ++k) {
+        const int g = lane + 32 * k;
+        const bool ok = r < rows && g < groups;
+        const long long off = (long long)(ok ? r : 0) * ld + (ok ? g : 0) * 8;
+        ra[t][k] = z4; rb[t][k] = z4; la[t][k] = z4; lb[t][k] = z4;
+        if (ok) ra[t][k] = __ldg(reinterpret_cast<const uint4*>(pre_r + off));
+        if (ok) rb[t][k] = __ldg(reinterpret_cast<const uint4*>(pre_f + off));
+        if (ok && lo_off) la[t][k] = __ldg(reinterpret_cast<const uint4*>(pre_r + lo_off + off));
+        if (ok && lo_off) lb[t][k] = __ldg(reinterpret_cast<const uint4*>(pre_f + lo_off + off));
+      }
+    }
+    float e[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int r = r0 + t * nwarps;
+      e[t] = 0.f;
+      if (r < rows) {
+        if (rnd) e[t] = rnd[r];
+        else {
+          curandStatePhilox4_32_10_t st;
+          curand_init(seed ^ 0x9E3779B97F4A7C15ull, (unsigned long long)r, stream_id * 256ull, &st);
+          e[t] = curand_uniform(&st);   // (0,1]; the reference's rand is [0,1)
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int r = r0 + t * nwarps;
+      if (r >= rows) break;
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < kGpHatGroups; ++k) {
+        const int g = lane + 32 * k;
+        if (g >= groups) continue;
+        const uint32_t a4[4] = {ra[t][k].x, ra[t][k].y, ra[t][k].z, ra[t][k].w}, b4[4] = {rb[t][k].x, rb[t][k].y, rb[t][k].z, rb[t][k].w};
+        const uint32_t c4[4] = {la[t][k].x, la[t][k].y, la[t][k].z, la[t][k].w}, d4[4] = {lb[t][k].x, lb[t][k].y, lb[t][k].z, lb[t][k].w};
+        float u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pa = ((j & 1) ? bf16_hi(a4[j >> 1]) : bf16_lo(a4[j >> 1])) + ((j & 1) ? bf16_hi(c4[j >> 1]) : bf16_lo(c4[j >> 1]));
+          const float pb = ((j & 1) ? bf16_hi(b4[j >> 1]) : bf16_lo(b4[j >> 1])) + ((j & 1) ? bf16_hi(d4[j >> 1]) : bf16_lo(d4[j >> 1]));
+          const float ah = e[t] * pa + (1.f - e[t]) * pb;
+          u[j] = ah > 0.f ? wv[k][j] : 0.f;
+          dot = fmaf(fmaxf(ah, 0.f), wv[k][j], dot);
+        }
+        store_bf16x8(U + (long long)r * ld + g * 8, u, lo_off);
+      }
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (lane < nslots) slots[(long long)lane * slot_ld + r] = lane == 0 ? dot : 0.f;
     }
   }
 }

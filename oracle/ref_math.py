@@ -212,16 +212,25 @@ def g_loss(variant, dg):
 
 
 # ---------------------------------------------------------------- gradient penalty
-def gradient_penalty(P, xhat, out_act, lam=10.0, K=1.0, pre="D.", q=_exact):
+def gradient_penalty(P, xhat, out_act, lam=10.0, K=1.0, pre="D.", q=_exact, a1=None):
     """lam * mean((||d D(xhat)/d xhat||_2 - K)^2) and its gradient w.r.t. D's
     parameters, in closed form.  Restates
     src/w_gp_gan.py:201-215 (out_act='relu') and src/dra_gan.py:208-220
     (out_act='sigmoid'); norm subgradient 0 at 0 like torch's norm backward.
-    q: operand-quantisation hook (bf16_points models the CUDA path)."""
+    q: operand-quantisation hook (bf16_points models the CUDA path).
+    a1: the hidden pre-activation of the xhat rows when the caller already has it (the CUDA WGAN-GP path never forms
+    xhat: the first layer is linear, a1(xhat) = eps a1(x) + (1-eps) a1(G(z)), gm_b200 gp_hat_kernel); with q = identity
+    this is the same number as linear(xhat, W1, b1)."""
     W1, b1 = P[pre + "linear.weight"], P[pre + "linear.bias"]
     w2 = P[pre + "discriminate.weight"]
-    xhat = q("xhat", xhat)
-    fw = d_forward(P, xhat, out_act, pre, q=q)
+    if a1 is None:
+        xhat = q("xhat", xhat)
+        fw = d_forward(P, xhat, out_act, pre, q=q)
+    else:
+        h = np.maximum(a1, 0)
+        s_ = linear(h, w2, P[pre + "discriminate.bias"])
+        d_ = sigmoid(s_) if out_act == "sigmoid" else (np.maximum(s_, 0) if out_act == "relu" else s_)
+        fw = dict(x=xhat, a1=a1, h=h, hq=h, s=s_, d=d_)
     B = xhat.shape[0]
     M = (fw["hq"] > 0).astype(xhat.dtype)
     if out_act == "relu":
@@ -259,11 +268,14 @@ def gradient_penalty(P, xhat, out_act, lam=10.0, K=1.0, pre="D.", q=_exact):
 
 
 # ---------------------------------------------------------------- train steps
-def gan_d_step(P, variant, images, z, aux=None, st=None, lam=10.0, q=_exact):
+def gan_d_step(P, variant, images, z, aux=None, st=None, lam=10.0, q=_exact, pre_points=None):
     """Trainer.train_D + D_loss.backward(), restricted to D's gradients (the G
     gradients the reference also computes are discarded at src/ns_gan.py:148).
     aux: for 'wgp' eps [B,1] (src/w_gp_gan.py:197); for 'dra' (delta [B,1],
-    u [B,X]) (src/dra_gan.py:200,205)."""
+    u [B,X]) (src/dra_gan.py:200,205).
+    pre_points: (a1 of the real rows, a1 of the fake rows) as STORED by the device (bf16), for 'wgp' with a quantising q:
+    the model is then evaluated at the device's storage points (a 1-ulp difference in a stored pre-activation - fp32
+    vs float64 accumulation order - moves a_hat by ~1e-3 and can flip a near-zero unit of the penalty's mask)."""
     act = D_OUT_ACT.get(variant, "sigmoid")
     gf = g_forward(P, z, q=q)
     fx = d_forward(P, images, act, q=q)
@@ -276,7 +288,15 @@ def gan_d_step(P, variant, images, z, aux=None, st=None, lam=10.0, q=_exact):
     if variant == "wgp":
         eps = aux
         xhat = eps * images + (1 - eps) * gf["out"]                   # src/w_gp_gan.py:201
-        gp, ggp, gi = gradient_penalty(P, xhat, "relu", lam=lam, q=q)
+        # the bf16-point model follows the CUDA path: pre-activations of the real / fake rows are stored (rounded), the
+        # xhat rows are not formed
+        if q is _exact:
+            a1h = None
+        elif pre_points is not None:
+            a1h = eps * pre_points[0] + (1 - eps) * pre_points[1]
+        else:
+            a1h = eps * q("a", fx["a1"]) + (1 - eps) * q("a", fg["a1"])
+        gp, ggp, gi = gradient_penalty(P, xhat, "relu", lam=lam, q=q, a1=a1h)
         L = L + gp
         grads = {k: grads[k] + ggp[k].reshape(grads[k].shape) for k in grads}
         info.update(gp=gp, gp_n=gi["n"])

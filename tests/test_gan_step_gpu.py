@@ -86,9 +86,22 @@ def test_step1_against_golden_and_oracle(case):
         eng.fisher_state(0.0, 1e-6)
     Lo, go, info = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), aux_o, st)
     stq = dict(st) if st else None
-    _, goq, _ = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), aux_o, stq, q=R.bf16_points)
     xd = torch.from_numpy(x).cuda()
     Ld = eng.d_grad(xd, noise=torch.from_numpy(z1).cuda(), aux=aux_d).item()
+    pre_pts = None
+    if case == "wgp":
+        # WGAN-GP never forms the x_hat rows: a_hat = eps a(x) + (1-eps) a(G(z)) from the STORED (bf16) pre-activations of
+        # the real / fake rows.  The bf16-point model is evaluated at those stored values: ~0.5 % of them differ by one
+        # bf16 ulp from a float64 evaluation (fp32 accumulation order, measured 120 of 25 600), which moves a_hat by
+        # ~1e-3 and flips about one near-zero unit of the penalty's mask per step (1e-3 on the gradient)
+        pre = eng.debug_read("Aall", 0, 2 * B, 400).cpu().numpy().astype(np.float64)
+        pre_pts = (pre[:B], pre[B:])
+        # ... and they ARE the model's values up to that: at most one ulp away, < 2 % of the elements
+        fake_q = R.g_forward(P, z1.astype(np.float64), q=R.bf16_points)["out"]
+        ref_pre = np.concatenate([R.bf16_round(R.d_forward(P, rows, "relu", q=R.bf16_points)["a1"]) for rows in (x.astype(np.float64), fake_q)])
+        assert np.abs(pre - ref_pre).max() <= 2.0 ** -7 * max(1.0, float(np.abs(ref_pre).max())), float(np.abs(pre - ref_pre).max())
+        assert (pre != ref_pre).mean() < 0.02, float((pre != ref_pre).mean())
+    _, goq, _ = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), aux_o, stq, q=R.bf16_points, pre_points=pre_pts)
     sc = eng.scores(2 * B).cpu().numpy()
     gD = [v.cpu().numpy() for v in eng.views(1, eng.grads[1])]
     rep = {}

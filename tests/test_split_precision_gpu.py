@@ -76,12 +76,16 @@ class DeviceReluSides:
         def d_forward(P, x, *a, **k):
             fw = self._d(P, x, *a, **k)
             reg = self.d_regions[min(self._calls, len(self.d_regions) - 1)]
-            buf, reg = reg if isinstance(reg, tuple) else ("Aall", reg)
+            reg = reg if isinstance(reg, tuple) else ("Aall", reg)
+            buf, reg, positive = reg if len(reg) == 3 else (reg[0], reg[1], False)
             self._calls += 1
             near = np.abs(fw["a1"]) < TOL_A
             if near.any():
                 n = fw["a1"].shape[0]
-                act = self.eng.debug_read(buf, reg * n, n, fw["a1"].shape[1]).cpu().numpy() != 0
+                # the buffers hold activations or the signed mask form w2 * relu'(a) (nonzero <=> active); WGAN-GP's real /
+                # fake rows hold PRE-activations (positive <=> active; regions flagged `positive`)
+                v = self.eng.debug_read(buf, reg * n, n, fw["a1"].shape[1]).cpu().numpy()
+                act = (v > 0) if positive else (v != 0)
                 for key in ("h", "hq"):
                     v = fw[key].copy()
                     v[near] = np.where(act[near], 1e-30, 0.0)
@@ -135,7 +139,8 @@ def test_step1_every_output_within_1e3(case):
     sc = eng.scores(2 * B).cpu().numpy()
     gD = [v.cpu().numpy() for v in eng.views(1, eng.grads[1])]
     # D hidden rows: real, fake, xhat (WGAN-GP keeps the x_hat rows only in mask form, in the U region of DHall)
-    with DeviceReluSides(eng, d_regions=[0, 1, ("DHall", 2) if case == "wgp" else 2], g_hidden=False) as sides_d:
+    regions = [("Aall", 0, True), ("Aall", 1, True), ("DHall", 2)] if case == "wgp" else [0, 1, 2]
+    with DeviceReluSides(eng, d_regions=regions, g_hidden=False) as sides_d:
         Lo, go, _ = R.gan_d_step(P, case, x.astype(np.float64), z1.astype(np.float64), aux_o, st)
     rep = {"D_loss_vs_golden": abs(Ld - float(fx["step1_D_loss"])) / max(abs(float(fx["step1_D_loss"])), 1e-3),
            "D_loss_vs_oracle": abs(Ld - Lo) / max(abs(Lo), 1e-3),
