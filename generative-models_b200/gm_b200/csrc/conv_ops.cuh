@@ -1,5 +1,5 @@
 // Building blocks of the DCGAN conv path (BASELINE configs[4]; the reference only recommends DCGAN, README.md:68,96 —
-// there is no reference implementation, see DESIGN.md §9): NHWC bf16 activations as row-major matrices [B*H*W, C], so
+// there is no reference implementation, see DESIGN.md §6b): NHWC bf16 activations as row-major matrices [B*H*W, C], so
 // that every convolution / transposed convolution is one tcgen05 GEMM (gemm_umma.cuh) between an im2col / col2im pass:
 //   conv   (k4 s2 p1): col = im2col(x) [B*Ho*Wo, 16*Cin];  y = col W^T        (W [Cout, (kh,kw,ci)])
 //   convT  (k4 s2 p1): col = x Wm^T    [B*Hi*Wi, 16*Cout]; y = col2im(col)    (Wm [(kh,kw,co), Cin])

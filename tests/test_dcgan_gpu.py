@@ -49,6 +49,47 @@ def test_im2col_col2im_match_torch_conv_ops():
     assert torch.equal(col3.float(), ref3.view(B, 3, 16, -1).permute(0, 3, 2, 1).reshape(B * 64, 48))
 
 
+def test_conv_ops_non_power_of_two_extents():
+    """Extents that take the generic division path of the index arithmetic (FastDiv shift < 0), an idle tail of the
+    BatchNorm thread mapping (256 % (C/8) != 0), and the fused col2im tails."""
+    from gm_b200 import dcgan as DC
+    B, H, W, Cin = 3, 12, 20, 24
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    xr = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).view(B * H * W, Cin)
+    L = (H // 2) * (W // 2)
+    col = torch.empty(B * L, 16 * Cin, device="cuda", dtype=torch.bfloat16)
+    DC._im2col(xr, B, H, W, Cin, col)
+    ref = torch.nn.functional.unfold(xr.float().view(B, H, W, Cin).permute(0, 3, 1, 2), 4, padding=1, stride=2)
+    assert torch.equal(col.float(), ref.view(B, Cin, 16, -1).permute(0, 3, 2, 1).reshape(B * L, 16 * Cin))
+    Hi, Wi, Co = 6, 10, 24
+    colr = torch.randn(B * Hi * Wi, 16 * Co, device="cuda", generator=g).to(torch.bfloat16)
+    aux = torch.randn(B * 4 * Hi * Wi, Co, device="cuda", generator=g).to(torch.bfloat16)
+    cols = colr.float().view(B, Hi * Wi, 16, Co).permute(0, 3, 2, 1).reshape(B, Co * 16, Hi * Wi)
+    fold = torch.nn.functional.fold(cols, (2 * Hi, 2 * Wi), 4, padding=1, stride=2).permute(0, 2, 3, 1).reshape(-1, Co)   # NHWC rows
+    a = aux.float()
+    for mode, want in ((DC.C2I_NONE, fold), (DC.C2I_SIGMOID, torch.sigmoid(fold)),
+                       (DC.C2I_LRELU_GRAD, torch.where(a > 0, fold, DC.SLOPE * fold)), (DC.C2I_SIGMOID_GRAD, fold * a * (1 - a))):
+        y = torch.empty(B * 4 * Hi * Wi, Co, device="cuda", dtype=torch.bfloat16)
+        DC._col2im(colr, B, Hi, Wi, Co, y, mode, aux if mode >= DC.C2I_LRELU_GRAD else None)
+        assert _nrel(y.float(), want) < 4e-3, mode
+    rows, Cc = 1000 + 13, 24
+    xb = (torch.randn(rows, Cc, device="cuda", generator=g) * 0.7 - 0.2).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(Cc, device="cuda", generator=g)).float()
+    beta = (0.1 * torch.randn(Cc, device="cuda", generator=g)).float()
+    dy = torch.randn(rows, Cc, device="cuda", generator=g).to(torch.bfloat16)
+    y, dx = torch.empty_like(xb), torch.empty_like(xb)
+    stats, dgb = torch.zeros(2, Cc, device="cuda"), torch.zeros(2, Cc, device="cuda")
+    DC._bn_fwd(xb, gamma, beta, DC.ACT_RELU, y, stats, None)
+    DC._bn_bwd(dy, xb, stats, gamma, beta, DC.ACT_RELU, dx, dgb)
+    xt = xb.float().requires_grad_()
+    gt, bt = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    yt = torch.relu(torch.nn.functional.batch_norm(xt, None, None, gt, bt, True, 0.1, 1e-5))
+    yt.backward(dy.float())
+    assert _nrel(y.float(), yt) < 4e-3 and _nrel(dx.float(), xt.grad) < 6e-3
+    assert _nrel(dgb[0], bt.grad) < 1e-3 and _nrel(dgb[1], gt.grad) < 1e-3
+
+
 def test_batchnorm_forward_backward_match_torch():
     from gm_b200 import dcgan as DC
     rows, Cc = 4096 + 37, 64

@@ -74,6 +74,31 @@ def test_gan_three_step_trajectory(case):
         np.testing.assert_allclose(st["LAMBDA"], fx["final_LAMBDA"][0], rtol=1e-4, atol=1e-12)
 
 
+def test_wgp_penalty_from_interpolated_preactivations_is_the_same_number():
+    """The CUDA WGAN-GP path never forms x_hat (gp_hat_kernel): D's first layer is linear, so the hidden pre-activation of
+    x_hat = eps x + (1-eps) G(z) is eps a(x) + (1-eps) a(G(z)).  The oracle's penalty fed with that pre-activation must be
+    the penalty of the reference's formulation (src/w_gp_gan.py:197-215, pinned by the golden fixture) to rounding."""
+    fx = load_case("gan_wgp")
+    P = params_dict(gm_init_weights(GAN_SHAPES, 1234), np.float64)
+    x = images_from_bits(fx).astype(np.float64)
+    z, eps = [d.astype(np.float64) for d in unpack_draws(fx, "step1_")[:2]]
+    fake = R.g_forward(P, z)["out"]
+    xhat = eps * x + (1 - eps) * fake
+    gp0, g0, i0 = R.gradient_penalty(P, xhat, "relu")
+    a1 = eps * R.d_forward(P, x, "relu")["a1"] + (1 - eps) * R.d_forward(P, fake, "relu")["a1"]
+    gp1, g1, i1 = R.gradient_penalty(P, xhat, "relu", a1=a1)
+    assert abs(gp0 - gp1) <= 1e-12 * max(1.0, abs(gp0))
+    np.testing.assert_allclose(i1["n"], i0["n"], rtol=1e-11, atol=1e-13)
+    for k in g0:
+        np.testing.assert_allclose(g1[k], g0[k], rtol=1e-9, atol=1e-13)
+    # and the quantising model evaluated at given storage points reduces to the plain one when the points are its own
+    q = R.bf16_points
+    fr, fg = R.d_forward(P, x, "relu", q=q), R.d_forward(P, R.g_forward(P, z, q=q)["out"], "relu", q=q)
+    La, ga, _ = R.gan_d_step(P, "wgp", x, z, eps, q=q)
+    Lb, gb, _ = R.gan_d_step(P, "wgp", x, z, eps, q=q, pre_points=(q("a", fr["a1"]), q("a", fg["a1"])))
+    assert La == Lb and all(np.array_equal(ga[k], gb[k]) for k in ga)
+
+
 def test_gan_oracle_float32_matches_float64():
     fx = load_case("gan_ns")
     x = images_from_bits(fx)
