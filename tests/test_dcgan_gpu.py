@@ -14,6 +14,7 @@ _REPORT = {}
 
 def _nrel(a, b):
     a, b = a.double().reshape(-1).cpu(), b.double().reshape(-1).cpu()
+    a, b = a.detach(), b.detach()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
