@@ -107,3 +107,16 @@ def test_dcgan_dropin_surface_without_a_gpu():
         model.G(torch.randn(2, 100))
     with pytest.raises(GmError):
         dc_gan.DCGAN(image_size=784)
+
+
+def test_space_to_depth_conv_identity():
+    """DESIGN 6b `Next`: the k4 s2 p1 convolution, its two gradients and the transposed convolution as four ROW-SHIFTED GEMMs
+    on the space-to-depth matrix (tools/s2d_conv_prototype.py) agree with torch to rounding, also for odd grid extents."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("s2d", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "s2d_conv_prototype.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    for kw in (dict(), dict(seed=1, B=3, H=4, W=4, C=8, Co=16), dict(seed=2, B=1, H=10, W=6, C=2, Co=3)):
+        err = m.check(**kw)
+        assert max(err.values()) < 1e-12, (kw, err)
